@@ -1,0 +1,213 @@
+/*
+ * qrs_b200.h — C ABI of libqrs_b200.so: the B200 (sm_100a) implementation of the
+ * LSH → top-k collaborative-filtering hot path of
+ * wamuumu/query-recommendation-system.
+ *
+ * The reference has no FFI: its "operator API" for this path is two Python
+ * classes (lsh.py:7-54 `LSH`, recommender.py:49-343 `Recommender`).  Each entry
+ * point below replaces one step of those classes and cites it; the Python
+ * mirror of the classes lives in query_recommendation_system_b200/{lsh,recommender}.py
+ * and calls these symbols through ctypes (INTEGRATION.md shows the binding a
+ * reference maintainer would add).
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, a CUDA stream passed as void* (cudaStream_t).
+ *   - every buffer is CALLER-OWNED DEVICE memory; nothing is allocated, freed or
+ *     retained by the library, and there is no global mutable state (fixes the
+ *     reference's class-level LSH.buckets, lsh.py:9).  Calls on different
+ *     streams/devices may run concurrently.
+ *   - return value: QRS_OK (0) or a negative qrs_status; no exceptions cross
+ *     the ABI.  Kernel launches are asynchronous on `stream`; a returned QRS_OK
+ *     means "enqueued".  Counters the host must read are written to device
+ *     memory the caller copies back itself.
+ *   - workspaces: every function that needs scratch has a *_workspace_bytes()
+ *     twin; `ws` must be 256-byte aligned and at least that large.
+ *   - "sets × elements" CSR: rowptr int64[n+1], colidx int32[nnz] ascending and
+ *     distinct within a row.  Binding A: set = query, element = dataset tuple
+ *     (recommender.py:68-103).  Binding B: set = user, element = rated query.
+ */
+#ifndef QRS_B200_H
+#define QRS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum qrs_status {
+  QRS_OK = 0,
+  QRS_ERR_INVALID_ARG = -1,   /* null pointer, negative size, K % b != 0 (lsh.py:20) ... */
+  QRS_ERR_UNSUPPORTED = -2,   /* shape outside what the kernels were built for */
+  QRS_ERR_WORKSPACE = -3,     /* workspace too small */
+  QRS_ERR_CUDA = -4           /* a CUDA runtime call failed; see qrs_last_cuda_error() */
+} qrs_status;
+
+#define QRS_MAX_TOPK 64          /* neighbour-table width limit (reference k = round(log_1.5 n) <= 45) */
+#define QRS_MAX_BANDS 256        /* the band index travels in 8 bits of a bucket record */
+#define QRS_HASH_BITS 24
+#define QRS_SENTINEL_HASH 0xFFFFFFu /* bucket record of an all-(-1) band: never grouped */
+
+int qrs_version(void);                       /* 100 * major + minor */
+const char *qrs_status_string(int status);
+const char *qrs_last_cuda_error(void);       /* thread-local text of the last CUDA failure */
+int qrs_device_sm_count(int device);         /* -1 on error */
+
+/* Bucket record (u64), the unit that is sorted, exchanged between GPUs and
+ * turned into candidate pairs:
+ *     bits 63..40  hash24 of the band's r int16 lanes (QRS_SENTINEL_HASH when the
+ *                  lanes are all -1, lsh.py:44-47)
+ *     bits 39..32  band index
+ *     bits 31..0   global set id
+ * Equal (hash24, band) is only a HINT that two sets share a bucket;
+ * qrs_pairs_score re-checks the exact lanes, so hash collisions cost work,
+ * never correctness. */
+
+/* ---------------------------------------------------------------- a1: MinHash
+ * Replaces Recommender.compute_signatures (recommender.py:105-143):
+ *   sig[s][i] = min_{e in set(s)} perm_i[e],  -1 for an empty set,
+ * where perm_i is the i-th np.random.permutation(m) (recommender.py:120),
+ * supplied by the host as the element-major table perm_tab[e*K + i].
+ */
+
+/* Setup: order_head[i*R + r] = the element e with perm_tab[e*K + i] == r, for
+ * r < R <= m — the first R entries of the reference's argsort (recommender.py:121),
+ * hash-major so that 32 consecutive ranks of one hash are one 128-byte line. */
+int qrs_perm_head_invert(const int32_t *perm_tab, int32_t m, int32_t K, int32_t R,
+                         int32_t *order_head, void *stream);
+
+#define QRS_MINHASH_AUTO 0         /* per set: first-touch when len*len >= m, else direct */
+#define QRS_MINHASH_DIRECT 1       /* per-nonzero gather-min from perm_tab                */
+#define QRS_MINHASH_FIRST_TOUCH 2  /* membership-map scan in permuted order (the reference's
+                                      own first-touch walk, recommender.py:125-129)       */
+
+/* Signatures + fused epilogue.  Optional outputs (pass NULL to skip):
+ *   norm2[s]   = sum_i sig[s][i]^2                       (for a8)
+ *   records[band*rec_stride + s] = bucket record of (set id_base + s, band);
+ *                requires 0 < b <= QRS_MAX_BANDS and K % b == 0.
+ * order_head/R may be NULL/0, which forces the DIRECT kernel; R must be a
+ * multiple of 32.  First-touch needs m <= qrs_minhash_max_elements(). */
+int64_t qrs_minhash_max_elements(void);
+int qrs_minhash_perm(const int64_t *rowptr, const int32_t *colidx, int64_t n, int32_t m,
+                     const int32_t *perm_tab, const int32_t *order_head, int32_t R,
+                     int32_t K, int32_t b, int64_t id_base,
+                     int32_t *sig, int64_t *norm2, uint64_t *records, int64_t rec_stride,
+                     int32_t mode, void *stream);
+
+/* ------------------------------------------------------ a2/a3: banding
+ * Replaces LSH.make_subvecs + the key construction of LSH.compute_buckets
+ * (lsh.py:17-38).  keys[s*b + band] = the r int16 lanes packed big-endian
+ * (lane 0 most significant) — the exact bucket id for r <= 4; for r > 4 (r <= 8)
+ * pass keys_hi as well (lanes 0..r-5 in keys_hi, last 4 lanes in keys).
+ * skipped[s*b + band] = 1 iff every lane is -1 (lsh.py:47). */
+int qrs_band_keys(const int32_t *sig, int64_t n, int32_t K, int32_t b,
+                  uint64_t *keys, uint64_t *keys_hi, uint8_t *skipped, void *stream);
+
+/* Bucket records (and optionally norm2) from an existing signature matrix; same
+ * layout as qrs_minhash_perm's. */
+int qrs_band_records(const int32_t *sig, int64_t n, int32_t K, int32_t b, int64_t id_base,
+                     uint64_t *records, int64_t rec_stride, int64_t *norm2, void *stream);
+
+/* ------------------------------------------------------ a3/a4: grouping
+ * Replaces the per-band dict insertion (lsh.py:35-37): a stable LSD radix sort
+ * of u64 keys on bits [bit_lo, bit_hi), independently for `segs` consecutive
+ * segments of `n_per_seg` keys.  On return the sorted keys are in `keys`.
+ * `tmp` has the size of `keys`. */
+size_t qrs_sort_workspace_bytes(int64_t n_per_seg, int32_t segs);
+int qrs_sort_u64(uint64_t *keys, uint64_t *tmp, int64_t n_per_seg, int32_t segs,
+                 int32_t bit_lo, int32_t bit_hi, void *ws, size_t ws_bytes, void *stream);
+
+/* ------------------------------------------------------ a5: candidate pairs
+ * Replaces LSH.get_candidates (lsh.py:40-54).
+ * Input: n_records records sorted on bits [32, 64) (any number of bands, one
+ * flat array).  slot_off u64[n_records + 1] receives the exclusive prefix sum of
+ * "number of earlier records in the same (hash24, band) run"; slot_off[n_records]
+ * is the number of pair slots = sum over runs of h*(h-1)/2, an upper bound on
+ * (and normally close to) the number of (pair, band) coincidences. */
+size_t qrs_pair_slots_workspace_bytes(int64_t n_records);
+int qrs_pair_slots(const uint64_t *records, int64_t n_records, uint64_t *slot_off,
+                   void *ws, size_t ws_bytes, void *stream);
+
+/* ------------------------------------------------------ a5 + a8: emit, dedup, score
+ * Replaces the global-set dedup of get_candidates (lsh.py:51-53) and the rounded
+ * cosine (recommender.py:203-204).  For every two members (i, j) of a run in
+ * band B, the pair is verified against the signatures themselves (exact int16
+ * lane equality, not-all-(-1)) and emitted iff B is the FIRST band in which the
+ * two signatures share a bucket — so every candidate pair is emitted exactly
+ * once and hash collisions cannot create false candidates.
+ *   pairs[t] = i << 32 | j  (i < j, global ids as stored in the records)
+ *   sim_milli[t] = rint(1000 * cos(sig_i, sig_j))   (np.around(.,3) * 1000)
+ * sig/norm2 are indexed by (id - sig_id_base).  *n_pairs (device u64, zeroed by
+ * the caller) counts emitted pairs; pairs beyond `capacity` are counted but not
+ * stored.  Output order is unspecified (set semantics).  sim_milli may be NULL
+ * (candidates only). */
+int qrs_pairs_score(const uint64_t *records, int64_t n_records, const uint64_t *slot_off,
+                    const int32_t *sig, const int64_t *norm2, int64_t sig_id_base,
+                    int32_t K, int32_t b,
+                    uint64_t *pairs, int32_t *sim_milli, int64_t capacity,
+                    unsigned long long *n_pairs, void *stream);
+
+/* Score an explicit pair list (ids index sig directly). */
+int qrs_pair_cosine(const int32_t *sig, const int64_t *norm2, int32_t K,
+                    const uint64_t *pairs, int64_t n_pairs, int32_t *sim_milli, void *stream);
+
+/* ------------------------------------------------------ a7 + a9: neighbour tables
+ * Replaces the adjacency build and top-k (recommender.py:183-210) with the
+ * canonical order (similarity descending, neighbour id ascending).
+ * Rows [row_base, row_base + n_rows) are produced; a pair end outside that
+ * range contributes only to the end inside it.
+ *   idx int32[n_rows*k] (-1 padded), val double[n_rows*k] (0 padded), cnt int32[n_rows]
+ * adj: u64[2*n_pairs] scratch for the adjacency lists. */
+size_t qrs_topk_workspace_bytes(int64_t n_rows);
+int qrs_topk_tables(const uint64_t *pairs, const int32_t *sim_milli, int64_t n_pairs,
+                    int64_t row_base, int64_t n_rows, int32_t k,
+                    uint64_t *adj, void *ws, size_t ws_bytes,
+                    int32_t *idx, double *val, int32_t *cnt, void *stream);
+
+/* ------------------------------------------------------ a10 + a11: prediction
+ * Replaces weighted_average (recommender.py:36-47) and the per-cell loop +
+ * hybrid rule of Recommender.compute_scores (recommender.py:311-331).
+ * Ratings: CSR users × queries, rowptr int64[U+1], colidx int32 ascending,
+ * val uint8 (0 = unrated; stored zeros are allowed and ignored).  Tables as
+ * produced by qrs_topk_tables (or by the host for the reference's PCA+BIRCH
+ * user branch, recommender.py:274-286); pass idx == NULL for an absent
+ * branch.  fp64, left-to-right in table order, no FMA contraction,
+ * round-half-even — bit-identical to the reference's arithmetic.
+ * User-table ids are GLOBAL user ids (rows of the CSR); the users predicted
+ * are [user_base, user_base + n_users), table row t ↔ user user_base + t.
+ *
+ * Dense form (drop-in for compute_scores at reference scale):
+ *   out int32[n_users*Q]: rated cells keep the rating, unrated cells get the
+ *   hybrid prediction (0 = "missed", recommender.py:341). */
+int qrs_predict_dense(const int64_t *rowptr, const int32_t *colidx, const uint8_t *val,
+                      int64_t U, int32_t Q,
+                      const int32_t *q_idx, const double *q_val, const int32_t *q_cnt, int32_t kq,
+                      const int32_t *u_idx, const double *u_val, const int32_t *u_cnt, int32_t ku,
+                      int64_t user_base, int64_t n_users, int32_t *out, void *stream);
+
+/* Sparse form for the scaled configurations (user branch only, query branch
+ * absent ⇒ q = 0): per user the non-zero predictions over unrated queries.
+ * The query axis is cut into nt = ceil(Q / tile) tiles of `tile` columns
+ * (a multiple of 32, <= qrs_predict_max_tile(); pick it so that one CSR row
+ * has ~16-32 entries per tile).  For user t and tile c,
+ *   row_start int64[n_users*nt], row_cnt int32[n_users*nt] (index t*nt + c)
+ * locate a contiguous slice of (cols int32[], preds uint8[]), ascending in
+ * col; slices are placed by an atomic cursor, so their order in the buffer is
+ * unspecified.  *cursor (device u64, zeroed by the caller) ends as the total
+ * count; writes beyond `capacity` are dropped (the count still advances).
+ * cols/preds may be NULL with capacity 0 for a counting pass. */
+int32_t qrs_predict_max_tile(void);
+size_t qrs_predict_sparse_workspace_bytes(int64_t U, int32_t Q, int32_t tile);
+int qrs_predict_sparse(const int64_t *rowptr, const int32_t *colidx, const uint8_t *val,
+                       int64_t U, int32_t Q,
+                       const int32_t *u_idx, const double *u_val, const int32_t *u_cnt, int32_t ku,
+                       int64_t user_base, int64_t n_users, int32_t tile,
+                       void *ws, size_t ws_bytes,
+                       int64_t *row_start, int32_t *row_cnt, int32_t *cols, uint8_t *preds,
+                       int64_t capacity, unsigned long long *cursor, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QRS_B200_H */

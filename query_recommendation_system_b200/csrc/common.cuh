@@ -1,0 +1,110 @@
+// Shared helpers for the libqrs_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "qrs_b200.h"
+
+namespace qrs {
+
+void set_cuda_error(cudaError_t e, const char *file, int line);
+
+#define QRS_CUDA(expr)                                        \
+  do {                                                        \
+    cudaError_t _e = (expr);                                  \
+    if (_e != cudaSuccess) {                                  \
+      ::qrs::set_cuda_error(_e, __FILE__, __LINE__);          \
+      return QRS_ERR_CUDA;                                    \
+    }                                                         \
+  } while (0)
+
+#define QRS_LAUNCH_CHECK() QRS_CUDA(cudaGetLastError())
+
+static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+template <typename T>
+__host__ __device__ constexpr T ceil_div(T a, T b) { return (a + b - 1) / b; }
+template <typename T>
+__host__ __device__ constexpr T round_up(T a, T b) { return ceil_div(a, b) * b; }
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xFFFFFFFFu;
+
+// SM count of the current device, cached per device (grids are sized in
+// multiples of it).
+int sm_count();
+
+// ---------------------------------------------------------------- bucket records
+// hash24 of one band: the r int16 lanes (low 16 bits of the signature values,
+// lsh.py:28) folded together.  Grouping is by (hash24, band); qrs_pairs_score
+// re-verifies every pair on the exact lanes, so collisions cost work, never
+// correctness.
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t h) {
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  return h;
+}
+__host__ __device__ __forceinline__ uint32_t band_hash_init(uint32_t band) {
+  return 0x9E3779B9u * (band + 1u);
+}
+__host__ __device__ __forceinline__ uint32_t band_hash_step(uint32_t h, uint32_t lane16) {
+  return mix32(h ^ lane16) * 0x9E3779B1u + 0x7F4A7C15u;
+}
+__host__ __device__ __forceinline__ uint32_t band_hash_finish(uint32_t h, bool all_neg) {
+  h = mix32(h) >> (32 - QRS_HASH_BITS);
+  if (h == QRS_SENTINEL_HASH) h = QRS_SENTINEL_HASH - 1u;
+  return all_neg ? QRS_SENTINEL_HASH : h;
+}
+__host__ __device__ __forceinline__ uint64_t make_record(uint32_t hash24, uint32_t band, uint32_t id) {
+  return (uint64_t(hash24) << 40) | (uint64_t(band & 0xFFu) << 32) | uint64_t(id);
+}
+__host__ __device__ __forceinline__ uint32_t rec_key(uint64_t rec) { return uint32_t(rec >> 32); }
+__host__ __device__ __forceinline__ uint32_t rec_hash(uint64_t rec) { return uint32_t(rec >> 40); }
+__host__ __device__ __forceinline__ uint32_t rec_band(uint64_t rec) { return uint32_t(rec >> 32) & 0xFFu; }
+__host__ __device__ __forceinline__ uint32_t rec_id(uint64_t rec) { return uint32_t(rec); }
+
+// record of (set, band) from r consecutive signature values
+__device__ __forceinline__ uint64_t band_record(const int *lanes, int r, uint32_t band, uint32_t id) {
+  uint32_t h = band_hash_init(band);
+  bool all_neg = true;
+  for (int c = 0; c < r; ++c) {
+    uint32_t l16 = uint32_t(lanes[c]) & 0xFFFFu;
+    all_neg = all_neg && (l16 == 0xFFFFu);
+    h = band_hash_step(h, l16);
+  }
+  return make_record(band_hash_finish(h, all_neg), band, id);
+}
+
+// ---------------------------------------------------------------- warp helpers
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+__device__ __forceinline__ unsigned lanemask_lt() {
+  unsigned m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+// streaming (read-once) global loads: keep them out of L1
+__device__ __forceinline__ int ld_stream_s32(const int *p) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint64_t ld_stream_u64(const uint64_t *p) {
+  uint64_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+
+// ---------------------------------------------------------------- device-wide scan
+// Exclusive prefix sum of u32 counts into u64 offsets (out[n] = total).
+// ws: scan_workspace_bytes(n).  Three launches: tile sums, one-CTA scan of the
+// tile sums, tile scan + carry-in.
+size_t scan_workspace_bytes(int64_t n);
+int exclusive_scan_u32_to_u64(const uint32_t *in, uint64_t *out, int64_t n, void *ws,
+                              size_t ws_bytes, cudaStream_t stream);
+
+}  // namespace qrs

@@ -1,0 +1,227 @@
+// a5 + a8 — candidate pairs out of the grouped bucket records (lsh.py:40-54), de-duplicated
+// across bands without a global set/sort, and scored with the rounded cosine of the
+// signature vectors (recommender.py:203-204) in the same pass.
+//
+//   pair_slots : record p gets one "slot" per earlier record of its (hash24, band) run;
+//                an exclusive scan of the slot counts load-balances the quadratic part.
+//   pairs_score: one warp per slot.  It reads both signature rows ONCE and derives from
+//                them (1) exact int16-lane equality in the slot's band (hash collisions are
+//                discarded), (2) whether an EARLIER band already puts the two sets in one
+//                bucket (then this slot is a duplicate of the pair emitted there), and
+//                (3) the int64 dot product for the cosine.
+#include "common.cuh"
+
+namespace qrs {
+
+constexpr int kPairThreads = 256;
+constexpr int kPairWarps = kPairThreads / 32;
+constexpr int kMaxSigWords = 32;   // K <= 1024
+
+__global__ void __launch_bounds__(256)
+pair_slot_count_kernel(const uint64_t *__restrict__ records, int64_t n, uint32_t *__restrict__ cnt) {
+  for (int64_t p = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; p < n; p += int64_t(gridDim.x) * blockDim.x) {
+    const uint32_t key = rec_key(records[p]);
+    uint32_t t = 0;
+    if ((key >> 8) != QRS_SENTINEL_HASH) {
+      while (int64_t(t) < p && rec_key(records[p - 1 - t]) == key) ++t;
+    }
+    cnt[p] = t;
+  }
+}
+
+__device__ __forceinline__ double cosine_of(long long dot, long long n2a, long long n2b) {
+  const double den = sqrt(double(n2a) * double(n2b));
+  return den == 0.0 ? 0.0 : double(dot) / den;
+}
+__device__ __forceinline__ int to_milli(double c) { return int(rint(c * 1000.0)); }
+
+// r consecutive bits of a multi-word mask starting at bit `start` (r <= 32)
+__device__ __forceinline__ uint32_t mask_bits(const uint32_t *m, int start, int r, int words) {
+  const int w = start >> 5, o = start & 31;
+  uint32_t v = m[w] >> o;
+  if (o + r > 32 && w + 1 < words) v |= m[w + 1] << (32 - o);
+  return r == 32 ? v : (v & ((1u << r) - 1u));
+}
+
+__global__ void __launch_bounds__(kPairThreads)
+pairs_score_kernel(const uint64_t *__restrict__ records, int64_t n_records, const uint64_t *__restrict__ slot_off,
+                   const int *__restrict__ sig, const long long *__restrict__ norm2, int64_t sig_id_base, int K,
+                   int b, uint64_t *__restrict__ pairs, int *__restrict__ sim_milli, int64_t capacity,
+                   unsigned long long *__restrict__ n_pairs) {
+  __shared__ uint32_t s_eq[kPairWarps][kMaxSigWords];
+  __shared__ uint32_t s_neg[kPairWarps][kMaxSigWords];
+  __shared__ uint64_t s_pair[kPairWarps][32];
+  __shared__ int s_sim[kPairWarps][32];
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int words = ceil_div(K, 32);
+  const int r = K / b;
+  const uint32_t full_r = r == 32 ? 0xFFFFFFFFu : ((1u << r) - 1u);
+  const uint64_t total = slot_off[n_records];
+  const uint64_t chunks = (total + 31) / 32;
+  const uint64_t warp_global = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = (uint64_t(gridDim.x) * blockDim.x) >> 5;
+
+  for (uint64_t c = warp_global; c < chunks; c += nwarps) {
+    // ---- each lane locates its own slot: record p = last index with slot_off[p] <= q
+    const uint64_t q = c * 32 + lane;
+    uint64_t recB = 0, recA = 0;
+    const bool have = q < total;
+    if (have) {
+      int64_t lo = 0, hi = n_records;   // invariant: slot_off[lo] <= q < slot_off[hi]
+      while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (slot_off[mid] <= q) lo = mid; else hi = mid;
+      }
+      const uint64_t tq = q - slot_off[lo];
+      const uint64_t tp = slot_off[lo + 1] - slot_off[lo];
+      recB = records[lo];
+      recA = records[lo - int64_t(tp) + int64_t(tq)];
+    }
+    const unsigned have_mask = __ballot_sync(kFull, have);
+    const int nslots = __popc(have_mask);
+    int nout = 0;
+
+    for (int sl = 0; sl < nslots; ++sl) {
+      const uint64_t ra = __shfl_sync(kFull, recA, sl), rb = __shfl_sync(kFull, recB, sl);
+      const int band = int(rec_band(rb));
+      uint32_t ia = rec_id(ra), ib = rec_id(rb);
+      if (ia > ib) { uint32_t t = ia; ia = ib; ib = t; }
+      const int *rowa = sig + (int64_t(ia) - sig_id_base) * K;
+      const int *rowb = sig + (int64_t(ib) - sig_id_base) * K;
+      long long dot = 0;
+      for (int w = 0; w < words; ++w) {
+        const int t = w * 32 + lane;
+        int va = 0, vb = 1;
+        if (t < K) { va = __ldg(rowa + t); vb = __ldg(rowb + t); }
+        const bool eq = ((va ^ vb) & 0xFFFF) == 0 && t < K;
+        const uint32_t em = __ballot_sync(kFull, eq);
+        const uint32_t nm = __ballot_sync(kFull, eq && (va & 0xFFFF) == 0xFFFF);
+        if (lane == 0) { s_eq[warp][w] = em; s_neg[warp][w] = nm; }
+        if (t < K) dot += (long long)va * (long long)vb;
+      }
+      __syncwarp();
+      // band test by lane: bands lane, lane+32, ... up to and including `band`
+      bool own = false, earlier = false;
+      for (int b0 = 0; b0 <= band; b0 += 32) {
+        const int bb = b0 + lane;
+        bool match = false;
+        if (bb <= band) {
+          const uint32_t e = mask_bits(s_eq[warp], bb * r, r, words);
+          const uint32_t ng = mask_bits(s_neg[warp], bb * r, r, words);
+          match = (e == full_r) && (ng != full_r);
+        }
+        const uint32_t mm = __ballot_sync(kFull, match);
+        const int own_lane = band - b0;   // lane holding `band` in this round, if any
+        if (own_lane < 32) {
+          own = (mm >> own_lane) & 1u;
+          earlier = earlier || (mm & ((1u << own_lane) - 1u)) != 0;
+        } else {
+          earlier = earlier || mm != 0;
+        }
+      }
+      __syncwarp();
+      if (own && !earlier) {
+        int milli = 0;
+        if (sim_milli != nullptr) {
+          dot = warp_sum_ll(dot);
+          if (lane == 0)
+            milli = to_milli(cosine_of(dot, norm2[int64_t(ia) - sig_id_base], norm2[int64_t(ib) - sig_id_base]));
+        }
+        if (lane == 0) {
+          s_pair[warp][nout] = (uint64_t(ia) << 32) | uint64_t(ib);
+          s_sim[warp][nout] = milli;
+        }
+        ++nout;
+      }
+    }
+    __syncwarp();
+    if (nout > 0) {
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(n_pairs, (unsigned long long)nout);
+      base = __shfl_sync(kFull, base, 0);
+      if (lane < nout && int64_t(base + lane) < capacity) {
+        pairs[base + lane] = s_pair[warp][lane];
+        if (sim_milli != nullptr) sim_milli[base + lane] = s_sim[warp][lane];
+      }
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(256)
+pair_cosine_kernel(const int *__restrict__ sig, const long long *__restrict__ norm2, int K,
+                   const uint64_t *__restrict__ pairs, int64_t n_pairs, int *__restrict__ sim_milli) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t p = warp_global; p < n_pairs; p += nwarps) {
+    const uint64_t pr = pairs[p];
+    const int64_t ia = int64_t(pr >> 32), ib = int64_t(pr & 0xFFFFFFFFu);
+    const int *rowa = sig + ia * K, *rowb = sig + ib * K;
+    long long dot = 0;
+    for (int t = lane; t < K; t += 32) dot += (long long)__ldg(rowa + t) * (long long)__ldg(rowb + t);
+    dot = warp_sum_ll(dot);
+    if (lane == 0) sim_milli[p] = to_milli(cosine_of(dot, norm2[ia], norm2[ib]));
+  }
+}
+
+}  // namespace qrs
+
+using namespace qrs;
+
+extern "C" {
+
+size_t qrs_pair_slots_workspace_bytes(int64_t n_records) {
+  if (n_records < 0) return 0;
+  return round_up<size_t>(size_t(n_records > 0 ? n_records : 1) * 4, 256) + scan_workspace_bytes(n_records);
+}
+
+int qrs_pair_slots(const uint64_t *records, int64_t n_records, uint64_t *slot_off, void *ws, size_t ws_bytes,
+                   void *stream) {
+  if (n_records < 0 || !slot_off || (n_records > 0 && !records)) return QRS_ERR_INVALID_ARG;
+  if (!ws || ws_bytes < qrs_pair_slots_workspace_bytes(n_records)) return QRS_ERR_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  uint32_t *cnt = static_cast<uint32_t *>(ws);
+  void *scan_ws = static_cast<char *>(ws) + round_up<size_t>(size_t(n_records > 0 ? n_records : 1) * 4, 256);
+  if (n_records > 0) {
+    int64_t blocks = ceil_div<int64_t>(n_records, 256);
+    const int64_t cap = int64_t(sm_count()) * 8;
+    if (blocks > cap) blocks = cap;
+    pair_slot_count_kernel<<<unsigned(blocks), 256, 0, st>>>(records, n_records, cnt);
+    QRS_LAUNCH_CHECK();
+  }
+  return exclusive_scan_u32_to_u64(cnt, slot_off, n_records, scan_ws, scan_workspace_bytes(n_records), st);
+}
+
+int qrs_pairs_score(const uint64_t *records, int64_t n_records, const uint64_t *slot_off, const int32_t *sig,
+                    const int64_t *norm2, int64_t sig_id_base, int32_t K, int32_t b, uint64_t *pairs,
+                    int32_t *sim_milli, int64_t capacity, unsigned long long *n_pairs, void *stream) {
+  if (n_records < 0 || !slot_off || !sig || !n_pairs || K <= 0 || b <= 0 || K % b != 0 || capacity < 0)
+    return QRS_ERR_INVALID_ARG;
+  if (capacity > 0 && !pairs) return QRS_ERR_INVALID_ARG;
+  if (sim_milli && !norm2) return QRS_ERR_INVALID_ARG;
+  if (K > kMaxSigWords * 32 || K / b > 32 || b > QRS_MAX_BANDS) return QRS_ERR_UNSUPPORTED;
+  if (n_records == 0) return QRS_OK;
+  const int grid = sm_count() * 8;
+  pairs_score_kernel<<<grid, kPairThreads, 0, as_stream(stream)>>>(
+      records, n_records, slot_off, sig, reinterpret_cast<const long long *>(norm2), sig_id_base, K, b, pairs,
+      sim_milli, capacity, n_pairs);
+  QRS_LAUNCH_CHECK();
+  return QRS_OK;
+}
+
+int qrs_pair_cosine(const int32_t *sig, const int64_t *norm2, int32_t K, const uint64_t *pairs, int64_t n_pairs,
+                    int32_t *sim_milli, void *stream) {
+  if (!sig || !norm2 || K <= 0 || n_pairs < 0 || !sim_milli || (n_pairs > 0 && !pairs)) return QRS_ERR_INVALID_ARG;
+  if (n_pairs == 0) return QRS_OK;
+  int64_t blocks = ceil_div<int64_t>(n_pairs, 8);
+  const int64_t cap = int64_t(sm_count()) * 8;
+  if (blocks > cap) blocks = cap;
+  pair_cosine_kernel<<<unsigned(blocks), 256, 0, as_stream(stream)>>>(
+      sig, reinterpret_cast<const long long *>(norm2), K, pairs, n_pairs, sim_milli);
+  QRS_LAUNCH_CHECK();
+  return QRS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,341 @@
+// a10 + a11 — similarity-weighted rating prediction (recommender.py:36-47) and the hybrid
+// rule of compute_scores (recommender.py:311-331).
+//
+// The reference visits every zero cell (i, j) and gathers column j at user i's neighbours.
+// Here the loop is turned inside out: for user i the neighbours' CSR rows are streamed in
+// table order and scattered into per-column fp64 accumulators (num += r*s, den += s), which
+// reproduces, per cell, exactly the reference's left-to-right fp64 sums — cells no
+// neighbour rated keep den == 0 and are "missed" (prediction 0) without being visited.
+//
+//   sparse form : one warp per (user, column tile); accumulators for the tile live in shared
+//                 memory, neighbour row segments are located through a per-row tile index
+//                 and loaded 8 neighbours ahead of the accumulation.
+//   dense form  : one CTA per user at reference scale, adds the query branch.
+#include "common.cuh"
+
+namespace qrs {
+
+// Python evaluates these in IEEE double; so does the host compiler (recommender.py:30-34, 324-331).
+constexpr double kQW = 0.6, kUW = 0.4, kDM = 60.0;
+constexpr double kOnlyQ_mul = kQW + (kUW * 0.5), kOnlyQ_add = kDM * (kUW * 0.5);
+constexpr double kOnlyU_mul = kUW + (kQW * 0.5), kOnlyU_add = kDM * (kQW * 0.5);
+
+__device__ __forceinline__ int hybrid_rule(double q, double u) {
+  if (u == 0.0 && q == 0.0) return 0;
+  double x;
+  if (u == 0.0) x = __dadd_rn(__dmul_rn(q, kOnlyQ_mul), kOnlyQ_add);
+  else if (q == 0.0) x = __dadd_rn(__dmul_rn(u, kOnlyU_mul), kOnlyU_add);
+  else x = __dadd_rn(__dmul_rn(q, kQW), __dmul_rn(u, kUW));
+  return int(rint(x));
+}
+
+// ------------------------------------------------------------------ tile index
+// tileptr[v*(nt+1) + t] = number of entries of row v with col < t*tile (t = 0..nt)
+__global__ void __launch_bounds__(256)
+tile_index_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ colidx, int64_t U, int tile, int nt,
+                  int *__restrict__ tileptr) {
+  const int64_t total = U * (nt + 1);
+  for (int64_t x = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; x < total; x += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t v = x / (nt + 1);
+    const int t = int(x - v * (nt + 1));
+    const int64_t lo = rowptr[v];
+    const int len = int(rowptr[v + 1] - lo);
+    const int64_t bound = int64_t(t) * tile;
+    int a = 0, e = len;   // first entry with col >= bound
+    while (a < e) {
+      const int mid = (a + e) >> 1;
+      if (int64_t(__ldg(colidx + lo + mid)) < bound) a = mid + 1; else e = mid;
+    }
+    tileptr[x] = a;
+  }
+}
+
+// ------------------------------------------------------------------ sparse form
+constexpr int kSpWarps = 4;
+constexpr int kSpAhead = 8;   // neighbour segments whose loads are in flight together
+
+__global__ void __launch_bounds__(kSpWarps * 32)
+predict_sparse_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ colidx,
+                      const uint8_t *__restrict__ val, int Q, const int *__restrict__ u_idx,
+                      const double *__restrict__ u_val, const int *__restrict__ u_cnt, int ku, int64_t user_base,
+                      int64_t n_users, int tile, int nt, const int *__restrict__ tileptr,
+                      int64_t *__restrict__ row_start, int *__restrict__ row_cnt, int *__restrict__ cols,
+                      uint8_t *__restrict__ preds, int64_t capacity, unsigned long long *__restrict__ cursor) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // per warp: double num[tile] | double den[tile] | u8 pbuf[tile]
+  const size_t per_warp = size_t(tile) * 17;
+  double *num = reinterpret_cast<double *>(smem_raw + size_t(warp) * round_up<size_t>(per_warp, 16));
+  double *den = num + tile;
+  uint8_t *pbuf = reinterpret_cast<uint8_t *>(den + tile);
+  for (int j = lane; j < tile; j += 32) { num[j] = 0.0; den[j] = 0.0; }
+  __syncwarp();
+
+  const int64_t items = n_users * nt;
+  const int64_t warp_global = int64_t(blockIdx.x) * kSpWarps + warp;
+  const int64_t nwarps = int64_t(gridDim.x) * kSpWarps;
+  const double NaN = __longlong_as_double(0x7FF8000000000000LL);
+
+  for (int64_t item = warp_global; item < items; item += nwarps) {
+    const int64_t ul = item / nt;                 // local user
+    const int t = int(item - ul * nt);
+    const int64_t ug = user_base + ul;            // global user = CSR row
+    const int q0 = t * tile;
+    const int width = min(tile, Q - q0);
+    const int c = min(u_cnt[ul], ku);
+
+    // ---- neighbour metadata, lane <-> neighbour (two rounds when k > 32)
+    for (int nb0 = 0; nb0 < c; nb0 += 32) {
+      const int me = nb0 + lane;
+      int64_t seg_a = 0;
+      int seg_n = 0;
+      double s_me = 0.0;
+      if (me < c) {
+        const int v = u_idx[ul * ku + me];
+        s_me = u_val[ul * ku + me];
+        const int *tp = tileptr + int64_t(v) * (nt + 1) + t;
+        const int a = __ldg(tp), e = __ldg(tp + 1);
+        seg_a = rowptr[v] + a;
+        seg_n = e - a;
+      }
+      const int nn = min(32, c - nb0);
+      for (int g0 = 0; g0 < nn; g0 += kSpAhead) {
+        int colv[kSpAhead];
+        int ratv[kSpAhead];
+        int cntv[kSpAhead];
+#pragma unroll
+        for (int g = 0; g < kSpAhead; ++g) {
+          const int src = min(g0 + g, nn - 1);
+          const int64_t a = __shfl_sync(kFull, seg_a, src);
+          int cn = __shfl_sync(kFull, seg_n, src);
+          if (g0 + g >= nn) cn = 0;
+          cntv[g] = cn;
+          colv[g] = -1;
+          ratv[g] = 0;
+          if (lane < cn) {
+            colv[g] = ld_stream_s32(colidx + a + lane);
+            ratv[g] = val[a + lane];
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < kSpAhead; ++g) {
+          const int src = min(g0 + g, nn - 1);
+          const double s = __shfl_sync(kFull, s_me, src);
+          const int64_t a = __shfl_sync(kFull, seg_a, src);
+          if (ratv[g] != 0) {
+            const int j = colv[g] - q0;
+            num[j] = __dadd_rn(num[j], __dmul_rn(double(ratv[g]), s));
+            den[j] = __dadd_rn(den[j], s);
+          }
+          // long segments: the remainder beyond the first 32 entries
+          for (int off = 32; off < cntv[g]; off += 32) {
+            if (off + lane < cntv[g]) {
+              const int r = val[a + off + lane];
+              if (r != 0) {
+                const int j = __ldg(colidx + a + off + lane) - q0;
+                num[j] = __dadd_rn(num[j], __dmul_rn(double(r), s));
+                den[j] = __dadd_rn(den[j], s);
+              }
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+
+    // ---- the user's own rated cells are not predicted (recommender.py:302)
+    {
+      const int *tp = tileptr + ug * (nt + 1) + t;
+      const int a = __ldg(tp), e = __ldg(tp + 1);
+      const int64_t base = rowptr[ug] + a;
+      for (int x = lane; x < e - a; x += 32)
+        if (val[base + x] != 0) den[__ldg(colidx + base + x) - q0] = NaN;
+    }
+    __syncwarp();
+
+    // ---- sweep: predictions into pbuf, accumulators back to zero
+    int total = 0;
+    for (int j0 = 0; j0 < width; j0 += 32) {
+      const int j = j0 + lane;
+      int p = 0;
+      if (j < width) {
+        const double d = den[j], nu = num[j];
+        if (d != 0.0 || nu != 0.0) { num[j] = 0.0; den[j] = 0.0; }
+        if (d == d && d != 0.0) p = hybrid_rule(0.0, nu / d);
+        pbuf[j] = uint8_t(p);
+      }
+      total += __popc(__ballot_sync(kFull, p != 0));
+    }
+    __syncwarp();
+    unsigned long long base = 0;
+    if (lane == 0) {
+      base = atomicAdd(cursor, (unsigned long long)total);
+      row_start[item] = int64_t(base);
+      row_cnt[item] = total;
+    }
+    base = __shfl_sync(kFull, base, 0);
+    if (total > 0 && int64_t(base) < capacity) {
+      int written = 0;
+      for (int j0 = 0; j0 < width; j0 += 32) {
+        const int j = j0 + lane;
+        const int p = j < width ? int(pbuf[j]) : 0;
+        const unsigned m = __ballot_sync(kFull, p != 0);
+        if (p != 0) {
+          const int64_t pos = int64_t(base) + written + __popc(m & lanemask_lt());
+          if (pos < capacity) { cols[pos] = q0 + j; preds[pos] = uint8_t(p); }
+        }
+        written += __popc(m);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------ dense form
+// smem: double num[Q] | double den[Q] | u8 own[Q]
+__global__ void __launch_bounds__(256)
+predict_dense_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ colidx,
+                     const uint8_t *__restrict__ val, int Q, const int *__restrict__ q_idx,
+                     const double *__restrict__ q_val, const int *__restrict__ q_cnt, int kq,
+                     const int *__restrict__ u_idx, const double *__restrict__ u_val,
+                     const int *__restrict__ u_cnt, int ku, int64_t user_base, int64_t n_users,
+                     int *__restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *num = reinterpret_cast<double *>(smem_raw);
+  double *den = num + Q;
+  uint8_t *own = reinterpret_cast<uint8_t *>(den + Q);
+  const int tid = threadIdx.x;
+  for (int64_t ul = blockIdx.x; ul < n_users; ul += gridDim.x) {
+    const int64_t ug = user_base + ul;
+    for (int j = tid; j < Q; j += blockDim.x) { num[j] = 0.0; den[j] = 0.0; own[j] = 0; }
+    __syncthreads();
+    {
+      const int64_t lo = rowptr[ug];
+      const int len = int(rowptr[ug + 1] - lo);
+      for (int x = tid; x < len; x += blockDim.x) own[colidx[lo + x]] = val[lo + x];
+    }
+    if (u_idx != nullptr) {
+      const int c = min(u_cnt[ul], ku);
+      for (int t = 0; t < c; ++t) {
+        const int v = u_idx[ul * ku + t];
+        const double s = u_val[ul * ku + t];
+        const int64_t lo = rowptr[v];
+        const int len = int(rowptr[v + 1] - lo);
+        for (int x = tid; x < len; x += blockDim.x) {
+          const int r = val[lo + x];
+          if (r != 0) {
+            const int j = colidx[lo + x];
+            num[j] = __dadd_rn(num[j], __dmul_rn(double(r), s));
+            den[j] = __dadd_rn(den[j], s);
+          }
+        }
+        __syncthreads();
+      }
+    }
+    __syncthreads();
+    for (int j = tid; j < Q; j += blockDim.x) {
+      int res = own[j];
+      if (res == 0) {
+        double q = 0.0;
+        if (q_idx != nullptr) {
+          const int c = min(q_cnt[j], kq);
+          double qn = 0.0, qw = 0.0;
+          for (int t = 0; t < c; ++t) {
+            const int r = own[q_idx[int64_t(j) * kq + t]];
+            const double s = q_val[int64_t(j) * kq + t];
+            qn = __dadd_rn(qn, __dmul_rn(double(r), s));
+            if (r != 0) qw = __dadd_rn(qw, s);
+          }
+          if (qw != 0.0) q = qn / qw;
+        }
+        const double u = den[j] != 0.0 ? num[j] / den[j] : 0.0;
+        res = hybrid_rule(q, u);
+      }
+      out[ul * Q + j] = res;
+    }
+    __syncthreads();
+  }
+}
+
+static size_t sparse_smem_bytes(int tile) { return size_t(kSpWarps) * round_up<size_t>(size_t(tile) * 17, 16); }
+
+}  // namespace qrs
+
+using namespace qrs;
+
+extern "C" {
+
+int32_t qrs_predict_max_tile(void) { return 2560; }   /* 4 warps x 17 B x 2560 = 170 KB */
+
+size_t qrs_predict_sparse_workspace_bytes(int64_t U, int32_t Q, int32_t tile) {
+  if (U < 0 || Q <= 0 || tile <= 0) return 0;
+  const int64_t nt = ceil_div<int64_t>(Q, tile);
+  return round_up<size_t>(size_t(U > 0 ? U : 1) * size_t(nt + 1) * 4, 256);
+}
+
+int qrs_predict_sparse(const int64_t *rowptr, const int32_t *colidx, const uint8_t *val, int64_t U, int32_t Q,
+                       const int32_t *u_idx, const double *u_val, const int32_t *u_cnt, int32_t ku,
+                       int64_t user_base, int64_t n_users, int32_t tile, void *ws, size_t ws_bytes,
+                       int64_t *row_start, int32_t *row_cnt, int32_t *cols, uint8_t *preds, int64_t capacity,
+                       unsigned long long *cursor, void *stream) {
+  if (!rowptr || U < 0 || Q <= 0 || !u_idx || !u_val || !u_cnt || ku <= 0 || user_base < 0 || n_users < 0 ||
+      user_base + n_users > U || !row_start || !row_cnt || !cursor || capacity < 0)
+    return QRS_ERR_INVALID_ARG;
+  if (capacity > 0 && (!cols || !preds)) return QRS_ERR_INVALID_ARG;
+  if (tile <= 0 || tile % 32 != 0) return QRS_ERR_INVALID_ARG;
+  if (tile > qrs_predict_max_tile() || ku > QRS_MAX_TOPK) return QRS_ERR_UNSUPPORTED;
+  if (!ws || ws_bytes < qrs_predict_sparse_workspace_bytes(U, Q, tile)) return QRS_ERR_WORKSPACE;
+  if (n_users == 0 || U == 0) return QRS_OK;
+  if (!colidx || !val) return QRS_ERR_INVALID_ARG;
+  cudaStream_t st = as_stream(stream);
+  const int nt = int(ceil_div<int64_t>(Q, tile));
+  int *tileptr = static_cast<int *>(ws);
+  {
+    const int64_t total = U * (nt + 1);
+    int64_t blocks = ceil_div<int64_t>(total, 256);
+    const int64_t cap = int64_t(sm_count()) * 8;
+    if (blocks > cap) blocks = cap;
+    tile_index_kernel<<<unsigned(blocks), 256, 0, st>>>(rowptr, colidx, U, tile, nt, tileptr);
+    QRS_LAUNCH_CHECK();
+  }
+  const size_t smem = sparse_smem_bytes(tile);
+  QRS_CUDA(cudaFuncSetAttribute(predict_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  int per_sm = 0;
+  QRS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, predict_sparse_kernel, kSpWarps * 32, smem));
+  if (per_sm < 1) return QRS_ERR_UNSUPPORTED;
+  const int64_t items = n_users * nt;
+  int64_t grid = int64_t(sm_count()) * per_sm;
+  const int64_t need = ceil_div<int64_t>(items, kSpWarps);
+  if (grid > need) grid = need;
+  predict_sparse_kernel<<<unsigned(grid), kSpWarps * 32, smem, st>>>(
+      rowptr, colidx, val, Q, u_idx, u_val, u_cnt, ku, user_base, n_users, tile, nt, tileptr, row_start, row_cnt,
+      cols, preds, capacity, cursor);
+  QRS_LAUNCH_CHECK();
+  return QRS_OK;
+}
+
+int qrs_predict_dense(const int64_t *rowptr, const int32_t *colidx, const uint8_t *val, int64_t U, int32_t Q,
+                      const int32_t *q_idx, const double *q_val, const int32_t *q_cnt, int32_t kq,
+                      const int32_t *u_idx, const double *u_val, const int32_t *u_cnt, int32_t ku,
+                      int64_t user_base, int64_t n_users, int32_t *out, void *stream) {
+  if (!rowptr || U < 0 || Q <= 0 || user_base < 0 || n_users < 0 || user_base + n_users > U || !out)
+    return QRS_ERR_INVALID_ARG;
+  if (q_idx && (!q_val || !q_cnt || kq <= 0)) return QRS_ERR_INVALID_ARG;
+  if (u_idx && (!u_val || !u_cnt || ku <= 0)) return QRS_ERR_INVALID_ARG;
+  const size_t smem = size_t(Q) * 17;
+  if (smem > 200 * 1024) return QRS_ERR_UNSUPPORTED;
+  if (n_users == 0) return QRS_OK;
+  if (!colidx || !val) return QRS_ERR_INVALID_ARG;
+  QRS_CUDA(cudaFuncSetAttribute(predict_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  int per_sm = 0;
+  QRS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, predict_dense_kernel, 256, smem));
+  if (per_sm < 1) return QRS_ERR_UNSUPPORTED;
+  int64_t grid = int64_t(sm_count()) * per_sm;
+  if (grid > n_users) grid = n_users;
+  predict_dense_kernel<<<unsigned(grid), 256, smem, as_stream(stream)>>>(
+      rowptr, colidx, val, Q, q_idx, q_val, q_cnt, kq, u_idx, u_val, u_cnt, ku, user_base, n_users, out);
+  QRS_LAUNCH_CHECK();
+  return QRS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,260 @@
+"""Device-resident LSH → top-k CF pipeline for Binding B (set = user row of the utility matrix,
+element = rated query): signatures → bucket records → grouping → candidate pairs +
+rounded cosine → neighbour tables → similarity-weighted predictions, i.e. the chain
+recommender.py:149 → 171-176 → 183-210 → 311-331 without ever leaving the GPU.
+
+Multi-GPU (one process per GPU, torch.distributed): rows are sharded contiguously; the
+signature matrix is all-gathered, bucket records are exchanged with an all-to-all keyed by the
+top bits of the bucket hash, pairs are scored where their bucket lands, scored pairs are sent
+to the owners of their two ends, and the ratings CSR is all-gathered for the prediction gathers.
+All arithmetic is in `stages` (CUDA kernels behind the C ABI); torch is plumbing.
+"""
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass, field
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import stages as cuda_stages
+
+
+@dataclass
+class PipelineOutput:
+    sig: torch.Tensor = None               # int32[n_local, K]
+    norm2: torch.Tensor = None             # int64[n_local]
+    pairs: torch.Tensor = None             # int64[P] packed (i << 32 | j), pairs scored on this rank
+    sims: torch.Tensor = None              # int32[P] rint(1000 cos)
+    n_slots: int = 0                       # pre-dedup (pair, band) coincidences examined on this rank
+    nbr_idx: torch.Tensor = None           # int32[n_local, k]
+    nbr_val: torch.Tensor = None           # float64[n_local, k]
+    nbr_cnt: torch.Tensor = None           # int32[n_local]
+    pred_row_start: torch.Tensor = None    # int64[n_local, nt]
+    pred_row_cnt: torch.Tensor = None      # int32[n_local, nt]
+    pred_cols: torch.Tensor = None         # int32[n_predictions]
+    pred_vals: torch.Tensor = None         # uint8[n_predictions]
+    n_predictions: int = 0
+    covered_cells: int = 0                 # zero cells of R decided (predicted or proven "missed")
+    stage_ms: Dict[str, float] = field(default_factory=dict)
+
+
+class _Timer:
+    """CUDA-event stage timer on the current stream (wall clock when the tensors are on the CPU,
+    which only happens under the test double)."""
+
+    def __init__(self, enabled: bool, cuda: bool):
+        self.enabled, self.cuda = enabled, cuda
+        self.marks = []
+
+    def mark(self, name: str):
+        if not self.enabled:
+            return
+        if self.cuda:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.marks.append((name, ev))
+        else:
+            self.marks.append((name, time.perf_counter()))
+
+    def result(self) -> Dict[str, float]:
+        out = {}
+        if not self.enabled or len(self.marks) < 2:
+            return out
+        if self.cuda:
+            torch.cuda.synchronize()
+        for (_, a), (name, b) in zip(self.marks[:-1], self.marks[1:]):
+            out[name] = out.get(name, 0.0) + (a.elapsed_time(b) if self.cuda else (b - a) * 1e3)
+        return out
+
+
+class LshCfPipeline:
+    def __init__(self, m: int, K: int, b: int, k: int, perm_tab, device="cuda", tile: Optional[int] = None,
+                 minhash_mode: int = _lib.MINHASH_AUTO, head_ranks: Optional[int] = None,
+                 group=None, stages=None, profile: bool = False):
+        """perm_tab: element-major permutation table int32[m, K] (numpy or tensor) — the K successive
+        np.random.permutation(m) draws of recommender.py:120, `oracle`-independent: the caller makes it."""
+        if K % b != 0:
+            raise AssertionError("K=%d is not a multiple of b=%d" % (K, b))      # lsh.py:20
+        self.m, self.K, self.b, self.k = int(m), int(K), int(b), int(k)
+        self.st = stages if stages is not None else cuda_stages
+        self.device = torch.device(device)
+        self.group = group
+        self.profile = profile
+        self.tile = tile
+        self.mode = minhash_mode
+        if isinstance(perm_tab, np.ndarray):
+            perm_tab = torch.from_numpy(np.ascontiguousarray(perm_tab.astype(np.int32, copy=False)))
+        self.perm_tab = perm_tab.to(self.device, torch.int32).contiguous()
+        assert tuple(self.perm_tab.shape) == (self.m, self.K)
+        self._head_ranks = head_ranks
+        self.order_head = None
+        self._head_for = None
+        self._pred_capacity = 0
+
+    # ------------------------------------------------------------------ distributed helpers
+    @property
+    def world(self) -> int:
+        import torch.distributed as dist
+        return dist.get_world_size(self.group) if (dist.is_available() and dist.is_initialized()) else 1
+
+    @property
+    def rank(self) -> int:
+        import torch.distributed as dist
+        return dist.get_rank(self.group) if (dist.is_available() and dist.is_initialized()) else 0
+
+    def _ensure_head(self, avg_len: float):
+        R = self._head_ranks if self._head_ranks is not None else self.st.choose_head_ranks(self.m, avg_len)
+        if self._head_for != R:
+            self.order_head = self.st.perm_head(self.perm_tab, R) if R > 0 else None
+            self._head_for = R
+
+    # ------------------------------------------------------------------ the path
+    def run(self, rowptr: torch.Tensor, colidx: torch.Tensor, val: Optional[torch.Tensor],
+            predict: bool = True) -> PipelineOutput:
+        """rowptr/colidx/val: this rank's shard (rows [rank*n_local, (rank+1)*n_local)) of the users×queries
+        CSR, on `self.device`.  Every rank must hold the same number of rows."""
+        st, G, rank = self.st, self.world, self.rank
+        out = PipelineOutput()
+        tm = _Timer(self.profile, self.device.type == "cuda")
+        n_local = rowptr.numel() - 1
+        row_base = rank * n_local
+        n_total = n_local * G
+        nnz = colidx.numel()
+        self._ensure_head(nnz / max(n_local, 1))
+        tm.mark("start")
+
+        # a1 + a2/a3: signatures, squared norms and bucket records in one kernel
+        sig, norm2, records = st.minhash(rowptr, colidx, self.m, self.perm_tab, self.order_head, b=self.b,
+                                         id_base=row_base, want_norm2=True, mode=self.mode)
+        out.sig, out.norm2 = sig, norm2
+        tm.mark("signatures+banding")
+
+        if G == 1:
+            flat = records.reshape(-1)
+            st.sort_u64(flat, n_local, self.b, 40, 64)
+            sig_all, norm2_all = sig, norm2
+            tm.mark("grouping")
+        else:
+            sig_all, norm2_all = self._all_gather_rows(sig), self._all_gather_rows(norm2)
+            tm.mark("exchange:signatures")
+            flat, lg = self._exchange_records(records.reshape(-1))
+            tm.mark("exchange:records")
+            st.sort_u64(flat, flat.numel(), 1, 32, 64 - lg)
+            tm.mark("grouping")
+
+        # a5 + a8: slots → verified, de-duplicated, scored pairs
+        slot_off = st.pair_slots(flat)
+        n_slots = int(slot_off[-1].item())
+        pairs, sims, counter = st.pairs_score(flat, slot_off, sig_all, norm2_all, self.b, n_slots, 0, True)
+        n_pairs = int(counter.item())
+        pairs, sims = pairs[:n_pairs], sims[:n_pairs]
+        out.pairs, out.sims, out.n_slots = pairs, sims, n_slots
+        tm.mark("pairs+cosine")
+
+        if G > 1:
+            pairs, sims = self._route_pairs(pairs, sims, n_local)
+            n_pairs = pairs.numel()
+            tm.mark("exchange:pairs")
+
+        # a7 + a9
+        idx, v, cnt = st.topk_tables(pairs, sims, n_pairs, row_base, n_local, self.k)
+        out.nbr_idx, out.nbr_val, out.nbr_cnt = idx, v, cnt
+        tm.mark("topk")
+
+        if predict:
+            assert val is not None
+            if G > 1:
+                rowptr_all, colidx_all, val_all = self._all_gather_csr(rowptr, colidx, val)
+                tm.mark("exchange:ratings")
+            else:
+                rowptr_all, colidx_all, val_all = rowptr, colidx, val
+            tile = self.tile or st.choose_predict_tile(self.m, nnz / max(n_local, 1))
+            cap = self._pred_capacity
+            while True:
+                rs, rc, cols, preds, cursor = st.predict_sparse(rowptr_all, colidx_all, val_all, self.m,
+                                                                (idx, v, cnt), row_base, n_local, tile, cap)
+                total = int(cursor.item())
+                if total <= cap:
+                    break
+                cap = self._pred_capacity = int(total * 1.02) + 1024      # exact size is now known; run again
+            out.pred_row_start, out.pred_row_cnt = rs, rc
+            out.pred_cols, out.pred_vals, out.n_predictions = cols[:total], preds[:total], total
+            rated = int((val != 0).sum().item()) if val.numel() else 0
+            out.covered_cells = n_local * self.m - rated
+            tm.mark("predict")
+        out.stage_ms = tm.result()
+        return out
+
+    # ------------------------------------------------------------------ exchanges (plumbing)
+    def _all_gather_rows(self, t: torch.Tensor) -> torch.Tensor:
+        import torch.distributed as dist
+        G = self.world
+        outt = torch.empty((t.shape[0] * G,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(outt, t.contiguous(), group=self.group)
+        return outt
+
+    def _all_to_all_var(self, send: torch.Tensor, send_counts: torch.Tensor) -> torch.Tensor:
+        """send is grouped by destination rank; send_counts int64[G] (host)."""
+        import torch.distributed as dist
+        G = self.world
+        sc = send_counts.to(send.device)
+        rcv = torch.empty_like(sc)
+        dist.all_to_all_single(rcv, sc, group=self.group)
+        rcv_l = rcv.cpu().tolist()
+        recv = torch.empty(int(sum(rcv_l)), dtype=send.dtype, device=send.device)
+        dist.all_to_all_single(recv, send, output_split_sizes=rcv_l, input_split_sizes=send_counts.tolist(),
+                               group=self.group)
+        return recv
+
+    def _exchange_records(self, flat: torch.Tensor):
+        """Bucket records go to rank = top log2(G) bits of hash24: one radix pass groups them by
+        destination, the split points come from a searchsorted on those bits."""
+        G = self.world
+        lg = G.bit_length() - 1
+        if (1 << lg) != G:
+            raise _lib.QrsError("the bucket exchange needs a power-of-two world size, got %d" % G)
+        self.st.sort_u64(flat, flat.numel(), 1, 64 - lg, 64)
+        dest = (flat >> (64 - lg)) & (G - 1)
+        bounds = torch.searchsorted(dest, torch.arange(G + 1, device=flat.device, dtype=dest.dtype))
+        counts = (bounds[1:] - bounds[:-1]).cpu()
+        return self._all_to_all_var(flat, counts), lg
+
+    def _route_pairs(self, pairs: torch.Tensor, sims: torch.Tensor, n_local: int):
+        """Each scored pair goes to the owner of i and (if different) the owner of j."""
+        G = self.world
+        oi = torch.div(pairs >> 32, n_local, rounding_mode="floor")
+        oj = torch.div(pairs & 0xFFFFFFFF, n_local, rounding_mode="floor")
+        both = torch.cat([pairs, pairs[oj != oi]])
+        sm = torch.cat([sims, sims[oj != oi]])
+        dest = torch.cat([oi, oj[oj != oi]])
+        order = torch.argsort(dest, stable=True)
+        counts = torch.bincount(dest, minlength=G).cpu()
+        p = self._all_to_all_var(both[order].contiguous(), counts)
+        s = self._all_to_all_var(sm[order].contiguous(), counts)
+        return p, s
+
+    def _all_gather_csr(self, rowptr, colidx, val):
+        import torch.distributed as dist
+        G = self.world
+        n_local = rowptr.numel() - 1
+        nnz = torch.tensor([colidx.numel()], dtype=torch.int64, device=colidx.device)
+        all_nnz = torch.empty(G, dtype=torch.int64, device=colidx.device)
+        dist.all_gather_into_tensor(all_nnz, nnz, group=self.group)
+        sizes = all_nnz.cpu().tolist()
+        mx = max(sizes)
+
+        def gather_padded(t):
+            pad = torch.zeros(mx, dtype=t.dtype, device=t.device)
+            pad[:t.numel()] = t
+            buf = torch.empty(G * mx, dtype=t.dtype, device=t.device)
+            dist.all_gather_into_tensor(buf, pad, group=self.group)
+            return torch.cat([buf[r * mx:r * mx + sizes[r]] for r in range(G)])
+
+        col_all, val_all = gather_padded(colidx), gather_padded(val)
+        lens = self._all_gather_rows((rowptr[1:] - rowptr[:-1]).contiguous())
+        rp = torch.zeros(n_local * G + 1, dtype=torch.int64, device=rowptr.device)
+        rp[1:] = torch.cumsum(lens, 0)
+        return rp, col_all, val_all

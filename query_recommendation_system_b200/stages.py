@@ -1,0 +1,236 @@
+"""Stage-level host wrappers: torch CUDA tensors in, torch CUDA tensors out, each a
+thin call into the C ABI (include/qrs_b200.h) on torch's current stream.
+
+torch is used for device memory and streams only; every computation below is a
+hand-written sm_100a kernel inside libqrs_b200.so.  u64 device data (bucket
+records, packed pairs) is carried in int64 tensors (same bits).
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import check, ptr
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and (not t.is_cuda or not t.is_contiguous()):
+            raise _lib.QrsError("stage inputs must be contiguous CUDA tensors (no CPU fallback exists)")
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+# --------------------------------------------------------------------------- a1
+def choose_head_ranks(m: int, avg_len: float) -> int:
+    """Ranks of each permutation kept in the first-touch head table: enough that a
+    set of average length misses it with probability < 1e-6, in [32, 2048], <= m."""
+    if m < 32:
+        return 0
+    p = min(max(avg_len, 1.0) / m, 0.999)
+    need = math.log(1e-6) / math.log1p(-p)
+    r = int(min(max(32, math.ceil(need / 32.0) * 32), 2048))
+    return min(r, (m // 32) * 32)
+
+
+def perm_head(perm_tab: torch.Tensor, R: int) -> Optional[torch.Tensor]:
+    """order_head[K, R] (recommender.py:121's argsort, first R ranks of each permutation)."""
+    _need_cuda(perm_tab)
+    m, K = perm_tab.shape
+    if R <= 0:
+        return None
+    assert perm_tab.dtype == torch.int32
+    out = torch.empty((K, R), dtype=torch.int32, device=perm_tab.device)
+    check(_lib.load().qrs_perm_head_invert(ptr(perm_tab), m, K, R, ptr(out), _stream()), "qrs_perm_head_invert")
+    return out
+
+
+def minhash(rowptr: torch.Tensor, colidx: torch.Tensor, m: int, perm_tab: torch.Tensor,
+            order_head: Optional[torch.Tensor], b: int = 0, id_base: int = 0,
+            want_norm2: bool = True, mode: int = _lib.MINHASH_AUTO,
+            out_sig: Optional[torch.Tensor] = None, out_norm2: Optional[torch.Tensor] = None,
+            out_records: Optional[torch.Tensor] = None):
+    """Recommender.compute_signatures (recommender.py:105-143) → sig int32[n, K]; with b > 0
+    also the bucket records int64[b, n] of LSH.compute_buckets (lsh.py:31-38)."""
+    _need_cuda(rowptr, colidx, perm_tab, order_head)
+    assert rowptr.dtype == torch.int64 and colidx.dtype == torch.int32 and perm_tab.dtype == torch.int32
+    n = rowptr.numel() - 1
+    K = perm_tab.shape[1]
+    assert perm_tab.shape[0] == m
+    dev = rowptr.device
+    sig = out_sig if out_sig is not None else torch.empty((n, K), dtype=torch.int32, device=dev)
+    norm2 = None
+    if want_norm2:
+        norm2 = out_norm2 if out_norm2 is not None else torch.empty(n, dtype=torch.int64, device=dev)
+    records = None
+    if b > 0:
+        records = out_records if out_records is not None else torch.empty((b, n), dtype=torch.int64, device=dev)
+    R = 0 if order_head is None else order_head.shape[1]
+    check(_lib.load().qrs_minhash_perm(ptr(rowptr), ptr(colidx), n, m, ptr(perm_tab), ptr(order_head), R, K, b,
+                                       id_base, ptr(sig), ptr(norm2), ptr(records), n, mode, _stream()),
+          "qrs_minhash_perm")
+    return sig, norm2, records
+
+
+# ------------------------------------------------------------------------ a2/a3
+def band_keys(sig: torch.Tensor, b: int):
+    """Exact bucket ids (lsh.py:17-38): keys int64[n, b] (+ keys_hi for r > 4), skipped uint8[n, b]."""
+    _need_cuda(sig)
+    n, K = sig.shape
+    if K % b != 0:
+        raise AssertionError("signature length %d is not a multiple of b=%d" % (K, b))   # lsh.py:20
+    r = K // b
+    keys = torch.empty((n, b), dtype=torch.int64, device=sig.device)
+    hi = torch.empty((n, b), dtype=torch.int64, device=sig.device) if r > 4 else None
+    skipped = torch.empty((n, b), dtype=torch.uint8, device=sig.device)
+    check(_lib.load().qrs_band_keys(ptr(sig), n, K, b, ptr(keys), ptr(hi), ptr(skipped), _stream()), "qrs_band_keys")
+    return keys, hi, skipped
+
+
+def band_records(sig: torch.Tensor, b: int, id_base: int = 0, want_norm2: bool = True):
+    _need_cuda(sig)
+    n, K = sig.shape
+    if K % b != 0:
+        raise AssertionError("signature length %d is not a multiple of b=%d" % (K, b))
+    records = torch.empty((b, n), dtype=torch.int64, device=sig.device)
+    norm2 = torch.empty(n, dtype=torch.int64, device=sig.device) if want_norm2 else None
+    check(_lib.load().qrs_band_records(ptr(sig), n, K, b, id_base, ptr(records), n, ptr(norm2), _stream()),
+          "qrs_band_records")
+    return records, norm2
+
+
+# ------------------------------------------------------------------------ a3/a4
+def sort_u64(keys: torch.Tensor, n_per_seg: int, segs: int, bit_lo: int, bit_hi: int,
+             tmp: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """In-place stable radix sort of `segs` segments of `n_per_seg` u64 keys on bits [bit_lo, bit_hi)."""
+    _need_cuda(keys, tmp)
+    assert keys.dtype == torch.int64 and keys.numel() == n_per_seg * segs
+    lib = _lib.load()
+    if tmp is None:
+        tmp = torch.empty_like(keys)
+    nbytes = lib.qrs_sort_workspace_bytes(n_per_seg, segs)
+    ws = _ws(nbytes, keys.device)
+    check(lib.qrs_sort_u64(ptr(keys), ptr(tmp), n_per_seg, segs, bit_lo, bit_hi, ptr(ws), ws.numel(), _stream()),
+          "qrs_sort_u64")
+    return keys
+
+
+# --------------------------------------------------------------------------- a5
+def pair_slots(records: torch.Tensor) -> torch.Tensor:
+    """slot_off int64[n_records + 1]; slot_off[-1] = Σ_runs h(h-1)/2 (lsh.py:49's combinations)."""
+    _need_cuda(records)
+    lib = _lib.load()
+    n = records.numel()
+    slot_off = torch.empty(n + 1, dtype=torch.int64, device=records.device)
+    ws = _ws(lib.qrs_pair_slots_workspace_bytes(n), records.device)
+    check(lib.qrs_pair_slots(ptr(records), n, ptr(slot_off), ptr(ws), ws.numel(), _stream()), "qrs_pair_slots")
+    return slot_off
+
+
+def pairs_score(records: torch.Tensor, slot_off: torch.Tensor, sig: torch.Tensor, norm2: Optional[torch.Tensor],
+                b: int, capacity: int, sig_id_base: int = 0, want_sims: bool = True):
+    """LSH.get_candidates (lsh.py:40-54) + rounded cosine (recommender.py:203-204).
+    Returns (pairs int64[capacity], sim_milli int32[capacity] | None, counter int64[1] on device)."""
+    _need_cuda(records, slot_off, sig, norm2)
+    dev = records.device
+    K = sig.shape[1]
+    pairs = torch.empty(max(capacity, 1), dtype=torch.int64, device=dev)
+    sims = torch.empty(max(capacity, 1), dtype=torch.int32, device=dev) if want_sims else None
+    counter = torch.zeros(1, dtype=torch.int64, device=dev)
+    check(_lib.load().qrs_pairs_score(ptr(records), records.numel(), ptr(slot_off), ptr(sig), ptr(norm2), sig_id_base,
+                                      K, b, ptr(pairs), ptr(sims), capacity, ptr(counter), _stream()),
+          "qrs_pairs_score")
+    return pairs, sims, counter
+
+
+def pair_cosine(sig: torch.Tensor, norm2: torch.Tensor, pairs: torch.Tensor) -> torch.Tensor:
+    _need_cuda(sig, norm2, pairs)
+    sims = torch.empty(pairs.numel(), dtype=torch.int32, device=sig.device)
+    check(_lib.load().qrs_pair_cosine(ptr(sig), ptr(norm2), sig.shape[1], ptr(pairs), pairs.numel(), ptr(sims),
+                                      _stream()), "qrs_pair_cosine")
+    return sims
+
+
+# ------------------------------------------------------------------------ a7/a9
+def topk_tables(pairs: torch.Tensor, sims: torch.Tensor, n_pairs: int, row_base: int, n_rows: int, k: int):
+    """Neighbour tables (recommender.py:183-210), canonical order: idx int32[n_rows, k] (-1 pad),
+    val float64[n_rows, k] (0 pad), cnt int32[n_rows]."""
+    _need_cuda(pairs, sims)
+    lib = _lib.load()
+    dev = pairs.device
+    adj = torch.empty(max(2 * n_pairs, 1), dtype=torch.int64, device=dev)
+    ws = _ws(lib.qrs_topk_workspace_bytes(n_rows), dev)
+    idx = torch.empty((n_rows, k), dtype=torch.int32, device=dev)
+    val = torch.empty((n_rows, k), dtype=torch.float64, device=dev)
+    cnt = torch.empty(n_rows, dtype=torch.int32, device=dev)
+    check(lib.qrs_topk_tables(ptr(pairs), ptr(sims), n_pairs, row_base, n_rows, k, ptr(adj), ptr(ws), ws.numel(),
+                              ptr(idx), ptr(val), ptr(cnt), _stream()), "qrs_topk_tables")
+    return idx, val, cnt
+
+
+# ---------------------------------------------------------------------- a10/a11
+Table = Tuple[torch.Tensor, torch.Tensor, torch.Tensor]
+
+
+def predict_dense(rowptr, colidx, val, Q: int, q_tab: Optional[Table], u_tab: Optional[Table],
+                  user_base: int = 0, n_users: Optional[int] = None) -> torch.Tensor:
+    """compute_scores' cell loop (recommender.py:311-331) → int32[n_users, Q]."""
+    _need_cuda(rowptr, colidx, val)
+    U = rowptr.numel() - 1
+    n_users = U - user_base if n_users is None else n_users
+    out = torch.empty((n_users, Q), dtype=torch.int32, device=rowptr.device)
+
+    def parts(tab):
+        if tab is None:
+            return None, None, None, 0
+        i, v, c = tab
+        _need_cuda(i, v, c)
+        assert i.dtype == torch.int32 and v.dtype == torch.float64 and c.dtype == torch.int32
+        return i, v, c, i.shape[1]
+
+    qi, qv, qc, kq = parts(q_tab)
+    ui, uv, uc, ku = parts(u_tab)
+    check(_lib.load().qrs_predict_dense(ptr(rowptr), ptr(colidx), ptr(val), U, Q, ptr(qi), ptr(qv), ptr(qc), kq,
+                                        ptr(ui), ptr(uv), ptr(uc), ku, user_base, n_users, ptr(out), _stream()),
+          "qrs_predict_dense")
+    return out
+
+
+def choose_predict_tile(Q: int, avg_len: float) -> int:
+    """Column tile of the sparse predictor: ~24 entries of an average row per tile."""
+    max_tile = _lib.load().qrs_predict_max_tile()
+    t = 24.0 * Q / max(avg_len, 1.0)
+    t = int(min(max(256, math.ceil(t / 32.0) * 32), max_tile))
+    return min(t, int(math.ceil(Q / 32.0) * 32)) if Q >= 32 else 32
+
+
+def predict_sparse(rowptr, colidx, val, Q: int, u_tab: Table, user_base: int, n_users: int, tile: int,
+                   capacity: int, out_cols: Optional[torch.Tensor] = None, out_preds: Optional[torch.Tensor] = None):
+    """User-branch predictions in sparse form.  Returns (row_start int64[n_users, nt],
+    row_cnt int32[n_users, nt], cols int32[capacity], preds uint8[capacity], cursor int64[1] on device)."""
+    _need_cuda(rowptr, colidx, val, *u_tab)
+    lib = _lib.load()
+    dev = rowptr.device
+    U = rowptr.numel() - 1
+    nt = (Q + tile - 1) // tile
+    ui, uv, uc = u_tab
+    assert ui.dtype == torch.int32 and uv.dtype == torch.float64 and uc.dtype == torch.int32
+    row_start = torch.empty((n_users, nt), dtype=torch.int64, device=dev)
+    row_cnt = torch.empty((n_users, nt), dtype=torch.int32, device=dev)
+    cols = out_cols if out_cols is not None else torch.empty(max(capacity, 1), dtype=torch.int32, device=dev)
+    preds = out_preds if out_preds is not None else torch.empty(max(capacity, 1), dtype=torch.uint8, device=dev)
+    cursor = torch.zeros(1, dtype=torch.int64, device=dev)
+    ws = _ws(lib.qrs_predict_sparse_workspace_bytes(U, Q, tile), dev)
+    check(lib.qrs_predict_sparse(ptr(rowptr), ptr(colidx), ptr(val), U, Q, ptr(ui), ptr(uv), ptr(uc), ui.shape[1],
+                                 user_base, n_users, tile, ptr(ws), ws.numel(), ptr(row_start), ptr(row_cnt),
+                                 ptr(cols), ptr(preds), capacity, ptr(cursor), _stream()), "qrs_predict_sparse")
+    return row_start, row_cnt, cols, preds, cursor
