@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""Benchmark of the LSH → top-k CF hot path (BASELINE.json metric: MinHash sigs/s, LSH candidate
+pairs/s, predicted ratings/s) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config C2] [--impl ours|reference]
+
+A "step" is one pass of the whole path (signatures → bucket records → grouping → candidate pairs +
+cosine → neighbour tables → predictions) over one synthetic utility matrix of the named config
+(generator.py schema, planted taste groups).  `value` = sets signed AND carried through
+the whole path per second, inputs resident in HBM; `stages` breaks it into sigs/s, pairs/s and
+ratings/s.  `e2e` is the same pass through the host-facing call with pinned HOST buffers (H2D of the
+CSR and D2H of the predictions inside the timed region).  N > 1: one rank per GPU (torchrun), row
+shards of the config's size per GPU (weak scaling), NCCL exchanges inside the step.
+
+`--impl reference` times the reference's CPU algorithm (oracle/port.py — /root/reference does not
+exist on the GPU box and is pure Python, so kind = "port") on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "MinHash sigs/s through the full LSH->CF path (signatures, banding, candidate pairs, cosine, top-k, predictions)"
+UNIT = "sigs/s"
+DATA_SEED = 20260102          # 20260101 + config id
+PERM_SEED = 7
+
+
+def perm_table(m, K, seed=PERM_SEED):
+    """K successive np.random.permutation(m) from the legacy global RNG (recommender.py:118-120)."""
+    np.random.seed(seed)
+    tab = np.empty((m, K), dtype=np.int32)
+    for i in range(K):
+        tab[:, i] = np.random.permutation(m)
+    return tab
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------ CPU side
+def cpu_sample(config, n_sets):
+    from query_recommendation_system_b200 import synth
+    n, m, density, K, b, k = synth.config_shape(config)
+    rowptr, colidx, val = synth.planted_csr(n_sets, m, density, seed=DATA_SEED, device="cpu")
+    return (rowptr.numpy(), colidx.numpy(), val.numpy()), (m, K, b, k)
+
+
+def run_cpu_port(config, n_sets):
+    from oracle import baseline
+    (rowptr, colidx, val), (m, K, b, k) = cpu_sample(config, n_sets)
+    t, counts = baseline.run_port_pipeline(rowptr, colidx, val, m, K, b, k, perm_seed=PERM_SEED)
+    return t, counts
+
+
+def reference_arm(args):
+    """bench.py --impl reference: the reference's CPU path (port) on a bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = args.steps, args.warmup
+    n_sets = int(max(8, min(64, (64 * 150.0 / (10.6 * (steps + warmup))) // 8 * 8)))
+    for _ in range(warmup):
+        run_cpu_port(args.config, n_sets)
+    t0 = time.perf_counter()
+    stage = {}
+    for _ in range(steps):
+        t, counts = run_cpu_port(args.config, n_sets)
+        for kx, v in t.items():
+            stage[kx] = stage.get(kx, 0.0) + v
+    wall = time.perf_counter() - t0
+    path_s = stage["total"] / steps
+    value = n_sets / path_s
+    sample = ("first %d sets of the %s matrix (closed sample: LSH and CF run over these sets only), whole path per "
+              "step; 1 Python thread, like the reference" % (n_sets, args.config))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": path_s * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int64/f64", "data": "synthetic",
+        "config": workload_config(args.config, 1, "n/a (CPU)"),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                         "host_cores": os.cpu_count(),
+                         "stage_seconds_per_step": {kx: v / steps for kx, v in stage.items()}, "counts": counts},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": wall,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(config, n_gpus, l2_note):
+    from query_recommendation_system_b200 import synth
+    n, m, density, K, b, k = synth.config_shape(config)
+    return {"workload": "%s: %d users x %d queries, %.3g%% density, K=%d hashes, b=%d bands x r=%d rows, top-k=%d, "
+                        "planted taste groups of 32 (SURVEY.md 8d), ratings 1..100"
+                        % (config, n, m, density * 100, K, b, K // b, k),
+            "sets_per_gpu": n, "elements": m, "density": density, "K": K, "b": b, "r": K // b, "k": k,
+            "parallelism": "row shards x%d, bucket all-to-all" % n_gpus if n_gpus > 1 else "single GPU",
+            "binding": "B (set = user row of the utility matrix, element = rated query)",
+            "permutations": "np.random.seed(%d); K x np.random.permutation(m) (setup, not timed)" % PERM_SEED,
+            "l2": l2_note}
+
+
+# ------------------------------------------------------------------------------------------ GPU side
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", default="C2")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sets", type=int, default=64)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from query_recommendation_system_b200 import _lib, synth
+    from query_recommendation_system_b200.pipeline import HostRunner, LshCfPipeline
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1 and args.gpus == 1, "launch with torchrun for --gpus > 1"
+
+    n, m, density, K, b, k = synth.config_shape(args.config)
+    lib = _lib.load()
+    rowptr, colidx, val = synth.planted_csr(n, m, density, seed=DATA_SEED, row_base=rank * n, device=dev)
+    nnz = int(colidx.numel())
+    tab = perm_table(m, K)
+    pipe = LshCfPipeline(m=m, K=K, b=b, k=k, perm_tab=tab, device=dev, profile=True)
+    input_bytes = rowptr.numel() * 8 + colidx.numel() * 4 + val.numel()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        out = pipe.run(rowptr, colidx, val)
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = lib.qrs_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage_ms = {}
+    barrier()
+    ev0.record()
+    outs = []
+    for _ in range(args.steps):
+        out = pipe.run(rowptr, colidx, val)
+        outs.append(out.stage_ms)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = lib.qrs_launch_count() - launches0
+    elapsed_ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    for d in outs:
+        for kx, v in d.items():
+            stage_ms[kx] = stage_ms.get(kx, 0.0) + v / args.steps
+
+    # per-rank counts → whole-job totals
+    counts = torch.tensor([out.pairs.numel(), out.n_slots, out.n_predictions, out.covered_cells], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(counts)
+    n_pairs, n_slots, n_pred, covered = [int(x) for x in counts.tolist()]
+    n_total = n * world
+    ms_per_step = elapsed_ms / args.steps
+    value = n_total / (ms_per_step * 1e-3)
+
+    # algorithmic bytes of the two heavy kernels from the actual data
+    lens = (rowptr[1:] - rowptr[:-1])
+    sig_bytes = 4 * nnz + 8 * (n + 1) + 4 * n * K + 8 * n * b + 8 * n
+    if world == 1:
+        idx = out.nbr_idx.long().clamp(min=0)
+        mask = torch.arange(k, device=dev)[None, :] < out.nbr_cnt[:, None]
+        gathered = int((lens[idx] * mask).sum().item())
+    else:
+        gathered = int(out.nbr_cnt.sum().item()) * (nnz // n)
+    pred_bytes = 5 * gathered + 5 * out.n_predictions
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    ms_sig = stage_ms.get("signatures+banding", float("nan"))
+    ms_pred = stage_ms.get("predict", float("nan"))
+    rl = {
+        "signatures+banding": {"bound": "hbm", "achieved": sig_bytes / (ms_sig * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                               "bytes_per_launch": sig_bytes, "ms": ms_sig, "launches_per_step": 1},
+        "predict": {"bound": "hbm", "achieved": pred_bytes / (ms_pred * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                    "bytes_per_launch": pred_bytes, "ms": ms_pred,
+                    "note": "stage = tile-index kernel + predict kernel + one cursor readback"},
+    }
+    for v in rl.values():
+        v["frac"] = v["achieved"] / peak
+    dominant = max(("signatures+banding", "predict"), key=lambda s: stage_ms.get(s, 0.0))
+    roofline = dict(rl[dominant])
+    roofline.update({"kernel": "predict_sparse_kernel" if dominant == "predict" else "minhash_kernel",
+                     "stage": dominant, "peak_source": peak_src, "traffic": None})
+
+    # ---------------------------------------------------------------- e2e: host buffers in, host results out
+    runner = HostRunner(pipe)
+    h_rowptr, h_colidx, h_val = [x.cpu().pin_memory() for x in (rowptr, colidx, val)]
+    for _ in range(2):
+        res = runner(h_rowptr, h_colidx, h_val)
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(e2e_steps):
+        res = runner(h_rowptr, h_colidx, h_val)
+    e1.record()
+    barrier()
+    e2e_wall_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    te = torch.tensor([e0.elapsed_time(e1) / e2e_steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_ms = float(te.item())
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32/int64 (signatures, buckets, cosine dot) + f64 (similarity, prediction)",
+            "data": "synthetic",
+            "config": workload_config(args.config, world, "inputs (%.0f MB CSR per GPU) exceed the 126 MB L2; no flush"
+                                      % (input_bytes / 1e6)),
+            "stages": {
+                "ms": stage_ms,
+                "sigs_per_s": n_total / (ms_sig * 1e-3) if world == 1 else n / (ms_sig * 1e-3) * world,
+                "candidate_pairs_per_s": n_pairs / (sum(stage_ms.get(s, 0.0) for s in ("grouping", "pairs+cosine")) * 1e-3),
+                "pair_slots_per_s": n_slots / (sum(stage_ms.get(s, 0.0) for s in ("grouping", "pairs+cosine")) * 1e-3),
+                "predicted_ratings_per_s": covered / (ms_pred * 1e-3),
+                "nonzero_predictions_per_s": n_pred / (ms_pred * 1e-3),
+                "counts": {"sets": n_total, "nnz_per_gpu": nnz, "candidate_pairs": n_pairs, "pair_slots": n_slots,
+                           "nonzero_predictions": n_pred, "covered_cells": covered},
+            },
+            "roofline": roofline, "rooflines": rl,
+            "e2e": {"value": n_total / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "wall_ms_per_step": e2e_wall_ms,
+                    "h2d_bytes_per_step": runner.h2d_bytes, "d2h_bytes_per_step": runner.d2h_bytes, "steps": e2e_steps,
+                    "call": "pipeline.HostRunner(pipe)(rowptr, colidx, val) with pinned host tensors; returns pinned "
+                            "sparse predictions + neighbour tables"},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            tc, cc = run_cpu_port(args.config, args.cpu_sets)
+            line["cpu_baseline"] = {
+                "value": args.cpu_sets / tc["total"], "unit": UNIT, "cores": 1, "kind": "port",
+                "host_cores": os.cpu_count(), "seconds": tc, "counts": cc,
+                "sample": "first %d sets of the %s matrix as a closed sample, whole path once; single Python thread "
+                          "(the reference is single-threaded)" % (args.cpu_sets, args.config)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -53,6 +53,9 @@ int qrs_version(void);                       /* 100 * major + minor */
 const char *qrs_status_string(int status);
 const char *qrs_last_cuda_error(void);       /* thread-local text of the last CUDA failure */
 int qrs_device_sm_count(int device);         /* -1 on error */
+/* Diagnostics: number of kernels this library has launched in the process so far
+ * (monotonic; the only process-wide state, never read by the kernels). */
+unsigned long long qrs_launch_count(void);
 
 /* Bucket record (u64), the unit that is sorted, exchanged between GPUs and
  * turned into candidate pairs:

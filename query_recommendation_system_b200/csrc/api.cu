@@ -1,11 +1,16 @@
 // libqrs_b200: status/error plumbing and the device-wide scan shared by the stages.
 #include <string.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace qrs {
 
 static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void set_cuda_error(cudaError_t e, const char *file, int line) {
   const char *base = strrchr(file, '/');
@@ -143,6 +148,8 @@ int exclusive_scan_u32_to_u64(const uint32_t *in, uint64_t *out, int64_t n, void
 extern "C" {
 
 int qrs_version(void) { return 100; }
+
+unsigned long long qrs_launch_count(void) { return qrs::g_launches.load(std::memory_order_relaxed); }
 
 const char *qrs_status_string(int status) {
   switch (status) {

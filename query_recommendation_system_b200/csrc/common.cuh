@@ -19,7 +19,13 @@ void set_cuda_error(cudaError_t e, const char *file, int line);
     }                                                         \
   } while (0)
 
-#define QRS_LAUNCH_CHECK() QRS_CUDA(cudaGetLastError())
+// every kernel launch goes through here: error check + the diagnostic launch counter
+void note_launch();
+#define QRS_LAUNCH_CHECK()            \
+  do {                                \
+    ::qrs::note_launch();             \
+    QRS_CUDA(cudaGetLastError());     \
+  } while (0)
 
 static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 

@@ -258,3 +258,49 @@ class LshCfPipeline:
         rp = torch.zeros(n_local * G + 1, dtype=torch.int64, device=rowptr.device)
         rp[1:] = torch.cumsum(lens, 0)
         return rp, col_all, val_all
+
+
+class HostRunner:
+    """The call a user of the drop-in makes with HOST data: pinned utility-matrix CSR in, sparse
+    predictions + neighbour tables out (pinned), host↔device copies on the same stream as the
+    kernels.  Buffers are allocated once and reused across calls."""
+
+    def __init__(self, pipe: LshCfPipeline):
+        self.pipe = pipe
+        self._dev = {}
+        self._host = {}
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def _dev_like(self, name, t):
+        buf = self._dev.get(name)
+        if buf is None or buf.numel() < t.numel() or buf.dtype != t.dtype:
+            buf = self._dev[name] = torch.empty(t.numel(), dtype=t.dtype, device=self.pipe.device)
+        return buf[:t.numel()]
+
+    def _host_like(self, name, t):
+        buf = self._host.get(name)
+        if buf is None or buf.numel() < t.numel() or buf.dtype != t.dtype:
+            buf = self._host[name] = torch.empty(int(t.numel() * 1.05) + 16, dtype=t.dtype, pin_memory=True)
+        return buf[:t.numel()]
+
+    def __call__(self, rowptr_h: torch.Tensor, colidx_h: torch.Tensor, val_h: torch.Tensor):
+        self.h2d_bytes = self.d2h_bytes = 0
+        dev_in = []
+        for name, t in (("rowptr", rowptr_h), ("colidx", colidx_h), ("val", val_h)):
+            d = self._dev_like(name, t)
+            d.copy_(t, non_blocking=True)
+            self.h2d_bytes += t.numel() * t.element_size()
+            dev_in.append(d)
+        out = self.pipe.run(*dev_in, predict=True)
+        res = {}
+        for name in ("pred_row_start", "pred_row_cnt", "pred_cols", "pred_vals", "nbr_idx", "nbr_val", "nbr_cnt"):
+            t = getattr(out, name).reshape(-1)
+            h = self._host_like(name, t)
+            h.copy_(t, non_blocking=True)
+            self.d2h_bytes += t.numel() * t.element_size()
+            res[name] = h
+        torch.cuda.current_stream().synchronize()
+        res["n_predictions"] = out.n_predictions
+        res["covered_cells"] = out.covered_cells
+        return res
