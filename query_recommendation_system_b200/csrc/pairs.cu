@@ -51,7 +51,7 @@ pairs_score_kernel(const uint64_t *__restrict__ records, int64_t n_records, cons
   __shared__ uint32_t s_eq[kPairWarps][kMaxSigWords];
   __shared__ uint32_t s_neg[kPairWarps][kMaxSigWords];
   __shared__ uint64_t s_pair[kPairWarps][32];
-  __shared__ int s_sim[kPairWarps][32];
+  __shared__ long long s_dot[kPairWarps][32];
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int words = ceil_div(K, 32);
@@ -122,27 +122,27 @@ pairs_score_kernel(const uint64_t *__restrict__ records, int64_t n_records, cons
       }
       __syncwarp();
       if (own && !earlier) {
-        int milli = 0;
-        if (sim_milli != nullptr) {
-          dot = warp_sum_ll(dot);
-          if (lane == 0)
-            milli = to_milli(cosine_of(dot, norm2[int64_t(ia) - sig_id_base], norm2[int64_t(ib) - sig_id_base]));
-        }
+        if (sim_milli != nullptr) dot = warp_sum_ll(dot);
         if (lane == 0) {
           s_pair[warp][nout] = (uint64_t(ia) << 32) | uint64_t(ib);
-          s_sim[warp][nout] = milli;
+          s_dot[warp][nout] = dot;
         }
         ++nout;
       }
     }
     __syncwarp();
     if (nout > 0) {
+      // the emitted pairs of this chunk: cosines in parallel (one lane each), one reservation, one store
       unsigned long long base = 0;
       if (lane == 0) base = atomicAdd(n_pairs, (unsigned long long)nout);
       base = __shfl_sync(kFull, base, 0);
       if (lane < nout && int64_t(base + lane) < capacity) {
-        pairs[base + lane] = s_pair[warp][lane];
-        if (sim_milli != nullptr) sim_milli[base + lane] = s_sim[warp][lane];
+        const uint64_t pr = s_pair[warp][lane];
+        pairs[base + lane] = pr;
+        if (sim_milli != nullptr) {
+          const int64_t a = int64_t(pr >> 32) - sig_id_base, bb = int64_t(pr & 0xFFFFFFFFu) - sig_id_base;
+          sim_milli[base + lane] = to_milli(cosine_of(s_dot[warp][lane], norm2[a], norm2[bb]));
+        }
       }
     }
     __syncwarp();

@@ -54,7 +54,14 @@ tile_index_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ co
 constexpr int kSpWarps = 4;
 constexpr int kSpAhead = 8;   // neighbour segments whose loads are in flight together
 
-__global__ void __launch_bounds__(kSpWarps * 32)
+struct __align__(16) Acc { double num, den; };
+
+// bytes of shared memory one warp needs for a tile: Acc[tile] | u16 jlist[tile] | u8 plist[tile] | metadata
+__host__ __device__ constexpr size_t sparse_warp_bytes(int tile) {
+  return round_up<size_t>(size_t(tile) * 19, 16) + 32 * (8 + 8 + 4);
+}
+
+__global__ void __launch_bounds__(kSpWarps * 32, 6)
 predict_sparse_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ colidx,
                       const uint8_t *__restrict__ val, int Q, const int *__restrict__ u_idx,
                       const double *__restrict__ u_val, const int *__restrict__ u_cnt, int ku, int64_t user_base,
@@ -63,18 +70,22 @@ predict_sparse_kernel(const int64_t *__restrict__ rowptr, const int *__restrict_
                       uint8_t *__restrict__ preds, int64_t capacity, unsigned long long *__restrict__ cursor) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // per warp: double num[tile] | double den[tile] | u8 pbuf[tile]
-  const size_t per_warp = size_t(tile) * 17;
-  double *num = reinterpret_cast<double *>(smem_raw + size_t(warp) * round_up<size_t>(per_warp, 16));
-  double *den = num + tile;
-  uint8_t *pbuf = reinterpret_cast<uint8_t *>(den + tile);
-  for (int j = lane; j < tile; j += 32) { num[j] = 0.0; den[j] = 0.0; }
+  unsigned char *mine = smem_raw + size_t(warp) * sparse_warp_bytes(tile);
+  Acc *acc = reinterpret_cast<Acc *>(mine);
+  uint16_t *jlist = reinterpret_cast<uint16_t *>(acc + tile);
+  uint8_t *plist = reinterpret_cast<uint8_t *>(jlist + tile);
+  unsigned char *meta = mine + round_up<size_t>(size_t(tile) * 19, 16);
+  int64_t *m_a = reinterpret_cast<int64_t *>(meta);          // first entry of the neighbour's segment
+  double *m_s = reinterpret_cast<double *>(meta + 32 * 8);   // its similarity
+  int *m_n = reinterpret_cast<int *>(meta + 32 * 16);        // entries in the segment
+  const Acc zero = {0.0, 0.0};
+  for (int j = lane; j < tile; j += 32) acc[j] = zero;
   __syncwarp();
 
   const int64_t items = n_users * nt;
   const int64_t warp_global = int64_t(blockIdx.x) * kSpWarps + warp;
   const int64_t nwarps = int64_t(gridDim.x) * kSpWarps;
-  const double NaN = __longlong_as_double(0x7FF8000000000000LL);
+  const unsigned lt = lanemask_lt();
 
   for (int64_t item = warp_global; item < items; item += nwarps) {
     const int64_t ul = item / nt;                 // local user
@@ -84,85 +95,114 @@ predict_sparse_kernel(const int64_t *__restrict__ rowptr, const int *__restrict_
     const int width = min(tile, Q - q0);
     const int c = min(u_cnt[ul], ku);
 
-    // ---- neighbour metadata, lane <-> neighbour (two rounds when k > 32)
     for (int nb0 = 0; nb0 < c; nb0 += 32) {
-      const int me = nb0 + lane;
-      int64_t seg_a = 0;
-      int seg_n = 0;
-      double s_me = 0.0;
-      if (me < c) {
-        const int v = u_idx[ul * ku + me];
-        s_me = u_val[ul * ku + me];
-        const int *tp = tileptr + int64_t(v) * (nt + 1) + t;
-        const int a = __ldg(tp), e = __ldg(tp + 1);
-        seg_a = rowptr[v] + a;
-        seg_n = e - a;
-      }
-      const int nn = min(32, c - nb0);
-      for (int g0 = 0; g0 < nn; g0 += kSpAhead) {
-        int colv[kSpAhead];
-        int ratv[kSpAhead];
-        int cntv[kSpAhead];
-#pragma unroll
-        for (int g = 0; g < kSpAhead; ++g) {
-          const int src = min(g0 + g, nn - 1);
-          const int64_t a = __shfl_sync(kFull, seg_a, src);
-          int cn = __shfl_sync(kFull, seg_n, src);
-          if (g0 + g >= nn) cn = 0;
-          cntv[g] = cn;
-          colv[g] = -1;
-          ratv[g] = 0;
-          if (lane < cn) {
-            colv[g] = ld_stream_s32(colidx + a + lane);
-            ratv[g] = val[a + lane];
-          }
+      // ---- neighbour metadata, lane <-> neighbour (two rounds when k > 32)
+      {
+        const int me = nb0 + lane;
+        if (me < c) {
+          const int v = u_idx[ul * ku + me];
+          const int *tp = tileptr + int64_t(v) * (nt + 1) + t;
+          const int a = __ldg(tp), e = __ldg(tp + 1);
+          m_a[lane] = rowptr[v] + a;
+          m_n[lane] = e - a;
+          m_s[lane] = u_val[ul * ku + me];
         }
-#pragma unroll
-        for (int g = 0; g < kSpAhead; ++g) {
-          const int src = min(g0 + g, nn - 1);
-          const double s = __shfl_sync(kFull, s_me, src);
-          const int64_t a = __shfl_sync(kFull, seg_a, src);
-          if (ratv[g] != 0) {
-            const int j = colv[g] - q0;
-            num[j] = __dadd_rn(num[j], __dmul_rn(double(ratv[g]), s));
-            den[j] = __dadd_rn(den[j], s);
-          }
-          // long segments: the remainder beyond the first 32 entries
-          for (int off = 32; off < cntv[g]; off += 32) {
-            if (off + lane < cntv[g]) {
-              const int r = val[a + off + lane];
-              if (r != 0) {
-                const int j = __ldg(colidx + a + off + lane) - q0;
-                num[j] = __dadd_rn(num[j], __dmul_rn(double(r), s));
-                den[j] = __dadd_rn(den[j], s);
+      }
+      __syncwarp();
+      const int nn = min(32, c - nb0);
+      // segments longer than one warp-load are rare (the tile is sized for ~24 entries per row);
+      // a group of neighbours containing one takes the generic loop, all others the unrolled one
+      const int my_n = lane < nn ? m_n[lane] : 0;
+      const unsigned long_mask = __ballot_sync(kFull, my_n > 32);
+      for (int g0 = 0; g0 < nn; g0 += kSpAhead) {
+        if ((long_mask >> g0) & ((1u << kSpAhead) - 1u)) {
+          const int g1 = min(nn, g0 + kSpAhead);
+          for (int g = g0; g < g1; ++g) {
+            const double s = m_s[g];
+            const int64_t a = m_a[g];
+            const int cn = m_n[g];
+            for (int off = 0; off < cn; off += 32) {
+              if (off + lane < cn) {
+                const int r = val[a + off + lane];
+                if (r != 0) {
+                  const int j = __ldg(colidx + a + off + lane) - q0;
+                  Acc x = acc[j];
+                  x.num = __dadd_rn(x.num, __dmul_rn(double(r), s));
+                  x.den = __dadd_rn(x.den, s);
+                  acc[j] = x;
+                }
               }
             }
+            __syncwarp();
           }
-          __syncwarp();
+          continue;
+        }
+        int colv[kSpAhead];
+        int ratv[kSpAhead];
+#pragma unroll
+        for (int g = 0; g < kSpAhead; ++g) {
+          ratv[g] = 0;
+          colv[g] = 0;
+          if (g0 + g < nn) {
+            const int64_t a = m_a[g0 + g];
+            if (lane < m_n[g0 + g]) {
+              colv[g] = ld_stream_s32(colidx + a + lane);
+              ratv[g] = val[a + lane];
+            }
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < kSpAhead; ++g) {
+          if (g0 + g < nn) {     // warp-uniform
+            if (ratv[g] != 0) {
+              const double s = m_s[g0 + g];
+              Acc x = acc[colv[g] - q0];
+              x.num = __dadd_rn(x.num, __dmul_rn(double(ratv[g]), s));
+              x.den = __dadd_rn(x.den, s);
+              acc[colv[g] - q0] = x;
+            }
+            __syncwarp();
+          }
         }
       }
+      __syncwarp();
     }
 
-    // ---- the user's own rated cells are not predicted (recommender.py:302)
+    // ---- the user's own rated cells are not predicted (recommender.py:302): drop what landed there
     {
       const int *tp = tileptr + ug * (nt + 1) + t;
       const int a = __ldg(tp), e = __ldg(tp + 1);
       const int64_t base = rowptr[ug] + a;
       for (int x = lane; x < e - a; x += 32)
-        if (val[base + x] != 0) den[__ldg(colidx + base + x) - q0] = NaN;
+        if (val[base + x] != 0) acc[__ldg(colidx + base + x) - q0] = zero;
     }
     __syncwarp();
 
-    // ---- sweep: predictions into pbuf, accumulators back to zero
-    int total = 0;
+    // ---- pass 1: ascending list of the touched columns
+    int touched = 0;
     for (int j0 = 0; j0 < width; j0 += 32) {
       const int j = j0 + lane;
-      int p = 0;
+      bool hit = false;
       if (j < width) {
-        const double d = den[j], nu = num[j];
-        if (d != 0.0 || nu != 0.0) { num[j] = 0.0; den[j] = 0.0; }
-        if (d == d && d != 0.0) p = hybrid_rule(0.0, nu / d);
-        pbuf[j] = uint8_t(p);
+        const Acc x = acc[j];
+        hit = x.den != 0.0 || x.num != 0.0;
+      }
+      const unsigned m = __ballot_sync(kFull, hit);
+      if (hit) jlist[touched + __popc(m & lt)] = uint16_t(j);
+      touched += __popc(m);
+    }
+    __syncwarp();
+    // ---- pass 2: prediction of every touched column (dense lanes), accumulators back to zero
+    int total = 0;
+    for (int x0 = 0; x0 < touched; x0 += 32) {
+      const int x = x0 + lane;
+      int p = 0;
+      if (x < touched) {
+        const int j = jlist[x];
+        const Acc a = acc[j];
+        acc[j] = zero;
+        if (a.den != 0.0) p = hybrid_rule(0.0, a.num / a.den);
+        plist[x] = uint8_t(p);
       }
       total += __popc(__ballot_sync(kFull, p != 0));
     }
@@ -174,15 +214,16 @@ predict_sparse_kernel(const int64_t *__restrict__ rowptr, const int *__restrict_
       row_cnt[item] = total;
     }
     base = __shfl_sync(kFull, base, 0);
+    // ---- pass 3: the slice, ascending in column
     if (total > 0 && int64_t(base) < capacity) {
       int written = 0;
-      for (int j0 = 0; j0 < width; j0 += 32) {
-        const int j = j0 + lane;
-        const int p = j < width ? int(pbuf[j]) : 0;
+      for (int x0 = 0; x0 < touched; x0 += 32) {
+        const int x = x0 + lane;
+        const int p = x < touched ? int(plist[x]) : 0;
         const unsigned m = __ballot_sync(kFull, p != 0);
         if (p != 0) {
-          const int64_t pos = int64_t(base) + written + __popc(m & lanemask_lt());
-          if (pos < capacity) { cols[pos] = q0 + j; preds[pos] = uint8_t(p); }
+          const int64_t pos = int64_t(base) + written + __popc(m & lt);
+          if (pos < capacity) { cols[pos] = q0 + int(jlist[x]); preds[pos] = uint8_t(p); }
         }
         written += __popc(m);
       }
@@ -257,7 +298,7 @@ predict_dense_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__
   }
 }
 
-static size_t sparse_smem_bytes(int tile) { return size_t(kSpWarps) * round_up<size_t>(size_t(tile) * 17, 16); }
+static size_t sparse_smem_bytes(int tile) { return size_t(kSpWarps) * sparse_warp_bytes(tile); }
 
 }  // namespace qrs
 
@@ -265,7 +306,7 @@ using namespace qrs;
 
 extern "C" {
 
-int32_t qrs_predict_max_tile(void) { return 2560; }   /* 4 warps x 17 B x 2560 = 170 KB */
+int32_t qrs_predict_max_tile(void) { return 2560; }   /* 4 warps x 19 B x 2560 = 195 KB */
 
 size_t qrs_predict_sparse_workspace_bytes(int64_t U, int32_t Q, int32_t tile) {
   if (U < 0 || Q <= 0 || tile <= 0) return 0;
