@@ -30,10 +30,11 @@ __device__ __forceinline__ int hybrid_rule(double q, double u) {
 }
 
 // ------------------------------------------------------------------ tile index
-// tileptr[v*(nt+1) + t] = number of entries of row v with col < t*tile (t = 0..nt)
+// tilepos[v*(nt+1) + t] = rowptr[v] + number of entries of row v with col < t*tile (t = 0..nt):
+// the absolute CSR position where tile t of row v starts; tile t ends where tile t+1 starts.
 __global__ void __launch_bounds__(256)
 tile_index_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ colidx, int64_t U, int tile, int nt,
-                  int *__restrict__ tileptr) {
+                  int64_t *__restrict__ tilepos) {
   const int64_t total = U * (nt + 1);
   for (int64_t x = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; x < total; x += int64_t(gridDim.x) * blockDim.x) {
     const int64_t v = x / (nt + 1);
@@ -46,7 +47,7 @@ tile_index_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ co
       const int mid = (a + e) >> 1;
       if (int64_t(__ldg(colidx + lo + mid)) < bound) a = mid + 1; else e = mid;
     }
-    tileptr[x] = a;
+    tilepos[x] = lo + a;
   }
 }
 
@@ -58,16 +59,19 @@ struct __align__(16) Acc { double num, den; };
 
 // bytes of shared memory one warp needs for a tile: Acc[tile] | u16 jlist[tile] | u8 plist[tile] | metadata
 __host__ __device__ constexpr size_t sparse_warp_bytes(int tile) {
-  return round_up<size_t>(size_t(tile) * 19, 16) + 32 * (8 + 8 + 4);
+  return round_up<size_t>(size_t(tile) * 19, 16) + 64 * (8 + 8 + 4);
 }
 
+// One warp per user (grid-stride), walking the column tiles in order so that the per-user state
+// (neighbour ids, similarities, segment cursors) is loaded once and every tile needs exactly one
+// new position per neighbour — fetched one tile ahead of its use.
 __global__ void __launch_bounds__(kSpWarps * 32, 6)
-predict_sparse_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ colidx,
-                      const uint8_t *__restrict__ val, int Q, const int *__restrict__ u_idx,
-                      const double *__restrict__ u_val, const int *__restrict__ u_cnt, int ku, int64_t user_base,
-                      int64_t n_users, int tile, int nt, const int *__restrict__ tileptr,
-                      int64_t *__restrict__ row_start, int *__restrict__ row_cnt, int *__restrict__ cols,
-                      uint8_t *__restrict__ preds, int64_t capacity, unsigned long long *__restrict__ cursor) {
+predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict__ val, int Q,
+                      const int *__restrict__ u_idx, const double *__restrict__ u_val,
+                      const int *__restrict__ u_cnt, int ku, int64_t user_base, int64_t n_users, int tile, int nt,
+                      const int64_t *__restrict__ tilepos, int64_t *__restrict__ row_start,
+                      int *__restrict__ row_cnt, int *__restrict__ cols, uint8_t *__restrict__ preds,
+                      int64_t capacity, unsigned long long *__restrict__ cursor) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned char *mine = smem_raw + size_t(warp) * sparse_warp_bytes(tile);
@@ -75,160 +79,181 @@ predict_sparse_kernel(const int64_t *__restrict__ rowptr, const int *__restrict_
   uint16_t *jlist = reinterpret_cast<uint16_t *>(acc + tile);
   uint8_t *plist = reinterpret_cast<uint8_t *>(jlist + tile);
   unsigned char *meta = mine + round_up<size_t>(size_t(tile) * 19, 16);
-  int64_t *m_a = reinterpret_cast<int64_t *>(meta);          // first entry of the neighbour's segment
-  double *m_s = reinterpret_cast<double *>(meta + 32 * 8);   // its similarity
-  int *m_n = reinterpret_cast<int *>(meta + 32 * 16);        // entries in the segment
+  int64_t *m_a = reinterpret_cast<int64_t *>(meta);           // [64] first entry of the neighbour's segment
+  double *m_s = reinterpret_cast<double *>(meta + 64 * 8);    // [64] its similarity
+  int *m_n = reinterpret_cast<int *>(meta + 64 * 16);         // [64] entries in the segment
   const Acc zero = {0.0, 0.0};
   for (int j = lane; j < tile; j += 32) acc[j] = zero;
   __syncwarp();
 
-  const int64_t items = n_users * nt;
   const int64_t warp_global = int64_t(blockIdx.x) * kSpWarps + warp;
   const int64_t nwarps = int64_t(gridDim.x) * kSpWarps;
   const unsigned lt = lanemask_lt();
+  const int stride = nt + 1;
 
-  for (int64_t item = warp_global; item < items; item += nwarps) {
-    const int64_t ul = item / nt;                 // local user
-    const int t = int(item - ul * nt);
+  for (int64_t ul = warp_global; ul < n_users; ul += nwarps) {
     const int64_t ug = user_base + ul;            // global user = CSR row
-    const int q0 = t * tile;
-    const int width = min(tile, Q - q0);
     const int c = min(u_cnt[ul], ku);
+    // lane <-> neighbour (slot 0: neighbours 0..31, slot 1: 32..63); cursors into each neighbour's row
+    const int64_t *tp[2];
+    int64_t cur[2], nxt[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int me = h * 32 + lane;
+      tp[h] = tilepos;
+      cur[h] = nxt[h] = 0;
+      if (me < c) {
+        const int v = u_idx[ul * ku + me];
+        m_s[me] = u_val[ul * ku + me];
+        tp[h] = tilepos + int64_t(v) * stride;
+        cur[h] = __ldg(tp[h]);
+        nxt[h] = __ldg(tp[h] + 1);
+      }
+    }
+    const int64_t *own_tp = tilepos + ug * stride;
+    int64_t own_cur = __ldg(own_tp), own_nxt = __ldg(own_tp + 1);
+    __syncwarp();
 
-    for (int nb0 = 0; nb0 < c; nb0 += 32) {
-      // ---- neighbour metadata, lane <-> neighbour (two rounds when k > 32)
-      {
-        const int me = nb0 + lane;
+    for (int t = 0; t < nt; ++t) {
+      const int q0 = t * tile;
+      const int width = min(tile, Q - q0);
+      // this tile's segments = [cur, nxt); fetch the end of the NEXT tile's segments now
+      int64_t ahead[2] = {0, 0};
+      int64_t own_ahead = 0;
+      const bool more = t + 1 < nt;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int me = h * 32 + lane;
         if (me < c) {
-          const int v = u_idx[ul * ku + me];
-          const int *tp = tileptr + int64_t(v) * (nt + 1) + t;
-          const int a = __ldg(tp), e = __ldg(tp + 1);
-          m_a[lane] = rowptr[v] + a;
-          m_n[lane] = e - a;
-          m_s[lane] = u_val[ul * ku + me];
+          m_a[me] = cur[h];
+          m_n[me] = int(nxt[h] - cur[h]);
+          if (more) ahead[h] = __ldg(tp[h] + t + 2);
         }
       }
+      if (more) own_ahead = __ldg(own_tp + t + 2);
       __syncwarp();
-      const int nn = min(32, c - nb0);
-      // segments longer than one warp-load are rare (the tile is sized for ~24 entries per row);
-      // a group of neighbours containing one takes the generic loop, all others the unrolled one
-      const int my_n = lane < nn ? m_n[lane] : 0;
-      const unsigned long_mask = __ballot_sync(kFull, my_n > 32);
-      for (int g0 = 0; g0 < nn; g0 += kSpAhead) {
-        if ((long_mask >> g0) & ((1u << kSpAhead) - 1u)) {
-          const int g1 = min(nn, g0 + kSpAhead);
-          for (int g = g0; g < g1; ++g) {
-            const double s = m_s[g];
-            const int64_t a = m_a[g];
-            const int cn = m_n[g];
-            for (int off = 0; off < cn; off += 32) {
-              if (off + lane < cn) {
-                const int r = val[a + off + lane];
-                if (r != 0) {
-                  const int j = __ldg(colidx + a + off + lane) - q0;
-                  Acc x = acc[j];
-                  x.num = __dadd_rn(x.num, __dmul_rn(double(r), s));
-                  x.den = __dadd_rn(x.den, s);
-                  acc[j] = x;
+
+      for (int nb0 = 0; nb0 < c; nb0 += 32) {
+        const int nn = min(32, c - nb0);
+        // segments longer than one warp-load are rare (the tile is sized for ~24 entries per row);
+        // a group of neighbours containing one takes the generic loop, all others the unrolled one
+        const int my_n = lane < nn ? m_n[nb0 + lane] : 0;
+        const unsigned long_mask = __ballot_sync(kFull, my_n > 32);
+        for (int g0 = 0; g0 < nn; g0 += kSpAhead) {
+          if ((long_mask >> g0) & ((1u << kSpAhead) - 1u)) {
+            const int g1 = min(nn, g0 + kSpAhead);
+            for (int g = g0; g < g1; ++g) {
+              const double s = m_s[nb0 + g];
+              const int64_t a = m_a[nb0 + g];
+              const int cn = m_n[nb0 + g];
+              for (int off = 0; off < cn; off += 32) {
+                if (off + lane < cn) {
+                  const int r = val[a + off + lane];
+                  if (r != 0) {
+                    const int j = __ldg(colidx + a + off + lane) - q0;
+                    Acc x = acc[j];
+                    x.num = __dadd_rn(x.num, __dmul_rn(double(r), s));
+                    x.den = __dadd_rn(x.den, s);
+                    acc[j] = x;
+                  }
                 }
               }
+              __syncwarp();
             }
-            __syncwarp();
+            continue;
           }
-          continue;
-        }
-        int colv[kSpAhead];
-        int ratv[kSpAhead];
+          int colv[kSpAhead];
+          int ratv[kSpAhead];
 #pragma unroll
-        for (int g = 0; g < kSpAhead; ++g) {
-          ratv[g] = 0;
-          colv[g] = 0;
-          if (g0 + g < nn) {
-            const int64_t a = m_a[g0 + g];
-            if (lane < m_n[g0 + g]) {
-              colv[g] = ld_stream_s32(colidx + a + lane);
-              ratv[g] = val[a + lane];
+          for (int g = 0; g < kSpAhead; ++g) {
+            ratv[g] = 0;
+            colv[g] = 0;
+            if (g0 + g < nn) {
+              const int64_t a = m_a[nb0 + g0 + g];
+              if (lane < m_n[nb0 + g0 + g]) {
+                colv[g] = ld_stream_s32(colidx + a + lane);
+                ratv[g] = val[a + lane];
+              }
+            }
+          }
+#pragma unroll
+          for (int g = 0; g < kSpAhead; ++g) {
+            if (g0 + g < nn) {     // warp-uniform
+              if (ratv[g] != 0) {
+                const double s = m_s[nb0 + g0 + g];
+                Acc x = acc[colv[g] - q0];
+                x.num = __dadd_rn(x.num, __dmul_rn(double(ratv[g]), s));
+                x.den = __dadd_rn(x.den, s);
+                acc[colv[g] - q0] = x;
+              }
+              __syncwarp();
             }
           }
         }
-#pragma unroll
-        for (int g = 0; g < kSpAhead; ++g) {
-          if (g0 + g < nn) {     // warp-uniform
-            if (ratv[g] != 0) {
-              const double s = m_s[g0 + g];
-              Acc x = acc[colv[g] - q0];
-              x.num = __dadd_rn(x.num, __dmul_rn(double(ratv[g]), s));
-              x.den = __dadd_rn(x.den, s);
-              acc[colv[g] - q0] = x;
-            }
-            __syncwarp();
+      }
+
+      // ---- the user's own rated cells are not predicted (recommender.py:302): drop what landed there
+      for (int64_t x = own_cur + lane; x < own_nxt; x += 32)
+        if (val[x] != 0) acc[__ldg(colidx + x) - q0] = zero;
+      __syncwarp();
+
+      // ---- pass 1: ascending list of the touched columns
+      int touched = 0;
+      for (int j0 = 0; j0 < width; j0 += 32) {
+        const int j = j0 + lane;
+        bool hit = false;
+        if (j < width) {
+          const Acc x = acc[j];
+          hit = x.den != 0.0 || x.num != 0.0;
+        }
+        const unsigned m = __ballot_sync(kFull, hit);
+        if (hit) jlist[touched + __popc(m & lt)] = uint16_t(j);
+        touched += __popc(m);
+      }
+      __syncwarp();
+      // ---- pass 2: prediction of every touched column (dense lanes), accumulators back to zero
+      int total = 0;
+      for (int x0 = 0; x0 < touched; x0 += 32) {
+        const int x = x0 + lane;
+        int p = 0;
+        if (x < touched) {
+          const int j = jlist[x];
+          const Acc a = acc[j];
+          acc[j] = zero;
+          if (a.den != 0.0) p = hybrid_rule(0.0, a.num / a.den);
+          plist[x] = uint8_t(p);
+        }
+        total += __popc(__ballot_sync(kFull, p != 0));
+      }
+      __syncwarp();
+      unsigned long long base = 0;
+      if (lane == 0) {
+        base = atomicAdd(cursor, (unsigned long long)total);
+        row_start[ul * nt + t] = int64_t(base);
+        row_cnt[ul * nt + t] = total;
+      }
+      base = __shfl_sync(kFull, base, 0);
+      // ---- pass 3: the slice, ascending in column
+      if (total > 0 && int64_t(base) < capacity) {
+        int written = 0;
+        for (int x0 = 0; x0 < touched; x0 += 32) {
+          const int x = x0 + lane;
+          const int p = x < touched ? int(plist[x]) : 0;
+          const unsigned m = __ballot_sync(kFull, p != 0);
+          if (p != 0) {
+            const int64_t pos = int64_t(base) + written + __popc(m & lt);
+            if (pos < capacity) { cols[pos] = q0 + int(jlist[x]); preds[pos] = uint8_t(p); }
           }
+          written += __popc(m);
         }
       }
       __syncwarp();
+      // advance the cursors to the next tile
+#pragma unroll
+      for (int h = 0; h < 2; ++h) { cur[h] = nxt[h]; nxt[h] = ahead[h]; }
+      own_cur = own_nxt;
+      own_nxt = own_ahead;
     }
-
-    // ---- the user's own rated cells are not predicted (recommender.py:302): drop what landed there
-    {
-      const int *tp = tileptr + ug * (nt + 1) + t;
-      const int a = __ldg(tp), e = __ldg(tp + 1);
-      const int64_t base = rowptr[ug] + a;
-      for (int x = lane; x < e - a; x += 32)
-        if (val[base + x] != 0) acc[__ldg(colidx + base + x) - q0] = zero;
-    }
-    __syncwarp();
-
-    // ---- pass 1: ascending list of the touched columns
-    int touched = 0;
-    for (int j0 = 0; j0 < width; j0 += 32) {
-      const int j = j0 + lane;
-      bool hit = false;
-      if (j < width) {
-        const Acc x = acc[j];
-        hit = x.den != 0.0 || x.num != 0.0;
-      }
-      const unsigned m = __ballot_sync(kFull, hit);
-      if (hit) jlist[touched + __popc(m & lt)] = uint16_t(j);
-      touched += __popc(m);
-    }
-    __syncwarp();
-    // ---- pass 2: prediction of every touched column (dense lanes), accumulators back to zero
-    int total = 0;
-    for (int x0 = 0; x0 < touched; x0 += 32) {
-      const int x = x0 + lane;
-      int p = 0;
-      if (x < touched) {
-        const int j = jlist[x];
-        const Acc a = acc[j];
-        acc[j] = zero;
-        if (a.den != 0.0) p = hybrid_rule(0.0, a.num / a.den);
-        plist[x] = uint8_t(p);
-      }
-      total += __popc(__ballot_sync(kFull, p != 0));
-    }
-    __syncwarp();
-    unsigned long long base = 0;
-    if (lane == 0) {
-      base = atomicAdd(cursor, (unsigned long long)total);
-      row_start[item] = int64_t(base);
-      row_cnt[item] = total;
-    }
-    base = __shfl_sync(kFull, base, 0);
-    // ---- pass 3: the slice, ascending in column
-    if (total > 0 && int64_t(base) < capacity) {
-      int written = 0;
-      for (int x0 = 0; x0 < touched; x0 += 32) {
-        const int x = x0 + lane;
-        const int p = x < touched ? int(plist[x]) : 0;
-        const unsigned m = __ballot_sync(kFull, p != 0);
-        if (p != 0) {
-          const int64_t pos = int64_t(base) + written + __popc(m & lt);
-          if (pos < capacity) { cols[pos] = q0 + int(jlist[x]); preds[pos] = uint8_t(p); }
-        }
-        written += __popc(m);
-      }
-    }
-    __syncwarp();
   }
 }
 
@@ -311,7 +336,7 @@ int32_t qrs_predict_max_tile(void) { return 2560; }   /* 4 warps x 19 B x 2560 =
 size_t qrs_predict_sparse_workspace_bytes(int64_t U, int32_t Q, int32_t tile) {
   if (U < 0 || Q <= 0 || tile <= 0) return 0;
   const int64_t nt = ceil_div<int64_t>(Q, tile);
-  return round_up<size_t>(size_t(U > 0 ? U : 1) * size_t(nt + 1) * 4, 256);
+  return round_up<size_t>(size_t(U > 0 ? U : 1) * size_t(nt + 1) * 8, 256);
 }
 
 int qrs_predict_sparse(const int64_t *rowptr, const int32_t *colidx, const uint8_t *val, int64_t U, int32_t Q,
@@ -330,13 +355,13 @@ int qrs_predict_sparse(const int64_t *rowptr, const int32_t *colidx, const uint8
   if (!colidx || !val) return QRS_ERR_INVALID_ARG;
   cudaStream_t st = as_stream(stream);
   const int nt = int(ceil_div<int64_t>(Q, tile));
-  int *tileptr = static_cast<int *>(ws);
+  int64_t *tilepos = static_cast<int64_t *>(ws);
   {
     const int64_t total = U * (nt + 1);
     int64_t blocks = ceil_div<int64_t>(total, 256);
     const int64_t cap = int64_t(sm_count()) * 8;
     if (blocks > cap) blocks = cap;
-    tile_index_kernel<<<unsigned(blocks), 256, 0, st>>>(rowptr, colidx, U, tile, nt, tileptr);
+    tile_index_kernel<<<unsigned(blocks), 256, 0, st>>>(rowptr, colidx, U, tile, nt, tilepos);
     QRS_LAUNCH_CHECK();
   }
   const size_t smem = sparse_smem_bytes(tile);
@@ -344,13 +369,12 @@ int qrs_predict_sparse(const int64_t *rowptr, const int32_t *colidx, const uint8
   int per_sm = 0;
   QRS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, predict_sparse_kernel, kSpWarps * 32, smem));
   if (per_sm < 1) return QRS_ERR_UNSUPPORTED;
-  const int64_t items = n_users * nt;
   int64_t grid = int64_t(sm_count()) * per_sm;
-  const int64_t need = ceil_div<int64_t>(items, kSpWarps);
+  const int64_t need = ceil_div<int64_t>(n_users, kSpWarps);
   if (grid > need) grid = need;
   predict_sparse_kernel<<<unsigned(grid), kSpWarps * 32, smem, st>>>(
-      rowptr, colidx, val, Q, u_idx, u_val, u_cnt, ku, user_base, n_users, tile, nt, tileptr, row_start, row_cnt,
-      cols, preds, capacity, cursor);
+      colidx, val, Q, u_idx, u_val, u_cnt, ku, user_base, n_users, tile, nt, tilepos, row_start, row_cnt, cols, preds,
+      capacity, cursor);
   QRS_LAUNCH_CHECK();
   return QRS_OK;
 }

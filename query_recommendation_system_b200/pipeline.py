@@ -73,7 +73,7 @@ class _Timer:
 class LshCfPipeline:
     def __init__(self, m: int, K: int, b: int, k: int, perm_tab, device="cuda", tile: Optional[int] = None,
                  minhash_mode: int = _lib.MINHASH_AUTO, head_ranks: Optional[int] = None,
-                 group=None, stages=None, profile: bool = False):
+                 group=None, stages=None, profile: bool = False, distributed: bool = True):
         """perm_tab: element-major permutation table int32[m, K] (numpy or tensor) — the K successive
         np.random.permutation(m) draws of recommender.py:120, `oracle`-independent: the caller makes it."""
         if K % b != 0:
@@ -82,6 +82,7 @@ class LshCfPipeline:
         self.st = stages if stages is not None else cuda_stages
         self.device = torch.device(device)
         self.group = group
+        self.distributed = distributed      # False: ignore an initialised process group (single-rank run)
         self.profile = profile
         self.tile = tile
         self.mode = minhash_mode
@@ -98,11 +99,15 @@ class LshCfPipeline:
     @property
     def world(self) -> int:
         import torch.distributed as dist
+        if not self.distributed:
+            return 1
         return dist.get_world_size(self.group) if (dist.is_available() and dist.is_initialized()) else 1
 
     @property
     def rank(self) -> int:
         import torch.distributed as dist
+        if not self.distributed:
+            return 0
         return dist.get_rank(self.group) if (dist.is_available() and dist.is_initialized()) else 0
 
     def _ensure_head(self, avg_len: float):

@@ -347,3 +347,15 @@ def test_predict_sparse_matches_oracle(tile):
     # counting pass (capacity 0) reports the same total without writing
     _, _, _, _, cursor0 = stages.predict_sparse(cu(rowptr), cu(colidx), cu(val), m, tab, user_base, n_users, tile, 0)
     assert int(cursor0.item()) == total
+
+
+def test_cpu_double_record_hash_matches_cuda():
+    """The CPU test double used for the gloo multi-rank tests builds bucket records with the same
+    hash24 | band | id layout as the CUDA kernels (csrc/common.cuh)."""
+    import cpu_stage_double as double
+    from query_recommendation_system_b200 import stages
+    g = load_golden("synth_wrap")
+    sig = g["sig"].astype(np.int64)
+    for b in (4, 8, 16):
+        rec, _ = stages.band_records(cu(sig, torch.int32), b, 1000)
+        assert np.array_equal(rec.cpu().numpy().view(np.uint64), double.band_records_np(sig, b, 1000))
