@@ -166,7 +166,8 @@ size_t qrs_topk_workspace_bytes(int64_t n_rows);
 int qrs_topk_tables(const uint64_t *pairs, const int32_t *sim_milli, int64_t n_pairs,
                     int64_t row_base, int64_t n_rows, int32_t k,
                     uint64_t *adj, void *ws, size_t ws_bytes,
-                    int32_t *idx, double *val, int32_t *cnt, void *stream);
+                    int32_t *idx, double *val, int32_t *milli /* optional: int32[n_rows*k], val * 1000 */,
+                    int32_t *cnt, void *stream);
 
 /* ------------------------------------------------------ a10 + a11: prediction
  * Replaces weighted_average (recommender.py:36-47) and the per-cell loop +
@@ -196,19 +197,29 @@ int qrs_predict_dense(const int64_t *rowptr, const int32_t *colidx, const uint8_
  * has ~16-32 entries per tile).  For user t and tile c,
  *   row_start int64[n_users*nt], row_cnt int32[n_users*nt] (index t*nt + c)
  * locate a contiguous slice of (cols int32[], preds uint8[]), ascending in
- * col; slices are placed by an atomic cursor, so their order in the buffer is
- * unspecified.  *cursor (device u64, zeroed by the caller) ends as the total
- * count; writes beyond `capacity` are dropped (the count still advances).
- * cols/preds may be NULL with capacity 0 for a counting pass. */
+ * col.  Slices are placed by atomic cursors, so their order in the buffer is
+ * unspecified: the buffer of `capacity` entries is cut into n_regions equal
+ * regions, each with its own cursor (one cursor would serialise millions of
+ * same-address atomics); cursors u64[n_regions] (device, zeroed by the caller)
+ * end as the number of entries REQUESTED in each region, writes beyond a
+ * region's capacity/n_regions entries are dropped (the count still advances),
+ * and row_start is an absolute index into cols/preds.  n_regions = 1 gives one
+ * dense buffer.  cols/preds may be NULL with capacity 0 for a counting pass. */
 int32_t qrs_predict_max_tile(void);
 size_t qrs_predict_sparse_workspace_bytes(int64_t U, int32_t Q, int32_t tile);
+/* u_milli (optional): the same similarities as integers, u_val[t] == u_milli[t] / 1000.0 exactly
+ * (what np.around(., 3) produces, recommender.py:204, 270; qrs_topk_tables emits it).  When given,
+ * the kernel accumulates exact integers (half the shared memory, no fp64 in the inner loop) and
+ * falls back to the reference's sequential fp64 arithmetic only for cells whose value is exactly
+ * half-way between two integers — the results are identical to the u_val path bit for bit. */
 int qrs_predict_sparse(const int64_t *rowptr, const int32_t *colidx, const uint8_t *val,
                        int64_t U, int32_t Q,
-                       const int32_t *u_idx, const double *u_val, const int32_t *u_cnt, int32_t ku,
+                       const int32_t *u_idx, const double *u_val, const int32_t *u_milli,
+                       const int32_t *u_cnt, int32_t ku,
                        int64_t user_base, int64_t n_users, int32_t tile,
                        void *ws, size_t ws_bytes,
                        int64_t *row_start, int32_t *row_cnt, int32_t *cols, uint8_t *preds,
-                       int64_t capacity, unsigned long long *cursor, void *stream);
+                       int64_t capacity, int32_t n_regions, unsigned long long *cursors, void *stream);
 
 #ifdef __cplusplus
 }

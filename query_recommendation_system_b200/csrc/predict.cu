@@ -57,32 +57,78 @@ constexpr int kSpAhead = 8;   // neighbour segments whose loads are in flight to
 
 struct __align__(16) Acc { double num, den; };
 
-// bytes of shared memory one warp needs for a tile: Acc[tile] | u16 jlist[tile] | u8 plist[tile] | metadata
-__host__ __device__ constexpr size_t sparse_warp_bytes(int tile) {
-  return round_up<size_t>(size_t(tile) * 19, 16) + 64 * (8 + 8 + 4);
+// Two accumulator flavours.
+//  F64  : {num, den} in fp64, updated in table order — the reference's arithmetic verbatim.
+//  MILLI: similarities are multiples of 0.001 (np.around(., 3), recommender.py:204/270), so
+//         N = sum r*milli, D = sum milli and the rater count are exact integers packed in one
+//         u64 (N << 32 | cnt << 20 | D).  round(0.7*N/D + 18) is then decided in exact integer
+//         arithmetic; it can differ from the reference's fp64 evaluation only when
+//         (7N + 180D) / (10D) is EXACTLY half-way between two integers (the fp64 rounding noise
+//         of ~1e-12 is far below the next possible distance 1/(20D) >= 7e-7), and exactly those
+//         cells are re-evaluated with the reference's sequential fp64 arithmetic.
+template <bool MILLI>
+struct AccOf { using type = Acc; };
+template <>
+struct AccOf<true> { using type = unsigned long long; };
+
+// bytes of shared memory one warp needs for a tile: acc[tile] | u16 jlist[tile] | u8 plist[tile] | metadata
+__host__ __device__ constexpr size_t sparse_warp_bytes(int tile, bool milli) {
+  return round_up<size_t>(size_t(tile) * (milli ? 11 : 19), 16) + 64 * (8 + 8 + 4 + 4);
+}
+
+__device__ __forceinline__ int predict_from(double num, double den) {
+  return den != 0.0 ? hybrid_rule(0.0, num / den) : 0;
+}
+
+// the reference's sequential fp64 evaluation of one cell, re-gathered from the neighbour segments
+__device__ __noinline__ int resolve_tie(const int *__restrict__ colidx, const uint8_t *__restrict__ val,
+                                        const int64_t *m_a, const int *m_n, const double *m_s, int c, int col) {
+  double num = 0.0, den = 0.0;
+  for (int t = 0; t < c; ++t) {
+    const int64_t a = m_a[t];
+    const int n = m_n[t];
+    int lo = 0, hi = n;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(colidx + a + mid) < col) lo = mid + 1; else hi = mid;
+    }
+    if (lo < n && __ldg(colidx + a + lo) == col) {
+      const int r = val[a + lo];
+      if (r != 0) {
+        num = __dadd_rn(num, __dmul_rn(double(r), m_s[t]));
+        den = __dadd_rn(den, m_s[t]);
+      }
+    }
+  }
+  return predict_from(num, den);
 }
 
 // One warp per user (grid-stride), walking the column tiles in order so that the per-user state
 // (neighbour ids, similarities, segment cursors) is loaded once and every tile needs exactly one
 // new position per neighbour — fetched one tile ahead of its use.
-__global__ void __launch_bounds__(kSpWarps * 32, 6)
+template <bool MILLI>
+__global__ void __launch_bounds__(kSpWarps * 32, MILLI ? 8 : 6)
 predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict__ val, int Q,
                       const int *__restrict__ u_idx, const double *__restrict__ u_val,
-                      const int *__restrict__ u_cnt, int ku, int64_t user_base, int64_t n_users, int tile, int nt,
-                      const int64_t *__restrict__ tilepos, int64_t *__restrict__ row_start,
-                      int *__restrict__ row_cnt, int *__restrict__ cols, uint8_t *__restrict__ preds,
-                      int64_t capacity, unsigned long long *__restrict__ cursor) {
+                      const int *__restrict__ u_milli, const int *__restrict__ u_cnt, int ku, int64_t user_base,
+                      int64_t n_users, int tile, int nt, const int64_t *__restrict__ tilepos,
+                      int64_t *__restrict__ row_start, int *__restrict__ row_cnt, int *__restrict__ cols,
+                      uint8_t *__restrict__ preds, int64_t region_cap, int n_regions,
+                      unsigned long long *__restrict__ cursors) {
+  using acc_t = typename AccOf<MILLI>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned char *mine = smem_raw + size_t(warp) * sparse_warp_bytes(tile);
-  Acc *acc = reinterpret_cast<Acc *>(mine);
+  unsigned char *mine = smem_raw + size_t(warp) * sparse_warp_bytes(tile, MILLI);
+  acc_t *acc = reinterpret_cast<acc_t *>(mine);
   uint16_t *jlist = reinterpret_cast<uint16_t *>(acc + tile);
   uint8_t *plist = reinterpret_cast<uint8_t *>(jlist + tile);
-  unsigned char *meta = mine + round_up<size_t>(size_t(tile) * 19, 16);
+  unsigned char *meta = mine + round_up<size_t>(size_t(tile) * (MILLI ? 11 : 19), 16);
   int64_t *m_a = reinterpret_cast<int64_t *>(meta);           // [64] first entry of the neighbour's segment
   double *m_s = reinterpret_cast<double *>(meta + 64 * 8);    // [64] its similarity
   int *m_n = reinterpret_cast<int *>(meta + 64 * 16);         // [64] entries in the segment
-  const Acc zero = {0.0, 0.0};
+  unsigned *m_inc = reinterpret_cast<unsigned *>(meta + 64 * 20);   // [64] MILLI: milli | 1 << 20
+  acc_t zero;
+  if constexpr (MILLI) zero = 0ull; else zero = Acc{0.0, 0.0};
   for (int j = lane; j < tile; j += 32) acc[j] = zero;
   __syncwarp();
 
@@ -90,6 +136,25 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
   const int64_t nwarps = int64_t(gridDim.x) * kSpWarps;
   const unsigned lt = lanemask_lt();
   const int stride = nt + 1;
+  // output slices are reserved from one of n_regions cursors (a single cursor would serialise
+  // millions of same-address atomics in L2); region r owns [r * region_cap, (r + 1) * region_cap)
+  const int region = int(warp_global % n_regions);
+  unsigned long long *cursor = cursors + region;
+  const int64_t region_base = int64_t(region) * region_cap;
+
+  // one contribution (rating r of neighbour slot g) to column slot j
+  auto add = [&](int j, int r, int g) {
+    if constexpr (MILLI) {
+      const unsigned inc = m_inc[g];
+      acc[j] += (static_cast<unsigned long long>(unsigned(r) * (inc & 0xFFFFFu)) << 32) | inc;
+    } else {
+      const double s = m_s[g];
+      Acc x = acc[j];
+      x.num = __dadd_rn(x.num, __dmul_rn(double(r), s));
+      x.den = __dadd_rn(x.den, s);
+      acc[j] = x;
+    }
+  };
 
   for (int64_t ul = warp_global; ul < n_users; ul += nwarps) {
     const int64_t ug = user_base + ul;            // global user = CSR row
@@ -104,7 +169,14 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
       cur[h] = nxt[h] = 0;
       if (me < c) {
         const int v = u_idx[ul * ku + me];
-        m_s[me] = u_val[ul * ku + me];
+        // MILLI: the table value IS milli/1000.0 (checked by the host), rebuilt here the way numpy does
+        if constexpr (MILLI) {
+          const int milli = u_milli[ul * ku + me];
+          m_s[me] = double(milli) / 1000.0;
+          m_inc[me] = unsigned(milli) | (1u << 20);
+        } else {
+          m_s[me] = u_val[ul * ku + me];
+        }
         tp[h] = tilepos + int64_t(v) * stride;
         cur[h] = __ldg(tp[h]);
         nxt[h] = __ldg(tp[h] + 1);
@@ -135,33 +207,11 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
 
       for (int nb0 = 0; nb0 < c; nb0 += 32) {
         const int nn = min(32, c - nb0);
-        // segments longer than one warp-load are rare (the tile is sized for ~24 entries per row);
-        // a group of neighbours containing one takes the generic loop, all others the unrolled one
+        // segments longer than one warp-load are the exception (the tile is sized for ~24 entries per
+        // row): their first 32 entries take the unrolled path like everyone else, the rest a short loop
         const int my_n = lane < nn ? m_n[nb0 + lane] : 0;
         const unsigned long_mask = __ballot_sync(kFull, my_n > 32);
         for (int g0 = 0; g0 < nn; g0 += kSpAhead) {
-          if ((long_mask >> g0) & ((1u << kSpAhead) - 1u)) {
-            const int g1 = min(nn, g0 + kSpAhead);
-            for (int g = g0; g < g1; ++g) {
-              const double s = m_s[nb0 + g];
-              const int64_t a = m_a[nb0 + g];
-              const int cn = m_n[nb0 + g];
-              for (int off = 0; off < cn; off += 32) {
-                if (off + lane < cn) {
-                  const int r = val[a + off + lane];
-                  if (r != 0) {
-                    const int j = __ldg(colidx + a + off + lane) - q0;
-                    Acc x = acc[j];
-                    x.num = __dadd_rn(x.num, __dmul_rn(double(r), s));
-                    x.den = __dadd_rn(x.den, s);
-                    acc[j] = x;
-                  }
-                }
-              }
-              __syncwarp();
-            }
-            continue;
-          }
           int colv[kSpAhead];
           int ratv[kSpAhead];
 #pragma unroll
@@ -179,12 +229,17 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
 #pragma unroll
           for (int g = 0; g < kSpAhead; ++g) {
             if (g0 + g < nn) {     // warp-uniform
-              if (ratv[g] != 0) {
-                const double s = m_s[nb0 + g0 + g];
-                Acc x = acc[colv[g] - q0];
-                x.num = __dadd_rn(x.num, __dmul_rn(double(ratv[g]), s));
-                x.den = __dadd_rn(x.den, s);
-                acc[colv[g] - q0] = x;
+              if (ratv[g] != 0) add(colv[g] - q0, ratv[g], nb0 + g0 + g);
+              if ((long_mask >> (g0 + g)) & 1u) {
+                const int64_t a = m_a[nb0 + g0 + g];
+                const int cn = m_n[nb0 + g0 + g];
+#pragma unroll 1
+                for (int off = 32; off < cn; off += 32) {
+                  if (off + lane < cn) {
+                    const int r = val[a + off + lane];
+                    if (r != 0) add(__ldg(colidx + a + off + lane) - q0, r, nb0 + g0 + g);
+                  }
+                }
               }
               __syncwarp();
             }
@@ -203,8 +258,12 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
         const int j = j0 + lane;
         bool hit = false;
         if (j < width) {
-          const Acc x = acc[j];
-          hit = x.den != 0.0 || x.num != 0.0;
+          if constexpr (MILLI) {
+            hit = acc[j] != 0ull;
+          } else {
+            const Acc x = acc[j];
+            hit = x.den != 0.0 || x.num != 0.0;
+          }
         }
         const unsigned m = __ballot_sync(kFull, hit);
         if (hit) jlist[touched + __popc(m & lt)] = uint16_t(j);
@@ -218,9 +277,26 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
         int p = 0;
         if (x < touched) {
           const int j = jlist[x];
-          const Acc a = acc[j];
+          const acc_t a = acc[j];
           acc[j] = zero;
-          if (a.den != 0.0) p = hybrid_rule(0.0, a.num / a.den);
+          if constexpr (MILLI) {
+            const unsigned lo = unsigned(a), N = unsigned(a >> 32);
+            const unsigned D = lo & 0xFFFFFu, raters = lo >> 20;
+            if (D != 0u) {
+              const unsigned X = 7u * N + 180u * D, Y = 10u * D;      // x = X / Y = 0.7 * N / D + 18
+              const unsigned q = X / Y, rem2 = 2u * (X - q * Y);
+              if (rem2 < Y) p = int(q);
+              else if (rem2 > Y) p = int(q) + 1;
+              else if (raters == 1u) {
+                const double s = double(D) / 1000.0;                   // the one rater's similarity
+                p = predict_from(__dmul_rn(double(N / D), s), s);
+              } else {
+                p = resolve_tie(colidx, val, m_a, m_n, m_s, c, q0 + j);
+              }
+            }
+          } else {
+            p = predict_from(a.num, a.den);
+          }
           plist[x] = uint8_t(p);
         }
         total += __popc(__ballot_sync(kFull, p != 0));
@@ -228,13 +304,13 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
       __syncwarp();
       unsigned long long base = 0;
       if (lane == 0) {
-        base = atomicAdd(cursor, (unsigned long long)total);
-        row_start[ul * nt + t] = int64_t(base);
+        if (total > 0) base = atomicAdd(cursor, (unsigned long long)total);
+        row_start[ul * nt + t] = region_base + int64_t(base);
         row_cnt[ul * nt + t] = total;
       }
       base = __shfl_sync(kFull, base, 0);
       // ---- pass 3: the slice, ascending in column
-      if (total > 0 && int64_t(base) < capacity) {
+      if (total > 0 && int64_t(base) < region_cap) {
         int written = 0;
         for (int x0 = 0; x0 < touched; x0 += 32) {
           const int x = x0 + lane;
@@ -242,7 +318,7 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
           const unsigned m = __ballot_sync(kFull, p != 0);
           if (p != 0) {
             const int64_t pos = int64_t(base) + written + __popc(m & lt);
-            if (pos < capacity) { cols[pos] = q0 + int(jlist[x]); preds[pos] = uint8_t(p); }
+            if (pos < region_cap) { cols[region_base + pos] = q0 + int(jlist[x]); preds[region_base + pos] = uint8_t(p); }
           }
           written += __popc(m);
         }
@@ -323,7 +399,29 @@ predict_dense_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__
   }
 }
 
-static size_t sparse_smem_bytes(int tile) { return size_t(kSpWarps) * sparse_warp_bytes(tile); }
+static size_t sparse_smem_bytes(int tile, bool milli) { return size_t(kSpWarps) * sparse_warp_bytes(tile, milli); }
+
+template <bool MILLI>
+static int launch_predict_sparse(const int *colidx, const uint8_t *val, int Q, const int *u_idx, const double *u_val,
+                                 const int *u_milli, const int *u_cnt, int ku, int64_t user_base, int64_t n_users,
+                                 int tile, int nt, const int64_t *tilepos, int64_t *row_start, int *row_cnt, int *cols,
+                                 uint8_t *preds, int64_t region_cap, int n_regions, unsigned long long *cursors,
+                                 cudaStream_t st) {
+  auto kern = predict_sparse_kernel<MILLI>;
+  const size_t smem = sparse_smem_bytes(tile, MILLI);
+  QRS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  int per_sm = 0;
+  QRS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSpWarps * 32, smem));
+  if (per_sm < 1) return QRS_ERR_UNSUPPORTED;
+  int64_t grid = int64_t(sm_count()) * per_sm;
+  const int64_t need = ceil_div<int64_t>(n_users, kSpWarps);
+  if (grid > need) grid = need;
+  kern<<<unsigned(grid), kSpWarps * 32, smem, st>>>(colidx, val, Q, u_idx, u_val, u_milli, u_cnt, ku, user_base,
+                                                    n_users, tile, nt, tilepos, row_start, row_cnt, cols, preds,
+                                                    region_cap, n_regions, cursors);
+  QRS_LAUNCH_CHECK();
+  return QRS_OK;
+}
 
 }  // namespace qrs
 
@@ -340,13 +438,14 @@ size_t qrs_predict_sparse_workspace_bytes(int64_t U, int32_t Q, int32_t tile) {
 }
 
 int qrs_predict_sparse(const int64_t *rowptr, const int32_t *colidx, const uint8_t *val, int64_t U, int32_t Q,
-                       const int32_t *u_idx, const double *u_val, const int32_t *u_cnt, int32_t ku,
-                       int64_t user_base, int64_t n_users, int32_t tile, void *ws, size_t ws_bytes,
+                       const int32_t *u_idx, const double *u_val, const int32_t *u_milli, const int32_t *u_cnt,
+                       int32_t ku, int64_t user_base, int64_t n_users, int32_t tile, void *ws, size_t ws_bytes,
                        int64_t *row_start, int32_t *row_cnt, int32_t *cols, uint8_t *preds, int64_t capacity,
-                       unsigned long long *cursor, void *stream) {
-  if (!rowptr || U < 0 || Q <= 0 || !u_idx || !u_val || !u_cnt || ku <= 0 || user_base < 0 || n_users < 0 ||
-      user_base + n_users > U || !row_start || !row_cnt || !cursor || capacity < 0)
+                       int32_t n_regions, unsigned long long *cursors, void *stream) {
+  if (!rowptr || U < 0 || Q <= 0 || !u_idx || (!u_val && !u_milli) || !u_cnt || ku <= 0 || user_base < 0 ||
+      n_users < 0 || user_base + n_users > U || !row_start || !row_cnt || !cursors || capacity < 0 || n_regions <= 0)
     return QRS_ERR_INVALID_ARG;
+  const int64_t region_cap = capacity / n_regions;
   if (capacity > 0 && (!cols || !preds)) return QRS_ERR_INVALID_ARG;
   if (tile <= 0 || tile % 32 != 0) return QRS_ERR_INVALID_ARG;
   if (tile > qrs_predict_max_tile() || ku > QRS_MAX_TOPK) return QRS_ERR_UNSUPPORTED;
@@ -364,19 +463,11 @@ int qrs_predict_sparse(const int64_t *rowptr, const int32_t *colidx, const uint8
     tile_index_kernel<<<unsigned(blocks), 256, 0, st>>>(rowptr, colidx, U, tile, nt, tilepos);
     QRS_LAUNCH_CHECK();
   }
-  const size_t smem = sparse_smem_bytes(tile);
-  QRS_CUDA(cudaFuncSetAttribute(predict_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  int per_sm = 0;
-  QRS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, predict_sparse_kernel, kSpWarps * 32, smem));
-  if (per_sm < 1) return QRS_ERR_UNSUPPORTED;
-  int64_t grid = int64_t(sm_count()) * per_sm;
-  const int64_t need = ceil_div<int64_t>(n_users, kSpWarps);
-  if (grid > need) grid = need;
-  predict_sparse_kernel<<<unsigned(grid), kSpWarps * 32, smem, st>>>(
-      colidx, val, Q, u_idx, u_val, u_cnt, ku, user_base, n_users, tile, nt, tilepos, row_start, row_cnt, cols, preds,
-      capacity, cursor);
-  QRS_LAUNCH_CHECK();
-  return QRS_OK;
+  if (u_milli)
+    return launch_predict_sparse<true>(colidx, val, Q, u_idx, u_val, u_milli, u_cnt, ku, user_base, n_users, tile, nt,
+                                       tilepos, row_start, row_cnt, cols, preds, region_cap, n_regions, cursors, st);
+  return launch_predict_sparse<false>(colidx, val, Q, u_idx, u_val, u_milli, u_cnt, ku, user_base, n_users, tile, nt,
+                                      tilepos, row_start, row_cnt, cols, preds, region_cap, n_regions, cursors, st);
 }
 
 int qrs_predict_dense(const int64_t *rowptr, const int32_t *colidx, const uint8_t *val, int64_t U, int32_t Q,

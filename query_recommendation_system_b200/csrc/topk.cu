@@ -80,7 +80,7 @@ __device__ __forceinline__ void bitonic_merge64(uint64_t &x0, uint64_t &x1, int 
 
 __global__ void __launch_bounds__(256)
 select_kernel(const uint64_t *__restrict__ adj, const uint64_t *__restrict__ row_off, int64_t n_rows, int k,
-              int *__restrict__ idx, double *__restrict__ val, int *__restrict__ cnt) {
+              int *__restrict__ idx, double *__restrict__ val, int *__restrict__ milli, int *__restrict__ cnt) {
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
@@ -110,11 +110,13 @@ select_kernel(const uint64_t *__restrict__ adj, const uint64_t *__restrict__ row
       const bool ok = lane < c;
       idx[row * k + lane] = ok ? int(uint32_t(h0)) : -1;
       val[row * k + lane] = ok ? double(1000 - int(uint32_t(h0 >> 32))) / 1000.0 : 0.0;
+      if (milli) milli[row * k + lane] = ok ? 1000 - int(uint32_t(h0 >> 32)) : 0;
     }
     if (lane + 32 < k) {
       const bool ok = lane + 32 < c;
       idx[row * k + lane + 32] = ok ? int(uint32_t(h1)) : -1;
       val[row * k + lane + 32] = ok ? double(1000 - int(uint32_t(h1 >> 32))) / 1000.0 : 0.0;
+      if (milli) milli[row * k + lane + 32] = ok ? 1000 - int(uint32_t(h1 >> 32)) : 0;
     }
   }
 }
@@ -133,7 +135,7 @@ size_t qrs_topk_workspace_bytes(int64_t n_rows) {
 
 int qrs_topk_tables(const uint64_t *pairs, const int32_t *sim_milli, int64_t n_pairs, int64_t row_base,
                     int64_t n_rows, int32_t k, uint64_t *adj, void *ws, size_t ws_bytes, int32_t *idx, double *val,
-                    int32_t *cnt, void *stream) {
+                    int32_t *milli, int32_t *cnt, void *stream) {
   if (n_pairs < 0 || n_rows < 0 || k <= 0 || !idx || !val || !cnt) return QRS_ERR_INVALID_ARG;
   if (n_pairs > 0 && (!pairs || !sim_milli || !adj)) return QRS_ERR_INVALID_ARG;
   if (k > QRS_MAX_TOPK) return QRS_ERR_UNSUPPORTED;
@@ -168,7 +170,7 @@ int qrs_topk_tables(const uint64_t *pairs, const int32_t *sim_milli, int64_t n_p
   }
   int64_t blocks = ceil_div<int64_t>(n_rows, 8);
   if (blocks > cap) blocks = cap;
-  select_kernel<<<unsigned(blocks), 256, 0, st>>>(adj, row_off, n_rows, k, idx, val, cnt);
+  select_kernel<<<unsigned(blocks), 256, 0, st>>>(adj, row_off, n_rows, k, idx, val, milli, cnt);
   QRS_LAUNCH_CHECK();
   return QRS_OK;
 }

@@ -84,6 +84,8 @@ class LshCfPipeline:
         self.group = group
         self.distributed = distributed      # False: ignore an initialised process group (single-rank run)
         self.profile = profile
+        self.integer_predict = True         # exact-integer accumulation in the predictor (identical results)
+        self.pred_regions = 1 if self.device.type != "cuda" else 256
         self.tile = tile
         self.mode = minhash_mode
         if isinstance(perm_tab, np.ndarray):
@@ -165,7 +167,7 @@ class LshCfPipeline:
             tm.mark("exchange:pairs")
 
         # a7 + a9
-        idx, v, cnt = st.topk_tables(pairs, sims, n_pairs, row_base, n_local, self.k)
+        idx, v, cnt, milli = st.topk_tables(pairs, sims, n_pairs, row_base, n_local, self.k, want_milli=True)
         out.nbr_idx, out.nbr_val, out.nbr_cnt = idx, v, cnt
         tm.mark("topk")
 
@@ -177,16 +179,22 @@ class LshCfPipeline:
             else:
                 rowptr_all, colidx_all, val_all = rowptr, colidx, val
             tile = self.tile or st.choose_predict_tile(self.m, nnz / max(n_local, 1))
-            cap = self._pred_capacity
+            # output slices are reserved from `regions` cursors; region capacity is learnt from a first
+            # (counting) call and kept for later steps, re-run only if a region would overflow
+            regions = self.pred_regions
+            rcap = self._pred_capacity
             while True:
-                rs, rc, cols, preds, cursor = st.predict_sparse(rowptr_all, colidx_all, val_all, self.m,
-                                                                (idx, v, cnt), row_base, n_local, tile, cap)
-                total = int(cursor.item())
-                if total <= cap:
+                rs, rc, cols, preds, cursors = st.predict_sparse(rowptr_all, colidx_all, val_all, self.m,
+                                                                 (idx, v, cnt), row_base, n_local, tile, rcap * regions,
+                                                                 u_milli=milli if self.integer_predict else None,
+                                                                 n_regions=regions)
+                need = int(cursors.max().item())
+                if need <= rcap:
                     break
-                cap = self._pred_capacity = int(total * 1.02) + 1024      # exact size is now known; run again
+                rcap = self._pred_capacity = int(need * 1.03) + 256
+            total = int(cursors.sum().item())
             out.pred_row_start, out.pred_row_cnt = rs, rc
-            out.pred_cols, out.pred_vals, out.n_predictions = cols[:total], preds[:total], total
+            out.pred_cols, out.pred_vals, out.n_predictions = cols, preds, total
             rated = int((val != 0).sum().item()) if val.numel() else 0
             out.covered_cells = n_local * self.m - rated
             tm.mark("predict")

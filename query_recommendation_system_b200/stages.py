@@ -161,9 +161,11 @@ def pair_cosine(sig: torch.Tensor, norm2: torch.Tensor, pairs: torch.Tensor) -> 
 
 
 # ------------------------------------------------------------------------ a7/a9
-def topk_tables(pairs: torch.Tensor, sims: torch.Tensor, n_pairs: int, row_base: int, n_rows: int, k: int):
+def topk_tables(pairs: torch.Tensor, sims: torch.Tensor, n_pairs: int, row_base: int, n_rows: int, k: int,
+                want_milli: bool = False):
     """Neighbour tables (recommender.py:183-210), canonical order: idx int32[n_rows, k] (-1 pad),
-    val float64[n_rows, k] (0 pad), cnt int32[n_rows]."""
+    val float64[n_rows, k] (0 pad), cnt int32[n_rows]; with want_milli a 4th tensor int32[n_rows, k]
+    holding val * 1000 exactly (the integer form the sparse predictor accumulates)."""
     _need_cuda(pairs, sims)
     lib = _lib.load()
     dev = pairs.device
@@ -172,9 +174,10 @@ def topk_tables(pairs: torch.Tensor, sims: torch.Tensor, n_pairs: int, row_base:
     idx = torch.empty((n_rows, k), dtype=torch.int32, device=dev)
     val = torch.empty((n_rows, k), dtype=torch.float64, device=dev)
     cnt = torch.empty(n_rows, dtype=torch.int32, device=dev)
+    milli = torch.empty((n_rows, k), dtype=torch.int32, device=dev) if want_milli else None
     check(lib.qrs_topk_tables(ptr(pairs), ptr(sims), n_pairs, row_base, n_rows, k, ptr(adj), ptr(ws), ws.numel(),
-                              ptr(idx), ptr(val), ptr(cnt), _stream()), "qrs_topk_tables")
-    return idx, val, cnt
+                              ptr(idx), ptr(val), ptr(milli), ptr(cnt), _stream()), "qrs_topk_tables")
+    return (idx, val, cnt, milli) if want_milli else (idx, val, cnt)
 
 
 # ---------------------------------------------------------------------- a10/a11
@@ -214,23 +217,30 @@ def choose_predict_tile(Q: int, avg_len: float) -> int:
 
 
 def predict_sparse(rowptr, colidx, val, Q: int, u_tab: Table, user_base: int, n_users: int, tile: int,
-                   capacity: int, out_cols: Optional[torch.Tensor] = None, out_preds: Optional[torch.Tensor] = None):
+                   capacity: int, out_cols: Optional[torch.Tensor] = None, out_preds: Optional[torch.Tensor] = None,
+                   u_milli: Optional[torch.Tensor] = None, n_regions: int = 1):
     """User-branch predictions in sparse form.  Returns (row_start int64[n_users, nt],
-    row_cnt int32[n_users, nt], cols int32[capacity], preds uint8[capacity], cursor int64[1] on device)."""
-    _need_cuda(rowptr, colidx, val, *u_tab)
+    row_cnt int32[n_users, nt], cols int32[capacity], preds uint8[capacity], cursors int64[n_regions] on
+    device = entries requested per region of capacity // n_regions entries).
+    u_milli: int32 table with u_val == u_milli / 1000.0 exactly (from topk_tables(want_milli=True)) selects
+    the exact-integer accumulation kernel; results are identical."""
+    _need_cuda(rowptr, colidx, val, u_milli, *u_tab)
     lib = _lib.load()
     dev = rowptr.device
     U = rowptr.numel() - 1
     nt = (Q + tile - 1) // tile
     ui, uv, uc = u_tab
+    assert u_milli is None or (u_milli.dtype == torch.int32 and u_milli.shape == ui.shape)
     assert ui.dtype == torch.int32 and uv.dtype == torch.float64 and uc.dtype == torch.int32
     row_start = torch.empty((n_users, nt), dtype=torch.int64, device=dev)
     row_cnt = torch.empty((n_users, nt), dtype=torch.int32, device=dev)
     cols = out_cols if out_cols is not None else torch.empty(max(capacity, 1), dtype=torch.int32, device=dev)
     preds = out_preds if out_preds is not None else torch.empty(max(capacity, 1), dtype=torch.uint8, device=dev)
-    cursor = torch.zeros(1, dtype=torch.int64, device=dev)
+    cursor = torch.zeros(n_regions, dtype=torch.int64, device=dev)
     ws = _ws(lib.qrs_predict_sparse_workspace_bytes(U, Q, tile), dev)
-    check(lib.qrs_predict_sparse(ptr(rowptr), ptr(colidx), ptr(val), U, Q, ptr(ui), ptr(uv), ptr(uc), ui.shape[1],
+    check(lib.qrs_predict_sparse(ptr(rowptr), ptr(colidx), ptr(val), U, Q, ptr(ui), ptr(uv), ptr(u_milli), ptr(uc),
+                                 ui.shape[1],
                                  user_base, n_users, tile, ptr(ws), ws.numel(), ptr(row_start), ptr(row_cnt),
-                                 ptr(cols), ptr(preds), capacity, ptr(cursor), _stream()), "qrs_predict_sparse")
+                                 ptr(cols), ptr(preds), capacity, n_regions, ptr(cursor), _stream()),
+          "qrs_predict_sparse")
     return row_start, row_cnt, cols, preds, cursor

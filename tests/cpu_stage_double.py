@@ -109,7 +109,7 @@ def pairs_score(records, slot_off, sig, norm2, b, capacity, sig_id_base=0, want_
     return pt, stt, torch.tensor([packed.size], dtype=torch.int64)
 
 
-def topk_tables(pairs, sims, n_pairs, row_base, n_rows, k):
+def topk_tables(pairs, sims, n_pairs, row_base, n_rows, k, want_milli=False):
     p = pairs.numpy().view(np.uint64)[:n_pairs]
     pr = np.stack([(p >> np.uint64(32)).astype(np.int64), (p & np.uint64(0xFFFFFFFF)).astype(np.int64)], 1)
     # the same pair can arrive once per owned end; the kernel counts each (row, neighbour) edge once per copy,
@@ -118,14 +118,18 @@ def topk_tables(pairs, sims, n_pairs, row_base, n_rows, k):
     n_all = max(row_base + n_rows, int(pr.max()) + 1 if pr.size else 0)
     idx, val, cnt = spec.topk_tables(n_all, pr, sims.numpy()[:n_pairs] / 1000.0, k)
     sl = slice(row_base, row_base + n_rows)
-    return torch.from_numpy(idx[sl].copy()), torch.from_numpy(val[sl].copy()), torch.from_numpy(cnt[sl].copy())
+    out = (torch.from_numpy(idx[sl].copy()), torch.from_numpy(val[sl].copy()), torch.from_numpy(cnt[sl].copy()))
+    if want_milli:
+        out = out + (torch.from_numpy(np.rint(val[sl] * 1000).astype(np.int32)),)
+    return out
 
 
 def choose_predict_tile(Q, avg_len):
     return max(32, int(math.ceil(Q / 3 / 32.0)) * 32)
 
 
-def predict_sparse(rowptr, colidx, val, Q, u_tab, user_base, n_users, tile, capacity, **kw):
+def predict_sparse(rowptr, colidx, val, Q, u_tab, user_base, n_users, tile, capacity, u_milli=None, n_regions=1, **kw):
+    assert n_regions == 1
     idx, v, cnt = [x.numpy() for x in u_tab]
     full_idx = np.full((user_base + n_users, idx.shape[1]), -1, np.int32)
     full_val = np.zeros((user_base + n_users, idx.shape[1]))

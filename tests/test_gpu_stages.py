@@ -315,13 +315,15 @@ def test_predict_dense_half_way_ties():
     assert np.array_equal(out.cpu().numpy().astype(np.int64), ref)
 
 
-@pytest.mark.parametrize("tile", [256, 512, 1024])
-def test_predict_sparse_matches_oracle(tile):
-    from query_recommendation_system_b200 import stages, synth
-    n, m, k = 1024, 3000, 19
-    rowptr_t, colidx_t, val_t = synth.planted_csr(n, m, 0.05, seed=20260103)
-    rowptr, colidx, val = rowptr_t.numpy(), colidx_t.numpy(), val_t.numpy()
-    rng = np.random.default_rng(3)
+def _sparse_case(n, m, k, seed, tie_heavy):
+    from query_recommendation_system_b200 import synth
+    rowptr_t, colidx_t, val_t = synth.planted_csr(n, m, 0.05, seed=seed)
+    rowptr, colidx, val = rowptr_t.numpy(), colidx_t.numpy(), val_t.numpy().copy()
+    rng = np.random.default_rng(seed)
+    if tie_heavy:
+        # ratings from {5, 15, 25, 35}: 0.7 * u + 18 lands exactly on .5 whenever the raters agree
+        val[:] = rng.choice(np.array([5, 15, 25, 35], np.uint8), size=val.size, p=[0.55, 0.25, 0.1, 0.1])
+        val[rng.random(val.size) < 0.02] = 0          # a few stored zeros (ignored like unrated cells)
     idx = np.full((n, k), -1, np.int32)
     sims = np.zeros((n, k))
     cnt = rng.integers(0, k + 1, n).astype(np.int32)
@@ -329,24 +331,47 @@ def test_predict_sparse_matches_oracle(tile):
         g0 = (i // 32) * 32
         cand = np.setdiff1d(np.arange(g0, g0 + 32), [i])
         idx[i, :cnt[i]] = rng.choice(cand, cnt[i], replace=False)
-        sims[i, :cnt[i]] = np.sort(rng.integers(300, 1000, cnt[i]))[::-1] / 1000.0
+        sims[i, :cnt[i]] = np.sort(rng.integers(0 if tie_heavy else 300, 1001, cnt[i]))[::-1] / 1000.0
+    return rowptr, colidx, val, idx, sims, cnt
+
+
+@pytest.mark.parametrize("tile,integer", [(256, False), (512, False), (1024, False), (256, True), (512, True), (1024, True)])
+@pytest.mark.parametrize("tie_heavy", [False, True])
+def test_predict_sparse_matches_oracle(tile, integer, tie_heavy):
+    from query_recommendation_system_b200 import stages
+    n, m, k = 1024, 3000, 19
+    rowptr, colidx, val, idx, sims, cnt = _sparse_case(n, m, k, 20260103 + int(tie_heavy), tie_heavy)
     user_base, n_users = 256, 512
     ref = spec.predict_user_branch_csr(rowptr, colidx, val, m, idx, sims, cnt, rows=range(user_base, user_base + n_users))
     total = sum(v[0].size for v in ref.values())
-    tab = (cu(idx[user_base:user_base + n_users]), cu(sims[user_base:user_base + n_users]),
-           cu(cnt[user_base:user_base + n_users]))
+    sl = slice(user_base, user_base + n_users)
+    tab = (cu(idx[sl]), cu(sims[sl]), cu(cnt[sl]))
+    milli = cu(np.rint(sims[sl] * 1000).astype(np.int32)) if integer else None
     rs, rc, cols, preds, cursor = stages.predict_sparse(cu(rowptr), cu(colidx), cu(val), m, tab, user_base, n_users,
-                                                        tile, capacity=total + 5)
+                                                        tile, capacity=total + 5, u_milli=milli)
     assert int(cursor.item()) == total
     rs, rc, cols, preds = rs.cpu().numpy(), rc.cpu().numpy(), cols.cpu().numpy(), preds.cpu().numpy()
+    n_tie = 0
     for t in range(n_users):
         gc = np.concatenate([cols[rs[t, c]:rs[t, c] + rc[t, c]] for c in range(rs.shape[1])])
         gp = np.concatenate([preds[rs[t, c]:rs[t, c] + rc[t, c]] for c in range(rs.shape[1])])
         rcols, rpreds = ref[user_base + t]
         assert np.array_equal(gc, rcols) and np.array_equal(gp.astype(np.int64), rpreds)
     # counting pass (capacity 0) reports the same total without writing
-    _, _, _, _, cursor0 = stages.predict_sparse(cu(rowptr), cu(colidx), cu(val), m, tab, user_base, n_users, tile, 0)
+    _, _, _, _, cursor0 = stages.predict_sparse(cu(rowptr), cu(colidx), cu(val), m, tab, user_base, n_users, tile, 0,
+                                                u_milli=milli)
     assert int(cursor0.item()) == total
+
+
+def test_topk_milli_table_is_exact(golden_synth):
+    from query_recommendation_system_b200 import stages
+    g = golden_synth
+    n, k, b = int(g["n"]), int(g["k"]), int(g["bands"][0])
+    pairs = g["b%d_candidates" % b].astype(np.int64)
+    packed = (pairs[:, 0].astype(np.uint64) << np.uint64(32)) | pairs[:, 1].astype(np.uint64)
+    milli = np.rint(g["b%d_pair_sims" % b] * 1000).astype(np.int32)
+    idx, val, cnt, mil = stages.topk_tables(cu(packed.view(np.int64)), cu(milli), pairs.shape[0], 0, n, k, want_milli=True)
+    assert np.array_equal(mil.cpu().numpy() / 1000.0, val.cpu().numpy())
 
 
 def test_cpu_double_record_hash_matches_cuda():
@@ -359,3 +384,31 @@ def test_cpu_double_record_hash_matches_cuda():
     for b in (4, 8, 16):
         rec, _ = stages.band_records(cu(sig, torch.int32), b, 1000)
         assert np.array_equal(rec.cpu().numpy().view(np.uint64), double.band_records_np(sig, b, 1000))
+
+
+def test_predict_sparse_regions_and_overflow():
+    """Slices reserved from several cursors: same per-user content; a too-small region drops writes but
+    still reports the demand, so the caller can size the buffer and run again."""
+    from query_recommendation_system_b200 import stages
+    n, m, k = 512, 2000, 11
+    rowptr, colidx, val, idx, sims, cnt = _sparse_case(n, m, k, 77, False)
+    ref = spec.predict_user_branch_csr(rowptr, colidx, val, m, idx, sims, cnt)
+    total = sum(v[0].size for v in ref.values())
+    tab = (cu(idx), cu(sims), cu(cnt))
+    milli = cu(np.rint(sims * 1000).astype(np.int32))
+    regions = 8
+    _, _, _, _, demand = stages.predict_sparse(cu(rowptr), cu(colidx), cu(val), m, tab, 0, n, 512, 0,
+                                               u_milli=milli, n_regions=regions)
+    assert int(demand.sum().item()) == total
+    rcap = int(demand.max().item())
+    rs, rc, cols, preds, cur = stages.predict_sparse(cu(rowptr), cu(colidx), cu(val), m, tab, 0, n, 512, rcap * regions,
+                                                     u_milli=milli, n_regions=regions)
+    assert torch.equal(cur, demand)
+    rs, rc, cols, preds = rs.cpu().numpy(), rc.cpu().numpy(), cols.cpu().numpy(), preds.cpu().numpy()
+    for t in range(n):
+        gc = np.concatenate([cols[rs[t, c]:rs[t, c] + rc[t, c]] for c in range(rs.shape[1])])
+        gp = np.concatenate([preds[rs[t, c]:rs[t, c] + rc[t, c]] for c in range(rs.shape[1])])
+        assert np.array_equal(gc, ref[t][0]) and np.array_equal(gp.astype(np.int64), ref[t][1])
+    # every slice lies inside its region
+    reg = rs // rcap
+    assert ((rs + rc - 1)[rc > 0] // rcap == reg[rc > 0]).all()
