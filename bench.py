@@ -308,7 +308,7 @@ def main():
             "roofline": roofline, "rooflines": rl,
             "e2e": {"value": n_total / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "wall_ms_per_step": e2e_wall_ms,
                     "h2d_bytes_per_step": runner.h2d_bytes, "d2h_bytes_per_step": runner.d2h_bytes, "steps": e2e_steps,
-                    "call": "pipeline.HostRunner(pipe)(rowptr, colidx, val) with pinned host tensors; returns pinned "
+                    "call": "pipeline.HostRunner(pipe, chunks=4)(rowptr, colidx, val) with pinned host tensors; returns pinned "
                             "sparse predictions + neighbour tables"},
             "gpu_launches": int(launches), "clocks": clocks,
         }

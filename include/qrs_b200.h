@@ -193,8 +193,8 @@ int qrs_predict_dense(const int64_t *rowptr, const int32_t *colidx, const uint8_
 /* Sparse form for the scaled configurations (user branch only, query branch
  * absent ⇒ q = 0): per user the non-zero predictions over unrated queries.
  * The query axis is cut into nt = ceil(Q / tile) tiles of `tile` columns
- * (a multiple of 32, <= qrs_predict_max_tile(); pick it so that one CSR row
- * has ~16-32 entries per tile).  For user t and tile c,
+ * (a multiple of 32, <= qrs_predict_max_tile(): as large as fits, one CTA
+ * accumulates one (user, tile) in shared memory).  For user t and tile c,
  *   row_start int64[n_users*nt], row_cnt int32[n_users*nt] (index t*nt + c)
  * locate a contiguous slice of (cols int32[], preds uint8[]), ascending in
  * col.  Slices are placed by atomic cursors, so their order in the buffer is
@@ -205,8 +205,8 @@ int qrs_predict_dense(const int64_t *rowptr, const int32_t *colidx, const uint8_
  * region's capacity/n_regions entries are dropped (the count still advances),
  * and row_start is an absolute index into cols/preds.  n_regions = 1 gives one
  * dense buffer.  cols/preds may be NULL with capacity 0 for a counting pass. */
-int32_t qrs_predict_max_tile(void);
-size_t qrs_predict_sparse_workspace_bytes(int64_t U, int32_t Q, int32_t tile);
+int32_t qrs_predict_max_tile(int32_t integer_tables /* 1 when u_milli is used */);
+size_t qrs_predict_sparse_workspace_bytes(int64_t U, int32_t Q, int32_t tile, int64_t capacity);
 /* u_milli (optional): the same similarities as integers, u_val[t] == u_milli[t] / 1000.0 exactly
  * (what np.around(., 3) produces, recommender.py:204, 270; qrs_topk_tables emits it).  When given,
  * the kernel accumulates exact integers (half the shared memory, no fp64 in the inner loop) and
@@ -218,7 +218,9 @@ int qrs_predict_sparse(const int64_t *rowptr, const int32_t *colidx, const uint8
                        const int32_t *u_cnt, int32_t ku,
                        int64_t user_base, int64_t n_users, int32_t tile,
                        void *ws, size_t ws_bytes,
-                       int64_t *row_start, int32_t *row_cnt, int32_t *cols, uint8_t *preds,
+                       int64_t *row_start, int32_t *row_cnt,
+                       void *cols /* int32[capacity], or uint16[capacity] when cols_u16 (Q <= 65536) */,
+                       int32_t cols_u16, uint8_t *preds,
                        int64_t capacity, int32_t n_regions, unsigned long long *cursors, void *stream);
 
 #ifdef __cplusplus

@@ -52,9 +52,6 @@ tile_index_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ co
 }
 
 // ------------------------------------------------------------------ sparse form
-constexpr int kSpWarps = 4;
-constexpr int kSpAhead = 8;   // neighbour segments whose loads are in flight together
-
 struct __align__(16) Acc { double num, den; };
 
 // Two accumulator flavours.
@@ -71,10 +68,20 @@ struct AccOf { using type = Acc; };
 template <>
 struct AccOf<true> { using type = unsigned long long; };
 
-// bytes of shared memory one warp needs for a tile: acc[tile] | u16 jlist[tile] | u8 plist[tile] | metadata
-__host__ __device__ constexpr size_t sparse_warp_bytes(int tile, bool milli) {
-  return round_up<size_t>(size_t(tile) * (milli ? 11 : 19), 16) + 64 * (8 + 8 + 4 + 4);
+constexpr int kSpThreads = 256;
+constexpr int kSpWarpsCta = kSpThreads / 32;
+constexpr int kSpAhead = 8;    // neighbours whose segment loads are in flight together (x2: double-buffered)
+
+// columns each warp sweeps in the output passes; the per-warp lists live at [w * range, (w + 1) * range)
+__host__ __device__ constexpr int sparse_warp_range(int tile) { return round_up(ceil_div(tile, kSpWarpsCta), 32); }
+
+// shared memory of one CTA: acc[tile] | u16 jlist[8*range] | u8 plist[8*range] | metadata
+__host__ __device__ constexpr size_t sparse_cta_bytes(int tile, bool milli) {
+  return round_up<size_t>(size_t(tile) * (milli ? 8 : 16), 16) +
+         round_up<size_t>(size_t(sparse_warp_range(tile)) * kSpWarpsCta * 3, 16) + 64 * (8 + 8 + 4 + 4) + 128;
 }
+
+constexpr int kTieMarker = 255;   // not a possible prediction: ratings <= 255 give at most 0.7 * 255 + 18 = 196.5
 
 __device__ __forceinline__ int predict_from(double num, double den) {
   return den != 0.0 ? hybrid_rule(0.0, num / den) : 0;
@@ -103,47 +110,51 @@ __device__ __noinline__ int resolve_tie(const int *__restrict__ colidx, const ui
   return predict_from(num, den);
 }
 
-// One warp per user (grid-stride), walking the column tiles in order so that the per-user state
-// (neighbour ids, similarities, segment cursors) is loaded once and every tile needs exactly one
-// new position per neighbour — fetched one tile ahead of its use.
+// One CTA per (user, column tile).  The neighbours' segments are streamed one after the other (table
+// order) by all 256 threads — entries of one neighbour hit distinct columns, so the shared-memory
+// read-modify-writes need no atomics, and a block barrier between neighbours keeps the reference's
+// left-to-right order per column.  The next neighbour's entries are loaded into registers before the
+// current one is accumulated.  The output passes are per warp over its own column range.
 template <bool MILLI>
-__global__ void __launch_bounds__(kSpWarps * 32, MILLI ? 8 : 6)
+__global__ void __launch_bounds__(kSpThreads, 2)
 predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict__ val, int Q,
                       const int *__restrict__ u_idx, const double *__restrict__ u_val,
                       const int *__restrict__ u_milli, const int *__restrict__ u_cnt, int ku, int64_t user_base,
                       int64_t n_users, int tile, int nt, const int64_t *__restrict__ tilepos,
                       int64_t *__restrict__ row_start, int *__restrict__ row_cnt, int *__restrict__ cols,
                       uint8_t *__restrict__ preds, int64_t region_cap, int n_regions,
-                      unsigned long long *__restrict__ cursors) {
+                      unsigned long long *__restrict__ cursors, unsigned long long *__restrict__ tie_count,
+                      ulonglong2 *__restrict__ tie_list, int64_t tie_capacity, int cols_u16) {
   using acc_t = typename AccOf<MILLI>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned char *mine = smem_raw + size_t(warp) * sparse_warp_bytes(tile, MILLI);
-  acc_t *acc = reinterpret_cast<acc_t *>(mine);
-  uint16_t *jlist = reinterpret_cast<uint16_t *>(acc + tile);
-  uint8_t *plist = reinterpret_cast<uint8_t *>(jlist + tile);
-  unsigned char *meta = mine + round_up<size_t>(size_t(tile) * (MILLI ? 11 : 19), 16);
-  int64_t *m_a = reinterpret_cast<int64_t *>(meta);           // [64] first entry of the neighbour's segment
-  double *m_s = reinterpret_cast<double *>(meta + 64 * 8);    // [64] its similarity
-  int *m_n = reinterpret_cast<int *>(meta + 64 * 16);         // [64] entries in the segment
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int range = sparse_warp_range(tile);
+  acc_t *acc = reinterpret_cast<acc_t *>(smem_raw);
+  unsigned char *ptr = smem_raw + round_up<size_t>(size_t(tile) * (MILLI ? 8 : 16), 16);
+  uint16_t *jlist = reinterpret_cast<uint16_t *>(ptr);
+  uint8_t *plist = reinterpret_cast<uint8_t *>(jlist + size_t(range) * kSpWarpsCta);
+  unsigned char *meta = ptr + round_up<size_t>(size_t(range) * kSpWarpsCta * 3, 16);
+  int64_t *m_a = reinterpret_cast<int64_t *>(meta);                 // [64] first entry of the neighbour's segment
+  double *m_s = reinterpret_cast<double *>(meta + 64 * 8);          // [64] its similarity
+  int *m_n = reinterpret_cast<int *>(meta + 64 * 16);               // [64] entries in the segment
   unsigned *m_inc = reinterpret_cast<unsigned *>(meta + 64 * 20);   // [64] MILLI: milli | 1 << 20
+  int *w_cnt = reinterpret_cast<int *>(meta + 64 * 24);             // [8] non-zero predictions per warp
+  int *w_off = w_cnt + 8;                                           // [8] exclusive prefix of w_cnt
+  unsigned long long *s_base = reinterpret_cast<unsigned long long *>(w_cnt + 16);
   acc_t zero;
   if constexpr (MILLI) zero = 0ull; else zero = Acc{0.0, 0.0};
-  for (int j = lane; j < tile; j += 32) acc[j] = zero;
-  __syncwarp();
+  for (int j = tid; j < tile; j += kSpThreads) acc[j] = zero;
+  __syncthreads();
 
-  const int64_t warp_global = int64_t(blockIdx.x) * kSpWarps + warp;
-  const int64_t nwarps = int64_t(gridDim.x) * kSpWarps;
   const unsigned lt = lanemask_lt();
   const int stride = nt + 1;
   // output slices are reserved from one of n_regions cursors (a single cursor would serialise
   // millions of same-address atomics in L2); region r owns [r * region_cap, (r + 1) * region_cap)
-  const int region = int(warp_global % n_regions);
+  const int region = int(blockIdx.x % n_regions);
   unsigned long long *cursor = cursors + region;
   const int64_t region_base = int64_t(region) * region_cap;
 
-  // one contribution (rating r of neighbour slot g) to column slot j
-  auto add = [&](int j, int r, int g) {
+  auto add = [&](int j, int r, int g) {          // one rating r of neighbour slot g into column slot j
     if constexpr (MILLI) {
       const unsigned inc = m_inc[g];
       acc[j] += (static_cast<unsigned long long>(unsigned(r) * (inc & 0xFFFFFu)) << 32) | inc;
@@ -156,180 +167,171 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
     }
   };
 
-  for (int64_t ul = warp_global; ul < n_users; ul += nwarps) {
+  const int64_t items = n_users * nt;
+  for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+    const int64_t ul = item / nt;                 // local user
+    const int t = int(item - ul * nt);
     const int64_t ug = user_base + ul;            // global user = CSR row
+    const int q0 = t * tile;
+    const int width = min(tile, Q - q0);
     const int c = min(u_cnt[ul], ku);
-    // lane <-> neighbour (slot 0: neighbours 0..31, slot 1: 32..63); cursors into each neighbour's row
-    const int64_t *tp[2];
-    int64_t cur[2], nxt[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int me = h * 32 + lane;
-      tp[h] = tilepos;
-      cur[h] = nxt[h] = 0;
-      if (me < c) {
-        const int v = u_idx[ul * ku + me];
-        // MILLI: the table value IS milli/1000.0 (checked by the host), rebuilt here the way numpy does
-        if constexpr (MILLI) {
-          const int milli = u_milli[ul * ku + me];
-          m_s[me] = double(milli) / 1000.0;
-          m_inc[me] = unsigned(milli) | (1u << 20);
-        } else {
-          m_s[me] = u_val[ul * ku + me];
-        }
-        tp[h] = tilepos + int64_t(v) * stride;
-        cur[h] = __ldg(tp[h]);
-        nxt[h] = __ldg(tp[h] + 1);
+    if (tid < c) {
+      const int v = u_idx[ul * ku + tid];
+      const int64_t *tp = tilepos + int64_t(v) * stride + t;
+      const int64_t a = __ldg(tp), e = __ldg(tp + 1);
+      m_a[tid] = a;
+      m_n[tid] = int(e - a);
+      if constexpr (MILLI) {
+        const int milli = u_milli[ul * ku + tid];
+        m_s[tid] = double(milli) / 1000.0;        // == the table's double (u_val == u_milli / 1000.0)
+        m_inc[tid] = unsigned(milli) | (1u << 20);
+      } else {
+        m_s[tid] = u_val[ul * ku + tid];
       }
     }
-    const int64_t *own_tp = tilepos + ug * stride;
-    int64_t own_cur = __ldg(own_tp), own_nxt = __ldg(own_tp + 1);
-    __syncwarp();
+    const int64_t own_a = __ldg(tilepos + ug * stride + t), own_e = __ldg(tilepos + ug * stride + t + 1);
+    __syncthreads();
 
-    for (int t = 0; t < nt; ++t) {
-      const int q0 = t * tile;
-      const int width = min(tile, Q - q0);
-      // this tile's segments = [cur, nxt); fetch the end of the NEXT tile's segments now
-      int64_t ahead[2] = {0, 0};
-      int64_t own_ahead = 0;
-      const bool more = t + 1 < nt;
+    // ---- neighbours in table order, kSpAhead at a time: the NEXT group's entries are loaded into
+    //      registers (one entry per thread and neighbour) before the current group is accumulated
+    int ncol[kSpAhead], nrat[kSpAhead];
+    auto fetch = [&](int g0) {
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int me = h * 32 + lane;
-        if (me < c) {
-          m_a[me] = cur[h];
-          m_n[me] = int(nxt[h] - cur[h]);
-          if (more) ahead[h] = __ldg(tp[h] + t + 2);
+      for (int g = 0; g < kSpAhead; ++g) {
+        nrat[g] = 0;
+        ncol[g] = 0;
+        if (g0 + g < c && tid < m_n[g0 + g]) {
+          const int64_t a = m_a[g0 + g];
+          ncol[g] = ld_stream_s32(colidx + a + tid);
+          nrat[g] = val[a + tid];
         }
       }
-      if (more) own_ahead = __ldg(own_tp + t + 2);
-      __syncwarp();
-
-      for (int nb0 = 0; nb0 < c; nb0 += 32) {
-        const int nn = min(32, c - nb0);
-        // segments longer than one warp-load are the exception (the tile is sized for ~24 entries per
-        // row): their first 32 entries take the unrolled path like everyone else, the rest a short loop
-        const int my_n = lane < nn ? m_n[nb0 + lane] : 0;
-        const unsigned long_mask = __ballot_sync(kFull, my_n > 32);
-        for (int g0 = 0; g0 < nn; g0 += kSpAhead) {
-          int colv[kSpAhead];
-          int ratv[kSpAhead];
+    };
+    fetch(0);
+    for (int g0 = 0; g0 < c; g0 += kSpAhead) {
+      int ccol[kSpAhead], crat[kSpAhead];
 #pragma unroll
-          for (int g = 0; g < kSpAhead; ++g) {
-            ratv[g] = 0;
-            colv[g] = 0;
-            if (g0 + g < nn) {
-              const int64_t a = m_a[nb0 + g0 + g];
-              if (lane < m_n[nb0 + g0 + g]) {
-                colv[g] = ld_stream_s32(colidx + a + lane);
-                ratv[g] = val[a + lane];
-              }
-            }
-          }
+      for (int g = 0; g < kSpAhead; ++g) { ccol[g] = ncol[g]; crat[g] = nrat[g]; }
+      if (g0 + kSpAhead < c) fetch(g0 + kSpAhead);
 #pragma unroll
-          for (int g = 0; g < kSpAhead; ++g) {
-            if (g0 + g < nn) {     // warp-uniform
-              if (ratv[g] != 0) add(colv[g] - q0, ratv[g], nb0 + g0 + g);
-              if ((long_mask >> (g0 + g)) & 1u) {
-                const int64_t a = m_a[nb0 + g0 + g];
-                const int cn = m_n[nb0 + g0 + g];
+      for (int g = 0; g < kSpAhead; ++g) {
+        if (g0 + g < c) {                           // block-uniform
+          if (crat[g] != 0) add(ccol[g] - q0, crat[g], g0 + g);
+          const int n = m_n[g0 + g];
+          if (n > kSpThreads) {                     // long segment: the rest straight from memory
+            const int64_t a = m_a[g0 + g];
 #pragma unroll 1
-                for (int off = 32; off < cn; off += 32) {
-                  if (off + lane < cn) {
-                    const int r = val[a + off + lane];
-                    if (r != 0) add(__ldg(colidx + a + off + lane) - q0, r, nb0 + g0 + g);
-                  }
-                }
-              }
-              __syncwarp();
+            for (int x = kSpThreads + tid; x < n; x += kSpThreads) {
+              const int r = val[a + x];
+              if (r != 0) add(__ldg(colidx + a + x) - q0, r, g0 + g);
             }
           }
+          __syncthreads();
         }
       }
+    }
 
-      // ---- the user's own rated cells are not predicted (recommender.py:302): drop what landed there
-      for (int64_t x = own_cur + lane; x < own_nxt; x += 32)
-        if (val[x] != 0) acc[__ldg(colidx + x) - q0] = zero;
-      __syncwarp();
+    // ---- the user's own rated cells are not predicted (recommender.py:302): drop what landed there
+    for (int64_t x = own_a + tid; x < own_e; x += kSpThreads)
+      if (val[x] != 0) acc[__ldg(colidx + x) - q0] = zero;
+    __syncthreads();
 
-      // ---- pass 1: ascending list of the touched columns
-      int touched = 0;
-      for (int j0 = 0; j0 < width; j0 += 32) {
-        const int j = j0 + lane;
-        bool hit = false;
-        if (j < width) {
-          if constexpr (MILLI) {
-            hit = acc[j] != 0ull;
-          } else {
-            const Acc x = acc[j];
-            hit = x.den != 0.0 || x.num != 0.0;
-          }
+    // ---- pass 1 (per warp, its own column range): ascending list of the touched columns
+    const int j_lo = warp * range, j_hi = min(width, j_lo + range);
+    uint16_t *wj = jlist + j_lo;
+    uint8_t *wp = plist + j_lo;
+    int touched = 0;
+    for (int j0 = j_lo; j0 < j_hi; j0 += 32) {
+      const int j = j0 + lane;
+      bool hit = false;
+      if (j < j_hi) {
+        if constexpr (MILLI) {
+          hit = acc[j] != 0ull;
+        } else {
+          const Acc x = acc[j];
+          hit = x.den != 0.0 || x.num != 0.0;
         }
-        const unsigned m = __ballot_sync(kFull, hit);
-        if (hit) jlist[touched + __popc(m & lt)] = uint16_t(j);
-        touched += __popc(m);
       }
-      __syncwarp();
-      // ---- pass 2: prediction of every touched column (dense lanes), accumulators back to zero
-      int total = 0;
-      for (int x0 = 0; x0 < touched; x0 += 32) {
-        const int x = x0 + lane;
-        int p = 0;
-        if (x < touched) {
-          const int j = jlist[x];
-          const acc_t a = acc[j];
-          acc[j] = zero;
-          if constexpr (MILLI) {
-            const unsigned lo = unsigned(a), N = unsigned(a >> 32);
-            const unsigned D = lo & 0xFFFFFu, raters = lo >> 20;
-            if (D != 0u) {
-              const unsigned X = 7u * N + 180u * D, Y = 10u * D;      // x = X / Y = 0.7 * N / D + 18
-              const unsigned q = X / Y, rem2 = 2u * (X - q * Y);
-              if (rem2 < Y) p = int(q);
-              else if (rem2 > Y) p = int(q) + 1;
-              else if (raters == 1u) {
-                const double s = double(D) / 1000.0;                   // the one rater's similarity
-                p = predict_from(__dmul_rn(double(N / D), s), s);
-              } else {
-                p = resolve_tie(colidx, val, m_a, m_n, m_s, c, q0 + j);
-              }
+      const unsigned m = __ballot_sync(kFull, hit);
+      if (hit) wj[touched + __popc(m & lt)] = uint16_t(j);
+      touched += __popc(m);
+    }
+    __syncwarp();
+    // ---- pass 2: prediction of every touched column (dense lanes), accumulators back to zero
+    int total = 0;
+    for (int x0 = 0; x0 < touched; x0 += 32) {
+      const int x = x0 + lane;
+      int p = 0;
+      if (x < touched) {
+        const int j = wj[x];
+        const acc_t a = acc[j];
+        acc[j] = zero;
+        if constexpr (MILLI) {
+          const unsigned lo = unsigned(a), N = unsigned(a >> 32);
+          const unsigned D = lo & 0xFFFFFu, raters = lo >> 20;
+          if (D != 0u) {
+            const unsigned X = 7u * N + 180u * D, Y = 10u * D;      // x = X / Y = 0.7 * N / D + 18
+            const unsigned q = X / Y, rem2 = 2u * (X - q * Y);
+            if (rem2 < Y) p = int(q);
+            else if (rem2 > Y) p = int(q) + 1;
+            else if (raters == 1u) {
+              const double s = double(D) / 1000.0;                   // the one rater's similarity
+              p = predict_from(__dmul_rn(double(N / D), s), s);
+            } else {
+              p = kTieMarker;      // several raters: settled after the slice position is known (pass 3)
             }
-          } else {
-            p = predict_from(a.num, a.den);
           }
-          plist[x] = uint8_t(p);
+        } else {
+          p = predict_from(a.num, a.den);
         }
-        total += __popc(__ballot_sync(kFull, p != 0));
+        wp[x] = uint8_t(p);
       }
-      __syncwarp();
+      total += __popc(__ballot_sync(kFull, p != 0));
+    }
+    if (lane == 0) w_cnt[warp] = total;
+    __syncthreads();
+    if (tid == 0) {
+      int sum = 0;
+#pragma unroll
+      for (int w = 0; w < kSpWarpsCta; ++w) { w_off[w] = sum; sum += w_cnt[w]; }
       unsigned long long base = 0;
-      if (lane == 0) {
-        if (total > 0) base = atomicAdd(cursor, (unsigned long long)total);
-        row_start[ul * nt + t] = region_base + int64_t(base);
-        row_cnt[ul * nt + t] = total;
-      }
-      base = __shfl_sync(kFull, base, 0);
-      // ---- pass 3: the slice, ascending in column
-      if (total > 0 && int64_t(base) < region_cap) {
+      if (sum > 0) base = atomicAdd(cursor, (unsigned long long)sum);
+      row_start[item] = region_base + int64_t(base);
+      row_cnt[item] = sum;
+      *s_base = base;
+    }
+    __syncthreads();
+    // ---- pass 3: the slice, ascending in column (warp ranges are ascending, lists are ascending)
+    {
+      const int64_t base = int64_t(*s_base) + w_off[warp];
+      if (total > 0 && base < region_cap) {
         int written = 0;
         for (int x0 = 0; x0 < touched; x0 += 32) {
           const int x = x0 + lane;
-          const int p = x < touched ? int(plist[x]) : 0;
+          const int p = x < touched ? int(wp[x]) : 0;
           const unsigned m = __ballot_sync(kFull, p != 0);
           if (p != 0) {
-            const int64_t pos = int64_t(base) + written + __popc(m & lt);
-            if (pos < region_cap) { cols[region_base + pos] = q0 + int(jlist[x]); preds[region_base + pos] = uint8_t(p); }
+            const int64_t pos = base + written + __popc(m & lt);
+            if (pos < region_cap) {
+              int pv = p;
+              if (MILLI && p == kTieMarker) {
+                const unsigned long long slot = atomicAdd(tie_count, 1ull);
+                if (int64_t(slot) < tie_capacity)
+                  tie_list[slot] = make_ulonglong2((unsigned long long)(region_base + pos),
+                                                   ((unsigned long long)(unsigned)ul << 32) | unsigned(q0 + int(wj[x])));
+                else
+                  pv = resolve_tie(colidx, val, m_a, m_n, m_s, c, q0 + int(wj[x]));   // list full: settle here
+              }
+              if (cols_u16) reinterpret_cast<uint16_t *>(cols)[region_base + pos] = uint16_t(q0 + int(wj[x]));
+              else cols[region_base + pos] = q0 + int(wj[x]);
+              preds[region_base + pos] = uint8_t(pv);
+            }
           }
           written += __popc(m);
         }
       }
-      __syncwarp();
-      // advance the cursors to the next tile
-#pragma unroll
-      for (int h = 0; h < 2; ++h) { cur[h] = nxt[h]; nxt[h] = ahead[h]; }
-      own_cur = own_nxt;
-      own_nxt = own_ahead;
     }
+    __syncthreads();
   }
 }
 
@@ -399,26 +401,77 @@ predict_dense_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__
   }
 }
 
-static size_t sparse_smem_bytes(int tile, bool milli) { return size_t(kSpWarps) * sparse_warp_bytes(tile, milli); }
+// Exact half-way cells with several raters (MILLI flavour): one warp per cell re-gathers the
+// neighbours' ratings of that column (lane <-> neighbour, binary search in the neighbour's row) and
+// replays the reference's sequential fp64 sums in table order.
+__global__ void __launch_bounds__(256)
+predict_tie_fixup_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ colidx,
+                         const uint8_t *__restrict__ val, const int *__restrict__ u_idx,
+                         const int *__restrict__ u_milli, const int *__restrict__ u_cnt, int ku,
+                         const unsigned long long *__restrict__ tie_count, const ulonglong2 *__restrict__ tie_list,
+                         int64_t tie_capacity, uint8_t *__restrict__ preds) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  int64_t n = int64_t(*tie_count);
+  if (n > tie_capacity) n = tie_capacity;
+  for (int64_t i = warp_global; i < n; i += nwarps) {
+    const ulonglong2 rec = tie_list[i];
+    const int64_t ul = int64_t(rec.y >> 32);
+    const int col = int(unsigned(rec.y));
+    const int c = min(u_cnt[ul], ku);
+    double num = 0.0, den = 0.0;
+    for (int t0 = 0; t0 < c; t0 += 32) {
+      int r = 0;
+      double s = 0.0;
+      if (t0 + lane < c) {
+        const int v = u_idx[ul * ku + t0 + lane];
+        s = double(u_milli[ul * ku + t0 + lane]) / 1000.0;
+        const int64_t a = rowptr[v];
+        const int len = int(rowptr[v + 1] - a);
+        int lo = 0, hi = len;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (__ldg(colidx + a + mid) < col) lo = mid + 1; else hi = mid;
+        }
+        if (lo < len && __ldg(colidx + a + lo) == col) r = val[a + lo];
+      }
+      const int nn = min(32, c - t0);
+      for (int t = 0; t < nn; ++t) {
+        const int rt = __shfl_sync(kFull, r, t);
+        const double st = __shfl_sync(kFull, s, t);
+        if (rt != 0) {
+          num = __dadd_rn(num, __dmul_rn(double(rt), st));
+          den = __dadd_rn(den, st);
+        }
+      }
+    }
+    if (lane == 0) preds[rec.x] = uint8_t(predict_from(num, den));
+  }
+}
+
+static size_t sparse_smem_bytes(int tile, bool milli) { return sparse_cta_bytes(tile, milli); }
 
 template <bool MILLI>
 static int launch_predict_sparse(const int *colidx, const uint8_t *val, int Q, const int *u_idx, const double *u_val,
                                  const int *u_milli, const int *u_cnt, int ku, int64_t user_base, int64_t n_users,
                                  int tile, int nt, const int64_t *tilepos, int64_t *row_start, int *row_cnt, int *cols,
                                  uint8_t *preds, int64_t region_cap, int n_regions, unsigned long long *cursors,
-                                 cudaStream_t st) {
+                                 unsigned long long *tie_count, ulonglong2 *tie_list, int64_t tie_capacity,
+                                 int cols_u16, cudaStream_t st) {
   auto kern = predict_sparse_kernel<MILLI>;
   const size_t smem = sparse_smem_bytes(tile, MILLI);
   QRS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   int per_sm = 0;
-  QRS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSpWarps * 32, smem));
+  QRS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSpThreads, smem));
   if (per_sm < 1) return QRS_ERR_UNSUPPORTED;
   int64_t grid = int64_t(sm_count()) * per_sm;
-  const int64_t need = ceil_div<int64_t>(n_users, kSpWarps);
+  const int64_t need = n_users * nt;
   if (grid > need) grid = need;
-  kern<<<unsigned(grid), kSpWarps * 32, smem, st>>>(colidx, val, Q, u_idx, u_val, u_milli, u_cnt, ku, user_base,
+  kern<<<unsigned(grid), kSpThreads, smem, st>>>(colidx, val, Q, u_idx, u_val, u_milli, u_cnt, ku, user_base,
                                                     n_users, tile, nt, tilepos, row_start, row_cnt, cols, preds,
-                                                    region_cap, n_regions, cursors);
+                                                    region_cap, n_regions, cursors, tie_count, tie_list, tie_capacity,
+                                                    cols_u16);
   QRS_LAUNCH_CHECK();
   return QRS_OK;
 }
@@ -429,32 +482,44 @@ using namespace qrs;
 
 extern "C" {
 
-int32_t qrs_predict_max_tile(void) { return 2560; }   /* 4 warps x 19 B x 2560 = 195 KB */
+/* largest column tile that still lets two CTAs share an SM (<= ~112 KB of shared memory each) */
+int32_t qrs_predict_max_tile(int32_t integer_tables) { return integer_tables ? 10048 : 5824; }
 
-size_t qrs_predict_sparse_workspace_bytes(int64_t U, int32_t Q, int32_t tile) {
-  if (U < 0 || Q <= 0 || tile <= 0) return 0;
+static int64_t tie_list_capacity(int64_t capacity) { return capacity / 32 + 65536; }
+
+size_t qrs_predict_sparse_workspace_bytes(int64_t U, int32_t Q, int32_t tile, int64_t capacity) {
+  if (U < 0 || Q <= 0 || tile <= 0 || capacity < 0) return 0;
   const int64_t nt = ceil_div<int64_t>(Q, tile);
-  return round_up<size_t>(size_t(U > 0 ? U : 1) * size_t(nt + 1) * 8, 256);
+  // tile index | tie counter | list of exact half-way cells awaiting their fp64 replay
+  return round_up<size_t>(size_t(U > 0 ? U : 1) * size_t(nt + 1) * 8, 256) + 256 +
+         round_up<size_t>(size_t(tie_list_capacity(capacity)) * 16, 256);
 }
 
 int qrs_predict_sparse(const int64_t *rowptr, const int32_t *colidx, const uint8_t *val, int64_t U, int32_t Q,
                        const int32_t *u_idx, const double *u_val, const int32_t *u_milli, const int32_t *u_cnt,
                        int32_t ku, int64_t user_base, int64_t n_users, int32_t tile, void *ws, size_t ws_bytes,
-                       int64_t *row_start, int32_t *row_cnt, int32_t *cols, uint8_t *preds, int64_t capacity,
-                       int32_t n_regions, unsigned long long *cursors, void *stream) {
+                       int64_t *row_start, int32_t *row_cnt, void *cols_any, int32_t cols_u16, uint8_t *preds,
+                       int64_t capacity, int32_t n_regions, unsigned long long *cursors, void *stream) {
+  int32_t *cols = static_cast<int32_t *>(cols_any);
+  if (cols_u16 && Q > 65536) return QRS_ERR_INVALID_ARG;
   if (!rowptr || U < 0 || Q <= 0 || !u_idx || (!u_val && !u_milli) || !u_cnt || ku <= 0 || user_base < 0 ||
       n_users < 0 || user_base + n_users > U || !row_start || !row_cnt || !cursors || capacity < 0 || n_regions <= 0)
     return QRS_ERR_INVALID_ARG;
   const int64_t region_cap = capacity / n_regions;
   if (capacity > 0 && (!cols || !preds)) return QRS_ERR_INVALID_ARG;
   if (tile <= 0 || tile % 32 != 0) return QRS_ERR_INVALID_ARG;
-  if (tile > qrs_predict_max_tile() || ku > QRS_MAX_TOPK) return QRS_ERR_UNSUPPORTED;
-  if (!ws || ws_bytes < qrs_predict_sparse_workspace_bytes(U, Q, tile)) return QRS_ERR_WORKSPACE;
+  if (tile > qrs_predict_max_tile(u_milli != nullptr) || ku > QRS_MAX_TOPK) return QRS_ERR_UNSUPPORTED;
+  if (!ws || ws_bytes < qrs_predict_sparse_workspace_bytes(U, Q, tile, capacity)) return QRS_ERR_WORKSPACE;
   if (n_users == 0 || U == 0) return QRS_OK;
   if (!colidx || !val) return QRS_ERR_INVALID_ARG;
   cudaStream_t st = as_stream(stream);
   const int nt = int(ceil_div<int64_t>(Q, tile));
   int64_t *tilepos = static_cast<int64_t *>(ws);
+  char *wsp = static_cast<char *>(ws) + round_up<size_t>(size_t(U) * size_t(nt + 1) * 8, 256);
+  unsigned long long *tie_count = reinterpret_cast<unsigned long long *>(wsp);
+  ulonglong2 *tie_list = reinterpret_cast<ulonglong2 *>(wsp + 256);
+  const int64_t tie_cap = tie_list_capacity(capacity);
+  QRS_CUDA(cudaMemsetAsync(tie_count, 0, 8, st));
   {
     const int64_t total = U * (nt + 1);
     int64_t blocks = ceil_div<int64_t>(total, 256);
@@ -463,11 +528,19 @@ int qrs_predict_sparse(const int64_t *rowptr, const int32_t *colidx, const uint8
     tile_index_kernel<<<unsigned(blocks), 256, 0, st>>>(rowptr, colidx, U, tile, nt, tilepos);
     QRS_LAUNCH_CHECK();
   }
-  if (u_milli)
-    return launch_predict_sparse<true>(colidx, val, Q, u_idx, u_val, u_milli, u_cnt, ku, user_base, n_users, tile, nt,
-                                       tilepos, row_start, row_cnt, cols, preds, region_cap, n_regions, cursors, st);
+  if (u_milli) {
+    int rc = launch_predict_sparse<true>(colidx, val, Q, u_idx, u_val, u_milli, u_cnt, ku, user_base, n_users, tile,
+                                         nt, tilepos, row_start, row_cnt, cols, preds, region_cap, n_regions, cursors,
+                                         tie_count, tie_list, tie_cap, cols_u16, st);
+    if (rc != QRS_OK || capacity == 0) return rc;
+    predict_tie_fixup_kernel<<<sm_count() * 8, 256, 0, st>>>(rowptr, colidx, val, u_idx, u_milli, u_cnt, ku, tie_count,
+                                                             tie_list, tie_cap, preds);
+    QRS_LAUNCH_CHECK();
+    return QRS_OK;
+  }
   return launch_predict_sparse<false>(colidx, val, Q, u_idx, u_val, u_milli, u_cnt, ku, user_base, n_users, tile, nt,
-                                      tilepos, row_start, row_cnt, cols, preds, region_cap, n_regions, cursors, st);
+                                      tilepos, row_start, row_cnt, cols, preds, region_cap, n_regions, cursors,
+                                      tie_count, tie_list, tie_cap, cols_u16, st);
 }
 
 int qrs_predict_dense(const int64_t *rowptr, const int32_t *colidx, const uint8_t *val, int64_t U, int32_t Q,

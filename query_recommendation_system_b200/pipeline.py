@@ -36,6 +36,7 @@ class PipelineOutput:
     pred_row_cnt: torch.Tensor = None      # int32[n_local, nt]
     pred_cols: torch.Tensor = None         # int32[n_predictions]
     pred_vals: torch.Tensor = None         # uint8[n_predictions]
+    pred_chunks: list = None               # per user chunk: {user_lo, n_users, row_start, row_cnt, cols, preds}
     n_predictions: int = 0
     covered_cells: int = 0                 # zero cells of R decided (predicted or proven "missed")
     stage_ms: Dict[str, float] = field(default_factory=dict)
@@ -95,7 +96,9 @@ class LshCfPipeline:
         self._head_ranks = head_ranks
         self.order_head = None
         self._head_for = None
-        self._pred_capacity = 0
+        self._pred_capacity = {}
+        self.predict_chunks = 1             # > 1: predictions are produced (and can be shipped) chunk by chunk
+        self.cols_u16 = False               # uint16 column ids in the prediction slices (needs m <= 65536)
 
     # ------------------------------------------------------------------ distributed helpers
     @property
@@ -120,7 +123,7 @@ class LshCfPipeline:
 
     # ------------------------------------------------------------------ the path
     def run(self, rowptr: torch.Tensor, colidx: torch.Tensor, val: Optional[torch.Tensor],
-            predict: bool = True) -> PipelineOutput:
+            predict: bool = True, chunk_sink=None) -> PipelineOutput:
         """rowptr/colidx/val: this rank's shard (rows [rank*n_local, (rank+1)*n_local)) of the users×queries
         CSR, on `self.device`.  Every rank must hold the same number of rows."""
         st, G, rank = self.st, self.world, self.rank
@@ -178,23 +181,40 @@ class LshCfPipeline:
                 tm.mark("exchange:ratings")
             else:
                 rowptr_all, colidx_all, val_all = rowptr, colidx, val
-            tile = self.tile or st.choose_predict_tile(self.m, nnz / max(n_local, 1))
-            # output slices are reserved from `regions` cursors; region capacity is learnt from a first
-            # (counting) call and kept for later steps, re-run only if a region would overflow
+            tile = self.tile or st.choose_predict_tile(self.m, nnz / max(n_local, 1), self.integer_predict)
+            # Users are predicted in `predict_chunks` consecutive chunks so that a caller-supplied sink can
+            # ship chunk i to the host while chunk i+1 is computed.  Inside a chunk the output slices are
+            # reserved from `regions` cursors; the region capacity is learnt from a first (counting) call and
+            # kept for later steps, re-run only if a region would overflow.
             regions = self.pred_regions
-            rcap = self._pred_capacity
-            while True:
-                rs, rc, cols, preds, cursors = st.predict_sparse(rowptr_all, colidx_all, val_all, self.m,
-                                                                 (idx, v, cnt), row_base, n_local, tile, rcap * regions,
-                                                                 u_milli=milli if self.integer_predict else None,
-                                                                 n_regions=regions)
-                need = int(cursors.max().item())
-                if need <= rcap:
-                    break
-                rcap = self._pred_capacity = int(need * 1.03) + 256
-            total = int(cursors.sum().item())
-            out.pred_row_start, out.pred_row_cnt = rs, rc
-            out.pred_cols, out.pred_vals, out.n_predictions = cols, preds, total
+            chunks = max(1, min(self.predict_chunks, n_local))
+            bounds = [n_local * ci // chunks for ci in range(chunks + 1)]
+            total = 0
+            out.pred_chunks = []
+            for ci in range(chunks):
+                lo, hi = bounds[ci], bounds[ci + 1]
+                rcap = self._pred_capacity.get((chunks, ci), 0)
+                tab = (idx[lo:hi], v[lo:hi], cnt[lo:hi])
+                mil = milli[lo:hi] if self.integer_predict else None
+                while True:
+                    rs, rc, cols, preds, cursors = st.predict_sparse(rowptr_all, colidx_all, val_all, self.m, tab,
+                                                                     row_base + lo, hi - lo, tile, rcap * regions,
+                                                                     u_milli=mil, n_regions=regions,
+                                                                     cols_u16=self.cols_u16)
+                    demand = cursors.cpu()
+                    need = int(demand.max().item())
+                    if need <= rcap:
+                        break
+                    rcap = self._pred_capacity[(chunks, ci)] = int(need * 1.03) + 256
+                total += int(demand.sum().item())
+                chunk = {"user_lo": lo, "n_users": hi - lo, "row_start": rs, "row_cnt": rc, "cols": cols, "preds": preds}
+                out.pred_chunks.append(chunk)
+                if chunk_sink is not None:
+                    chunk_sink(ci, chunk)
+            if chunks == 1:
+                out.pred_row_start, out.pred_row_cnt = rs, rc
+                out.pred_cols, out.pred_vals = cols, preds
+            out.n_predictions = total
             rated = int((val != 0).sum().item()) if val.numel() else 0
             out.covered_cells = n_local * self.m - rated
             tm.mark("predict")
@@ -274,14 +294,19 @@ class LshCfPipeline:
 
 
 class HostRunner:
-    """The call a user of the drop-in makes with HOST data: pinned utility-matrix CSR in, sparse
-    predictions + neighbour tables out (pinned), host↔device copies on the same stream as the
-    kernels.  Buffers are allocated once and reused across calls."""
+    """The call a user of the drop-in makes with HOST data: pinned utility-matrix CSR in; sparse
+    predictions + neighbour tables out, in pinned host memory.  Host↔device copies are part of the
+    call: the CSR goes up on the compute stream, predictions come back chunk by chunk on a second
+    stream while the next chunk of users is being predicted (column ids as uint16 when they fit).
+    Buffers are allocated once and reused across calls."""
 
-    def __init__(self, pipe: LshCfPipeline):
+    def __init__(self, pipe: LshCfPipeline, chunks: int = 4):
         self.pipe = pipe
+        pipe.predict_chunks = chunks
+        pipe.cols_u16 = pipe.m <= 65536
         self._dev = {}
         self._host = {}
+        self.copy_stream = torch.cuda.Stream(device=pipe.device)
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
@@ -297,23 +322,45 @@ class HostRunner:
             buf = self._host[name] = torch.empty(int(t.numel() * 1.05) + 16, dtype=t.dtype, pin_memory=True)
         return buf[:t.numel()]
 
+    def _ship(self, name, t, res, key=None):
+        """D2H of one device tensor into its pinned twin on the copy stream (after the producing kernels)."""
+        t = t.reshape(-1)
+        h = self._host_like(name, t)
+        h.copy_(t, non_blocking=True)
+        t.record_stream(self.copy_stream)
+        self.d2h_bytes += t.numel() * t.element_size()
+        res[key or name] = h
+
     def __call__(self, rowptr_h: torch.Tensor, colidx_h: torch.Tensor, val_h: torch.Tensor):
         self.h2d_bytes = self.d2h_bytes = 0
+        compute = torch.cuda.current_stream()
         dev_in = []
         for name, t in (("rowptr", rowptr_h), ("colidx", colidx_h), ("val", val_h)):
             d = self._dev_like(name, t)
             d.copy_(t, non_blocking=True)
             self.h2d_bytes += t.numel() * t.element_size()
             dev_in.append(d)
-        out = self.pipe.run(*dev_in, predict=True)
-        res = {}
-        for name in ("pred_row_start", "pred_row_cnt", "pred_cols", "pred_vals", "nbr_idx", "nbr_val", "nbr_cnt"):
-            t = getattr(out, name).reshape(-1)
-            h = self._host_like(name, t)
-            h.copy_(t, non_blocking=True)
-            self.d2h_bytes += t.numel() * t.element_size()
-            res[name] = h
-        torch.cuda.current_stream().synchronize()
+        res = {"chunks": []}
+
+        def sink(ci, chunk):
+            ready = torch.cuda.Event()
+            ready.record(compute)
+            host_chunk = {"user_lo": chunk["user_lo"], "n_users": chunk["n_users"]}
+            with torch.cuda.stream(self.copy_stream):
+                self.copy_stream.wait_event(ready)
+                for key in ("row_start", "row_cnt", "cols", "preds"):
+                    self._ship("c%d_%s" % (ci, key), chunk[key], host_chunk, key)
+            res["chunks"].append(host_chunk)
+
+        out = self.pipe.run(*dev_in, predict=True, chunk_sink=sink)
+        ready = torch.cuda.Event()
+        ready.record(compute)
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(ready)
+            for name in ("nbr_idx", "nbr_val", "nbr_cnt"):
+                self._ship(name, getattr(out, name), res)
+        self.copy_stream.synchronize()
+        compute.synchronize()
         res["n_predictions"] = out.n_predictions
         res["covered_cells"] = out.covered_cells
         return res

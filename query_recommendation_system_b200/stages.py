@@ -208,17 +208,20 @@ def predict_dense(rowptr, colidx, val, Q: int, q_tab: Optional[Table], u_tab: Op
     return out
 
 
-def choose_predict_tile(Q: int, avg_len: float) -> int:
-    """Column tile of the sparse predictor: ~24 entries of an average row per tile."""
-    max_tile = _lib.load().qrs_predict_max_tile()
-    t = 24.0 * Q / max(avg_len, 1.0)
-    t = int(min(max(256, math.ceil(t / 32.0) * 32), max_tile))
-    return min(t, int(math.ceil(Q / 32.0) * 32)) if Q >= 32 else 32
+def choose_predict_tile(Q: int, avg_len: float = 0.0, integer_tables: bool = True) -> int:
+    """Column tile of the sparse predictor.  One CTA of 256 threads accumulates one (user, tile) and holds one
+    entry of a neighbour's segment per thread, so the tile is sized for ~184 entries of an average row
+    (longer segments take a slower tail loop), capped by the shared memory of one CTA, then balanced."""
+    max_tile = _lib.load().qrs_predict_max_tile(1 if integer_tables else 0)
+    want = max_tile if avg_len <= 0 else 184.0 * Q / max(avg_len, 1.0)
+    tile = int(min(max(256, want), max_tile))
+    nt = max(1, math.ceil(Q / tile))
+    return int(min(max_tile, max(32, math.ceil(math.ceil(Q / nt) / 32.0) * 32)))
 
 
 def predict_sparse(rowptr, colidx, val, Q: int, u_tab: Table, user_base: int, n_users: int, tile: int,
                    capacity: int, out_cols: Optional[torch.Tensor] = None, out_preds: Optional[torch.Tensor] = None,
-                   u_milli: Optional[torch.Tensor] = None, n_regions: int = 1):
+                   u_milli: Optional[torch.Tensor] = None, n_regions: int = 1, cols_u16: bool = False):
     """User-branch predictions in sparse form.  Returns (row_start int64[n_users, nt],
     row_cnt int32[n_users, nt], cols int32[capacity], preds uint8[capacity], cursors int64[n_regions] on
     device = entries requested per region of capacity // n_regions entries).
@@ -234,13 +237,16 @@ def predict_sparse(rowptr, colidx, val, Q: int, u_tab: Table, user_base: int, n_
     assert ui.dtype == torch.int32 and uv.dtype == torch.float64 and uc.dtype == torch.int32
     row_start = torch.empty((n_users, nt), dtype=torch.int64, device=dev)
     row_cnt = torch.empty((n_users, nt), dtype=torch.int32, device=dev)
-    cols = out_cols if out_cols is not None else torch.empty(max(capacity, 1), dtype=torch.int32, device=dev)
+    cols_dtype = torch.int16 if cols_u16 else torch.int32      # int16 storage carries uint16 column ids
+    cols = out_cols if out_cols is not None else torch.empty(max(capacity, 1), dtype=cols_dtype, device=dev)
+    assert cols.dtype == cols_dtype
     preds = out_preds if out_preds is not None else torch.empty(max(capacity, 1), dtype=torch.uint8, device=dev)
     cursor = torch.zeros(n_regions, dtype=torch.int64, device=dev)
-    ws = _ws(lib.qrs_predict_sparse_workspace_bytes(U, Q, tile), dev)
+    ws = _ws(lib.qrs_predict_sparse_workspace_bytes(U, Q, tile, capacity), dev)
     check(lib.qrs_predict_sparse(ptr(rowptr), ptr(colidx), ptr(val), U, Q, ptr(ui), ptr(uv), ptr(u_milli), ptr(uc),
                                  ui.shape[1],
                                  user_base, n_users, tile, ptr(ws), ws.numel(), ptr(row_start), ptr(row_cnt),
-                                 ptr(cols), ptr(preds), capacity, n_regions, ptr(cursor), _stream()),
+                                 ptr(cols), 1 if cols_u16 else 0, ptr(preds), capacity, n_regions, ptr(cursor),
+                                 _stream()),
           "qrs_predict_sparse")
     return row_start, row_cnt, cols, preds, cursor

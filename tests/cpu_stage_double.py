@@ -124,7 +124,7 @@ def topk_tables(pairs, sims, n_pairs, row_base, n_rows, k, want_milli=False):
     return out
 
 
-def choose_predict_tile(Q, avg_len):
+def choose_predict_tile(Q, avg_len=0.0, integer_tables=True):
     return max(32, int(math.ceil(Q / 3 / 32.0)) * 32)
 
 

@@ -46,8 +46,8 @@ def test_version_status_strings_and_workspace_queries(lib):
     assert lib.qrs_sort_workspace_bytes(100_000, 32) > 0
     assert lib.qrs_pair_slots_workspace_bytes(3_200_000) >= 4 * 3_200_000
     assert lib.qrs_topk_workspace_bytes(100_000) > 16 * 100_000
-    assert lib.qrs_predict_max_tile() % 32 == 0
-    assert lib.qrs_predict_sparse_workspace_bytes(1000, 10_000, 480) >= 1000 * 22 * 8
+    assert lib.qrs_predict_max_tile(1) % 32 == 0 and lib.qrs_predict_max_tile(0) % 32 == 0
+    assert lib.qrs_predict_sparse_workspace_bytes(1000, 10_000, 480, 0) >= 1000 * 22 * 8
     assert lib.qrs_minhash_max_elements() >= 1_000_000
 
 

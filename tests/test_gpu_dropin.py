@@ -116,3 +116,43 @@ def test_binding_b_seam_and_band_override():
     assert sorted(qs) == np.flatnonzero(cnt).tolist()
     for i, e in qs.items():
         assert np.array_equal(e["indexes"], idx[i, :cnt[i]]) and np.array_equal(e["values"], val[i, :cnt[i]])
+
+
+def test_host_runner_chunked_u16_matches_device_run():
+    """The host-facing call (pinned CSR in, pinned predictions out, 4 user chunks shipped on a copy stream,
+    uint16 column ids) returns the same predictions as the device-resident single-chunk run."""
+    import torch
+    from oracle import spec
+    from query_recommendation_system_b200 import synth
+    from query_recommendation_system_b200.pipeline import HostRunner, LshCfPipeline
+    n, m, K, b, k = 3000, 1500, 64, 16, 20
+    rowptr, colidx, val = synth.planted_csr(n, m, 0.05, seed=21)
+    tab = spec.permutation_table(m, K, seed=7)
+    pipe = LshCfPipeline(m=m, K=K, b=b, k=k, perm_tab=tab, device="cuda")
+    ref = pipe.run(rowptr.cuda(), colidx.cuda(), val.cuda())
+    rs, rc = ref.pred_row_start.cpu().numpy(), ref.pred_row_cnt.cpu().numpy()
+    cols, preds = ref.pred_cols.cpu().numpy(), ref.pred_vals.cpu().numpy()
+
+    runner = HostRunner(pipe, chunks=4)
+    res = None
+    for _ in range(2):            # second call reuses the learnt capacities and pinned buffers
+        res = runner(rowptr.pin_memory(), colidx.pin_memory(), val.pin_memory())
+    assert res["n_predictions"] == ref.n_predictions and len(res["chunks"]) == 4
+    assert runner.d2h_bytes > 0 and runner.h2d_bytes == rowptr.numel() * 8 + colidx.numel() * 4 + val.numel()
+    assert torch.equal(res["nbr_idx"].reshape(n, k), ref.nbr_idx.cpu())
+    seen = 0
+    for ch in res["chunks"]:
+        nt = rs.shape[1]
+        crs = ch["row_start"].numpy().reshape(ch["n_users"], nt)
+        crc = ch["row_cnt"].numpy().reshape(ch["n_users"], nt)
+        ccols = ch["cols"].numpy().view(np.uint16)
+        cpreds = ch["preds"].numpy()
+        for t in range(0, ch["n_users"], 37):
+            u = ch["user_lo"] + t
+            mine_c = np.concatenate([ccols[crs[t, x]:crs[t, x] + crc[t, x]] for x in range(nt)]).astype(np.int64)
+            mine_p = np.concatenate([cpreds[crs[t, x]:crs[t, x] + crc[t, x]] for x in range(nt)])
+            ref_c = np.concatenate([cols[rs[u, x]:rs[u, x] + rc[u, x]] for x in range(nt)]).astype(np.int64)
+            ref_p = np.concatenate([preds[rs[u, x]:rs[u, x] + rc[u, x]] for x in range(nt)])
+            assert np.array_equal(mine_c, ref_c) and np.array_equal(mine_p, ref_p)
+        seen += ch["n_users"]
+    assert seen == n
