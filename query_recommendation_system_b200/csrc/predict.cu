@@ -68,9 +68,10 @@ struct AccOf { using type = Acc; };
 template <>
 struct AccOf<true> { using type = unsigned long long; };
 
-constexpr int kSpThreads = 256;
+constexpr int kSpThreads = 288;   // 9 warps: two entries per thread cover a 576-entry neighbour segment
 constexpr int kSpWarpsCta = kSpThreads / 32;
-constexpr int kSpAhead = 8;    // neighbours whose segment loads are in flight together (x2: double-buffered)
+constexpr int kSpAhead = 4;    // neighbours whose segment loads are in flight together (x2: double-buffered)
+constexpr int kSpSpan = 2 * kSpThreads;   // CSR positions one CTA pass covers: two consecutive entries per thread
 
 // columns each warp sweeps in the output passes; the per-warp lists live at [w * range, (w + 1) * range)
 __host__ __device__ constexpr int sparse_warp_range(int tile) { return round_up(ceil_div(tile, kSpWarpsCta), 32); }
@@ -78,7 +79,7 @@ __host__ __device__ constexpr int sparse_warp_range(int tile) { return round_up(
 // shared memory of one CTA: acc[tile] | u16 jlist[8*range] | u8 plist[8*range] | metadata
 __host__ __device__ constexpr size_t sparse_cta_bytes(int tile, bool milli) {
   return round_up<size_t>(size_t(tile) * (milli ? 8 : 16), 16) +
-         round_up<size_t>(size_t(sparse_warp_range(tile)) * kSpWarpsCta * 3, 16) + 64 * (8 + 8 + 4 + 4) + 128;
+         round_up<size_t>(size_t(sparse_warp_range(tile)) * kSpWarpsCta * 3, 16) + 64 * (8 + 8 + 4 + 4) + 192;
 }
 
 constexpr int kTieMarker = 255;   // not a possible prediction: ratings <= 255 give at most 0.7 * 255 + 18 = 196.5
@@ -124,7 +125,8 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
                       int64_t *__restrict__ row_start, int *__restrict__ row_cnt, int *__restrict__ cols,
                       uint8_t *__restrict__ preds, int64_t region_cap, int n_regions,
                       unsigned long long *__restrict__ cursors, unsigned long long *__restrict__ tie_count,
-                      ulonglong2 *__restrict__ tie_list, int64_t tie_capacity, int cols_u16) {
+                      ulonglong2 *__restrict__ tie_list, int64_t tie_capacity, int cols_u16,
+                      const uint8_t *__restrict__ single_tab) {
   using acc_t = typename AccOf<MILLI>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -138,9 +140,9 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
   double *m_s = reinterpret_cast<double *>(meta + 64 * 8);          // [64] its similarity
   int *m_n = reinterpret_cast<int *>(meta + 64 * 16);               // [64] entries in the segment
   unsigned *m_inc = reinterpret_cast<unsigned *>(meta + 64 * 20);   // [64] MILLI: milli | 1 << 20
-  int *w_cnt = reinterpret_cast<int *>(meta + 64 * 24);             // [8] non-zero predictions per warp
-  int *w_off = w_cnt + 8;                                           // [8] exclusive prefix of w_cnt
-  unsigned long long *s_base = reinterpret_cast<unsigned long long *>(w_cnt + 16);
+  int *w_cnt = reinterpret_cast<int *>(meta + 64 * 24);             // [16] non-zero predictions per warp
+  int *w_off = w_cnt + 16;                                          // [16] exclusive prefix of w_cnt
+  unsigned long long *s_base = reinterpret_cast<unsigned long long *>(w_cnt + 32);
   acc_t zero;
   if constexpr (MILLI) zero = 0ull; else zero = Acc{0.0, 0.0};
   for (int j = tid; j < tile; j += kSpThreads) acc[j] = zero;
@@ -156,8 +158,9 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
 
   auto add = [&](int j, int r, int g) {          // one rating r of neighbour slot g into column slot j
     if constexpr (MILLI) {
+      // u64 = r (8 bits, meaningful for a single rater) | N = sum r*milli (24) | raters (12) | D = sum milli (20)
       const unsigned inc = m_inc[g];
-      acc[j] += (static_cast<unsigned long long>(unsigned(r) * (inc & 0xFFFFFu)) << 32) | inc;
+      acc[j] += (static_cast<unsigned long long>((unsigned(r) << 24) + unsigned(r) * (inc & 0xFFFFFu)) << 32) | inc;
     } else {
       const double s = m_s[g];
       Acc x = acc[j];
@@ -193,37 +196,48 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
     __syncthreads();
 
     // ---- neighbours in table order, kSpAhead at a time: the NEXT group's entries are loaded into
-    //      registers (one entry per thread and neighbour) before the current group is accumulated
-    int ncol[kSpAhead], nrat[kSpAhead];
+    //      registers before the current group is accumulated.  A thread takes two consecutive CSR
+    //      positions of the segment (one 8-byte column load + one 2-byte rating load from an even position).
+    int2 ncol[kSpAhead];
+    unsigned nrat[kSpAhead];
     auto fetch = [&](int g0) {
 #pragma unroll
       for (int g = 0; g < kSpAhead; ++g) {
-        nrat[g] = 0;
-        ncol[g] = 0;
-        if (g0 + g < c && tid < m_n[g0 + g]) {
+        nrat[g] = 0u;
+        ncol[g] = make_int2(0, 0);
+        if (g0 + g < c) {
           const int64_t a = m_a[g0 + g];
-          ncol[g] = ld_stream_s32(colidx + a + tid);
-          nrat[g] = val[a + tid];
+          const int64_t e = a + m_n[g0 + g];
+          const int64_t p0 = (a & ~int64_t(1)) + 2 * tid;        // even position
+          if (p0 < e) {
+            ncol[g] = *reinterpret_cast<const int2 *>(colidx + p0);
+            unsigned rr = *reinterpret_cast<const unsigned short *>(val + p0);
+            if (p0 < a) rr &= 0xFF00u;                            // position before the segment
+            if (p0 + 1 >= e) rr &= 0x00FFu;                       // position after the segment
+            nrat[g] = rr;
+          }
         }
       }
     };
     fetch(0);
     for (int g0 = 0; g0 < c; g0 += kSpAhead) {
-      int ccol[kSpAhead], crat[kSpAhead];
+      int2 ccol[kSpAhead];
+      unsigned crat[kSpAhead];
 #pragma unroll
       for (int g = 0; g < kSpAhead; ++g) { ccol[g] = ncol[g]; crat[g] = nrat[g]; }
       if (g0 + kSpAhead < c) fetch(g0 + kSpAhead);
 #pragma unroll
       for (int g = 0; g < kSpAhead; ++g) {
         if (g0 + g < c) {                           // block-uniform
-          if (crat[g] != 0) add(ccol[g] - q0, crat[g], g0 + g);
-          const int n = m_n[g0 + g];
-          if (n > kSpThreads) {                     // long segment: the rest straight from memory
-            const int64_t a = m_a[g0 + g];
+          if (crat[g] & 0xFFu) add(ccol[g].x - q0, int(crat[g] & 0xFFu), g0 + g);
+          if (crat[g] >> 8) add(ccol[g].y - q0, int(crat[g] >> 8), g0 + g);
+          const int64_t a = m_a[g0 + g];
+          const int64_t e = a + m_n[g0 + g];
+          if ((a & ~int64_t(1)) + kSpSpan < e) {    // long segment: the rest straight from memory
 #pragma unroll 1
-            for (int x = kSpThreads + tid; x < n; x += kSpThreads) {
-              const int r = val[a + x];
-              if (r != 0) add(__ldg(colidx + a + x) - q0, r, g0 + g);
+            for (int64_t x = (a & ~int64_t(1)) + kSpSpan + tid; x < e; x += kSpThreads) {
+              const int r = val[x];
+              if (r != 0) add(__ldg(colidx + x) - q0, r, g0 + g);
             }
           }
           __syncthreads();
@@ -236,25 +250,31 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
       if (val[x] != 0) acc[__ldg(colidx + x) - q0] = zero;
     __syncthreads();
 
-    // ---- pass 1 (per warp, its own column range): ascending list of the touched columns
+    // ---- pass 1 (per warp, its own column range): ascending list of the touched columns, two per lane
     const int j_lo = warp * range, j_hi = min(width, j_lo + range);
     uint16_t *wj = jlist + j_lo;
     uint8_t *wp = plist + j_lo;
     int touched = 0;
-    for (int j0 = j_lo; j0 < j_hi; j0 += 32) {
-      const int j = j0 + lane;
-      bool hit = false;
-      if (j < j_hi) {
-        if constexpr (MILLI) {
-          hit = acc[j] != 0ull;
-        } else {
-          const Acc x = acc[j];
-          hit = x.den != 0.0 || x.num != 0.0;
+    for (int j0 = j_lo; j0 < j_hi; j0 += 64) {
+      const int j = j0 + 2 * lane;
+      bool hit0 = false, hit1 = false;
+      if constexpr (MILLI) {
+        if (j + 1 < j_hi) {
+          const ulonglong2 x = *reinterpret_cast<const ulonglong2 *>(acc + j);   // j is even, acc is 16-byte aligned
+          hit0 = x.x != 0ull;
+          hit1 = x.y != 0ull;
+        } else if (j < j_hi) {
+          hit0 = acc[j] != 0ull;
         }
+      } else {
+        if (j < j_hi) { const Acc x = acc[j]; hit0 = x.den != 0.0 || x.num != 0.0; }
+        if (j + 1 < j_hi) { const Acc x = acc[j + 1]; hit1 = x.den != 0.0 || x.num != 0.0; }
       }
-      const unsigned m = __ballot_sync(kFull, hit);
-      if (hit) wj[touched + __popc(m & lt)] = uint16_t(j);
-      touched += __popc(m);
+      const unsigned m0 = __ballot_sync(kFull, hit0), m1 = __ballot_sync(kFull, hit1);
+      const int before = touched + __popc(m0 & lt) + __popc(m1 & lt);
+      if (hit0) wj[before] = uint16_t(j);
+      if (hit1) wj[before + (hit0 ? 1 : 0)] = uint16_t(j + 1);
+      touched += __popc(m0) + __popc(m1);
     }
     __syncwarp();
     // ---- pass 2: prediction of every touched column (dense lanes), accumulators back to zero
@@ -267,18 +287,19 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
         const acc_t a = acc[j];
         acc[j] = zero;
         if constexpr (MILLI) {
-          const unsigned lo = unsigned(a), N = unsigned(a >> 32);
+          const unsigned lo = unsigned(a), hi = unsigned(a >> 32);
           const unsigned D = lo & 0xFFFFFu, raters = lo >> 20;
           if (D != 0u) {
-            const unsigned X = 7u * N + 180u * D, Y = 10u * D;      // x = X / Y = 0.7 * N / D + 18
-            const unsigned q = X / Y, rem2 = 2u * (X - q * Y);
-            if (rem2 < Y) p = int(q);
-            else if (rem2 > Y) p = int(q) + 1;
-            else if (raters == 1u) {
-              const double s = double(D) / 1000.0;                   // the one rater's similarity
-              p = predict_from(__dmul_rn(double(N / D), s), s);
+            if (raters == 1u) {
+              // one rater: the prediction depends on (rating, milli) only — looked up, no division
+              p = single_tab[(hi >> 24) * 1001u + D];
             } else {
-              p = kTieMarker;      // several raters: settled after the slice position is known (pass 3)
+              const unsigned N = hi & 0xFFFFFFu;
+              const unsigned X = 7u * N + 180u * D, Y = 10u * D;    // x = X / Y = 0.7 * N / D + 18
+              const unsigned q = X / Y, rem2 = 2u * (X - q * Y);
+              if (rem2 < Y) p = int(q);
+              else if (rem2 > Y) p = int(q) + 1;
+              else p = kTieMarker;   // exact half-way: settled after the slice position is known (pass 3)
             }
           }
         } else {
@@ -401,6 +422,20 @@ predict_dense_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__
   }
 }
 
+// single_tab[r * 1001 + milli] = the reference's fp64 result for a cell with exactly one rater of rating r and
+// similarity milli / 1000: num = r*s, W = s, u = num / W, round(u * 0.7 + 18)   (recommender.py:36-47, 327)
+__global__ void __launch_bounds__(256) single_rater_table_kernel(uint8_t *__restrict__ tab) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 256 * 1001) return;
+  const int r = i / 1001, milli = i - r * 1001;
+  int p = 0;
+  if (r != 0 && milli != 0) {
+    const double s = double(milli) / 1000.0;
+    p = predict_from(__dmul_rn(double(r), s), s);
+  }
+  tab[i] = uint8_t(p);
+}
+
 // Exact half-way cells with several raters (MILLI flavour): one warp per cell re-gathers the
 // neighbours' ratings of that column (lane <-> neighbour, binary search in the neighbour's row) and
 // replays the reference's sequential fp64 sums in table order.
@@ -458,7 +493,7 @@ static int launch_predict_sparse(const int *colidx, const uint8_t *val, int Q, c
                                  int tile, int nt, const int64_t *tilepos, int64_t *row_start, int *row_cnt, int *cols,
                                  uint8_t *preds, int64_t region_cap, int n_regions, unsigned long long *cursors,
                                  unsigned long long *tie_count, ulonglong2 *tie_list, int64_t tie_capacity,
-                                 int cols_u16, cudaStream_t st) {
+                                 int cols_u16, const uint8_t *single_tab, cudaStream_t st) {
   auto kern = predict_sparse_kernel<MILLI>;
   const size_t smem = sparse_smem_bytes(tile, MILLI);
   QRS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
@@ -471,7 +506,7 @@ static int launch_predict_sparse(const int *colidx, const uint8_t *val, int Q, c
   kern<<<unsigned(grid), kSpThreads, smem, st>>>(colidx, val, Q, u_idx, u_val, u_milli, u_cnt, ku, user_base,
                                                     n_users, tile, nt, tilepos, row_start, row_cnt, cols, preds,
                                                     region_cap, n_regions, cursors, tie_count, tie_list, tie_capacity,
-                                                    cols_u16);
+                                                    cols_u16, single_tab);
   QRS_LAUNCH_CHECK();
   return QRS_OK;
 }
@@ -486,12 +521,13 @@ extern "C" {
 int32_t qrs_predict_max_tile(int32_t integer_tables) { return integer_tables ? 10048 : 5824; }
 
 static int64_t tie_list_capacity(int64_t capacity) { return capacity / 32 + 65536; }
+constexpr size_t kSingleTabBytes = round_up<size_t>(256 * 1001, 256);
 
 size_t qrs_predict_sparse_workspace_bytes(int64_t U, int32_t Q, int32_t tile, int64_t capacity) {
   if (U < 0 || Q <= 0 || tile <= 0 || capacity < 0) return 0;
   const int64_t nt = ceil_div<int64_t>(Q, tile);
-  // tile index | tie counter | list of exact half-way cells awaiting their fp64 replay
-  return round_up<size_t>(size_t(U > 0 ? U : 1) * size_t(nt + 1) * 8, 256) + 256 +
+  // tile index | tie counter | single-rater table | list of exact half-way cells awaiting their fp64 replay
+  return round_up<size_t>(size_t(U > 0 ? U : 1) * size_t(nt + 1) * 8, 256) + 256 + kSingleTabBytes +
          round_up<size_t>(size_t(tie_list_capacity(capacity)) * 16, 256);
 }
 
@@ -517,9 +553,14 @@ int qrs_predict_sparse(const int64_t *rowptr, const int32_t *colidx, const uint8
   int64_t *tilepos = static_cast<int64_t *>(ws);
   char *wsp = static_cast<char *>(ws) + round_up<size_t>(size_t(U) * size_t(nt + 1) * 8, 256);
   unsigned long long *tie_count = reinterpret_cast<unsigned long long *>(wsp);
-  ulonglong2 *tie_list = reinterpret_cast<ulonglong2 *>(wsp + 256);
+  uint8_t *single_tab = reinterpret_cast<uint8_t *>(wsp + 256);
+  ulonglong2 *tie_list = reinterpret_cast<ulonglong2 *>(wsp + 256 + kSingleTabBytes);
   const int64_t tie_cap = tie_list_capacity(capacity);
   QRS_CUDA(cudaMemsetAsync(tie_count, 0, 8, st));
+  if (u_milli) {
+    single_rater_table_kernel<<<ceil_div(256 * 1001, 256), 256, 0, st>>>(single_tab);
+    QRS_LAUNCH_CHECK();
+  }
   {
     const int64_t total = U * (nt + 1);
     int64_t blocks = ceil_div<int64_t>(total, 256);
@@ -531,7 +572,7 @@ int qrs_predict_sparse(const int64_t *rowptr, const int32_t *colidx, const uint8
   if (u_milli) {
     int rc = launch_predict_sparse<true>(colidx, val, Q, u_idx, u_val, u_milli, u_cnt, ku, user_base, n_users, tile,
                                          nt, tilepos, row_start, row_cnt, cols, preds, region_cap, n_regions, cursors,
-                                         tie_count, tie_list, tie_cap, cols_u16, st);
+                                         tie_count, tie_list, tie_cap, cols_u16, single_tab, st);
     if (rc != QRS_OK || capacity == 0) return rc;
     predict_tie_fixup_kernel<<<sm_count() * 8, 256, 0, st>>>(rowptr, colidx, val, u_idx, u_milli, u_cnt, ku, tie_count,
                                                              tie_list, tie_cap, preds);
@@ -540,7 +581,7 @@ int qrs_predict_sparse(const int64_t *rowptr, const int32_t *colidx, const uint8
   }
   return launch_predict_sparse<false>(colidx, val, Q, u_idx, u_val, u_milli, u_cnt, ku, user_base, n_users, tile, nt,
                                       tilepos, row_start, row_cnt, cols, preds, region_cap, n_regions, cursors,
-                                      tie_count, tie_list, tie_cap, cols_u16, st);
+                                      tie_count, tie_list, tie_cap, cols_u16, single_tab, st);
 }
 
 int qrs_predict_dense(const int64_t *rowptr, const int32_t *colidx, const uint8_t *val, int64_t U, int32_t Q,

@@ -136,6 +136,13 @@ class LshCfPipeline:
         self._ensure_head(nnz / max(n_local, 1))
         tm.mark("start")
 
+        # the ratings of all shards are needed only by the prediction gathers: start that all-gather now, on a
+        # second stream and its own communicator, so it overlaps the LSH stages and their exchanges
+        csr_all = None
+        if G > 1 and predict:
+            csr_all = self._background(lambda: self._all_gather_csr(rowptr, colidx, val, self._bg_group()),
+                                       (rowptr, colidx, val))
+
         # a1 + a2/a3: signatures, squared norms and bucket records in one kernel
         sig, norm2, records = st.minhash(rowptr, colidx, self.m, self.perm_tab, self.order_head, b=self.b,
                                          id_base=row_base, want_norm2=True, mode=self.mode)
@@ -177,7 +184,7 @@ class LshCfPipeline:
         if predict:
             assert val is not None
             if G > 1:
-                rowptr_all, colidx_all, val_all = self._all_gather_csr(rowptr, colidx, val)
+                rowptr_all, colidx_all, val_all = csr_all()
                 tm.mark("exchange:ratings")
             else:
                 rowptr_all, colidx_all, val_all = rowptr, colidx, val
@@ -222,11 +229,39 @@ class LshCfPipeline:
         return out
 
     # ------------------------------------------------------------------ exchanges (plumbing)
-    def _all_gather_rows(self, t: torch.Tensor) -> torch.Tensor:
+    def _bg_group(self):
+        """A second communicator for the background all-gather (collectives of one communicator run in order)."""
+        import torch.distributed as dist
+        if getattr(self, "_bg", None) is None:
+            self._bg = dist.new_group(ranks=list(range(self.world))) if self.group is None else self.group
+        return self._bg
+
+    def _background(self, fn, inputs):
+        """Run `fn` on a side CUDA stream (inline on the CPU test double); returns a getter that joins it."""
+        if self.device.type != "cuda":
+            res = fn()
+            return lambda: res
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        main = torch.cuda.current_stream()
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            res = fn()
+        for t in inputs:
+            t.record_stream(self._side)
+
+        def join():
+            torch.cuda.current_stream().wait_stream(self._side)
+            for t in res:
+                t.record_stream(torch.cuda.current_stream())
+            return res
+        return join
+
+    def _all_gather_rows(self, t: torch.Tensor, group=None) -> torch.Tensor:
         import torch.distributed as dist
         G = self.world
         outt = torch.empty((t.shape[0] * G,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-        dist.all_gather_into_tensor(outt, t.contiguous(), group=self.group)
+        dist.all_gather_into_tensor(outt, t.contiguous(), group=group if group is not None else self.group)
         return outt
 
     def _all_to_all_var(self, send: torch.Tensor, send_counts: torch.Tensor) -> torch.Tensor:
@@ -269,13 +304,14 @@ class LshCfPipeline:
         s = self._all_to_all_var(sm[order].contiguous(), counts)
         return p, s
 
-    def _all_gather_csr(self, rowptr, colidx, val):
+    def _all_gather_csr(self, rowptr, colidx, val, group=None):
         import torch.distributed as dist
+        group = group if group is not None else self.group
         G = self.world
         n_local = rowptr.numel() - 1
         nnz = torch.tensor([colidx.numel()], dtype=torch.int64, device=colidx.device)
         all_nnz = torch.empty(G, dtype=torch.int64, device=colidx.device)
-        dist.all_gather_into_tensor(all_nnz, nnz, group=self.group)
+        dist.all_gather_into_tensor(all_nnz, nnz, group=group)
         sizes = all_nnz.cpu().tolist()
         mx = max(sizes)
 
@@ -283,11 +319,11 @@ class LshCfPipeline:
             pad = torch.zeros(mx, dtype=t.dtype, device=t.device)
             pad[:t.numel()] = t
             buf = torch.empty(G * mx, dtype=t.dtype, device=t.device)
-            dist.all_gather_into_tensor(buf, pad, group=self.group)
+            dist.all_gather_into_tensor(buf, pad, group=group)
             return torch.cat([buf[r * mx:r * mx + sizes[r]] for r in range(G)])
 
         col_all, val_all = gather_padded(colidx), gather_padded(val)
-        lens = self._all_gather_rows((rowptr[1:] - rowptr[:-1]).contiguous())
+        lens = self._all_gather_rows((rowptr[1:] - rowptr[:-1]).contiguous(), group)
         rp = torch.zeros(n_local * G + 1, dtype=torch.int64, device=rowptr.device)
         rp[1:] = torch.cumsum(lens, 0)
         return rp, col_all, val_all

@@ -209,14 +209,15 @@ def predict_dense(rowptr, colidx, val, Q: int, q_tab: Optional[Table], u_tab: Op
 
 
 def choose_predict_tile(Q: int, avg_len: float = 0.0, integer_tables: bool = True) -> int:
-    """Column tile of the sparse predictor.  One CTA of 256 threads accumulates one (user, tile) and holds one
-    entry of a neighbour's segment per thread, so the tile is sized for ~184 entries of an average row
-    (longer segments take a slower tail loop), capped by the shared memory of one CTA, then balanced."""
+    """Column tile of the sparse predictor.  One CTA of 288 threads accumulates one (user, tile) and takes two
+    consecutive entries of a neighbour's segment per thread (576 per pass; longer segments take a slower tail
+    loop): the fewest equal tiles such that a tile fits one CTA's shared memory and an average row leaves
+    <= ~520 entries in it."""
     max_tile = _lib.load().qrs_predict_max_tile(1 if integer_tables else 0)
-    want = max_tile if avg_len <= 0 else 184.0 * Q / max(avg_len, 1.0)
-    tile = int(min(max(256, want), max_tile))
-    nt = max(1, math.ceil(Q / tile))
-    return int(min(max_tile, max(32, math.ceil(math.ceil(Q / nt) / 32.0) * 32)))
+    nt = max(1, math.ceil(Q / max_tile))
+    while avg_len > 0 and avg_len / nt > 520.0 and math.ceil(Q / nt) > 256:
+        nt += 1
+    return int(min(max_tile, max(64, math.ceil(math.ceil(Q / nt) / 64.0) * 64)))
 
 
 def predict_sparse(rowptr, colidx, val, Q: int, u_tab: Table, user_base: int, n_users: int, tile: int,
