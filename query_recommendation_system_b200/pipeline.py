@@ -272,7 +272,7 @@ class LshCfPipeline:
         rcv = torch.empty_like(sc)
         dist.all_to_all_single(rcv, sc, group=self.group)
         rcv_l = rcv.cpu().tolist()
-        recv = torch.empty(int(sum(rcv_l)), dtype=send.dtype, device=send.device)
+        recv = torch.empty((int(sum(rcv_l)),) + tuple(send.shape[1:]), dtype=send.dtype, device=send.device)
         dist.all_to_all_single(recv, send, output_split_sizes=rcv_l, input_split_sizes=send_counts.tolist(),
                                group=self.group)
         return recv
@@ -291,18 +291,19 @@ class LshCfPipeline:
         return self._all_to_all_var(flat, counts), lg
 
     def _route_pairs(self, pairs: torch.Tensor, sims: torch.Tensor, n_local: int):
-        """Each scored pair goes to the owner of i and (if different) the owner of j."""
+        """Each scored pair goes to the owner of i and (if different) the owner of j; (pair, similarity)
+        travel as one two-column record so that a single all-to-all moves both."""
         G = self.world
         oi = torch.div(pairs >> 32, n_local, rounding_mode="floor")
         oj = torch.div(pairs & 0xFFFFFFFF, n_local, rounding_mode="floor")
-        both = torch.cat([pairs, pairs[oj != oi]])
-        sm = torch.cat([sims, sims[oj != oi]])
-        dest = torch.cat([oi, oj[oj != oi]])
+        cross = oj != oi
+        rec = torch.stack([pairs, sims.to(torch.int64)], dim=1)
+        rec = torch.cat([rec, rec[cross]])
+        dest = torch.cat([oi, oj[cross]])
         order = torch.argsort(dest, stable=True)
         counts = torch.bincount(dest, minlength=G).cpu()
-        p = self._all_to_all_var(both[order].contiguous(), counts)
-        s = self._all_to_all_var(sm[order].contiguous(), counts)
-        return p, s
+        got = self._all_to_all_var(rec[order].contiguous(), counts)
+        return got[:, 0].contiguous(), got[:, 1].to(torch.int32).contiguous()
 
     def _all_gather_csr(self, rowptr, colidx, val, group=None):
         import torch.distributed as dist
