@@ -136,13 +136,6 @@ class LshCfPipeline:
         self._ensure_head(nnz / max(n_local, 1))
         tm.mark("start")
 
-        # the ratings of all shards are needed only by the prediction gathers: start that all-gather now, on a
-        # second stream and its own communicator, so it overlaps the LSH stages and their exchanges
-        csr_all = None
-        if G > 1 and predict:
-            csr_all = self._background(lambda: self._all_gather_csr(rowptr, colidx, val, self._bg_group()),
-                                       (rowptr, colidx, val))
-
         # a1 + a2/a3: signatures, squared norms and bucket records in one kernel
         sig, norm2, records = st.minhash(rowptr, colidx, self.m, self.perm_tab, self.order_head, b=self.b,
                                          id_base=row_base, want_norm2=True, mode=self.mode)
@@ -183,8 +176,13 @@ class LshCfPipeline:
 
         if predict:
             assert val is not None
+            pred_base = row_base
             if G > 1:
-                rowptr_all, colidx_all, val_all = csr_all()
+                # only the neighbour rows that live on other ranks are fetched (deduplicated), appended to the local
+                # CSR, and the neighbour ids are re-pointed at the extended row numbering
+                rowptr_all, colidx_all, val_all, idx = self._fetch_remote_rows(rowptr, colidx, val, idx, cnt,
+                                                                               n_local, row_base)
+                pred_base = 0
                 tm.mark("exchange:ratings")
             else:
                 rowptr_all, colidx_all, val_all = rowptr, colidx, val
@@ -205,7 +203,7 @@ class LshCfPipeline:
                 mil = milli[lo:hi] if self.integer_predict else None
                 while True:
                     rs, rc, cols, preds, cursors = st.predict_sparse(rowptr_all, colidx_all, val_all, self.m, tab,
-                                                                     row_base + lo, hi - lo, tile, rcap * regions,
+                                                                     pred_base + lo, hi - lo, tile, rcap * regions,
                                                                      u_milli=mil, n_regions=regions,
                                                                      cols_u16=self.cols_u16)
                     demand = cursors.cpu()
@@ -229,34 +227,6 @@ class LshCfPipeline:
         return out
 
     # ------------------------------------------------------------------ exchanges (plumbing)
-    def _bg_group(self):
-        """A second communicator for the background all-gather (collectives of one communicator run in order)."""
-        import torch.distributed as dist
-        if getattr(self, "_bg", None) is None:
-            self._bg = dist.new_group(ranks=list(range(self.world))) if self.group is None else self.group
-        return self._bg
-
-    def _background(self, fn, inputs):
-        """Run `fn` on a side CUDA stream (inline on the CPU test double); returns a getter that joins it."""
-        if self.device.type != "cuda":
-            res = fn()
-            return lambda: res
-        if getattr(self, "_side", None) is None:
-            self._side = torch.cuda.Stream(device=self.device)
-        main = torch.cuda.current_stream()
-        self._side.wait_stream(main)
-        with torch.cuda.stream(self._side):
-            res = fn()
-        for t in inputs:
-            t.record_stream(self._side)
-
-        def join():
-            torch.cuda.current_stream().wait_stream(self._side)
-            for t in res:
-                t.record_stream(torch.cuda.current_stream())
-            return res
-        return join
-
     def _all_gather_rows(self, t: torch.Tensor, group=None) -> torch.Tensor:
         import torch.distributed as dist
         G = self.world
@@ -264,7 +234,7 @@ class LshCfPipeline:
         dist.all_gather_into_tensor(outt, t.contiguous(), group=group if group is not None else self.group)
         return outt
 
-    def _all_to_all_var(self, send: torch.Tensor, send_counts: torch.Tensor) -> torch.Tensor:
+    def _all_to_all_var(self, send: torch.Tensor, send_counts: torch.Tensor, return_counts: bool = False):
         """send is grouped by destination rank; send_counts int64[G] (host)."""
         import torch.distributed as dist
         G = self.world
@@ -275,7 +245,7 @@ class LshCfPipeline:
         recv = torch.empty((int(sum(rcv_l)),) + tuple(send.shape[1:]), dtype=send.dtype, device=send.device)
         dist.all_to_all_single(recv, send, output_split_sizes=rcv_l, input_split_sizes=send_counts.tolist(),
                                group=self.group)
-        return recv
+        return (recv, rcv_l) if return_counts else recv
 
     def _exchange_records(self, flat: torch.Tensor):
         """Bucket records go to rank = top log2(G) bits of hash24: one radix pass groups them by
@@ -305,29 +275,41 @@ class LshCfPipeline:
         got = self._all_to_all_var(rec[order].contiguous(), counts)
         return got[:, 0].contiguous(), got[:, 1].to(torch.int32).contiguous()
 
-    def _all_gather_csr(self, rowptr, colidx, val, group=None):
-        import torch.distributed as dist
-        group = group if group is not None else self.group
+    def _fetch_remote_rows(self, rowptr, colidx, val, idx, cnt, n_local: int, row_base: int):
+        """Request/response exchange of the ratings rows this rank's neighbour tables point at on other ranks.
+        Returns the extended CSR (local rows first, fetched rows after, in ascending global id) and the
+        neighbour table re-indexed into it."""
         G = self.world
-        n_local = rowptr.numel() - 1
-        nnz = torch.tensor([colidx.numel()], dtype=torch.int64, device=colidx.device)
-        all_nnz = torch.empty(G, dtype=torch.int64, device=colidx.device)
-        dist.all_gather_into_tensor(all_nnz, nnz, group=group)
-        sizes = all_nnz.cpu().tolist()
-        mx = max(sizes)
-
-        def gather_padded(t):
-            pad = torch.zeros(mx, dtype=t.dtype, device=t.device)
-            pad[:t.numel()] = t
-            buf = torch.empty(G * mx, dtype=t.dtype, device=t.device)
-            dist.all_gather_into_tensor(buf, pad, group=group)
-            return torch.cat([buf[r * mx:r * mx + sizes[r]] for r in range(G)])
-
-        col_all, val_all = gather_padded(colidx), gather_padded(val)
-        lens = self._all_gather_rows((rowptr[1:] - rowptr[:-1]).contiguous(), group)
-        rp = torch.zeros(n_local * G + 1, dtype=torch.int64, device=rowptr.device)
-        rp[1:] = torch.cumsum(lens, 0)
-        return rp, col_all, val_all
+        dev = idx.device
+        k = idx.shape[1]
+        live = torch.arange(k, device=dev)[None, :] < cnt[:, None]
+        ids = idx.to(torch.int64)
+        is_remote = live & ((ids < row_base) | (ids >= row_base + n_local))
+        need = torch.unique(ids[is_remote])                                # sorted ⇒ grouped by owner
+        owner = torch.div(need, n_local, rounding_mode="floor")
+        req, req_counts = self._all_to_all_var(need, torch.bincount(owner, minlength=G).cpu(), return_counts=True)
+        # serve the requests: lengths first, then the concatenated entries
+        r = req - row_base
+        starts, lens = rowptr[r], rowptr[r + 1] - rowptr[r]
+        tot = int(lens.sum().item()) if lens.numel() else 0
+        first = torch.cumsum(lens, 0) - lens
+        pos = torch.repeat_interleave(starts - first, lens) + torch.arange(tot, device=dev)
+        rc = torch.tensor(req_counts, dtype=torch.int64, device=dev)      # rows each source asked for
+        ends = torch.cumsum(rc, 0)
+        csum = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(lens, 0)])
+        ent_counts = (csum[ends] - csum[ends - rc]).cpu()                  # entries going back to each source
+        lens_got = self._all_to_all_var(lens.contiguous(), torch.tensor(req_counts))
+        col_got = self._all_to_all_var(colidx[pos].contiguous(), ent_counts)
+        val_got = self._all_to_all_var(val[pos].contiguous(), ent_counts)
+        # extended CSR and re-indexed table
+        rp = torch.cat([rowptr, rowptr[-1] + torch.cumsum(lens_got, 0)])
+        col_all = torch.cat([colidx, col_got])
+        val_all = torch.cat([val, val_got])
+        local_ix = ids - row_base
+        remote_ix = n_local + torch.searchsorted(need, ids.clamp(min=0))
+        new_idx = torch.where(is_remote, remote_ix, local_ix)
+        new_idx = torch.where(live, new_idx, torch.full_like(new_idx, -1)).to(torch.int32)
+        return rp, col_all, val_all, new_idx.contiguous()
 
 
 class HostRunner:

@@ -44,9 +44,8 @@ def planted_csr(n: int, m: int, density: float, seed: int, group: int = 32, row_
     [row_base, row_base + n) of the (conceptually unbounded) planted matrix."""
     dev = torch.device(device)
     base = max(1, round(density * m))
-    assert row_base % group == 0, "shards must start on a taste-group boundary"
-    g_lo = row_base // group
-    n_groups = (n + group - 1) // group
+    g_lo = row_base // group                      # a shard may start (and end) inside a taste group
+    n_groups = (row_base % group + n + group - 1) // group
     P = 1 << 20
     keys_all = []
     for c0 in range(0, n_groups, group_chunk):

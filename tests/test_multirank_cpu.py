@@ -19,7 +19,7 @@ for p in (ROOT, HERE):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-N_PER_RANK, M, K, B, TOPK = 96, 400, 32, 8, 7
+N_PER_RANK, M, K, B, TOPK = 80, 400, 32, 8, 7      # 80 % 32 != 0: a taste group straddles the two ranks
 
 
 def _free_port():
@@ -84,6 +84,8 @@ def test_two_ranks_equal_one_rank(tmp_path):
     order = np.argsort(got)
     assert np.array_equal(got[order], cand) and np.array_equal(got_s[order], sims)
     assert all(r["pairs"].size > 0 for r in ranks), "the bucket exchange left a rank without work"
+    cross = ((pr[:, 0] // N_PER_RANK) != (pr[:, 1] // N_PER_RANK)).sum()
+    assert cross > 0, "no candidate pair spans the two ranks: remote-row fetch would be untested"
 
     idx, v, cnt = spec.topk_tables(n, pr, sims / 1000.0, TOPK)
     ref = spec.predict_user_branch_csr(rowptr, colidx, val, M, idx, v, cnt)
