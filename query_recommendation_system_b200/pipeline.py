@@ -261,19 +261,21 @@ class LshCfPipeline:
         return self._all_to_all_var(flat, counts), lg
 
     def _route_pairs(self, pairs: torch.Tensor, sims: torch.Tensor, n_local: int):
-        """Each scored pair goes to the owner of i and (if different) the owner of j; (pair, similarity)
-        travel as one two-column record so that a single all-to-all moves both."""
+        """Each scored pair goes to the owner of i and (if different) the owner of j.  Pair and similarity
+        travel as ONE int64 (i << 37 | j << 11 | sim + 1000; ids < 2^26) so a single all-to-all moves both."""
         G = self.world
-        oi = torch.div(pairs >> 32, n_local, rounding_mode="floor")
-        oj = torch.div(pairs & 0xFFFFFFFF, n_local, rounding_mode="floor")
+        if n_local * G >= (1 << 26):
+            raise _lib.QrsError("pair routing packs ids into 26 bits; %d sets do not fit" % (n_local * G))
+        i, j = pairs >> 32, pairs & 0xFFFFFFFF
+        oi = torch.div(i, n_local, rounding_mode="floor")
+        oj = torch.div(j, n_local, rounding_mode="floor")
+        rec = (i << 37) | (j << 11) | (sims.to(torch.int64) + 1000)
         cross = oj != oi
-        rec = torch.stack([pairs, sims.to(torch.int64)], dim=1)
         rec = torch.cat([rec, rec[cross]])
-        dest = torch.cat([oi, oj[cross]])
-        order = torch.argsort(dest, stable=True)
+        dest, order = torch.sort(torch.cat([oi, oj[cross]]), stable=True)
         counts = torch.bincount(dest, minlength=G).cpu()
-        got = self._all_to_all_var(rec[order].contiguous(), counts)
-        return got[:, 0].contiguous(), got[:, 1].to(torch.int32).contiguous()
+        got = self._all_to_all_var(rec[order], counts)
+        return ((got >> 37) << 32) | ((got >> 11) & 0x3FFFFFF), ((got & 0x7FF) - 1000).to(torch.int32)
 
     def _fetch_remote_rows(self, rowptr, colidx, val, idx, cnt, n_local: int, row_base: int):
         """Request/response exchange of the ratings rows this rank's neighbour tables point at on other ranks.
@@ -286,6 +288,12 @@ class LshCfPipeline:
         ids = idx.to(torch.int64)
         is_remote = live & ((ids < row_base) | (ids >= row_base + n_local))
         need = torch.unique(ids[is_remote])                                # sorted ⇒ grouped by owner
+        import torch.distributed as dist
+        any_need = torch.tensor([need.numel()], dtype=torch.int64, device=dev)
+        dist.all_reduce(any_need, op=dist.ReduceOp.MAX, group=self.group)
+        if int(any_need.item()) == 0:                                      # every neighbour of every rank is local
+            new_idx = torch.where(live, ids - row_base, torch.full_like(ids, -1)).to(torch.int32)
+            return rowptr, colidx, val, new_idx.contiguous()
         owner = torch.div(need, n_local, rounding_mode="floor")
         req, req_counts = self._all_to_all_var(need, torch.bincount(owner, minlength=G).cpu(), return_counts=True)
         # serve the requests: lengths first, then the concatenated entries
