@@ -234,17 +234,20 @@ class LshCfPipeline:
         dist.all_gather_into_tensor(outt, t.contiguous(), group=group if group is not None else self.group)
         return outt
 
-    def _all_to_all_var(self, send: torch.Tensor, send_counts: torch.Tensor, return_counts: bool = False):
-        """send is grouped by destination rank; send_counts int64[G] (host)."""
+    def _all_to_all_var(self, send: torch.Tensor, send_counts, return_counts: bool = False, recv_counts=None):
+        """send is grouped by destination rank; send_counts: G host ints.  The receive split is exchanged first
+        unless the caller already knows it (recv_counts)."""
         import torch.distributed as dist
-        G = self.world
-        sc = send_counts.to(send.device)
-        rcv = torch.empty_like(sc)
-        dist.all_to_all_single(rcv, sc, group=self.group)
-        rcv_l = rcv.cpu().tolist()
+        send_l = [int(x) for x in (send_counts.tolist() if hasattr(send_counts, "tolist") else send_counts)]
+        if recv_counts is None:
+            sc = torch.tensor(send_l, dtype=torch.int64, device=send.device)
+            rcv = torch.empty_like(sc)
+            dist.all_to_all_single(rcv, sc, group=self.group)
+            rcv_l = rcv.cpu().tolist()
+        else:
+            rcv_l = [int(x) for x in recv_counts]
         recv = torch.empty((int(sum(rcv_l)),) + tuple(send.shape[1:]), dtype=send.dtype, device=send.device)
-        dist.all_to_all_single(recv, send, output_split_sizes=rcv_l, input_split_sizes=send_counts.tolist(),
-                               group=self.group)
+        dist.all_to_all_single(recv, send, output_split_sizes=rcv_l, input_split_sizes=send_l, group=self.group)
         return (recv, rcv_l) if return_counts else recv
 
     def _exchange_records(self, flat: torch.Tensor):
@@ -295,20 +298,24 @@ class LshCfPipeline:
             new_idx = torch.where(live, ids - row_base, torch.full_like(ids, -1)).to(torch.int32)
             return rowptr, colidx, val, new_idx.contiguous()
         owner = torch.div(need, n_local, rounding_mode="floor")
-        req, req_counts = self._all_to_all_var(need, torch.bincount(owner, minlength=G).cpu(), return_counts=True)
-        # serve the requests: lengths first, then the concatenated entries
+        need_counts = torch.bincount(owner, minlength=G).cpu().tolist()   # rows I ask of each owner
+        req, req_counts = self._all_to_all_var(need, need_counts, return_counts=True)
+        # serve the requests: lengths first, then the concatenated entries (column | rating << 32 in one int64)
         r = req - row_base
         starts, lens = rowptr[r], rowptr[r + 1] - rowptr[r]
-        tot = int(lens.sum().item()) if lens.numel() else 0
-        first = torch.cumsum(lens, 0) - lens
-        pos = torch.repeat_interleave(starts - first, lens) + torch.arange(tot, device=dev)
+        csum = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(lens, 0)])
         rc = torch.tensor(req_counts, dtype=torch.int64, device=dev)      # rows each source asked for
         ends = torch.cumsum(rc, 0)
-        csum = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(lens, 0)])
-        ent_counts = (csum[ends] - csum[ends - rc]).cpu()                  # entries going back to each source
-        lens_got = self._all_to_all_var(lens.contiguous(), torch.tensor(req_counts))
-        col_got = self._all_to_all_var(colidx[pos].contiguous(), ent_counts)
-        val_got = self._all_to_all_var(val[pos].contiguous(), ent_counts)
+        ent_send = (csum[ends] - csum[ends - rc]).cpu().tolist()           # entries going back to each source
+        tot = int(sum(ent_send))
+        pos = torch.repeat_interleave(starts - csum[:-1], lens) + torch.arange(tot, device=dev)
+        lens_got = self._all_to_all_var(lens.contiguous(), req_counts, recv_counts=need_counts)
+        gsum = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(lens_got, 0)])
+        nends = torch.cumsum(torch.tensor(need_counts, dtype=torch.int64, device=dev), 0)
+        ent_recv = (gsum[nends] - gsum[nends - torch.tensor(need_counts, dtype=torch.int64, device=dev)]).cpu().tolist()
+        ent = colidx[pos].to(torch.int64) | (val[pos].to(torch.int64) << 32)
+        ent_got = self._all_to_all_var(ent, ent_send, recv_counts=ent_recv)
+        col_got, val_got = (ent_got & 0xFFFFFFFF).to(torch.int32), (ent_got >> 32).to(torch.uint8)
         # extended CSR and re-indexed table
         rp = torch.cat([rowptr, rowptr[-1] + torch.cumsum(lens_got, 0)])
         col_all = torch.cat([colidx, col_got])
