@@ -223,6 +223,15 @@ int qrs_predict_sparse(const int64_t *rowptr, const int32_t *colidx, const uint8
                        int32_t cols_u16, uint8_t *preds,
                        int64_t capacity, int32_t n_regions, unsigned long long *cursors, void *stream);
 
+/* ------------------------------------------------------ multi-GPU plumbing
+ * Rows of the ratings CSR are sharded across GPUs; the prediction gathers neighbour rows
+ * (recommender.py:320), so rows requested by other ranks are packed for sending:
+ * out[out_off[t] .. out_off[t+1]) = row rows[t] (local row ids; out_off = exclusive prefix of the
+ * rows' lengths, n_rows + 1 entries). */
+int qrs_gather_rows(const int64_t *rowptr, const int32_t *colidx, const uint8_t *val,
+                    const int64_t *rows, int64_t n_rows, const int64_t *out_off,
+                    int32_t *out_col, uint8_t *out_val, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

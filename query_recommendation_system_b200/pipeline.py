@@ -300,7 +300,7 @@ class LshCfPipeline:
         owner = torch.div(need, n_local, rounding_mode="floor")
         need_counts = torch.bincount(owner, minlength=G).cpu().tolist()   # rows I ask of each owner
         req, req_counts = self._all_to_all_var(need, need_counts, return_counts=True)
-        # serve the requests: lengths first, then the concatenated entries (column | rating << 32 in one int64)
+        # serve the requests: lengths first, then the rows packed by a gather kernel
         r = req - row_base
         starts, lens = rowptr[r], rowptr[r + 1] - rowptr[r]
         csum = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(lens, 0)])
@@ -308,14 +308,14 @@ class LshCfPipeline:
         ends = torch.cumsum(rc, 0)
         ent_send = (csum[ends] - csum[ends - rc]).cpu().tolist()           # entries going back to each source
         tot = int(sum(ent_send))
-        pos = torch.repeat_interleave(starts - csum[:-1], lens) + torch.arange(tot, device=dev)
+        col_send, val_send = self.st.gather_rows(rowptr, colidx, val, r.contiguous(), csum, tot)
         lens_got = self._all_to_all_var(lens.contiguous(), req_counts, recv_counts=need_counts)
         gsum = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(lens_got, 0)])
-        nends = torch.cumsum(torch.tensor(need_counts, dtype=torch.int64, device=dev), 0)
-        ent_recv = (gsum[nends] - gsum[nends - torch.tensor(need_counts, dtype=torch.int64, device=dev)]).cpu().tolist()
-        ent = colidx[pos].to(torch.int64) | (val[pos].to(torch.int64) << 32)
-        ent_got = self._all_to_all_var(ent, ent_send, recv_counts=ent_recv)
-        col_got, val_got = (ent_got & 0xFFFFFFFF).to(torch.int32), (ent_got >> 32).to(torch.uint8)
+        nc = torch.tensor(need_counts, dtype=torch.int64, device=dev)
+        nends = torch.cumsum(nc, 0)
+        ent_recv = (gsum[nends] - gsum[nends - nc]).cpu().tolist()
+        col_got = self._all_to_all_var(col_send.contiguous(), ent_send, recv_counts=ent_recv)
+        val_got = self._all_to_all_var(val_send.contiguous(), ent_send, recv_counts=ent_recv)
         # extended CSR and re-indexed table
         rp = torch.cat([rowptr, rowptr[-1] + torch.cumsum(lens_got, 0)])
         col_all = torch.cat([colidx, col_got])

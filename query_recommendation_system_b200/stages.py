@@ -251,3 +251,14 @@ def predict_sparse(rowptr, colidx, val, Q: int, u_tab: Table, user_base: int, n_
                                  _stream()),
           "qrs_predict_sparse")
     return row_start, row_cnt, cols, preds, cursor
+
+
+# ---------------------------------------------------------------------- multi-GPU plumbing
+def gather_rows(rowptr, colidx, val, rows: torch.Tensor, out_off: torch.Tensor, total: int):
+    """Pack CSR rows `rows` (local ids) into contiguous (col int32[total], val uint8[total]) send buffers."""
+    _need_cuda(rowptr, colidx, val, rows, out_off)
+    col = torch.empty(max(total, 1), dtype=torch.int32, device=rowptr.device)
+    v = torch.empty(max(total, 1), dtype=torch.uint8, device=rowptr.device)
+    check(_lib.load().qrs_gather_rows(ptr(rowptr), ptr(colidx), ptr(val), ptr(rows), rows.numel(), ptr(out_off),
+                                      ptr(col), ptr(v), _stream()), "qrs_gather_rows")
+    return col[:total], v[:total]

@@ -158,3 +158,13 @@ def predict_sparse(rowptr, colidx, val, Q, u_tab, user_base, n_users, tile, capa
     ct[:w] = torch.from_numpy(cols[:w].astype(np.int32))
     pt[:w] = torch.from_numpy(preds[:w].astype(np.uint8))
     return torch.from_numpy(rs), torch.from_numpy(rc), ct, pt, torch.tensor([pos], dtype=torch.int64)
+
+
+def gather_rows(rowptr, colidx, val, rows, out_off, total):
+    rp, ci, va = rowptr.numpy(), colidx.numpy(), val.numpy()
+    cols = [ci[rp[r]:rp[r + 1]] for r in rows.numpy()]
+    vals = [va[rp[r]:rp[r + 1]] for r in rows.numpy()]
+    c = np.concatenate(cols) if cols else np.zeros(0, np.int32)
+    v = np.concatenate(vals) if vals else np.zeros(0, np.uint8)
+    assert c.size == total
+    return torch.from_numpy(c.astype(np.int32)), torch.from_numpy(v.astype(np.uint8))
