@@ -45,8 +45,11 @@ def perm_table(m, K, seed=PERM_SEED):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi clocks / throttle reasons DURING the timed region: the sampler runs from before the
+    warm-up (nvidia-smi needs a moment to start), every line carries a timestamp, and only the lines that
+    fall between mark_start() and mark_end() are summarised (all lines under load if the region was
+    shorter than the sampling period)."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -54,11 +57,12 @@ class ClockSampler:
         self.gpu = gpu_index
         self.lines = []
         self.proc = None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -66,29 +70,45 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
+
+        def summarise(lines):
+            sm, mx, reasons = [], [], set()
+            for _, ln in lines:
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 10:
+                    continue
+                try:
+                    sm.append(float(f[2]))
+                    mx.append(float(f[3]))
+                except ValueError:
+                    continue
+                for nm, v in zip(names, f[6:10]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            return sm, mx, reasons
+
+        inside = [x for x in self.lines if self.t0 is not None and self.t0 <= x[0] <= (self.t1 or x[0]) + 0.03]
+        window = "timed region"
+        sm, mx, reasons = summarise(inside)
+        if not sm:
+            window = "warm-up + timed region (the timed region was shorter than one sampling period)"
+            sm, mx, reasons = summarise(self.lines)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------------------------------ CPU side
@@ -198,17 +218,18 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     warm = max(args.warmup, 3)
     for _ in range(warm):
         out = pipe.run(rowptr, colidx, val)
     barrier()
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = lib.qrs_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stage_ms = {}
     barrier()
+    sampler.mark_start()
     ev0.record()
     outs = []
     for _ in range(args.steps):
@@ -216,6 +237,7 @@ def main():
         outs.append(out.stage_ms)
     ev1.record()
     barrier()
+    sampler.mark_end()
     clocks = sampler.stop()
     launches = lib.qrs_launch_count() - launches0
     elapsed_ms = ev0.elapsed_time(ev1)
