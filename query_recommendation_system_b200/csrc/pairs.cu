@@ -149,6 +149,90 @@ pairs_score_kernel(const uint64_t *__restrict__ records, int64_t n_records, cons
   }
 }
 
+// r == 4 and K a multiple of 128 (the headline configs 128/32x4 and 256/64x4): a lane's 16-byte load
+// of row elements [128c + 4*lane, +4) IS band 32c + lane, so one ballot per 128 elements yields the
+// whole band-match mask and no shared-memory mask staging is needed.
+__global__ void __launch_bounds__(kPairThreads)
+pairs_score_r4_kernel(const uint64_t *__restrict__ records, int64_t n_records, const uint64_t *__restrict__ slot_off,
+                      const int *__restrict__ sig, const long long *__restrict__ norm2, int64_t sig_id_base, int K,
+                      uint64_t *__restrict__ pairs, int *__restrict__ sim_milli, int64_t capacity,
+                      unsigned long long *__restrict__ n_pairs) {
+  __shared__ uint64_t s_pair[kPairWarps][32];
+  __shared__ long long s_dot[kPairWarps][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int chunks128 = K >> 7;
+  const uint64_t total = slot_off[n_records];
+  const uint64_t chunks = (total + 31) / 32;
+  const uint64_t warp_global = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = (uint64_t(gridDim.x) * blockDim.x) >> 5;
+
+  for (uint64_t c = warp_global; c < chunks; c += nwarps) {
+    const uint64_t q = c * 32 + lane;
+    uint64_t recB = 0, recA = 0;
+    const bool have = q < total;
+    if (have) {
+      int64_t lo = 0, hi = n_records;   // invariant: slot_off[lo] <= q < slot_off[hi]
+      while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (slot_off[mid] <= q) lo = mid; else hi = mid;
+      }
+      const uint64_t tq = q - slot_off[lo];
+      const uint64_t tp = slot_off[lo + 1] - slot_off[lo];
+      recB = records[lo];
+      recA = records[lo - int64_t(tp) + int64_t(tq)];
+    }
+    const int nslots = __popc(__ballot_sync(kFull, have));
+    int nout = 0;
+    for (int sl = 0; sl < nslots; ++sl) {
+      const uint64_t ra = __shfl_sync(kFull, recA, sl), rb = __shfl_sync(kFull, recB, sl);
+      const int band = int(rec_band(rb));
+      uint32_t ia = rec_id(ra), ib = rec_id(rb);
+      if (ia > ib) { uint32_t t = ia; ia = ib; ib = t; }
+      const int4 *rowa = reinterpret_cast<const int4 *>(sig + (int64_t(ia) - sig_id_base) * K) + lane;
+      const int4 *rowb = reinterpret_cast<const int4 *>(sig + (int64_t(ib) - sig_id_base) * K) + lane;
+      long long dot = 0;
+      bool own = false, earlier = false;
+      for (int ch = 0; ch < chunks128; ++ch) {
+        const int4 a = __ldg(rowa + ch * 32), b4 = __ldg(rowb + ch * 32);
+        const unsigned dx = unsigned(a.x ^ b4.x) | unsigned(a.y ^ b4.y) | unsigned(a.z ^ b4.z) | unsigned(a.w ^ b4.w);
+        const unsigned an = unsigned(a.x & a.y & a.z & a.w);
+        const bool match = (dx & 0xFFFFu) == 0u && (an & 0xFFFFu) != 0xFFFFu;   // equal int16 lanes, not all -1
+        const unsigned mm = __ballot_sync(kFull, match);
+        const int rel = band - ch * 32;                                          // band's lane in this chunk
+        if (rel >= 32) earlier = earlier || mm != 0u;
+        else if (rel >= 0) {
+          own = (mm >> rel) & 1u;
+          earlier = earlier || (mm & ((1u << rel) - 1u)) != 0u;
+        }
+        dot += (long long)a.x * b4.x + (long long)a.y * b4.y + (long long)a.z * b4.z + (long long)a.w * b4.w;
+      }
+      if (own && !earlier) {
+        if (sim_milli != nullptr) dot = warp_sum_ll(dot);
+        if (lane == 0) {
+          s_pair[warp][nout] = (uint64_t(ia) << 32) | uint64_t(ib);
+          s_dot[warp][nout] = dot;
+        }
+        ++nout;
+      }
+    }
+    __syncwarp();
+    if (nout > 0) {
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(n_pairs, (unsigned long long)nout);
+      base = __shfl_sync(kFull, base, 0);
+      if (lane < nout && int64_t(base + lane) < capacity) {
+        const uint64_t pr = s_pair[warp][lane];
+        pairs[base + lane] = pr;
+        if (sim_milli != nullptr) {
+          const int64_t a = int64_t(pr >> 32) - sig_id_base, bb = int64_t(pr & 0xFFFFFFFFu) - sig_id_base;
+          sim_milli[base + lane] = to_milli(cosine_of(s_dot[warp][lane], norm2[a], norm2[bb]));
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
 __global__ void __launch_bounds__(256)
 pair_cosine_kernel(const int *__restrict__ sig, const long long *__restrict__ norm2, int K,
                    const uint64_t *__restrict__ pairs, int64_t n_pairs, int *__restrict__ sim_milli) {
@@ -204,6 +288,13 @@ int qrs_pairs_score(const uint64_t *records, int64_t n_records, const uint64_t *
   if (K > kMaxSigWords * 32 || K / b > 32 || b > QRS_MAX_BANDS) return QRS_ERR_UNSUPPORTED;
   if (n_records == 0) return QRS_OK;
   const int grid = sm_count() * 8;
+  if (K / b == 4 && K % 128 == 0) {
+    pairs_score_r4_kernel<<<grid, kPairThreads, 0, as_stream(stream)>>>(
+        records, n_records, slot_off, sig, reinterpret_cast<const long long *>(norm2), sig_id_base, K, pairs, sim_milli,
+        capacity, n_pairs);
+    QRS_LAUNCH_CHECK();
+    return QRS_OK;
+  }
   pairs_score_kernel<<<grid, kPairThreads, 0, as_stream(stream)>>>(
       records, n_records, slot_off, sig, reinterpret_cast<const long long *>(norm2), sig_id_base, K, b, pairs,
       sim_milli, capacity, n_pairs);

@@ -183,6 +183,22 @@ def test_candidates_seeded_planted_vs_oracle():
         assert np.array_equal(sims.cpu().numpy()[srt], spec.cosine_milli(sig, unpack(pairs)[srt]))
 
 
+def test_candidates_k256_b64_fast_path_vs_oracle():
+    # r = 4 with K = 256: two 128-element chunks per row in the 16-byte-load kernel
+    from query_recommendation_system_b200 import synth
+    n, m, K, b = 2048, 3000, 256, 64
+    rowptr, colidx, _ = synth.planted_csr(n, m, 0.04, seed=20260105)
+    tab = spec.permutation_table(m, K, seed=7)
+    sig = spec.signatures(rowptr.numpy(), colidx.numpy(), tab)
+    sig[5] = -1                                  # an empty set: all bands all -1
+    sig[40:44, 128:132] = 65535                  # a band whose lanes wrap to -1 (lsh.py:28, 47) in the second chunk
+    pairs, sims = _gpu_candidates(sig, b)
+    got = np.sort(pairs.cpu().numpy().view(np.uint64))
+    assert np.array_equal(got, spec.candidates_packed(sig, b))
+    srt = np.argsort(pairs.cpu().numpy().view(np.uint64))
+    assert np.array_equal(sims.cpu().numpy()[srt], spec.cosine_milli(sig, unpack(pairs)[srt]))
+
+
 def test_candidates_degenerate_inputs():
     # all sets empty → every band all -1 → no candidates (lsh.py:47); all identical → all pairs
     K, b = 32, 8
