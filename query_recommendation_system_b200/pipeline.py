@@ -86,7 +86,11 @@ class LshCfPipeline:
         self.distributed = distributed      # False: ignore an initialised process group (single-rank run)
         self.profile = profile
         self.integer_predict = True         # exact-integer accumulation in the predictor (identical results)
-        self.pred_regions = 1 if self.device.type != "cuda" else 256
+        # output-slice cursors: one per SM, so that every region serves the same number of CTAs of the
+        # prediction kernel (its grid is a multiple of the SM count) and the regions fill evenly
+        self.pred_regions = 1
+        if self.device.type == "cuda":
+            self.pred_regions = max(1, _lib.load().qrs_device_sm_count(self.device.index or 0))
         self.tile = tile
         self.mode = minhash_mode
         if isinstance(perm_tab, np.ndarray):
