@@ -182,7 +182,7 @@ def main():
     ap.add_argument("--config", default="C2")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sets", type=int, default=64)
+    ap.add_argument("--cpu-sets", type=int, default=160)
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
@@ -330,7 +330,7 @@ def main():
             "roofline": roofline, "rooflines": rl,
             "e2e": {"value": n_total / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "wall_ms_per_step": e2e_wall_ms,
                     "h2d_bytes_per_step": runner.h2d_bytes, "d2h_bytes_per_step": runner.d2h_bytes, "steps": e2e_steps,
-                    "call": "pipeline.HostRunner(pipe, chunks=4)(rowptr, colidx, val) with pinned host tensors; returns pinned "
+                    "call": "pipeline.HostRunner(pipe, chunks=4, cols_format=auto)(rowptr, colidx, val) with pinned host tensors; returns pinned "
                             "sparse predictions + neighbour tables"},
             "gpu_launches": int(launches), "clocks": clocks,
         }

@@ -200,11 +200,21 @@ int qrs_predict_dense(const int64_t *rowptr, const int32_t *colidx, const uint8_
  * col.  Slices are placed by atomic cursors, so their order in the buffer is
  * unspecified: the buffer of `capacity` entries is cut into n_regions equal
  * regions, each with its own cursor (one cursor would serialise millions of
- * same-address atomics); cursors u64[n_regions] (device, zeroed by the caller)
+ * same-address atomics); cursors u64[n_regions + 1] (device, zeroed by the caller)
  * end as the number of entries REQUESTED in each region, writes beyond a
  * region's capacity/n_regions entries are dropped (the count still advances),
  * and row_start is an absolute index into cols/preds.  n_regions = 1 gives one
  * dense buffer.  cols/preds may be NULL with capacity 0 for a counting pass. */
+/* How the predicted columns are reported:
+ *   QRS_COLS_I32 / QRS_COLS_U16: cols is int32[capacity] / uint16[capacity] (Q <= 65536), one entry per
+ *       non-zero prediction, aligned with preds;
+ *   QRS_COLS_BITMAP: cols is uint32[n_users * nt * tile / 32], zeroed by the caller (tile % 64 == 0): bit c of
+ *       word (t*nt + tile_index) * tile/32 + c/32 marks column tile_index*tile + c as touched by a neighbour;
+ *       preds then holds one byte per TOUCHED column in ascending order (0 = no prediction), row_cnt
+ *       counts those bytes, and cursors[n_regions] (one extra u64) receives the number of non-zero ones. */
+#define QRS_COLS_I32 0
+#define QRS_COLS_U16 1
+#define QRS_COLS_BITMAP 2
 int32_t qrs_predict_max_tile(int32_t integer_tables /* 1 when u_milli is used */);
 size_t qrs_predict_sparse_workspace_bytes(int64_t U, int32_t Q, int32_t tile, int64_t capacity);
 /* u_milli (optional): the same similarities as integers, u_val[t] == u_milli[t] / 1000.0 exactly
@@ -219,8 +229,7 @@ int qrs_predict_sparse(const int64_t *rowptr, const int32_t *colidx, const uint8
                        int64_t user_base, int64_t n_users, int32_t tile,
                        void *ws, size_t ws_bytes,
                        int64_t *row_start, int32_t *row_cnt,
-                       void *cols /* int32[capacity], or uint16[capacity] when cols_u16 (Q <= 65536) */,
-                       int32_t cols_u16, uint8_t *preds,
+                       void *cols, int32_t cols_mode /* QRS_COLS_* */, uint8_t *preds,
                        int64_t capacity, int32_t n_regions, unsigned long long *cursors, void *stream);
 
 /* ------------------------------------------------------ multi-GPU plumbing

@@ -79,10 +79,19 @@ __host__ __device__ constexpr int sparse_warp_range(int tile) { return round_up(
 // shared memory of one CTA: acc[tile] | u16 jlist[8*range] | u8 plist[8*range] | metadata
 __host__ __device__ constexpr size_t sparse_cta_bytes(int tile, bool milli) {
   return round_up<size_t>(size_t(tile) * (milli ? 8 : 16), 16) +
-         round_up<size_t>(size_t(sparse_warp_range(tile)) * kSpWarpsCta * 3, 16) + 64 * (8 + 8 + 4 + 4) + 192;
+         round_up<size_t>(size_t(sparse_warp_range(tile)) * kSpWarpsCta * 3, 16) + 64 * (8 + 8 + 4 + 4) + 256;
 }
 
 constexpr int kTieMarker = 255;   // not a possible prediction: ratings <= 255 give at most 0.7 * 255 + 18 = 196.5
+
+// bits of a 16-bit value moved to the even positions of a 32-bit word
+__device__ __forceinline__ unsigned spread16(unsigned x) {
+  x = (x | (x << 8)) & 0x00FF00FFu;
+  x = (x | (x << 4)) & 0x0F0F0F0Fu;
+  x = (x | (x << 2)) & 0x33333333u;
+  x = (x | (x << 1)) & 0x55555555u;
+  return x;
+}
 
 __device__ __forceinline__ int predict_from(double num, double den) {
   return den != 0.0 ? hybrid_rule(0.0, num / den) : 0;
@@ -125,7 +134,7 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
                       int64_t *__restrict__ row_start, int *__restrict__ row_cnt, int *__restrict__ cols,
                       uint8_t *__restrict__ preds, int64_t region_cap, int n_regions,
                       unsigned long long *__restrict__ cursors, unsigned long long *__restrict__ tie_count,
-                      ulonglong2 *__restrict__ tie_list, int64_t tie_capacity, int cols_u16,
+                      ulonglong2 *__restrict__ tie_list, int64_t tie_capacity, int cols_mode,
                       const uint8_t *__restrict__ single_tab) {
   using acc_t = typename AccOf<MILLI>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -142,7 +151,8 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
   unsigned *m_inc = reinterpret_cast<unsigned *>(meta + 64 * 20);   // [64] MILLI: milli | 1 << 20
   int *w_cnt = reinterpret_cast<int *>(meta + 64 * 24);             // [16] non-zero predictions per warp
   int *w_off = w_cnt + 16;                                          // [16] exclusive prefix of w_cnt
-  unsigned long long *s_base = reinterpret_cast<unsigned long long *>(w_cnt + 32);
+  int *w_nz = w_cnt + 32;                                           // [16] non-zero predictions per warp
+  unsigned long long *s_base = reinterpret_cast<unsigned long long *>(w_cnt + 48);
   acc_t zero;
   if constexpr (MILLI) zero = 0ull; else zero = Acc{0.0, 0.0};
   for (int j = tid; j < tile; j += kSpThreads) acc[j] = zero;
@@ -251,6 +261,7 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
     __syncthreads();
 
     // ---- pass 1 (per warp, its own column range): ascending list of the touched columns, two per lane
+    const bool bitmap = cols_mode == 2;
     const int j_lo = warp * range, j_hi = min(width, j_lo + range);
     uint16_t *wj = jlist + j_lo;
     uint8_t *wp = plist + j_lo;
@@ -271,6 +282,13 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
         if (j + 1 < j_hi) { const Acc x = acc[j + 1]; hit1 = x.den != 0.0 || x.num != 0.0; }
       }
       const unsigned m0 = __ballot_sync(kFull, hit0), m1 = __ballot_sync(kFull, hit1);
+      if (bitmap && lane < 2) {
+        // m0 / m1 hold the even / odd columns of this 64-column window: interleave them into two words
+        const unsigned e = lane == 0 ? (m0 & 0xFFFFu) : (m0 >> 16), o = lane == 0 ? (m1 & 0xFFFFu) : (m1 >> 16);
+        const int first_col = j0 + 32 * lane;
+        if (first_col < j_hi)
+          reinterpret_cast<unsigned *>(cols)[item * (tile >> 5) + (first_col >> 5)] = spread16(e) | (spread16(o) << 1);
+      }
       const int before = touched + __popc(m0 & lt) + __popc(m1 & lt);
       if (hit0) wj[before] = uint16_t(j);
       if (hit1) wj[before + (hit0 ? 1 : 0)] = uint16_t(j + 1);
@@ -309,14 +327,17 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
       }
       total += __popc(__ballot_sync(kFull, p != 0));
     }
-    if (lane == 0) w_cnt[warp] = total;
+    const int nonzero = total;
+    if (bitmap) total = touched;      // bitmap form: one prediction byte per touched column (0 = no prediction)
+    if (lane == 0) { w_cnt[warp] = total; w_nz[warp] = nonzero; }
     __syncthreads();
     if (tid == 0) {
-      int sum = 0;
+      int sum = 0, nz = 0;
 #pragma unroll
-      for (int w = 0; w < kSpWarpsCta; ++w) { w_off[w] = sum; sum += w_cnt[w]; }
+      for (int w = 0; w < kSpWarpsCta; ++w) { w_off[w] = sum; sum += w_cnt[w]; nz += w_nz[w]; }
       unsigned long long base = 0;
       if (sum > 0) base = atomicAdd(cursor, (unsigned long long)sum);
+      if (bitmap && nz > 0) atomicAdd(cursors + n_regions, (unsigned long long)nz);   // non-zero predictions (stats)
       row_start[item] = region_base + int64_t(base);
       row_cnt[item] = sum;
       *s_base = base;
@@ -330,8 +351,9 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
         for (int x0 = 0; x0 < touched; x0 += 32) {
           const int x = x0 + lane;
           const int p = x < touched ? int(wp[x]) : 0;
-          const unsigned m = __ballot_sync(kFull, p != 0);
-          if (p != 0) {
+          const bool keep = bitmap ? x < touched : p != 0;
+          const unsigned m = __ballot_sync(kFull, keep);
+          if (keep) {
             const int64_t pos = base + written + __popc(m & lt);
             if (pos < region_cap) {
               int pv = p;
@@ -343,8 +365,8 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
                 else
                   pv = resolve_tie(colidx, val, m_a, m_n, m_s, c, q0 + int(wj[x]));   // list full: settle here
               }
-              if (cols_u16) reinterpret_cast<uint16_t *>(cols)[region_base + pos] = uint16_t(q0 + int(wj[x]));
-              else cols[region_base + pos] = q0 + int(wj[x]);
+              if (cols_mode == 1) reinterpret_cast<uint16_t *>(cols)[region_base + pos] = uint16_t(q0 + int(wj[x]));
+              else if (cols_mode == 0) cols[region_base + pos] = q0 + int(wj[x]);
               preds[region_base + pos] = uint8_t(pv);
             }
           }
@@ -493,7 +515,7 @@ static int launch_predict_sparse(const int *colidx, const uint8_t *val, int Q, c
                                  int tile, int nt, const int64_t *tilepos, int64_t *row_start, int *row_cnt, int *cols,
                                  uint8_t *preds, int64_t region_cap, int n_regions, unsigned long long *cursors,
                                  unsigned long long *tie_count, ulonglong2 *tie_list, int64_t tie_capacity,
-                                 int cols_u16, const uint8_t *single_tab, cudaStream_t st) {
+                                 int cols_mode, const uint8_t *single_tab, cudaStream_t st) {
   auto kern = predict_sparse_kernel<MILLI>;
   const size_t smem = sparse_smem_bytes(tile, MILLI);
   QRS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
@@ -506,7 +528,7 @@ static int launch_predict_sparse(const int *colidx, const uint8_t *val, int Q, c
   kern<<<unsigned(grid), kSpThreads, smem, st>>>(colidx, val, Q, u_idx, u_val, u_milli, u_cnt, ku, user_base,
                                                     n_users, tile, nt, tilepos, row_start, row_cnt, cols, preds,
                                                     region_cap, n_regions, cursors, tie_count, tie_list, tie_capacity,
-                                                    cols_u16, single_tab);
+                                                    cols_mode, single_tab);
   QRS_LAUNCH_CHECK();
   return QRS_OK;
 }
@@ -534,10 +556,11 @@ size_t qrs_predict_sparse_workspace_bytes(int64_t U, int32_t Q, int32_t tile, in
 int qrs_predict_sparse(const int64_t *rowptr, const int32_t *colidx, const uint8_t *val, int64_t U, int32_t Q,
                        const int32_t *u_idx, const double *u_val, const int32_t *u_milli, const int32_t *u_cnt,
                        int32_t ku, int64_t user_base, int64_t n_users, int32_t tile, void *ws, size_t ws_bytes,
-                       int64_t *row_start, int32_t *row_cnt, void *cols_any, int32_t cols_u16, uint8_t *preds,
+                       int64_t *row_start, int32_t *row_cnt, void *cols_any, int32_t cols_mode, uint8_t *preds,
                        int64_t capacity, int32_t n_regions, unsigned long long *cursors, void *stream) {
   int32_t *cols = static_cast<int32_t *>(cols_any);
-  if (cols_u16 && Q > 65536) return QRS_ERR_INVALID_ARG;
+  if (cols_mode < 0 || cols_mode > 2 || (cols_mode == 1 && Q > 65536) || (cols_mode == 2 && tile % 64 != 0))
+    return QRS_ERR_INVALID_ARG;
   if (!rowptr || U < 0 || Q <= 0 || !u_idx || (!u_val && !u_milli) || !u_cnt || ku <= 0 || user_base < 0 ||
       n_users < 0 || user_base + n_users > U || !row_start || !row_cnt || !cursors || capacity < 0 || n_regions <= 0)
     return QRS_ERR_INVALID_ARG;
@@ -572,7 +595,7 @@ int qrs_predict_sparse(const int64_t *rowptr, const int32_t *colidx, const uint8
   if (u_milli) {
     int rc = launch_predict_sparse<true>(colidx, val, Q, u_idx, u_val, u_milli, u_cnt, ku, user_base, n_users, tile,
                                          nt, tilepos, row_start, row_cnt, cols, preds, region_cap, n_regions, cursors,
-                                         tie_count, tie_list, tie_cap, cols_u16, single_tab, st);
+                                         tie_count, tie_list, tie_cap, cols_mode, single_tab, st);
     if (rc != QRS_OK || capacity == 0) return rc;
     predict_tie_fixup_kernel<<<sm_count() * 8, 256, 0, st>>>(rowptr, colidx, val, u_idx, u_milli, u_cnt, ku, tie_count,
                                                              tie_list, tie_cap, preds);
@@ -581,7 +604,7 @@ int qrs_predict_sparse(const int64_t *rowptr, const int32_t *colidx, const uint8
   }
   return launch_predict_sparse<false>(colidx, val, Q, u_idx, u_val, u_milli, u_cnt, ku, user_base, n_users, tile, nt,
                                       tilepos, row_start, row_cnt, cols, preds, region_cap, n_regions, cursors,
-                                      tie_count, tie_list, tie_cap, cols_u16, single_tab, st);
+                                      tie_count, tie_list, tie_cap, cols_mode, single_tab, st);
 }
 
 int qrs_predict_dense(const int64_t *rowptr, const int32_t *colidx, const uint8_t *val, int64_t U, int32_t Q,

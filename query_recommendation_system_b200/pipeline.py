@@ -102,7 +102,7 @@ class LshCfPipeline:
         self._head_for = None
         self._pred_capacity = {}
         self.predict_chunks = 1             # > 1: predictions are produced (and can be shipped) chunk by chunk
-        self.cols_u16 = False               # uint16 column ids in the prediction slices (needs m <= 65536)
+        self.cols_mode = 0                  # prediction columns as int32 ids (0), uint16 ids (1) or a bitmap (2)
 
     # ------------------------------------------------------------------ distributed helpers
     @property
@@ -202,21 +202,24 @@ class LshCfPipeline:
             out.pred_chunks = []
             for ci in range(chunks):
                 lo, hi = bounds[ci], bounds[ci + 1]
-                rcap = self._pred_capacity.get((chunks, ci), 0)
+                rcap = self._pred_capacity.get((chunks, ci, self.cols_mode), 0)
                 tab = (idx[lo:hi], v[lo:hi], cnt[lo:hi])
                 mil = milli[lo:hi] if self.integer_predict else None
                 while True:
                     rs, rc, cols, preds, cursors = st.predict_sparse(rowptr_all, colidx_all, val_all, self.m, tab,
                                                                      pred_base + lo, hi - lo, tile, rcap * regions,
                                                                      u_milli=mil, n_regions=regions,
-                                                                     cols_u16=self.cols_u16)
+                                                                     cols_mode=self.cols_mode)
                     demand = cursors.cpu()
+                    nonzero = int(demand[-1].item()) if self.cols_mode == 2 else int(demand.sum().item())
+                    demand = demand[:regions]
                     need = int(demand.max().item())
                     if need <= rcap:
                         break
-                    rcap = self._pred_capacity[(chunks, ci)] = int(need * 1.03) + 256
-                total += int(demand.sum().item())
-                chunk = {"user_lo": lo, "n_users": hi - lo, "row_start": rs, "row_cnt": rc, "cols": cols, "preds": preds}
+                    rcap = self._pred_capacity[(chunks, ci, self.cols_mode)] = int(need * 1.03) + 256
+                total += nonzero
+                chunk = {"user_lo": lo, "n_users": hi - lo, "row_start": rs, "row_cnt": rc, "cols": cols, "preds": preds,
+                         "cols_mode": self.cols_mode, "tile": tile}
                 out.pred_chunks.append(chunk)
                 if chunk_sink is not None:
                     chunk_sink(ci, chunk)
@@ -338,10 +341,15 @@ class HostRunner:
     stream while the next chunk of users is being predicted (column ids as uint16 when they fit).
     Buffers are allocated once and reused across calls."""
 
-    def __init__(self, pipe: LshCfPipeline, chunks: int = 4):
+    def __init__(self, pipe: LshCfPipeline, chunks: int = 4, cols_format: str = "auto"):
+        """cols_format: "i32" | "u16" | "bitmap" | "auto" (u16 when the column ids fit, switching to the
+        touched-column bitmap once a call has shown that more than 1/16 of the cells get a prediction —
+        the point where m/8 bitmap bytes per user beat 2 bytes per prediction)."""
         self.pipe = pipe
         pipe.predict_chunks = chunks
-        pipe.cols_u16 = pipe.m <= 65536
+        self.cols_format = cols_format
+        fits16 = pipe.m <= 65536
+        pipe.cols_mode = {"i32": 0, "u16": 1, "bitmap": 2, "auto": 1 if fits16 else 0}[cols_format]
         self._dev = {}
         self._host = {}
         self.copy_stream = torch.cuda.Stream(device=pipe.device)
@@ -383,7 +391,8 @@ class HostRunner:
         def sink(ci, chunk):
             ready = torch.cuda.Event()
             ready.record(compute)
-            host_chunk = {"user_lo": chunk["user_lo"], "n_users": chunk["n_users"]}
+            host_chunk = {"user_lo": chunk["user_lo"], "n_users": chunk["n_users"], "cols_mode": chunk["cols_mode"],
+                          "tile": chunk["tile"]}
             with torch.cuda.stream(self.copy_stream):
                 self.copy_stream.wait_event(ready)
                 for key in ("row_start", "row_cnt", "cols", "preds"):
@@ -401,4 +410,8 @@ class HostRunner:
         compute.synchronize()
         res["n_predictions"] = out.n_predictions
         res["covered_cells"] = out.covered_cells
+        if self.cols_format == "auto" and self.pipe.cols_mode != 2:
+            n_local = rowptr_h.numel() - 1
+            if out.n_predictions * 16 > n_local * self.pipe.m:
+                self.pipe.cols_mode = 2          # later calls ship bitmap + one byte per touched column
         return res

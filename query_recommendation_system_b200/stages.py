@@ -225,7 +225,7 @@ def choose_predict_tile(Q: int, avg_len: float = 0.0, integer_tables: bool = Tru
 
 def predict_sparse(rowptr, colidx, val, Q: int, u_tab: Table, user_base: int, n_users: int, tile: int,
                    capacity: int, out_cols: Optional[torch.Tensor] = None, out_preds: Optional[torch.Tensor] = None,
-                   u_milli: Optional[torch.Tensor] = None, n_regions: int = 1, cols_u16: bool = False):
+                   u_milli: Optional[torch.Tensor] = None, n_regions: int = 1, cols_mode: int = 0):
     """User-branch predictions in sparse form.  Returns (row_start int64[n_users, nt],
     row_cnt int32[n_users, nt], cols int32[capacity], preds uint8[capacity], cursors int64[n_regions] on
     device = entries requested per region of capacity // n_regions entries).
@@ -241,19 +241,23 @@ def predict_sparse(rowptr, colidx, val, Q: int, u_tab: Table, user_base: int, n_
     assert ui.dtype == torch.int32 and uv.dtype == torch.float64 and uc.dtype == torch.int32
     row_start = torch.empty((n_users, nt), dtype=torch.int64, device=dev)
     row_cnt = torch.empty((n_users, nt), dtype=torch.int32, device=dev)
-    cols_dtype = torch.int16 if cols_u16 else torch.int32      # int16 storage carries uint16 column ids
-    cols = out_cols if out_cols is not None else torch.empty(max(capacity, 1), dtype=cols_dtype, device=dev)
+    # cols_mode 0: int32 ids; 1: uint16 ids (int16 storage); 2: touched-column bitmap per (user, tile), zeroed here
+    cols_dtype = torch.int16 if cols_mode == 1 else torch.int32
+    if cols_mode == 2:
+        cols = torch.zeros(n_users * nt * (tile // 32), dtype=torch.int32, device=dev)
+    else:
+        cols = out_cols if out_cols is not None else torch.empty(max(capacity, 1), dtype=cols_dtype, device=dev)
     assert cols.dtype == cols_dtype
     preds = out_preds if out_preds is not None else torch.empty(max(capacity, 1), dtype=torch.uint8, device=dev)
-    cursor = torch.zeros(n_regions, dtype=torch.int64, device=dev)
+    cursor = torch.zeros(n_regions + 1, dtype=torch.int64, device=dev)   # [n_regions] = non-zero count (bitmap mode)
     ws = _ws(lib.qrs_predict_sparse_workspace_bytes(U, Q, tile, capacity), dev)
     check(lib.qrs_predict_sparse(ptr(rowptr), ptr(colidx), ptr(val), U, Q, ptr(ui), ptr(uv), ptr(u_milli), ptr(uc),
                                  ui.shape[1],
                                  user_base, n_users, tile, ptr(ws), ws.numel(), ptr(row_start), ptr(row_cnt),
-                                 ptr(cols), 1 if cols_u16 else 0, ptr(preds), capacity, n_regions, ptr(cursor),
+                                 ptr(cols), cols_mode, ptr(preds), capacity, n_regions, ptr(cursor),
                                  _stream()),
           "qrs_predict_sparse")
-    return row_start, row_cnt, cols, preds, cursor
+    return row_start, row_cnt, cols, preds, cursor[:n_regions] if cols_mode != 2 else cursor
 
 
 # ---------------------------------------------------------------------- multi-GPU plumbing

@@ -118,9 +118,28 @@ def test_binding_b_seam_and_band_override():
         assert np.array_equal(e["indexes"], idx[i, :cnt[i]]) and np.array_equal(e["values"], val[i, :cnt[i]])
 
 
-def test_host_runner_chunked_u16_matches_device_run():
+def _decode_chunk_user(ch, t, nt):
+    """(columns, predictions) of local user t of a HostRunner chunk, whatever the column format."""
+    crs = ch["row_start"].numpy().reshape(ch["n_users"], nt)
+    crc = ch["row_cnt"].numpy().reshape(ch["n_users"], nt)
+    cpreds = ch["preds"].numpy()
+    ps = np.concatenate([cpreds[crs[t, x]:crs[t, x] + crc[t, x]] for x in range(nt)])
+    if ch["cols_mode"] == 2:
+        words = ch["tile"] // 32
+        bm = ch["cols"].numpy().view(np.uint32).reshape(ch["n_users"], nt, words)[t]
+        bits = np.unpackbits(bm.view(np.uint8).reshape(nt, words * 4), axis=1, bitorder="little")
+        cs = np.concatenate([x * ch["tile"] + np.flatnonzero(bits[x]) for x in range(nt)])
+        assert cs.size == ps.size
+        return cs[ps != 0].astype(np.int64), ps[ps != 0]
+    ccols = ch["cols"].numpy().view(np.uint16) if ch["cols_mode"] == 1 else ch["cols"].numpy()
+    cs = np.concatenate([ccols[crs[t, x]:crs[t, x] + crc[t, x]] for x in range(nt)]).astype(np.int64)
+    return cs, ps
+
+
+@pytest.mark.parametrize("fmt", ["u16", "bitmap", "auto", "i32"])
+def test_host_runner_chunked_matches_device_run(fmt):
     """The host-facing call (pinned CSR in, pinned predictions out, 4 user chunks shipped on a copy stream,
-    uint16 column ids) returns the same predictions as the device-resident single-chunk run."""
+    compact column formats) returns the same predictions as the device-resident single-chunk run."""
     import torch
     from oracle import spec
     from query_recommendation_system_b200 import synth
@@ -132,25 +151,22 @@ def test_host_runner_chunked_u16_matches_device_run():
     ref = pipe.run(rowptr.cuda(), colidx.cuda(), val.cuda())
     rs, rc = ref.pred_row_start.cpu().numpy(), ref.pred_row_cnt.cpu().numpy()
     cols, preds = ref.pred_cols.cpu().numpy(), ref.pred_vals.cpu().numpy()
+    nt = rs.shape[1]
 
-    runner = HostRunner(pipe, chunks=4)
+    runner = HostRunner(pipe, chunks=4, cols_format=fmt)
     res = None
-    for _ in range(2):            # second call reuses the learnt capacities and pinned buffers
+    for _ in range(3):            # later calls reuse the learnt capacities / switch format in "auto"
         res = runner(rowptr.pin_memory(), colidx.pin_memory(), val.pin_memory())
     assert res["n_predictions"] == ref.n_predictions and len(res["chunks"]) == 4
     assert runner.d2h_bytes > 0 and runner.h2d_bytes == rowptr.numel() * 8 + colidx.numel() * 4 + val.numel()
     assert torch.equal(res["nbr_idx"].reshape(n, k), ref.nbr_idx.cpu())
+    if fmt in ("bitmap", "auto"):
+        assert all(ch["cols_mode"] == 2 for ch in res["chunks"])
     seen = 0
     for ch in res["chunks"]:
-        nt = rs.shape[1]
-        crs = ch["row_start"].numpy().reshape(ch["n_users"], nt)
-        crc = ch["row_cnt"].numpy().reshape(ch["n_users"], nt)
-        ccols = ch["cols"].numpy().view(np.uint16)
-        cpreds = ch["preds"].numpy()
         for t in range(0, ch["n_users"], 37):
             u = ch["user_lo"] + t
-            mine_c = np.concatenate([ccols[crs[t, x]:crs[t, x] + crc[t, x]] for x in range(nt)]).astype(np.int64)
-            mine_p = np.concatenate([cpreds[crs[t, x]:crs[t, x] + crc[t, x]] for x in range(nt)])
+            mine_c, mine_p = _decode_chunk_user(ch, t, nt)
             ref_c = np.concatenate([cols[rs[u, x]:rs[u, x] + rc[u, x]] for x in range(nt)]).astype(np.int64)
             ref_p = np.concatenate([preds[rs[u, x]:rs[u, x] + rc[u, x]] for x in range(nt)])
             assert np.array_equal(mine_c, ref_c) and np.array_equal(mine_p, ref_p)
