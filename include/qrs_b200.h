@@ -208,7 +208,7 @@ int qrs_predict_dense(const int64_t *rowptr, const int32_t *colidx, const uint8_
 /* How the predicted columns are reported:
  *   QRS_COLS_I32 / QRS_COLS_U16: cols is int32[capacity] / uint16[capacity] (Q <= 65536), one entry per
  *       non-zero prediction, aligned with preds;
- *   QRS_COLS_BITMAP: cols is uint32[n_users * nt * tile / 32], zeroed by the caller (tile % 64 == 0): bit c of
+ *   QRS_COLS_BITMAP: cols is uint32[n_users * nt * tile / 32], zeroed by the caller: bit c of
  *       word (t*nt + tile_index) * tile/32 + c/32 marks column tile_index*tile + c as touched by a neighbour;
  *       preds then holds one byte per TOUCHED column in ascending order (0 = no prediction), row_cnt
  *       counts those bytes, and cursors[n_regions] (one extra u64) receives the number of non-zero ones. */

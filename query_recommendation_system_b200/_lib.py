@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqrs_b200.so")
+LIB_PATH = os.environ.get("QRS_B200_LIB", os.path.join(_HERE, "libqrs_b200.so"))   # override: debugging builds only
 
 QRS_OK = 0
 MINHASH_AUTO, MINHASH_DIRECT, MINHASH_FIRST_TOUCH = 0, 1, 2

@@ -79,9 +79,11 @@ __host__ __device__ constexpr int sparse_warp_range(int tile) { return round_up(
 // shared memory of one CTA: acc[tile] | u16 jlist[8*range] | u8 plist[8*range] | metadata
 __host__ __device__ constexpr size_t sparse_cta_bytes(int tile, bool milli) {
   return round_up<size_t>(size_t(tile) * (milli ? 8 : 16), 16) +
-         round_up<size_t>(size_t(sparse_warp_range(tile)) * kSpWarpsCta * 3, 16) + 64 * (8 + 8 + 4 + 4) + 256;
+         round_up<size_t>(size_t(sparse_warp_range(tile)) * kSpWarpsCta * 3, 16) + 64 * (8 + 8 + 4 + 4) + 256 +
+         (milli ? 26 * 32 * 4 : 0);
 }
 
+constexpr int kTieBitWords = 26 * 32;   // single-rater half-way bits: 26 ratings (5, 15, .., 255) x 1024 milli
 constexpr int kTieMarker = 255;   // not a possible prediction: ratings <= 255 give at most 0.7 * 255 + 18 = 196.5
 
 // bits of a 16-bit value moved to the even positions of a 32-bit word
@@ -135,7 +137,7 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
                       uint8_t *__restrict__ preds, int64_t region_cap, int n_regions,
                       unsigned long long *__restrict__ cursors, unsigned long long *__restrict__ tie_count,
                       ulonglong2 *__restrict__ tie_list, int64_t tie_capacity, int cols_mode,
-                      const uint8_t *__restrict__ single_tab) {
+                      const unsigned *__restrict__ tie_bits_g) {
   using acc_t = typename AccOf<MILLI>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -153,9 +155,12 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
   int *w_off = w_cnt + 16;                                          // [16] exclusive prefix of w_cnt
   int *w_nz = w_cnt + 32;                                           // [16] non-zero predictions per warp
   unsigned long long *s_base = reinterpret_cast<unsigned long long *>(w_cnt + 48);
+  unsigned *tie_bits = reinterpret_cast<unsigned *>(w_cnt + 64);    // [26 * 32] MILLI: single-rater half-way bits
   acc_t zero;
   if constexpr (MILLI) zero = 0ull; else zero = Acc{0.0, 0.0};
   for (int j = tid; j < tile; j += kSpThreads) acc[j] = zero;
+  if constexpr (MILLI)
+    for (int w = tid; w < kTieBitWords; w += kSpThreads) tie_bits[w] = tie_bits_g[w];
   __syncthreads();
 
   const unsigned lt = lanemask_lt();
@@ -266,6 +271,7 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
     uint16_t *wj = jlist + j_lo;
     uint8_t *wp = plist + j_lo;
     int touched = 0;
+#pragma unroll 2
     for (int j0 = j_lo; j0 < j_hi; j0 += 64) {
       const int j = j0 + 2 * lane;
       bool hit0 = false, hit1 = false;
@@ -297,6 +303,7 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
     __syncwarp();
     // ---- pass 2: prediction of every touched column (dense lanes), accumulators back to zero
     int total = 0;
+#pragma unroll 2
     for (int x0 = 0; x0 < touched; x0 += 32) {
       const int x = x0 + lane;
       int p = 0;
@@ -309,8 +316,10 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
           const unsigned D = lo & 0xFFFFFu, raters = lo >> 20;
           if (D != 0u) {
             if (raters == 1u) {
-              // one rater: the prediction depends on (rating, milli) only — looked up, no division
-              p = single_tab[(hi >> 24) * 1001u + D];
+              // one rater: x = (7r + 180) / 10 exactly; half-way cases take the fp64 chain's bit
+              const unsigned r1 = hi >> 24, x10 = 7u * r1 + 180u, q = x10 / 10u, rem = x10 - 10u * q;
+              p = int(q) + (rem > 5u ? 1 : 0);
+              if (rem == 5u) p += int((tie_bits[(r1 / 10u) * 32u + (D >> 5)] >> (D & 31u)) & 1u);
             } else {
               const unsigned N = hi & 0xFFFFFFu;
               const unsigned X = 7u * N + 180u * D, Y = 10u * D;    // x = X / Y = 0.7 * N / D + 18
@@ -444,18 +453,24 @@ predict_dense_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__
   }
 }
 
-// single_tab[r * 1001 + milli] = the reference's fp64 result for a cell with exactly one rater of rating r and
-// similarity milli / 1000: num = r*s, W = s, u = num / W, round(u * 0.7 + 18)   (recommender.py:36-47, 327)
-__global__ void __launch_bounds__(256) single_rater_table_kernel(uint8_t *__restrict__ tab) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 256 * 1001) return;
-  const int r = i / 1001, milli = i - r * 1001;
-  int p = 0;
-  if (r != 0 && milli != 0) {
-    const double s = double(milli) / 1000.0;
-    p = predict_from(__dmul_rn(double(r), s), s);
+// One rater of rating r and similarity milli/1000: the exact value is x = (7r + 180) / 10, independent of milli,
+// so round(x) is an integer expression unless x is half-way (r = 10t + 5); for those 26 ratings the
+// reference's fp64 chain  u = (r*s)/s, round(u*0.7 + 18)  (recommender.py:36-47, 327) lands on the lower
+// or the upper neighbour depending on milli — one BIT per (t, milli), 26 x 1024 bits, kept in shared memory.
+__global__ void __launch_bounds__(256) single_rater_tie_bits_kernel(unsigned *__restrict__ bits) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;      // one 32-bit word per thread
+  if (w >= kTieBitWords) return;
+  const int t = w >> 5, r = 10 * t + 5;
+  unsigned word = 0;
+  for (int b = 0; b < 32; ++b) {
+    const int milli = (w & 31) * 32 + b;
+    if (milli >= 1 && milli <= 1000) {
+      const double s = double(milli) / 1000.0;
+      const int p = predict_from(__dmul_rn(double(r), s), s);
+      if (p == (7 * r + 180) / 10 + 1) word |= 1u << b;
+    }
   }
-  tab[i] = uint8_t(p);
+  bits[w] = word;
 }
 
 // Exact half-way cells with several raters (MILLI flavour): one warp per cell re-gathers the
@@ -515,7 +530,7 @@ static int launch_predict_sparse(const int *colidx, const uint8_t *val, int Q, c
                                  int tile, int nt, const int64_t *tilepos, int64_t *row_start, int *row_cnt, int *cols,
                                  uint8_t *preds, int64_t region_cap, int n_regions, unsigned long long *cursors,
                                  unsigned long long *tie_count, ulonglong2 *tie_list, int64_t tie_capacity,
-                                 int cols_mode, const uint8_t *single_tab, cudaStream_t st) {
+                                 int cols_mode, const unsigned *single_tab, cudaStream_t st) {
   auto kern = predict_sparse_kernel<MILLI>;
   const size_t smem = sparse_smem_bytes(tile, MILLI);
   QRS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
@@ -540,10 +555,10 @@ using namespace qrs;
 extern "C" {
 
 /* largest column tile that still lets two CTAs share an SM (<= ~112 KB of shared memory each) */
-int32_t qrs_predict_max_tile(int32_t integer_tables) { return integer_tables ? 10048 : 5824; }
+int32_t qrs_predict_max_tile(int32_t integer_tables) { return integer_tables ? 10016 : 5824; }
 
 static int64_t tie_list_capacity(int64_t capacity) { return capacity / 32 + 65536; }
-constexpr size_t kSingleTabBytes = round_up<size_t>(256 * 1001, 256);
+constexpr size_t kSingleTabBytes = round_up<size_t>(26 * 32 * 4, 256);
 
 size_t qrs_predict_sparse_workspace_bytes(int64_t U, int32_t Q, int32_t tile, int64_t capacity) {
   if (U < 0 || Q <= 0 || tile <= 0 || capacity < 0) return 0;
@@ -559,7 +574,7 @@ int qrs_predict_sparse(const int64_t *rowptr, const int32_t *colidx, const uint8
                        int64_t *row_start, int32_t *row_cnt, void *cols_any, int32_t cols_mode, uint8_t *preds,
                        int64_t capacity, int32_t n_regions, unsigned long long *cursors, void *stream) {
   int32_t *cols = static_cast<int32_t *>(cols_any);
-  if (cols_mode < 0 || cols_mode > 2 || (cols_mode == 1 && Q > 65536) || (cols_mode == 2 && tile % 64 != 0))
+  if (cols_mode < 0 || cols_mode > 2 || (cols_mode == 1 && Q > 65536) || (cols_mode == 2 && tile % 32 != 0))
     return QRS_ERR_INVALID_ARG;
   if (!rowptr || U < 0 || Q <= 0 || !u_idx || (!u_val && !u_milli) || !u_cnt || ku <= 0 || user_base < 0 ||
       n_users < 0 || user_base + n_users > U || !row_start || !row_cnt || !cursors || capacity < 0 || n_regions <= 0)
@@ -576,12 +591,12 @@ int qrs_predict_sparse(const int64_t *rowptr, const int32_t *colidx, const uint8
   int64_t *tilepos = static_cast<int64_t *>(ws);
   char *wsp = static_cast<char *>(ws) + round_up<size_t>(size_t(U) * size_t(nt + 1) * 8, 256);
   unsigned long long *tie_count = reinterpret_cast<unsigned long long *>(wsp);
-  uint8_t *single_tab = reinterpret_cast<uint8_t *>(wsp + 256);
+  unsigned *single_tab = reinterpret_cast<unsigned *>(wsp + 256);
   ulonglong2 *tie_list = reinterpret_cast<ulonglong2 *>(wsp + 256 + kSingleTabBytes);
   const int64_t tie_cap = tie_list_capacity(capacity);
   QRS_CUDA(cudaMemsetAsync(tie_count, 0, 8, st));
   if (u_milli) {
-    single_rater_table_kernel<<<ceil_div(256 * 1001, 256), 256, 0, st>>>(single_tab);
+    single_rater_tie_bits_kernel<<<ceil_div(26 * 32, 256), 256, 0, st>>>(single_tab);
     QRS_LAUNCH_CHECK();
   }
   {

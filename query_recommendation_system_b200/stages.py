@@ -220,7 +220,7 @@ def choose_predict_tile(Q: int, avg_len: float = 0.0, integer_tables: bool = Tru
     nt = max(1, math.ceil(Q / max_tile))
     while avg_len > 0 and avg_len / nt > PREDICT_SEGMENT_TARGET and math.ceil(Q / nt) > 256:
         nt += 1
-    return int(min(max_tile, max(64, math.ceil(math.ceil(Q / nt) / 64.0) * 64)))
+    return int(min(max_tile, max(32, math.ceil(math.ceil(Q / nt) / 32.0) * 32)))
 
 
 def predict_sparse(rowptr, colidx, val, Q: int, u_tab: Table, user_base: int, n_users: int, tile: int,
