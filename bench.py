@@ -286,8 +286,13 @@ def main():
         v["frac"] = v["achieved"] / peak
     dominant = max(("signatures+banding", "predict"), key=lambda s: stage_ms.get(s, 0.0))
     roofline = dict(rl[dominant])
-    roofline.update({"kernel": "predict_sparse_kernel" if dominant == "predict" else "minhash_kernel",
-                     "stage": dominant, "peak_source": peak_src, "traffic": None})
+    kernel_name = "predict_sparse_kernel" if dominant == "predict" else "minhash_kernel"
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")     # DRAM bytes per launch from the committed ncu capture
+    if world == 1 and args.config == "C2" and os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(kernel_name)
+    roofline.update({"kernel": kernel_name, "stage": dominant, "peak_source": peak_src + " (of measured)",
+                     "traffic": traffic, "traffic_source": "profiles/r1_traffic.json (ncu --set full, same command)"})
 
     # ---------------------------------------------------------------- e2e: host buffers in, host results out
     runner = HostRunner(pipe)
