@@ -192,6 +192,7 @@ int qrs_predict_dense(const int64_t *rowptr, const int32_t *colidx, const uint8_
 
 /* Sparse form for the scaled configurations (user branch only, query branch
  * absent ⇒ q = 0): per user the non-zero predictions over unrated queries.
+ * The CSR must hold fewer than 2^31 entries (positions are 32-bit inside the kernel).
  * The query axis is cut into nt = ceil(Q / tile) tiles of `tile` columns
  * (a multiple of 32, <= qrs_predict_max_tile(): as large as fits, one CTA
  * accumulates one (user, tile) in shared memory).  For user t and tile c,

@@ -79,8 +79,7 @@ __host__ __device__ constexpr int sparse_warp_range(int tile) { return round_up(
 // shared memory of one CTA: acc[tile] | u16 jlist[8*range] | u8 plist[8*range] | metadata
 __host__ __device__ constexpr size_t sparse_cta_bytes(int tile, bool milli) {
   return round_up<size_t>(size_t(tile) * (milli ? 8 : 16), 16) +
-         round_up<size_t>(size_t(sparse_warp_range(tile)) * kSpWarpsCta * 3, 16) + 64 * (8 + 8 + 4 + 4) + 256 +
-         (milli ? 26 * 32 * 4 : 0);
+         round_up<size_t>(size_t(sparse_warp_range(tile)) * kSpWarpsCta * 3, 16) + 64 * 8 + 256 + 26 * 32 * 4 + 64 * 16;
 }
 
 constexpr int kTieBitWords = 26 * 32;   // single-rater half-way bits: 26 ratings (5, 15, .., 255) x 1024 milli
@@ -101,11 +100,10 @@ __device__ __forceinline__ int predict_from(double num, double den) {
 
 // the reference's sequential fp64 evaluation of one cell, re-gathered from the neighbour segments
 __device__ __noinline__ int resolve_tie(const int *__restrict__ colidx, const uint8_t *__restrict__ val,
-                                        const int64_t *m_a, const int *m_n, const double *m_s, int c, int col) {
+                                        const int4 *meta4, const double *m_s, int c, int col) {
   double num = 0.0, den = 0.0;
   for (int t = 0; t < c; ++t) {
-    const int64_t a = m_a[t];
-    const int n = m_n[t];
+    const int a = meta4[t].y, n = meta4[t].z - a;
     int lo = 0, hi = n;
     while (lo < hi) {
       const int mid = (lo + hi) >> 1;
@@ -147,20 +145,21 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
   uint16_t *jlist = reinterpret_cast<uint16_t *>(ptr);
   uint8_t *plist = reinterpret_cast<uint8_t *>(jlist + size_t(range) * kSpWarpsCta);
   unsigned char *meta = ptr + round_up<size_t>(size_t(range) * kSpWarpsCta * 3, 16);
-  int64_t *m_a = reinterpret_cast<int64_t *>(meta);                 // [64] first entry of the neighbour's segment
-  double *m_s = reinterpret_cast<double *>(meta + 64 * 8);          // [64] its similarity
-  int *m_n = reinterpret_cast<int *>(meta + 64 * 16);               // [64] entries in the segment
-  unsigned *m_inc = reinterpret_cast<unsigned *>(meta + 64 * 20);   // [64] MILLI: milli | 1 << 20
-  int *w_cnt = reinterpret_cast<int *>(meta + 64 * 24);             // [16] non-zero predictions per warp
+  double *m_s = reinterpret_cast<double *>(meta);                    // [64] similarity of each neighbour
+  int *w_cnt = reinterpret_cast<int *>(meta + 64 * 8);              // [16] prediction bytes per warp
   int *w_off = w_cnt + 16;                                          // [16] exclusive prefix of w_cnt
   int *w_nz = w_cnt + 32;                                           // [16] non-zero predictions per warp
   unsigned long long *s_base = reinterpret_cast<unsigned long long *>(w_cnt + 48);
   unsigned *tie_bits = reinterpret_cast<unsigned *>(w_cnt + 64);    // [26 * 32] MILLI: single-rater half-way bits
+  // [64] per neighbour, one 16-byte broadcast load: {even-aligned first position, first position, end position,
+  // MILLI increment}; positions are 32-bit (nnz < 2^31, checked by the host side)
+  int4 *meta4 = reinterpret_cast<int4 *>(w_cnt + 64 + kTieBitWords);
   acc_t zero;
   if constexpr (MILLI) zero = 0ull; else zero = Acc{0.0, 0.0};
   for (int j = tid; j < tile; j += kSpThreads) acc[j] = zero;
   if constexpr (MILLI)
     for (int w = tid; w < kTieBitWords; w += kSpThreads) tie_bits[w] = tie_bits_g[w];
+  if (tid < 64) meta4[tid] = make_int4(0, 0, 0, 0);
   __syncthreads();
 
   const unsigned lt = lanemask_lt();
@@ -171,10 +170,10 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
   unsigned long long *cursor = cursors + region;
   const int64_t region_base = int64_t(region) * region_cap;
 
-  auto add = [&](int j, int r, int g) {          // one rating r of neighbour slot g into column slot j
+  // one rating r of a neighbour into column slot j (inc: MILLI increment milli | 1 << 20; g: neighbour slot)
+  auto add = [&](int j, int r, unsigned inc, int g) {
     if constexpr (MILLI) {
       // u64 = r (8 bits, meaningful for a single rater) | N = sum r*milli (24) | raters (12) | D = sum milli (20)
-      const unsigned inc = m_inc[g];
       acc[j] += (static_cast<unsigned long long>((unsigned(r) << 24) + unsigned(r) * (inc & 0xFFFFFu)) << 32) | inc;
     } else {
       const double s = m_s[g];
@@ -193,69 +192,77 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
     const int q0 = t * tile;
     const int width = min(tile, Q - q0);
     const int c = min(u_cnt[ul], ku);
-    if (tid < c) {
-      const int v = u_idx[ul * ku + tid];
-      const int64_t *tp = tilepos + int64_t(v) * stride + t;
-      const int64_t a = __ldg(tp), e = __ldg(tp + 1);
-      m_a[tid] = a;
-      m_n[tid] = int(e - a);
-      if constexpr (MILLI) {
-        const int milli = u_milli[ul * ku + tid];
-        m_s[tid] = double(milli) / 1000.0;        // == the table's double (u_val == u_milli / 1000.0)
-        m_inc[tid] = unsigned(milli) | (1u << 20);
-      } else {
-        m_s[tid] = u_val[ul * ku + tid];
+    const int c4 = round_up(c, kSpAhead);         // padded with empty neighbours: no bounds checks in the loop
+    bool is_long = false;
+    if (tid < c4) {
+      int4 mt = make_int4(0, 0, 0, 0);
+      if (tid < c) {
+        const int v = u_idx[ul * ku + tid];
+        const int64_t *tp = tilepos + int64_t(v) * stride + t;
+        const int64_t a = __ldg(tp), e = __ldg(tp + 1);
+        unsigned inc = 0;
+        if constexpr (MILLI) {
+          const int milli = u_milli[ul * ku + tid];
+          m_s[tid] = double(milli) / 1000.0;        // == the table's double (u_val == u_milli / 1000.0)
+          inc = unsigned(milli) | (1u << 20);
+        } else {
+          m_s[tid] = u_val[ul * ku + tid];
+        }
+        mt = make_int4(int(a) & ~1, int(a), int(e), int(inc));
+        is_long = (int(a) & ~1) + kSpSpan < int(e);
       }
+      meta4[tid] = mt;
     }
     const int64_t own_a = __ldg(tilepos + ug * stride + t), own_e = __ldg(tilepos + ug * stride + t + 1);
-    __syncthreads();
+    const bool any_long = __syncthreads_or(is_long);
 
-    // ---- neighbours in table order, kSpAhead at a time: the NEXT group's entries are loaded into
-    //      registers before the current group is accumulated.  A thread takes two consecutive CSR
-    //      positions of the segment (one 8-byte column load + one 2-byte rating load from an even position).
-    int2 ncol[kSpAhead];
-    unsigned nrat[kSpAhead];
-    auto fetch = [&](int g0) {
+    // ---- neighbours in table order, kSpAhead at a time, two register sets in ping-pong: the NEXT group's
+    //      entries are being loaded while the current group is accumulated.  A thread takes two consecutive
+    //      CSR positions of a segment (one 8-byte column load + one 2-byte rating load from an even position).
+    struct Group { int2 col[kSpAhead]; unsigned rat[kSpAhead]; unsigned inc[kSpAhead]; };
+    auto load_group = [&](Group &G, int g0) {
 #pragma unroll
       for (int g = 0; g < kSpAhead; ++g) {
-        nrat[g] = 0u;
-        ncol[g] = make_int2(0, 0);
-        if (g0 + g < c) {
-          const int64_t a = m_a[g0 + g];
-          const int64_t e = a + m_n[g0 + g];
-          const int64_t p0 = (a & ~int64_t(1)) + 2 * tid;        // even position
-          if (p0 < e) {
-            ncol[g] = *reinterpret_cast<const int2 *>(colidx + p0);
-            unsigned rr = *reinterpret_cast<const unsigned short *>(val + p0);
-            if (p0 < a) rr &= 0xFF00u;                            // position before the segment
-            if (p0 + 1 >= e) rr &= 0x00FFu;                       // position after the segment
-            nrat[g] = rr;
-          }
+        const int4 mt = meta4[g0 + g];
+        const int p0 = mt.x + 2 * tid;
+        G.inc[g] = unsigned(mt.w);
+        G.rat[g] = 0u;
+        G.col[g] = make_int2(0, 0);
+        if (p0 < mt.z) {
+          G.col[g] = *reinterpret_cast<const int2 *>(colidx + p0);
+          unsigned rr = *reinterpret_cast<const unsigned short *>(val + p0);
+          if (p0 < mt.y) rr &= 0xFF00u;                           // position before the segment
+          if (p0 + 1 >= mt.z) rr &= 0x00FFu;                      // position after the segment
+          G.rat[g] = rr;
         }
       }
     };
-    fetch(0);
-    for (int g0 = 0; g0 < c; g0 += kSpAhead) {
-      int2 ccol[kSpAhead];
-      unsigned crat[kSpAhead];
-#pragma unroll
-      for (int g = 0; g < kSpAhead; ++g) { ccol[g] = ncol[g]; crat[g] = nrat[g]; }
-      if (g0 + kSpAhead < c) fetch(g0 + kSpAhead);
+    auto process_group = [&](const Group &G, int g0) {
 #pragma unroll
       for (int g = 0; g < kSpAhead; ++g) {
-        if (g0 + g < c) {                           // block-uniform
-          if (crat[g] & 0xFFu) add(ccol[g].x - q0, int(crat[g] & 0xFFu), g0 + g);
-          if (crat[g] >> 8) add(ccol[g].y - q0, int(crat[g] >> 8), g0 + g);
-          const int64_t a = m_a[g0 + g];
-          const int64_t e = a + m_n[g0 + g];
-          if ((a & ~int64_t(1)) + kSpSpan < e) {    // long segment: the rest straight from memory
+        if (G.rat[g] & 0xFFu) add(G.col[g].x - q0, int(G.rat[g] & 0xFFu), G.inc[g], g0 + g);
+        if (G.rat[g] >> 8) add(G.col[g].y - q0, int(G.rat[g] >> 8), G.inc[g], g0 + g);
+        if (any_long) {                             // block-uniform; the rest of a long segment straight from memory
+          const int4 mt = meta4[g0 + g];
 #pragma unroll 1
-            for (int64_t x = (a & ~int64_t(1)) + kSpSpan + tid; x < e; x += kSpThreads) {
-              const int r = val[x];
-              if (r != 0) add(__ldg(colidx + x) - q0, r, g0 + g);
-            }
+          for (int x = mt.x + kSpSpan + tid; x < mt.z; x += kSpThreads) {
+            const int r = val[x];
+            if (r != 0) add(__ldg(colidx + x) - q0, r, unsigned(mt.w), g0 + g);
           }
-          __syncthreads();
+        }
+        __syncthreads();
+      }
+    };
+    {
+      Group A, B;
+      if (c4 > 0) load_group(A, 0);
+      for (int g0 = 0; g0 < c4; g0 += 2 * kSpAhead) {
+        const bool more = g0 + kSpAhead < c4;
+        if (more) load_group(B, g0 + kSpAhead);
+        process_group(A, g0);
+        if (more) {
+          if (g0 + 2 * kSpAhead < c4) load_group(A, g0 + 2 * kSpAhead);
+          process_group(B, g0 + kSpAhead);
         }
       }
     }
@@ -372,7 +379,7 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
                   tie_list[slot] = make_ulonglong2((unsigned long long)(region_base + pos),
                                                    ((unsigned long long)(unsigned)ul << 32) | unsigned(q0 + int(wj[x])));
                 else
-                  pv = resolve_tie(colidx, val, m_a, m_n, m_s, c, q0 + int(wj[x]));   // list full: settle here
+                  pv = resolve_tie(colidx, val, meta4, m_s, c, q0 + int(wj[x]));   // list full: settle here
               }
               if (cols_mode == 1) reinterpret_cast<uint16_t *>(cols)[region_base + pos] = uint16_t(q0 + int(wj[x]));
               else if (cols_mode == 0) cols[region_base + pos] = q0 + int(wj[x]);

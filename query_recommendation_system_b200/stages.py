@@ -232,6 +232,8 @@ def predict_sparse(rowptr, colidx, val, Q: int, u_tab: Table, user_base: int, n_
     u_milli: int32 table with u_val == u_milli / 1000.0 exactly (from topk_tables(want_milli=True)) selects
     the exact-integer accumulation kernel; results are identical."""
     _need_cuda(rowptr, colidx, val, u_milli, *u_tab)
+    if colidx.numel() >= 2 ** 31:
+        raise _lib.QrsError("qrs_predict_sparse addresses the ratings CSR with 32-bit positions (nnz < 2^31 per GPU)")
     lib = _lib.load()
     dev = rowptr.device
     U = rowptr.numel() - 1
