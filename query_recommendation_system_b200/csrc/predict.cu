@@ -330,7 +330,11 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
             } else {
               const unsigned N = hi & 0xFFFFFFu;
               const unsigned X = 7u * N + 180u * D, Y = 10u * D;    // x = X / Y = 0.7 * N / D + 18
-              const unsigned q = X / Y, rem2 = 2u * (X - q * Y);
+              // q = X / Y via a float estimate (q < 256, estimate off by at most one) corrected exactly
+              unsigned q = unsigned(__fdividef(float(X), float(Y)));
+              int rem = int(X - q * Y);
+              if (rem < 0) { --q; rem += int(Y); } else if (rem >= int(Y)) { ++q; rem -= int(Y); }
+              const unsigned rem2 = 2u * unsigned(rem);
               if (rem2 < Y) p = int(q);
               else if (rem2 > Y) p = int(q) + 1;
               else p = kTieMarker;   // exact half-way: settled after the slice position is known (pass 3)
