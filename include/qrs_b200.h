@@ -206,13 +206,13 @@ int qrs_predict_dense(const int64_t *rowptr, const int32_t *colidx, const uint8_
  * region's capacity/n_regions entries are dropped (the count still advances),
  * and row_start is an absolute index into cols/preds.  n_regions = 1 gives one
  * dense buffer.  cols/preds may be NULL with capacity 0 for a counting pass. */
-/* How the predicted columns are reported:
- *   QRS_COLS_I32 / QRS_COLS_U16: cols is int32[capacity] / uint16[capacity] (Q <= 65536), one entry per
- *       non-zero prediction, aligned with preds;
- *   QRS_COLS_BITMAP: cols is uint32[n_users * nt * tile / 32], zeroed by the caller: bit c of
- *       word (t*nt + tile_index) * tile/32 + c/32 marks column tile_index*tile + c as touched by a neighbour;
- *       preds then holds one byte per TOUCHED column in ascending order (0 = no prediction), row_cnt
- *       counts those bytes, and cursors[n_regions] (one extra u64) receives the number of non-zero ones. */
+/* Every column a neighbour contributed to (and the user has not rated) gets ONE prediction byte in the
+ * slice, ascending in column; with u_milli the byte is never 0, with u_val it is 0 when the similarity
+ * sums cancel (weightSum == 0 or prediction 0, recommender.py:44).  row_cnt counts those bytes and
+ * cursors[n_regions] (one extra u64) receives the number of non-zero ones.  How the columns are reported:
+ *   QRS_COLS_I32 / QRS_COLS_U16: cols is int32[capacity] / uint16[capacity] (Q <= 65536), aligned with preds;
+ *   QRS_COLS_BITMAP: cols is uint32[n_users * nt * tile / 32], zeroed by the caller: bit c of word
+ *       (t*nt + tile_index) * tile/32 + c/32 marks column tile_index*tile + c as having a byte in preds. */
 #define QRS_COLS_I32 0
 #define QRS_COLS_U16 1
 #define QRS_COLS_BITMAP 2

@@ -76,23 +76,13 @@ constexpr int kSpSpan = 2 * kSpThreads;   // CSR positions one CTA pass covers: 
 // columns each warp sweeps in the output passes; the per-warp lists live at [w * range, (w + 1) * range)
 __host__ __device__ constexpr int sparse_warp_range(int tile) { return round_up(ceil_div(tile, kSpWarpsCta), 32); }
 
-// shared memory of one CTA: acc[tile] | u16 jlist[8*range] | u8 plist[8*range] | metadata
+// shared memory of one CTA: acc[tile] | u16 jlist[warps*range] | metadata
 __host__ __device__ constexpr size_t sparse_cta_bytes(int tile, bool milli) {
   return round_up<size_t>(size_t(tile) * (milli ? 8 : 16), 16) +
-         round_up<size_t>(size_t(sparse_warp_range(tile)) * kSpWarpsCta * 3, 16) + 64 * 8 + 256 + 26 * 32 * 4 + 64 * 16;
+         round_up<size_t>(size_t(sparse_warp_range(tile)) * kSpWarpsCta * 2, 16) + 64 * 8 + 256 + 26 * 32 * 4 + 64 * 16;
 }
 
 constexpr int kTieBitWords = 26 * 32;   // single-rater half-way bits: 26 ratings (5, 15, .., 255) x 1024 milli
-constexpr int kTieMarker = 255;   // not a possible prediction: ratings <= 255 give at most 0.7 * 255 + 18 = 196.5
-
-// bits of a 16-bit value moved to the even positions of a 32-bit word
-__device__ __forceinline__ unsigned spread16(unsigned x) {
-  x = (x | (x << 8)) & 0x00FF00FFu;
-  x = (x | (x << 4)) & 0x0F0F0F0Fu;
-  x = (x | (x << 2)) & 0x33333333u;
-  x = (x | (x << 1)) & 0x55555555u;
-  return x;
-}
 
 __device__ __forceinline__ int predict_from(double num, double den) {
   return den != 0.0 ? hybrid_rule(0.0, num / den) : 0;
@@ -143,12 +133,10 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
   acc_t *acc = reinterpret_cast<acc_t *>(smem_raw);
   unsigned char *ptr = smem_raw + round_up<size_t>(size_t(tile) * (MILLI ? 8 : 16), 16);
   uint16_t *jlist = reinterpret_cast<uint16_t *>(ptr);
-  uint8_t *plist = reinterpret_cast<uint8_t *>(jlist + size_t(range) * kSpWarpsCta);
-  unsigned char *meta = ptr + round_up<size_t>(size_t(range) * kSpWarpsCta * 3, 16);
+  unsigned char *meta = ptr + round_up<size_t>(size_t(range) * kSpWarpsCta * 2, 16);
   double *m_s = reinterpret_cast<double *>(meta);                    // [64] similarity of each neighbour
   int *w_cnt = reinterpret_cast<int *>(meta + 64 * 8);              // [16] prediction bytes per warp
   int *w_off = w_cnt + 16;                                          // [16] exclusive prefix of w_cnt
-  int *w_nz = w_cnt + 32;                                           // [16] non-zero predictions per warp
   unsigned long long *s_base = reinterpret_cast<unsigned long long *>(w_cnt + 48);
   unsigned *tie_bits = reinterpret_cast<unsigned *>(w_cnt + 64);    // [26 * 32] MILLI: single-rater half-way bits
   // [64] per neighbour, one 16-byte broadcast load: {even-aligned first position, first position, end position,
@@ -185,6 +173,7 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
   };
 
   const int64_t items = n_users * nt;
+  long long nz_total = 0;
   for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
     const int64_t ul = item / nt;                 // local user
     const int t = int(item - ul * nt);
@@ -272,56 +261,71 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
       if (val[x] != 0) acc[__ldg(colidx + x) - q0] = zero;
     __syncthreads();
 
-    // ---- pass 1 (per warp, its own column range): ascending list of the touched columns, two per lane
+    // ---- pass 1 (per warp, its own column range): ascending list of the columns that get a prediction byte.
+    //      A lane looks at columns j0 + lane and j0 + 32 + lane, so the two ballots ARE the bitmap words.
     const bool bitmap = cols_mode == 2;
     const int j_lo = warp * range, j_hi = min(width, j_lo + range);
     uint16_t *wj = jlist + j_lo;
-    uint8_t *wp = plist + j_lo;
     int touched = 0;
 #pragma unroll 2
     for (int j0 = j_lo; j0 < j_hi; j0 += 64) {
-      const int j = j0 + 2 * lane;
+      const int ja = j0 + lane, jb = ja + 32;
       bool hit0 = false, hit1 = false;
       if constexpr (MILLI) {
-        if (j + 1 < j_hi) {
-          const ulonglong2 x = *reinterpret_cast<const ulonglong2 *>(acc + j);   // j is even, acc is 16-byte aligned
-          hit0 = x.x != 0ull;
-          hit1 = x.y != 0ull;
-        } else if (j < j_hi) {
-          hit0 = acc[j] != 0ull;
+        // listed iff D != 0 (then the prediction is >= 18); an accumulator whose similarities are all 0 is
+        // cleared right here and predicts nothing (weightSum == 0, recommender.py:44)
+        if (ja < j_hi) {
+          const unsigned long long x = acc[ja];
+          hit0 = (unsigned(x) & 0xFFFFFu) != 0u;
+          if (!hit0 && x != 0ull) acc[ja] = 0ull;
+        }
+        if (jb < j_hi) {
+          const unsigned long long x = acc[jb];
+          hit1 = (unsigned(x) & 0xFFFFFu) != 0u;
+          if (!hit1 && x != 0ull) acc[jb] = 0ull;
         }
       } else {
-        if (j < j_hi) { const Acc x = acc[j]; hit0 = x.den != 0.0 || x.num != 0.0; }
-        if (j + 1 < j_hi) { const Acc x = acc[j + 1]; hit1 = x.den != 0.0 || x.num != 0.0; }
+        if (ja < j_hi) { const Acc x = acc[ja]; hit0 = x.den != 0.0 || x.num != 0.0; }
+        if (jb < j_hi) { const Acc x = acc[jb]; hit1 = x.den != 0.0 || x.num != 0.0; }
       }
       const unsigned m0 = __ballot_sync(kFull, hit0), m1 = __ballot_sync(kFull, hit1);
-      if (bitmap && lane < 2) {
-        // m0 / m1 hold the even / odd columns of this 64-column window: interleave them into two words
-        const unsigned e = lane == 0 ? (m0 & 0xFFFFu) : (m0 >> 16), o = lane == 0 ? (m1 & 0xFFFFu) : (m1 >> 16);
-        const int first_col = j0 + 32 * lane;
-        if (first_col < j_hi)
-          reinterpret_cast<unsigned *>(cols)[item * (tile >> 5) + (first_col >> 5)] = spread16(e) | (spread16(o) << 1);
-      }
-      const int before = touched + __popc(m0 & lt) + __popc(m1 & lt);
-      if (hit0) wj[before] = uint16_t(j);
-      if (hit1) wj[before + (hit0 ? 1 : 0)] = uint16_t(j + 1);
-      touched += __popc(m0) + __popc(m1);
+      if (bitmap && lane < 2 && j0 + 32 * lane < j_hi)
+        reinterpret_cast<unsigned *>(cols)[item * (tile >> 5) + (j0 >> 5) + lane] = lane == 0 ? m0 : m1;
+      const int n0 = __popc(m0);
+      if (hit0) wj[touched + __popc(m0 & lt)] = uint16_t(ja);
+      if (hit1) wj[touched + n0 + __popc(m1 & lt)] = uint16_t(jb);
+      touched += n0 + __popc(m1);
     }
-    __syncwarp();
-    // ---- pass 2: prediction of every touched column (dense lanes), accumulators back to zero
-    int total = 0;
+    if (lane == 0) w_cnt[warp] = touched;
+    __syncthreads();
+    if (tid == 0) {
+      int sum = 0;
+#pragma unroll
+      for (int w = 0; w < kSpWarpsCta; ++w) { w_off[w] = sum; sum += w_cnt[w]; }
+      unsigned long long base = 0;
+      if (sum > 0) base = atomicAdd(cursor, (unsigned long long)sum);
+      row_start[item] = region_base + int64_t(base);
+      row_cnt[item] = sum;
+      *s_base = base;
+    }
+    __syncthreads();
+    // ---- pass 2: one prediction byte per listed column, written straight into the reserved slice (ascending:
+    //      warp ranges are ascending, lists are ascending); accumulators back to zero
+    {
+      const int64_t wbase = int64_t(*s_base) + w_off[warp];
+      int nz = 0;
 #pragma unroll 2
-    for (int x0 = 0; x0 < touched; x0 += 32) {
-      const int x = x0 + lane;
-      int p = 0;
-      if (x < touched) {
-        const int j = wj[x];
-        const acc_t a = acc[j];
-        acc[j] = zero;
-        if constexpr (MILLI) {
-          const unsigned lo = unsigned(a), hi = unsigned(a >> 32);
-          const unsigned D = lo & 0xFFFFFu, raters = lo >> 20;
-          if (D != 0u) {
+      for (int x0 = 0; x0 < touched; x0 += 32) {
+        const int x = x0 + lane;
+        int p = 0;
+        if (x < touched) {
+          const int j = wj[x];
+          const acc_t a = acc[j];
+          acc[j] = zero;
+          bool tie = false;
+          if constexpr (MILLI) {
+            const unsigned lo = unsigned(a), hi = unsigned(a >> 32);
+            const unsigned D = lo & 0xFFFFFu, raters = lo >> 20;
             if (raters == 1u) {
               // one rater: x = (7r + 180) / 10 exactly; half-way cases take the fp64 chain's bit
               const unsigned r1 = hi >> 24, x10 = 7u * r1 + 180u, q = x10 / 10u, rem = x10 - 10u * q;
@@ -335,67 +339,35 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
               int rem = int(X - q * Y);
               if (rem < 0) { --q; rem += int(Y); } else if (rem >= int(Y)) { ++q; rem -= int(Y); }
               const unsigned rem2 = 2u * unsigned(rem);
-              if (rem2 < Y) p = int(q);
-              else if (rem2 > Y) p = int(q) + 1;
-              else p = kTieMarker;   // exact half-way: settled after the slice position is known (pass 3)
+              p = int(q) + (rem2 > Y ? 1 : 0);
+              tie = rem2 == Y;          // exact half-way: the reference's fp64 rounding noise decides (fix-up kernel)
             }
+          } else {
+            p = predict_from(a.num, a.den);
           }
-        } else {
-          p = predict_from(a.num, a.den);
-        }
-        wp[x] = uint8_t(p);
-      }
-      total += __popc(__ballot_sync(kFull, p != 0));
-    }
-    const int nonzero = total;
-    if (bitmap) total = touched;      // bitmap form: one prediction byte per touched column (0 = no prediction)
-    if (lane == 0) { w_cnt[warp] = total; w_nz[warp] = nonzero; }
-    __syncthreads();
-    if (tid == 0) {
-      int sum = 0, nz = 0;
-#pragma unroll
-      for (int w = 0; w < kSpWarpsCta; ++w) { w_off[w] = sum; sum += w_cnt[w]; nz += w_nz[w]; }
-      unsigned long long base = 0;
-      if (sum > 0) base = atomicAdd(cursor, (unsigned long long)sum);
-      if (bitmap && nz > 0) atomicAdd(cursors + n_regions, (unsigned long long)nz);   // non-zero predictions (stats)
-      row_start[item] = region_base + int64_t(base);
-      row_cnt[item] = sum;
-      *s_base = base;
-    }
-    __syncthreads();
-    // ---- pass 3: the slice, ascending in column (warp ranges are ascending, lists are ascending)
-    {
-      const int64_t base = int64_t(*s_base) + w_off[warp];
-      if (total > 0 && base < region_cap) {
-        int written = 0;
-        for (int x0 = 0; x0 < touched; x0 += 32) {
-          const int x = x0 + lane;
-          const int p = x < touched ? int(wp[x]) : 0;
-          const bool keep = bitmap ? x < touched : p != 0;
-          const unsigned m = __ballot_sync(kFull, keep);
-          if (keep) {
-            const int64_t pos = base + written + __popc(m & lt);
-            if (pos < region_cap) {
-              int pv = p;
-              if (MILLI && p == kTieMarker) {
-                const unsigned long long slot = atomicAdd(tie_count, 1ull);
-                if (int64_t(slot) < tie_capacity)
-                  tie_list[slot] = make_ulonglong2((unsigned long long)(region_base + pos),
-                                                   ((unsigned long long)(unsigned)ul << 32) | unsigned(q0 + int(wj[x])));
-                else
-                  pv = resolve_tie(colidx, val, meta4, m_s, c, q0 + int(wj[x]));   // list full: settle here
-              }
-              if (cols_mode == 1) reinterpret_cast<uint16_t *>(cols)[region_base + pos] = uint16_t(q0 + int(wj[x]));
-              else if (cols_mode == 0) cols[region_base + pos] = q0 + int(wj[x]);
-              preds[region_base + pos] = uint8_t(pv);
+          const int64_t pos = wbase + x;
+          if (pos < region_cap) {
+            if (MILLI && tie) {
+              const unsigned long long slot = atomicAdd(tie_count, 1ull);
+              if (int64_t(slot) < tie_capacity)
+                tie_list[slot] = make_ulonglong2((unsigned long long)(region_base + pos),
+                                                 ((unsigned long long)(unsigned)ul << 32) | unsigned(q0 + j));
+              else
+                p = resolve_tie(colidx, val, meta4, m_s, c, q0 + j);   // list full: settle here
             }
+            if (cols_mode == 1) reinterpret_cast<uint16_t *>(cols)[region_base + pos] = uint16_t(q0 + j);
+            else if (cols_mode == 0) cols[region_base + pos] = q0 + j;
+            preds[region_base + pos] = uint8_t(p);
           }
-          written += __popc(m);
         }
+        nz += __popc(__ballot_sync(kFull, p != 0));
       }
+      nz_total += nz;
     }
     __syncthreads();
   }
+  // non-zero predictions of this launch (statistics): one atomic per warp
+  if (lane == 0 && nz_total > 0) atomicAdd(cursors + n_regions, (unsigned long long)nz_total);
 }
 
 // ------------------------------------------------------------------ dense form

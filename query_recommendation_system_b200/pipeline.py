@@ -206,12 +206,12 @@ class LshCfPipeline:
                 tab = (idx[lo:hi], v[lo:hi], cnt[lo:hi])
                 mil = milli[lo:hi] if self.integer_predict else None
                 while True:
-                    rs, rc, cols, preds, cursors = st.predict_sparse(rowptr_all, colidx_all, val_all, self.m, tab,
+                    rs, rc, cols, preds, cursors, nzc = st.predict_sparse(rowptr_all, colidx_all, val_all, self.m, tab,
                                                                      pred_base + lo, hi - lo, tile, rcap * regions,
                                                                      u_milli=mil, n_regions=regions,
                                                                      cols_mode=self.cols_mode)
-                    demand = cursors.cpu()
-                    nonzero = int(demand[-1].item()) if self.cols_mode == 2 else int(demand.sum().item())
+                    demand = torch.cat([cursors, nzc]).cpu()
+                    nonzero = int(demand[-1].item())
                     demand = demand[:regions]
                     need = int(demand.max().item())
                     if need <= rcap:

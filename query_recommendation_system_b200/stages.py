@@ -227,8 +227,8 @@ def predict_sparse(rowptr, colidx, val, Q: int, u_tab: Table, user_base: int, n_
                    capacity: int, out_cols: Optional[torch.Tensor] = None, out_preds: Optional[torch.Tensor] = None,
                    u_milli: Optional[torch.Tensor] = None, n_regions: int = 1, cols_mode: int = 0):
     """User-branch predictions in sparse form.  Returns (row_start int64[n_users, nt],
-    row_cnt int32[n_users, nt], cols int32[capacity], preds uint8[capacity], cursors int64[n_regions] on
-    device = entries requested per region of capacity // n_regions entries).
+    row_cnt int32[n_users, nt], cols, preds uint8[capacity], cursors int64[n_regions] on device = entries
+    requested per region of capacity // n_regions entries, nonzero int64[1] = non-zero predictions).
     u_milli: int32 table with u_val == u_milli / 1000.0 exactly (from topk_tables(want_milli=True)) selects
     the exact-integer accumulation kernel; results are identical."""
     _need_cuda(rowptr, colidx, val, u_milli, *u_tab)
@@ -259,7 +259,7 @@ def predict_sparse(rowptr, colidx, val, Q: int, u_tab: Table, user_base: int, n_
                                  ptr(cols), cols_mode, ptr(preds), capacity, n_regions, ptr(cursor),
                                  _stream()),
           "qrs_predict_sparse")
-    return row_start, row_cnt, cols, preds, cursor[:n_regions] if cols_mode != 2 else cursor
+    return row_start, row_cnt, cols, preds, cursor[:n_regions], cursor[n_regions:]
 
 
 # ---------------------------------------------------------------------- multi-GPU plumbing

@@ -157,7 +157,8 @@ def predict_sparse(rowptr, colidx, val, Q, u_tab, user_base, n_users, tile, capa
     w = min(capacity, pos)
     ct[:w] = torch.from_numpy(cols[:w].astype(np.int32))
     pt[:w] = torch.from_numpy(preds[:w].astype(np.uint8))
-    return torch.from_numpy(rs), torch.from_numpy(rc), ct, pt, torch.tensor([pos], dtype=torch.int64)
+    return (torch.from_numpy(rs), torch.from_numpy(rc), ct, pt, torch.tensor([pos], dtype=torch.int64),
+            torch.tensor([pos], dtype=torch.int64))
 
 
 def gather_rows(rowptr, colidx, val, rows, out_off, total):

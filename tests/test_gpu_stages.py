@@ -363,9 +363,9 @@ def test_predict_sparse_matches_oracle(tile, integer, tie_heavy):
     sl = slice(user_base, user_base + n_users)
     tab = (cu(idx[sl]), cu(sims[sl]), cu(cnt[sl]))
     milli = cu(np.rint(sims[sl] * 1000).astype(np.int32)) if integer else None
-    rs, rc, cols, preds, cursor = stages.predict_sparse(cu(rowptr), cu(colidx), cu(val), m, tab, user_base, n_users,
+    rs, rc, cols, preds, cursor, nz = stages.predict_sparse(cu(rowptr), cu(colidx), cu(val), m, tab, user_base, n_users,
                                                         tile, capacity=total + 5, u_milli=milli)
-    assert int(cursor.item()) == total
+    assert int(cursor.item()) == total and int(nz.item()) == total
     rs, rc, cols, preds = rs.cpu().numpy(), rc.cpu().numpy(), cols.cpu().numpy(), preds.cpu().numpy()
     n_tie = 0
     for t in range(n_users):
@@ -374,7 +374,7 @@ def test_predict_sparse_matches_oracle(tile, integer, tie_heavy):
         rcols, rpreds = ref[user_base + t]
         assert np.array_equal(gc, rcols) and np.array_equal(gp.astype(np.int64), rpreds)
     # counting pass (capacity 0) reports the same total without writing
-    _, _, _, _, cursor0 = stages.predict_sparse(cu(rowptr), cu(colidx), cu(val), m, tab, user_base, n_users, tile, 0,
+    _, _, _, _, cursor0, _ = stages.predict_sparse(cu(rowptr), cu(colidx), cu(val), m, tab, user_base, n_users, tile, 0,
                                                 u_milli=milli)
     assert int(cursor0.item()) == total
 
@@ -413,11 +413,11 @@ def test_predict_sparse_regions_and_overflow():
     tab = (cu(idx), cu(sims), cu(cnt))
     milli = cu(np.rint(sims * 1000).astype(np.int32))
     regions = 8
-    _, _, _, _, demand = stages.predict_sparse(cu(rowptr), cu(colidx), cu(val), m, tab, 0, n, 512, 0,
+    _, _, _, _, demand, _ = stages.predict_sparse(cu(rowptr), cu(colidx), cu(val), m, tab, 0, n, 512, 0,
                                                u_milli=milli, n_regions=regions)
     assert int(demand.sum().item()) == total
     rcap = int(demand.max().item())
-    rs, rc, cols, preds, cur = stages.predict_sparse(cu(rowptr), cu(colidx), cu(val), m, tab, 0, n, 512, rcap * regions,
+    rs, rc, cols, preds, cur, nz = stages.predict_sparse(cu(rowptr), cu(colidx), cu(val), m, tab, 0, n, 512, rcap * regions,
                                                      u_milli=milli, n_regions=regions)
     assert torch.equal(cur, demand)
     rs, rc, cols, preds = rs.cpu().numpy(), rc.cpu().numpy(), cols.cpu().numpy(), preds.cpu().numpy()
