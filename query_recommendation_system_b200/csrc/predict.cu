@@ -68,7 +68,7 @@ struct AccOf { using type = Acc; };
 template <>
 struct AccOf<true> { using type = unsigned long long; };
 
-constexpr int kSpThreads = 288;   // 9 warps: two entries per thread cover a 576-entry neighbour segment
+constexpr int kSpThreads = 384;   // 12 warps: two entries per thread cover a 768-entry neighbour segment
 constexpr int kSpWarpsCta = kSpThreads / 32;
 constexpr int kSpAhead = 4;    // neighbours whose segment loads are in flight together (x2: double-buffered)
 constexpr int kSpSpan = 2 * kSpThreads;   // CSR positions one CTA pass covers: two consecutive entries per thread

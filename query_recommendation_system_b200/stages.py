@@ -208,14 +208,14 @@ def predict_dense(rowptr, colidx, val, Q: int, q_tab: Optional[Table], u_tab: Op
     return out
 
 
-PREDICT_SEGMENT_TARGET = 520.0     # ~0.9 x the 576 entries one CTA pass covers (csrc/predict.cu kSpSpan)
+PREDICT_SEGMENT_TARGET = 690.0     # ~0.9 x the 768 entries one CTA pass covers (csrc/predict.cu kSpSpan)
 
 
 def choose_predict_tile(Q: int, avg_len: float = 0.0, integer_tables: bool = True) -> int:
-    """Column tile of the sparse predictor.  One CTA of 288 threads accumulates one (user, tile) and takes two
-    consecutive entries of a neighbour's segment per thread (576 per pass; longer segments take a slower tail
+    """Column tile of the sparse predictor.  One CTA of 384 threads accumulates one (user, tile) and takes two
+    consecutive entries of a neighbour's segment per thread (768 per pass; longer segments take a slower tail
     loop): the fewest equal tiles such that a tile fits one CTA's shared memory and an average row leaves
-    <= ~520 entries in it."""
+    <= ~690 entries in it."""
     max_tile = _lib.load().qrs_predict_max_tile(1 if integer_tables else 0)
     nt = max(1, math.ceil(Q / max_tile))
     while avg_len > 0 and avg_len / nt > PREDICT_SEGMENT_TARGET and math.ceil(Q / nt) > 256:
