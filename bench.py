@@ -294,6 +294,20 @@ def main():
     roofline.update({"kernel": kernel_name, "stage": dominant, "peak_source": peak_src + " (of measured)",
                      "traffic": traffic, "traffic_source": "profiles/r1_traffic.json (ncu --set full, same command)"})
 
+    # ---------------------------------------------------------------- f-2 extra: per-user top-10 recommendations
+    topn = None
+    if world == 1 and out.pred_row_start is not None:
+        for _ in range(2):
+            pipe.recommend_top_n(out, 10)
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0e.record()
+        for _ in range(5):
+            pipe.recommend_top_n(out, 10)
+        t1e.record()
+        torch.cuda.synchronize()
+        topn = {"ms": t0e.elapsed_time(t1e) / 5, "N": 10,
+                "note": "qrs_recommend_topn over the sparse predictions of the last step (outside the timed step)"}
+
     # ---------------------------------------------------------------- e2e: host buffers in, host results out
     runner = HostRunner(pipe)
     h_rowptr, h_colidx, h_val = [x.cpu().pin_memory() for x in (rowptr, colidx, val)]
@@ -337,7 +351,7 @@ def main():
                     "h2d_bytes_per_step": runner.h2d_bytes, "d2h_bytes_per_step": runner.d2h_bytes, "steps": e2e_steps,
                     "call": "pipeline.HostRunner(pipe, chunks=4, cols_format=auto)(rowptr, colidx, val) with pinned host tensors; returns pinned "
                             "sparse predictions + neighbour tables"},
-            "gpu_launches": int(launches), "clocks": clocks,
+            "gpu_launches": int(launches), "clocks": clocks, "recommend_top_n": topn,
         }
         if world == 1 and not args.no_cpu_baseline:
             tc, cc = run_cpu_port(args.config, args.cpu_sets)

@@ -233,6 +233,15 @@ int qrs_predict_sparse(const int64_t *rowptr, const int32_t *colidx, const uint8
                        void *cols, int32_t cols_mode /* QRS_COLS_* */, uint8_t *preds,
                        int64_t capacity, int32_t n_regions, unsigned long long *cursors, void *stream);
 
+/* ------------------------------------------------------ f-2: per-user top-N recommendations
+ * Replaces what Recommender.top_k_queries serves (recommender.py:345-374): per user the N largest non-zero
+ * predictions among the cells just predicted, from the sparse output of qrs_predict_sparse (QRS_COLS_I32 or
+ * QRS_COLS_U16), ordered prediction descending, column ascending.
+ *   out_idx int32[n_users*N] (-1 padded), out_val uint8[n_users*N] (0 padded), out_cnt int32[n_users]; N <= 64. */
+int qrs_recommend_topn(const int64_t *row_start, const int32_t *row_cnt, const void *cols, int32_t cols_mode,
+                       const uint8_t *preds, int64_t n_users, int32_t nt, int32_t N,
+                       int32_t *out_idx, uint8_t *out_val, int32_t *out_cnt, void *stream);
+
 /* ------------------------------------------------------ multi-GPU plumbing
  * Rows of the ratings CSR are sharded across GPUs; the prediction gathers neighbour rows
  * (recommender.py:320), so rows requested by other ranks are packed for sending:

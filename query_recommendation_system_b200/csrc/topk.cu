@@ -3,6 +3,7 @@
 // (similarity descending, neighbour id ascending) in registers with a 64-wide bitonic
 // network — two keys per lane, never touching shared or local memory.
 #include "common.cuh"
+#include "bitonic.cuh"
 
 namespace qrs {
 
@@ -35,49 +36,6 @@ fill_kernel(const uint64_t *__restrict__ pairs, const int *__restrict__ sim_mill
   }
 }
 
-// compare-exchange step of the 64-key network (key e = lane + 32*slot)
-__device__ __forceinline__ void cx_shfl(uint64_t &x, int j, bool ascending, int lane) {
-  const uint64_t other = __shfl_xor_sync(kFull, x, j);
-  const bool lower = (lane & j) == 0;
-  const uint64_t mn = x < other ? x : other, mx = x < other ? other : x;
-  x = (lower == ascending) ? mn : mx;
-}
-__device__ __forceinline__ void cx_local(uint64_t &a, uint64_t &b, bool ascending) {
-  const uint64_t mn = a < b ? a : b, mx = a < b ? b : a;
-  a = ascending ? mn : mx;
-  b = ascending ? mx : mn;
-}
-__device__ __forceinline__ void bitonic_sort64(uint64_t &x0, uint64_t &x1, int lane) {
-#pragma unroll
-  for (int k = 2; k <= 32; k <<= 1) {
-#pragma unroll
-    for (int j = k >> 1; j >= 1; j >>= 1) {
-      // slot 0 holds e = lane, slot 1 holds e = lane + 32; (e & k) is the same for both when k <= 16,
-      // and for k == 32 slot 1 runs descending
-      const bool asc0 = (lane & k) == 0;
-      const bool asc1 = k == 32 ? false : asc0;
-      cx_shfl(x0, j, k == 32 ? true : asc0, lane);
-      cx_shfl(x1, j, asc1, lane);
-    }
-  }
-  // k = 64: everything ascending; j = 32 is the in-thread exchange
-  cx_local(x0, x1, true);
-#pragma unroll
-  for (int j = 16; j >= 1; j >>= 1) {
-    cx_shfl(x0, j, true, lane);
-    cx_shfl(x1, j, true, lane);
-  }
-}
-// sorts a bitonic 64-sequence ascending
-__device__ __forceinline__ void bitonic_merge64(uint64_t &x0, uint64_t &x1, int lane) {
-  cx_local(x0, x1, true);
-#pragma unroll
-  for (int j = 16; j >= 1; j >>= 1) {
-    cx_shfl(x0, j, true, lane);
-    cx_shfl(x1, j, true, lane);
-  }
-}
-
 __global__ void __launch_bounds__(256)
 select_kernel(const uint64_t *__restrict__ adj, const uint64_t *__restrict__ row_off, int64_t n_rows, int k,
               int *__restrict__ idx, double *__restrict__ val, int *__restrict__ milli, int *__restrict__ cnt) {
@@ -91,17 +49,7 @@ select_kernel(const uint64_t *__restrict__ adj, const uint64_t *__restrict__ row
     for (uint64_t base = lo; base < hi; base += 64) {
       uint64_t n0 = base + lane < hi ? adj[base + lane] : INF;
       uint64_t n1 = base + 32 + lane < hi ? adj[base + 32 + lane] : INF;
-      bitonic_sort64(n0, n1, lane);
-      if (base == lo) {
-        h0 = n0; h1 = n1;
-      } else {
-        // lowest 64 of two ascending lists: min(h[e], n[63 - e]) is bitonic
-        const uint64_t r1 = __shfl_sync(kFull, n1, 31 - lane);   // n[63 - lane]
-        const uint64_t r0 = __shfl_sync(kFull, n0, 31 - lane);   // n[31 - lane] = n[63 - (lane + 32)]
-        h0 = h0 < r1 ? h0 : r1;
-        h1 = h1 < r0 ? h1 : r0;
-        bitonic_merge64(h0, h1, lane);
-      }
+      bitonic_keep_lowest64(h0, h1, n0, n1, lane);
     }
     const uint64_t deg = hi - lo;
     const int c = deg < uint64_t(k) ? int(deg) : k;
@@ -176,3 +124,79 @@ int qrs_topk_tables(const uint64_t *pairs, const int32_t *sim_milli, int64_t n_p
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------ f-2: per-user top-N recommendations
+// Replaces what Recommender.top_k_queries serves (recommender.py:345-374: among the just-predicted cells of a
+// user with prediction != 0, the k largest predictions) without materialising a dense users x queries matrix:
+// one warp per user walks the user's sparse prediction slices and keeps the best 64 (prediction descending,
+// column ascending — the reference's order inside ties comes from an unstable argsort and is unspecified).
+namespace qrs {
+
+__global__ void __launch_bounds__(256)
+topn_kernel(const int64_t *__restrict__ row_start, const int *__restrict__ row_cnt, const void *__restrict__ cols,
+            int cols_u16, const uint8_t *__restrict__ preds, int64_t n_users, int nt, int N,
+            int *__restrict__ out_idx, uint8_t *__restrict__ out_val, int *__restrict__ out_cnt) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  const uint64_t INF = ~uint64_t(0);
+  for (int64_t u = warp_global; u < n_users; u += nwarps) {
+    uint64_t h0 = INF, h1 = INF;
+    int64_t seen = 0;
+    for (int t = 0; t < nt; ++t) {
+      const int64_t lo = row_start[u * nt + t];
+      const int n = row_cnt[u * nt + t];
+      for (int base = 0; base < n; base += 64) {
+        uint64_t k0 = INF, k1 = INF;
+        {
+          const int x = base + lane;
+          if (x < n) {
+            const unsigned p = preds[lo + x];
+            const unsigned c = cols_u16 ? unsigned(static_cast<const uint16_t *>(cols)[lo + x])
+                                        : unsigned(static_cast<const int *>(cols)[lo + x]);
+            if (p != 0) { k0 = (uint64_t(255u - p) << 32) | c; }
+          }
+          const int y = x + 32;
+          if (y < n) {
+            const unsigned p = preds[lo + y];
+            const unsigned c = cols_u16 ? unsigned(static_cast<const uint16_t *>(cols)[lo + y])
+                                        : unsigned(static_cast<const int *>(cols)[lo + y]);
+            if (p != 0) { k1 = (uint64_t(255u - p) << 32) | c; }
+          }
+        }
+        seen += __popc(__ballot_sync(kFull, k0 != INF)) + __popc(__ballot_sync(kFull, k1 != INF));
+        bitonic_keep_lowest64(h0, h1, k0, k1, lane);
+      }
+    }
+    const int c = seen < N ? int(seen) : N;
+    if (lane == 0) out_cnt[u] = c;
+    if (lane < N) {
+      const bool ok = lane < c;
+      out_idx[u * N + lane] = ok ? int(uint32_t(h0)) : -1;
+      out_val[u * N + lane] = ok ? uint8_t(255u - unsigned(h0 >> 32)) : 0;
+    }
+    if (lane + 32 < N) {
+      const bool ok = lane + 32 < c;
+      out_idx[u * N + lane + 32] = ok ? int(uint32_t(h1)) : -1;
+      out_val[u * N + lane + 32] = ok ? uint8_t(255u - unsigned(h1 >> 32)) : 0;
+    }
+  }
+}
+
+}  // namespace qrs
+
+extern "C" int qrs_recommend_topn(const int64_t *row_start, const int32_t *row_cnt, const void *cols, int32_t cols_mode,
+                                  const uint8_t *preds, int64_t n_users, int32_t nt, int32_t N, int32_t *out_idx,
+                                  uint8_t *out_val, int32_t *out_cnt, void *stream) {
+  if (n_users < 0 || nt <= 0 || N <= 0 || !row_start || !row_cnt || !out_idx || !out_val || !out_cnt)
+    return QRS_ERR_INVALID_ARG;
+  if (N > QRS_MAX_TOPK || (cols_mode != QRS_COLS_I32 && cols_mode != QRS_COLS_U16)) return QRS_ERR_UNSUPPORTED;
+  if (n_users == 0) return QRS_OK;
+  int64_t blocks = qrs::ceil_div<int64_t>(n_users, 8);
+  const int64_t cap = int64_t(qrs::sm_count()) * 8;
+  if (blocks > cap) blocks = cap;
+  qrs::topn_kernel<<<unsigned(blocks), 256, 0, qrs::as_stream(stream)>>>(row_start, row_cnt, cols, cols_mode == QRS_COLS_U16,
+                                                                       preds, n_users, nt, N, out_idx, out_val, out_cnt);
+  QRS_LAUNCH_CHECK();
+  return QRS_OK;
+}

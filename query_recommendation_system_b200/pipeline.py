@@ -233,6 +233,14 @@ class LshCfPipeline:
         out.stage_ms = tm.result()
         return out
 
+    def recommend_top_n(self, out: PipelineOutput, N: int = 10):
+        """What Recommender.top_k_queries serves (recommender.py:345-374), for every user of this rank at once:
+        the N best non-zero predictions among the cells just predicted, without a dense users x queries matrix.
+        Returns (idx int32[n_local, N] (-1 pad), val uint8[n_local, N], cnt int32[n_local])."""
+        if out.pred_row_start is None:
+            raise _lib.QrsError("recommend_top_n needs the single-chunk device output of run() (int32/uint16 columns)")
+        return self.st.recommend_topn(out.pred_row_start, out.pred_row_cnt, out.pred_cols, out.pred_vals, N)
+
     # ------------------------------------------------------------------ exchanges (plumbing)
     def _all_gather_rows(self, t: torch.Tensor, group=None) -> torch.Tensor:
         import torch.distributed as dist

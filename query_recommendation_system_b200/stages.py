@@ -262,6 +262,22 @@ def predict_sparse(rowptr, colidx, val, Q: int, u_tab: Table, user_base: int, n_
     return row_start, row_cnt, cols, preds, cursor[:n_regions], cursor[n_regions:]
 
 
+# ---------------------------------------------------------------------- f-2: top-N recommendations
+def recommend_topn(row_start, row_cnt, cols, preds, N: int):
+    """Per user the N best non-zero predictions (recommender.py:345-374) from predict_sparse's output
+    (int32 or uint16 columns): idx int32[n_users, N] (-1 pad), val uint8[n_users, N], cnt int32[n_users]."""
+    _need_cuda(row_start, row_cnt, cols, preds)
+    n_users, nt = row_start.shape
+    mode = 1 if cols.dtype == torch.int16 else 0
+    dev = row_start.device
+    idx = torch.empty((n_users, N), dtype=torch.int32, device=dev)
+    val = torch.empty((n_users, N), dtype=torch.uint8, device=dev)
+    cnt = torch.empty(n_users, dtype=torch.int32, device=dev)
+    check(_lib.load().qrs_recommend_topn(ptr(row_start), ptr(row_cnt), ptr(cols), mode, ptr(preds), n_users, nt, N,
+                                         ptr(idx), ptr(val), ptr(cnt), _stream()), "qrs_recommend_topn")
+    return idx, val, cnt
+
+
 # ---------------------------------------------------------------------- multi-GPU plumbing
 def gather_rows(rowptr, colidx, val, rows: torch.Tensor, out_off: torch.Tensor, total: int):
     """Pack CSR rows `rows` (local ids) into contiguous (col int32[total], val uint8[total]) send buffers."""

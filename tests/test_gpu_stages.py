@@ -428,3 +428,25 @@ def test_predict_sparse_regions_and_overflow():
     # every slice lies inside its region
     reg = rs // rcap
     assert ((rs + rc - 1)[rc > 0] // rcap == reg[rc > 0]).all()
+
+
+@pytest.mark.parametrize("N", [1, 10, 40, 64])
+def test_recommend_topn_matches_numpy(N):
+    """f-2: per-user top-N over the sparse predictions == argsort of the same user's predictions
+    (prediction descending, column ascending), recommender.py:345-374."""
+    from query_recommendation_system_b200 import stages
+    n, m, k = 608, 2500, 15          # a multiple of the 32-row taste groups the neighbour ids are drawn from
+    rowptr, colidx, val, idx, sims, cnt = _sparse_case(n, m, k, 91, False)
+    ref = spec.predict_user_branch_csr(rowptr, colidx, val, m, idx, sims, cnt)
+    total = sum(v[0].size for v in ref.values())
+    tab = (cu(idx), cu(sims), cu(cnt))
+    for tile, mode in ((512, 0), (1024, 1)):
+        rs, rc, cols, preds, _, _ = stages.predict_sparse(cu(rowptr), cu(colidx), cu(val), m, tab, 0, n, tile, total + 8,
+                                                          u_milli=cu(np.rint(sims * 1000).astype(np.int32)), cols_mode=mode)
+        tidx, tval, tcnt = [x.cpu().numpy() for x in stages.recommend_topn(rs, rc, cols, preds, N)]
+        for u in range(n):
+            c, p = ref[u]
+            order = np.lexsort((c, -p))[:N]
+            assert tcnt[u] == order.size
+            assert np.array_equal(tidx[u, :order.size], c[order]) and np.array_equal(tval[u, :order.size], p[order])
+            assert (tidx[u, order.size:] == -1).all() and (tval[u, order.size:] == 0).all()
