@@ -152,12 +152,16 @@ class LshCfPipeline:
             sig_all, norm2_all = sig, norm2
             tm.mark("grouping")
         else:
-            sig_all, norm2_all = self._all_gather_rows(sig), self._all_gather_rows(norm2)
-            tm.mark("exchange:signatures")
+            # the gathered signatures are first needed by the pair scoring: gather them on a second stream and
+            # communicator while the bucket records are exchanged and sorted
+            sig_join = self._background(lambda: (self._all_gather_rows(sig, self._bg_group()),
+                                                 self._all_gather_rows(norm2, self._bg_group())), (sig, norm2))
             flat, lg = self._exchange_records(records.reshape(-1))
             tm.mark("exchange:records")
             st.sort_u64(flat, flat.numel(), 1, 32, 64 - lg)
             tm.mark("grouping")
+            sig_all, norm2_all = sig_join()
+            tm.mark("exchange:signatures")
 
         # a5 + a8: slots → verified, de-duplicated, scored pairs
         slot_off = st.pair_slots(flat)
@@ -242,6 +246,34 @@ class LshCfPipeline:
         return self.st.recommend_topn(out.pred_row_start, out.pred_row_cnt, out.pred_cols, out.pred_vals, N)
 
     # ------------------------------------------------------------------ exchanges (plumbing)
+    def _bg_group(self):
+        """A second communicator for background collectives (collectives of one communicator run in order)."""
+        import torch.distributed as dist
+        if getattr(self, "_bg", None) is None:
+            self._bg = dist.new_group(ranks=list(range(self.world))) if self.group is None else self.group
+        return self._bg
+
+    def _background(self, fn, inputs):
+        """Run `fn` on a side CUDA stream (inline on the CPU test double); returns a getter that joins it."""
+        if self.device.type != "cuda":
+            res = fn()
+            return lambda: res
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        main = torch.cuda.current_stream()
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            res = fn()
+        for t in inputs:
+            t.record_stream(self._side)
+
+        def join():
+            torch.cuda.current_stream().wait_stream(self._side)
+            for t in res:
+                t.record_stream(torch.cuda.current_stream())
+            return res
+        return join
+
     def _all_gather_rows(self, t: torch.Tensor, group=None) -> torch.Tensor:
         import torch.distributed as dist
         G = self.world
@@ -329,7 +361,11 @@ class LshCfPipeline:
         nc = torch.tensor(need_counts, dtype=torch.int64, device=dev)
         nends = torch.cumsum(nc, 0)
         ent_recv = (gsum[nends] - gsum[nends - nc]).cpu().tolist()
-        col_got = self._all_to_all_var(col_send.contiguous(), ent_send, recv_counts=ent_recv)
+        if self.m <= 65536:      # column ids fit 16 bits: ship them as such (3 instead of 5 bytes per entry)
+            col_got = self._all_to_all_var(col_send.to(torch.int16).contiguous(), ent_send, recv_counts=ent_recv)
+            col_got = col_got.to(torch.int32) & 0xFFFF
+        else:
+            col_got = self._all_to_all_var(col_send.contiguous(), ent_send, recv_counts=ent_recv)
         val_got = self._all_to_all_var(val_send.contiguous(), ent_send, recv_counts=ent_recv)
         # extended CSR and re-indexed table
         rp = torch.cat([rowptr, rowptr[-1] + torch.cumsum(lens_got, 0)])
