@@ -362,8 +362,9 @@ class LshCfPipeline:
         nends = torch.cumsum(nc, 0)
         ent_recv = (gsum[nends] - gsum[nends - nc]).cpu().tolist()
         if self.m <= 65536:      # column ids fit 16 bits: ship them as such (3 instead of 5 bytes per entry)
-            col_got = self._all_to_all_var(col_send.to(torch.int16).contiguous(), ent_send, recv_counts=ent_recv)
-            col_got = col_got.to(torch.int32) & 0xFFFF
+            got = self._all_to_all_var(col_send.to(torch.int16).contiguous().view(torch.uint8),
+                                       [2 * x for x in ent_send], recv_counts=[2 * x for x in ent_recv])
+            col_got = got.view(torch.int16).to(torch.int32) & 0xFFFF
         else:
             col_got = self._all_to_all_var(col_send.contiguous(), ent_send, recv_counts=ent_recv)
         val_got = self._all_to_all_var(val_send.contiguous(), ent_send, recv_counts=ent_recv)
