@@ -140,6 +140,12 @@ class LshCfPipeline:
         self._ensure_head(nnz / max(n_local, 1))
         tm.mark("start")
 
+        lens_join = None
+        if G > 1 and predict:
+            # row lengths of every shard (4 bytes per row): lets the remote-row exchange size its buffers locally
+            lens_join = self._background(
+                lambda: (self._all_gather_rows((rowptr[1:] - rowptr[:-1]).contiguous(), self._bg_group()),), (rowptr,))
+
         # a1 + a2/a3: signatures, squared norms and bucket records in one kernel
         sig, norm2, records = st.minhash(rowptr, colidx, self.m, self.perm_tab, self.order_head, b=self.b,
                                          id_base=row_base, want_norm2=True, mode=self.mode)
@@ -189,7 +195,7 @@ class LshCfPipeline:
                 # only the neighbour rows that live on other ranks are fetched (deduplicated), appended to the local
                 # CSR, and the neighbour ids are re-pointed at the extended row numbering
                 rowptr_all, colidx_all, val_all, idx = self._fetch_remote_rows(rowptr, colidx, val, idx, cnt,
-                                                                               n_local, row_base)
+                                                                               n_local, row_base, lens_join()[0])
                 pred_base = 0
                 tm.mark("exchange:ratings")
             else:
@@ -327,10 +333,12 @@ class LshCfPipeline:
         got = self._all_to_all_var(rec[order], counts)
         return ((got >> 37) << 32) | ((got >> 11) & 0x3FFFFFF), ((got & 0x7FF) - 1000).to(torch.int32)
 
-    def _fetch_remote_rows(self, rowptr, colidx, val, idx, cnt, n_local: int, row_base: int):
+    def _fetch_remote_rows(self, rowptr, colidx, val, idx, cnt, n_local: int, row_base: int, lens_all=None):
         """Request/response exchange of the ratings rows this rank's neighbour tables point at on other ranks.
         Returns the extended CSR (local rows first, fetched rows after, in ascending global id) and the
-        neighbour table re-indexed into it."""
+        neighbour table re-indexed into it.  lens_all: row lengths of ALL ranks' rows (gathered in the
+        background at the start of the step), so the requester sizes its receive buffers without a round trip."""
+        import torch.distributed as dist
         G = self.world
         dev = idx.device
         k = idx.shape[1]
@@ -338,29 +346,32 @@ class LshCfPipeline:
         ids = idx.to(torch.int64)
         is_remote = live & ((ids < row_base) | (ids >= row_base + n_local))
         need = torch.unique(ids[is_remote])                                # sorted ⇒ grouped by owner
-        import torch.distributed as dist
-        any_need = torch.tensor([need.numel()], dtype=torch.int64, device=dev)
-        dist.all_reduce(any_need, op=dist.ReduceOp.MAX, group=self.group)
-        if int(any_need.item()) == 0:                                      # every neighbour of every rank is local
+        owner = torch.div(need, n_local, rounding_mode="floor")
+        # one all-gather of the G x G request-count matrix tells every rank who asks whom for how many rows
+        mine = torch.bincount(owner, minlength=G)
+        counts = torch.empty(G * G, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(counts, mine, group=self.group)
+        counts = counts.view(G, G).cpu()
+        if int(counts.sum().item()) == 0:                                  # every neighbour of every rank is local
             new_idx = torch.where(live, ids - row_base, torch.full_like(ids, -1)).to(torch.int32)
             return rowptr, colidx, val, new_idx.contiguous()
-        owner = torch.div(need, n_local, rounding_mode="floor")
-        need_counts = torch.bincount(owner, minlength=G).cpu().tolist()   # rows I ask of each owner
-        req, req_counts = self._all_to_all_var(need, need_counts, return_counts=True)
-        # serve the requests: lengths first, then the rows packed by a gather kernel
+        need_counts = counts[self.rank].tolist()                           # rows I ask of each owner
+        req_counts = counts[:, self.rank].tolist()                         # rows each rank asks of me
+        req = self._all_to_all_var(need, need_counts, recv_counts=req_counts)
+        # serve the requests: the rows packed by a gather kernel; both sides know every row length
         r = req - row_base
-        starts, lens = rowptr[r], rowptr[r + 1] - rowptr[r]
+        lens = rowptr[r + 1] - rowptr[r]
         csum = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(lens, 0)])
-        rc = torch.tensor(req_counts, dtype=torch.int64, device=dev)      # rows each source asked for
-        ends = torch.cumsum(rc, 0)
-        ent_send = (csum[ends] - csum[ends - rc]).cpu().tolist()           # entries going back to each source
+        lens_got = lens_all[need] if lens_all is not None else \
+            self._all_to_all_var(lens.contiguous(), req_counts, recv_counts=need_counts)
+        gsum = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(lens_got, 0)])
+        rends = torch.cumsum(torch.tensor(req_counts, dtype=torch.int64, device=dev), 0)
+        nends = torch.cumsum(torch.tensor(need_counts, dtype=torch.int64, device=dev), 0)
+        splits = torch.cat([csum[rends], gsum[nends]]).cpu()               # ONE readback for both split tables
+        ent_send = torch.diff(splits[:G], prepend=torch.zeros(1, dtype=torch.int64)).tolist()
+        ent_recv = torch.diff(splits[G:], prepend=torch.zeros(1, dtype=torch.int64)).tolist()
         tot = int(sum(ent_send))
         col_send, val_send = self.st.gather_rows(rowptr, colidx, val, r.contiguous(), csum, tot)
-        lens_got = self._all_to_all_var(lens.contiguous(), req_counts, recv_counts=need_counts)
-        gsum = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(lens_got, 0)])
-        nc = torch.tensor(need_counts, dtype=torch.int64, device=dev)
-        nends = torch.cumsum(nc, 0)
-        ent_recv = (gsum[nends] - gsum[nends - nc]).cpu().tolist()
         if self.m <= 65536:      # column ids fit 16 bits: ship them as such (3 instead of 5 bytes per entry)
             got = self._all_to_all_var(col_send.to(torch.int16).contiguous().view(torch.uint8),
                                        [2 * x for x in ent_send], recv_counts=[2 * x for x in ent_recv])
