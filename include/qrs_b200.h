@@ -233,6 +233,20 @@ int qrs_predict_sparse(const int64_t *rowptr, const int32_t *colidx, const uint8
                        void *cols, int32_t cols_mode /* QRS_COLS_* */, uint8_t *preds,
                        int64_t capacity, int32_t n_regions, unsigned long long *cursors, void *stream);
 
+/* ------------------------------------------------------ f-1: set construction
+ * Replaces the predicate evaluation of Recommender.compute_shingles (recommender.py:68-103): answer sets of
+ * conjunctive `attr = value` queries over the dictionary-encoded table, as the sets x elements CSR that
+ * qrs_minhash_perm consumes (set = query, element = tuple index, ascending).
+ *   table_cm int32[F * drows] column-major codes; queries int32[n_queries * F], -1 = no condition on that
+ *   attribute (the reference's "", recommender.py:83), any other negative = a value absent from the column.
+ * qrs_answer_sets_count writes rowptr int64[n_queries + 1]; the caller reads rowptr[n_queries], allocates
+ * colidx and calls qrs_answer_sets_fill.  F <= 32. */
+size_t qrs_answer_sets_workspace_bytes(int64_t n_queries);
+int qrs_answer_sets_count(const int32_t *table_cm, int64_t drows, int32_t F, const int32_t *queries,
+                          int64_t n_queries, int64_t *rowptr, void *ws, size_t ws_bytes, void *stream);
+int qrs_answer_sets_fill(const int32_t *table_cm, int64_t drows, int32_t F, const int32_t *queries,
+                         int64_t n_queries, const int64_t *rowptr, int32_t *colidx, void *stream);
+
 /* ------------------------------------------------------ f-2: per-user top-N recommendations
  * Replaces what Recommender.top_k_queries serves (recommender.py:345-374): per user the N largest non-zero
  * predictions among the cells just predicted, from the sparse output of qrs_predict_sparse (QRS_COLS_I32 or

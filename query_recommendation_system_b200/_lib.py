@@ -47,6 +47,9 @@ SIGNATURES = {
     "qrs_pair_cosine": (C.c_int, [_p, _p, _i32, _p, _i64, _p, _p]),
     "qrs_topk_workspace_bytes": (_sz, [_i64]),
     "qrs_topk_tables": (C.c_int, [_p, _p, _i64, _i64, _i64, _i32, _p, _p, _sz, _p, _p, _p, _p, _p]),
+    "qrs_answer_sets_workspace_bytes": (_sz, [_i64]),
+    "qrs_answer_sets_count": (C.c_int, [_p, _i64, _i32, _p, _i64, _p, _p, _sz, _p]),
+    "qrs_answer_sets_fill": (C.c_int, [_p, _i64, _i32, _p, _i64, _p, _p, _p]),
     "qrs_recommend_topn": (C.c_int, [_p, _p, _p, _i32, _p, _i64, _i32, _i32, _p, _p, _p, _p]),
     "qrs_gather_rows": (C.c_int, [_p, _p, _p, _p, _i64, _p, _p, _p, _p]),
     "qrs_predict_dense": (C.c_int, [_p, _p, _p, _i64, _i32, _p, _p, _p, _i32, _p, _p, _p, _i32, _i64, _i64, _p, _p]),

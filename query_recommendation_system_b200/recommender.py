@@ -8,10 +8,10 @@ internal stage methods `compute_shingles / compute_signatures / compute_querySim
 compute_userSimilarities` with their reference return types, and the module constants.
 
 On the GPU: signatures (a1), banding + grouping + candidate pairs + cosine (a2-a8), top-k neighbour
-tables (a9) and the per-cell weighted averages + hybrid rule (a10-a11).  On the host, as in the
-reference and out of this path's scope: evaluating the string predicates
-of the queries (compute_shingles), the PCA + BIRCH user clustering (compute_userSimilarities), CSV
-parsing and the interactive prompt.  The reference reads its tables through `datatable`, which is
+tables (a9), the per-cell weighted averages + hybrid rule (a10-a11) and — the first "next" row, f-1 —
+the predicate evaluation of compute_shingles on dictionary-encoded columns.  On the host, as in the
+reference and out of this path's scope: the PCA + BIRCH user clustering
+(compute_userSimilarities), CSV parsing and the interactive prompt.  The reference reads its tables through `datatable`, which is
 not installable here; `init` accepts anything with `.to_numpy()` (datatable Frames, pandas
 DataFrames) or plain arrays.
 """
@@ -142,30 +142,36 @@ class Recommender:
         frame = pd.DataFrame(data, columns=list(self.datasetFeatures), dtype=str) if data else pd.DataFrame()
         return frame, indexes
 
-    # ------------------------------------------------------------------ set construction (host, out of scope)
+    # ------------------------------------------------------------------ set construction (f-1)
     def compute_shingles(self):
         """recommender.py:68-103: answer set of every conjunctive query → {tuple index: [query ids]}.
-        Also leaves the sets × elements CSR (query × tuple) the signature kernel consumes."""
+        The columns are dictionary-encoded on the host once; the predicate evaluation (the reference's pandas
+        boolean masks, one per query and attribute) runs on the GPU (qrs_answer_sets_*) and leaves the
+        sets × elements CSR (query × tuple) the signature kernel consumes."""
         drows = self.dataset.shape[0]
         nq = self.queriesIDs.size
-        cols = {ft: self.dataset[ft].to_numpy() for ft in self.datasetFeatures}
-        shingles = {d: [] for d in range(drows)}
-        rowptr = np.zeros(nq + 1, np.int64)
-        chunks = []
-        for q in range(nq):
-            mask = np.ones(drows, dtype=bool)
-            for ft_i, ft in enumerate(self.datasetFeatures):
-                want = self.queries[q][ft_i]
+        F = len(self.datasetFeatures)
+        dev = _device(self._device_arg)
+        table = np.empty((F, drows), dtype=np.int32)
+        qcodes = np.full((nq, F), -1, dtype=np.int32)
+        for fi, ft in enumerate(self.datasetFeatures):
+            values, inverse = np.unique(self.dataset[ft].to_numpy().astype(str), return_inverse=True)
+            table[fi] = inverse
+            code_of = {v: c for c, v in enumerate(values.tolist())}
+            for q in range(nq):
+                want = self.queries[q][fi]
                 if want != "":
-                    mask &= cols[ft] == want
-            answer = np.flatnonzero(mask)
+                    qcodes[q, fi] = code_of.get(str(want), -2)          # -2: the value never occurs → empty answer
+        rowptr_d, colidx_d = stages.answer_sets(torch.from_numpy(table).to(dev), torch.from_numpy(qcodes).to(dev))
+        self._sets_dev = (rowptr_d, colidx_d)
+        self._sets_rowptr = rowptr_d.cpu().numpy()
+        self._sets_colidx = colidx_d.cpu().numpy()
+        shingles = {d: [] for d in range(drows)}
+        for q in range(nq):
+            answer = self._sets_colidx[self._sets_rowptr[q]:self._sets_rowptr[q + 1]]
             self.tupleCount[q] = answer.size
             for ind in answer:
                 shingles[int(ind)].append(q)
-            chunks.append(answer.astype(np.int32))
-            rowptr[q + 1] = rowptr[q] + answer.size
-        self._sets_rowptr = rowptr
-        self._sets_colidx = np.concatenate(chunks) if chunks else np.zeros(0, np.int32)
         return shingles
 
     def set_sets_csr(self, rowptr, colidx, n_elements: int):
@@ -173,6 +179,7 @@ class Recommender:
         queries) instead of evaluating string predicates."""
         self._sets_rowptr = np.asarray(rowptr, np.int64)
         self._sets_colidx = np.asarray(colidx, np.int32)
+        self._sets_dev = None
         self._n_elements = int(n_elements)
 
     # ------------------------------------------------------------------ a1
@@ -190,8 +197,11 @@ class Recommender:
         tab = np.empty((m, K), dtype=np.int32)
         for i in range(K):
             tab[:, i] = np.random.permutation(m)                        # recommender.py:120
-        rowptr = torch.from_numpy(self._sets_rowptr).to(dev)
-        colidx = torch.from_numpy(self._sets_colidx).to(dev)
+        if getattr(self, "_sets_dev", None) is not None:
+            rowptr, colidx = self._sets_dev                              # left on the device by compute_shingles
+        else:
+            rowptr = torch.from_numpy(self._sets_rowptr).to(dev)
+            colidx = torch.from_numpy(self._sets_colidx).to(dev)
         n = rowptr.numel() - 1
         tab_d = torch.from_numpy(tab).to(dev)
         R = stages.choose_head_ranks(m, colidx.numel() / max(n, 1))

@@ -262,6 +262,28 @@ def predict_sparse(rowptr, colidx, val, Q: int, u_tab: Table, user_base: int, n_
     return row_start, row_cnt, cols, preds, cursor[:n_regions], cursor[n_regions:]
 
 
+# ---------------------------------------------------------------------- f-1: set construction
+def answer_sets(table_cm: torch.Tensor, queries: torch.Tensor):
+    """compute_shingles' predicate evaluation (recommender.py:76-95) on dictionary codes: table_cm int32[F, drows],
+    queries int32[nQ, F] (-1 = no condition) → CSR (rowptr int64[nQ + 1], colidx int32[nnz]) of the answer sets."""
+    _need_cuda(table_cm, queries)
+    assert table_cm.dtype == torch.int32 and queries.dtype == torch.int32
+    F, drows = table_cm.shape
+    nq = queries.shape[0]
+    assert queries.shape[1] == F
+    lib = _lib.load()
+    dev = table_cm.device
+    rowptr = torch.empty(nq + 1, dtype=torch.int64, device=dev)
+    ws = _ws(lib.qrs_answer_sets_workspace_bytes(nq), dev)
+    check(lib.qrs_answer_sets_count(ptr(table_cm), drows, F, ptr(queries), nq, ptr(rowptr), ptr(ws), ws.numel(),
+                                    _stream()), "qrs_answer_sets_count")
+    nnz = int(rowptr[-1].item())
+    colidx = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+    check(lib.qrs_answer_sets_fill(ptr(table_cm), drows, F, ptr(queries), nq, ptr(rowptr), ptr(colidx), _stream()),
+          "qrs_answer_sets_fill")
+    return rowptr, colidx[:nnz]
+
+
 # ---------------------------------------------------------------------- f-2: top-N recommendations
 def recommend_topn(row_start, row_cnt, cols, preds, N: int):
     """Per user the N best non-zero predictions (recommender.py:345-374) from predict_sparse's output

@@ -450,3 +450,29 @@ def test_recommend_topn_matches_numpy(N):
             assert tcnt[u] == order.size
             assert np.array_equal(tidx[u, :order.size], c[order]) and np.array_equal(tval[u, :order.size], p[order])
             assert (tidx[u, order.size:] == -1).all() and (tval[u, order.size:] == 0).all()
+
+
+def test_answer_sets_match_numpy_masks():
+    """f-1: conjunctive attr = value predicates over a dictionary-encoded table (recommender.py:76-95), incl.
+    wildcard-only queries (every tuple), impossible values (empty answer) and a tuple count that is not a
+    multiple of 32."""
+    from query_recommendation_system_b200 import stages
+    rng = np.random.default_rng(12)
+    drows, F, nq = 4999, 5, 300
+    card = [3, 40, 7, 90, 2]
+    table = np.stack([rng.integers(0, c, drows) for c in card]).astype(np.int32)       # [F, drows]
+    queries = np.full((nq, F), -1, np.int32)
+    for q in range(nq):
+        for f in rng.choice(F, size=rng.integers(0, 4), replace=False):
+            queries[q, f] = rng.integers(0, card[f])
+    queries[7, 2] = -2                                   # a value that does not occur
+    rowptr, colidx = stages.answer_sets(cu(table), cu(queries))
+    rowptr, colidx = rowptr.cpu().numpy(), colidx.cpu().numpy()
+    for q in range(nq):
+        mask = np.ones(drows, bool)
+        for f in range(F):
+            if queries[q, f] != -1:
+                mask &= table[f] == queries[q, f]
+        assert np.array_equal(colidx[rowptr[q]:rowptr[q + 1]], np.flatnonzero(mask))
+    assert rowptr[8] == rowptr[7]                        # the impossible query has an empty answer set
+    assert rowptr[-1] == colidx.size
