@@ -173,6 +173,39 @@ def workload_config(config, n_gpus, l2_note):
             "l2": l2_note}
 
 
+def sweep(args):
+    """BASELINE.json configs[4]: band/row sweep (b x r in {16x8, 32x4, 64x2}, K = 128) on the named config's matrix —
+    candidate-pair volume vs throughput of the grouping + pair/similarity kernels.  One JSON line, not the bench line."""
+    import torch
+    from query_recommendation_system_b200 import stages, synth
+    from query_recommendation_system_b200.lsh import group_and_pair
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    n, m, density, _, _, _ = synth.config_shape(args.config)
+    K = 128
+    rowptr, colidx, _ = synth.planted_csr(n, m, density, seed=DATA_SEED, device=dev)
+    tab = torch.from_numpy(perm_table(m, K)).to(dev)
+    head = stages.perm_head(tab, stages.choose_head_ranks(m, colidx.numel() / n))
+    sig, norm2, _ = stages.minhash(rowptr, colidx, m, tab, head, b=0)
+    rows = []
+    for b in (16, 32, 64):
+        times = []
+        for it in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            records, _ = stages.band_records(sig, b, 0, want_norm2=False)
+            pairs, sims, n_slots = group_and_pair(records, n, b, sig, norm2, b, True)
+            e1.record()
+            torch.cuda.synchronize()
+            if it > 0:
+                times.append(e0.elapsed_time(e1))
+        ms = float(np.median(times))
+        rows.append({"b": b, "r": K // b, "pair_slots": int(n_slots), "candidate_pairs": int(pairs.numel()), "ms": ms,
+                     "candidate_pairs_per_s": pairs.numel() / (ms * 1e-3), "pair_slots_per_s": n_slots / (ms * 1e-3)})
+    print(json.dumps({"sweep": "banding + grouping + pairs + cosine, K=128", "config": args.config, "sets": n,
+                      "elements": m, "density": density, "rows": rows}))
+
+
 # ------------------------------------------------------------------------------------------ GPU side
 def main():
     ap = argparse.ArgumentParser()
@@ -183,9 +216,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sets", type=int, default=160)
+    ap.add_argument("--sweep", action="store_true", help="band/row sweep of the LSH stages (extra, not the bench line)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
+        return
+    if args.sweep:
+        sweep(args)
         return
 
     import torch
