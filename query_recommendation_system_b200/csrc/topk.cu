@@ -165,6 +165,9 @@ topn_kernel(const int64_t *__restrict__ row_start, const int *__restrict__ row_c
           }
         }
         seen += __popc(__ballot_sync(kFull, k0 != INF)) + __popc(__ballot_sync(kFull, k1 != INF));
+        // nothing in this chunk beats the 64th best kept so far: skip the sort + merge
+        const uint64_t worst = __shfl_sync(kFull, h1, 31);
+        if (__ballot_sync(kFull, k0 < worst || k1 < worst) == 0u) continue;
         bitonic_keep_lowest64(h0, h1, k0, k1, lane);
       }
     }

@@ -127,7 +127,7 @@ class LshCfPipeline:
 
     # ------------------------------------------------------------------ the path
     def run(self, rowptr: torch.Tensor, colidx: torch.Tensor, val: Optional[torch.Tensor],
-            predict: bool = True, chunk_sink=None) -> PipelineOutput:
+            predict: bool = True, chunk_sink=None, val_ready=None) -> PipelineOutput:
         """rowptr/colidx/val: this rank's shard (rows [rank*n_local, (rank+1)*n_local)) of the users×queries
         CSR, on `self.device`.  Every rank must hold the same number of rows."""
         st, G, rank = self.st, self.world, self.rank
@@ -190,6 +190,8 @@ class LshCfPipeline:
 
         if predict:
             assert val is not None
+            if val_ready is not None:          # the ratings were still being uploaded while the LSH stages ran
+                torch.cuda.current_stream().wait_event(val_ready)
             pred_base = row_base
             if G > 1:
                 # only the neighbour rows that live on other ranks are fetched (deduplicated), appended to the local
@@ -437,11 +439,21 @@ class HostRunner:
         self.h2d_bytes = self.d2h_bytes = 0
         compute = torch.cuda.current_stream()
         dev_in = []
-        for name, t in (("rowptr", rowptr_h), ("colidx", colidx_h), ("val", val_h)):
+        for name, t in (("rowptr", rowptr_h), ("colidx", colidx_h)):
             d = self._dev_like(name, t)
             d.copy_(t, non_blocking=True)
             self.h2d_bytes += t.numel() * t.element_size()
             dev_in.append(d)
+        # the rating values are needed only by the prediction stage: upload them on the copy stream while the
+        # signature / LSH stages run
+        d_val = self._dev_like("val", val_h)
+        self.copy_stream.wait_stream(compute)          # the buffer may still be read by the previous call
+        with torch.cuda.stream(self.copy_stream):
+            d_val.copy_(val_h, non_blocking=True)
+            val_ready = torch.cuda.Event()
+            val_ready.record(self.copy_stream)
+        self.h2d_bytes += val_h.numel() * val_h.element_size()
+        dev_in.append(d_val)
         res = {"chunks": []}
 
         def sink(ci, chunk):
@@ -455,7 +467,7 @@ class HostRunner:
                     self._ship("c%d_%s" % (ci, key), chunk[key], host_chunk, key)
             res["chunks"].append(host_chunk)
 
-        out = self.pipe.run(*dev_in, predict=True, chunk_sink=sink)
+        out = self.pipe.run(*dev_in, predict=True, chunk_sink=sink, val_ready=val_ready)
         ready = torch.cuda.Event()
         ready.record(compute)
         with torch.cuda.stream(self.copy_stream):
