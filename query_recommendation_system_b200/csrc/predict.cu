@@ -7,9 +7,11 @@
 // reproduces, per cell, exactly the reference's left-to-right fp64 sums — cells no
 // neighbour rated keep den == 0 and are "missed" (prediction 0) without being visited.
 //
-//   sparse form : one warp per (user, column tile); accumulators for the tile live in shared
-//                 memory, neighbour row segments are located through a per-row tile index
-//                 and loaded 8 neighbours ahead of the accumulation.
+//   sparse form : one CTA per (user, column tile); accumulators for the tile live in shared
+//                 memory (exact integers when the similarities are multiples of 0.001, fp64
+//                 otherwise), neighbour row segments are located through a per-row tile index
+//                 and loaded a group of neighbours ahead of the accumulation; only the columns
+//                 a neighbour touched are swept, predicted and written.
 //   dense form  : one CTA per user at reference scale, adds the query branch.
 #include "common.cuh"
 
@@ -111,10 +113,11 @@ __device__ __noinline__ int resolve_tie(const int *__restrict__ colidx, const ui
 }
 
 // One CTA per (user, column tile).  The neighbours' segments are streamed one after the other (table
-// order) by all 256 threads — entries of one neighbour hit distinct columns, so the shared-memory
+// order) by all threads — entries of one neighbour hit distinct columns, so the shared-memory
 // read-modify-writes need no atomics, and a block barrier between neighbours keeps the reference's
-// left-to-right order per column.  The next neighbour's entries are loaded into registers before the
-// current one is accumulated.  The output passes are per warp over its own column range.
+// left-to-right order per column.  The next group of neighbours is being loaded into a second
+// register set while the current group is accumulated.  The output sweep is per warp over its own
+// column range: list the touched columns, reserve one slice for the CTA, predict into the slice.
 template <bool MILLI>
 __global__ void __launch_bounds__(kSpThreads, 2)
 predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict__ val, int Q,

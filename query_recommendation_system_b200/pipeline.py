@@ -6,7 +6,8 @@ recommender.py:149 → 171-176 → 183-210 → 311-331 without ever leaving the 
 Multi-GPU (one process per GPU, torch.distributed): rows are sharded contiguously; the
 signature matrix is all-gathered, bucket records are exchanged with an all-to-all keyed by the
 top bits of the bucket hash, pairs are scored where their bucket lands, scored pairs are sent
-to the owners of their two ends, and the ratings CSR is all-gathered for the prediction gathers.
+to the owners of their two ends, and only the neighbour rows that live on other ranks are fetched
+(request/response all-to-all) for the prediction gathers.
 All arithmetic is in `stages` (CUDA kernels behind the C ABI); torch is plumbing.
 """
 from __future__ import annotations
