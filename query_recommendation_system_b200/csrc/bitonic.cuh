@@ -60,4 +60,16 @@ __device__ __forceinline__ void bitonic_keep_lowest64(uint64_t &h0, uint64_t &h1
   bitonic_merge64(h0, h1, lane);
 }
 
+// insert one key into the ascending 64-key list (the largest key falls off the end)
+__device__ __forceinline__ void sorted_insert64(uint64_t &h0, uint64_t &h1, uint64_t key, int lane) {
+  const int pos = __popc(__ballot_sync(kFull, h0 < key)) + __popc(__ballot_sync(kFull, h1 < key));   // keys below it
+  const uint64_t up0 = __shfl_up_sync(kFull, h0, 1);
+  uint64_t up1 = __shfl_up_sync(kFull, h1, 1);
+  const uint64_t carry = __shfl_sync(kFull, h0, 31);       // element 31 moves to element 32
+  if (lane == 0) up1 = carry;
+  const int e0 = lane, e1 = lane + 32;
+  h0 = e0 < pos ? h0 : (e0 == pos ? key : up0);
+  h1 = e1 < pos ? h1 : (e1 == pos ? key : up1);
+}
+
 }  // namespace qrs

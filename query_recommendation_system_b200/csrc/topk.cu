@@ -165,10 +165,23 @@ topn_kernel(const int64_t *__restrict__ row_start, const int *__restrict__ row_c
           }
         }
         seen += __popc(__ballot_sync(kFull, k0 != INF)) + __popc(__ballot_sync(kFull, k1 != INF));
-        // nothing in this chunk beats the 64th best kept so far: skip the sort + merge
+        // only keys better than the 64th best kept so far matter: a few are inserted one by one, many (the
+        // first chunks, while the list fills) go through the sort + merge network
         const uint64_t worst = __shfl_sync(kFull, h1, 31);
-        if (__ballot_sync(kFull, k0 < worst || k1 < worst) == 0u) continue;
-        bitonic_keep_lowest64(h0, h1, k0, k1, lane);
+        unsigned b0 = __ballot_sync(kFull, k0 < worst), b1 = __ballot_sync(kFull, k1 < worst);
+        if ((b0 | b1) == 0u) continue;
+        if (__popc(b0) + __popc(b1) > 8) {
+          bitonic_keep_lowest64(h0, h1, k0, k1, lane);
+        } else {
+          for (; b0 != 0u; b0 &= b0 - 1u) {
+            const uint64_t key = __shfl_sync(kFull, k0, __ffs(b0) - 1);
+            if (key < __shfl_sync(kFull, h1, 31)) sorted_insert64(h0, h1, key, lane);
+          }
+          for (; b1 != 0u; b1 &= b1 - 1u) {
+            const uint64_t key = __shfl_sync(kFull, k1, __ffs(b1) - 1);
+            if (key < __shfl_sync(kFull, h1, 31)) sorted_insert64(h0, h1, key, lane);
+          }
+        }
       }
     }
     const int c = seen < N ? int(seen) : N;
