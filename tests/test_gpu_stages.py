@@ -476,3 +476,37 @@ def test_answer_sets_match_numpy_masks():
         assert np.array_equal(colidx[rowptr[q]:rowptr[q + 1]], np.flatnonzero(mask))
     assert rowptr[8] == rowptr[7]                        # the impossible query has an empty answer set
     assert rowptr[-1] == colidx.size
+
+
+def test_pair_cosine_explicit_list(golden_synth):
+    """qrs_pair_cosine: rounded cosine of an explicit pair list == the oracle's np.around(cos, 3) * 1000."""
+    from query_recommendation_system_b200 import stages
+    g = golden_synth
+    sig = g["sig"].astype(np.int64)
+    b = int(g["bands"][0])
+    pairs = g["b%d_candidates" % b].astype(np.int64)
+    packed = (pairs[:, 0].astype(np.uint64) << np.uint64(32)) | pairs[:, 1].astype(np.uint64)
+    sig_d = cu(sig, torch.int32)
+    _, norm2 = stages.band_records(sig_d, b, 0)
+    got = stages.pair_cosine(sig_d, norm2, cu(packed.view(np.int64)))
+    assert np.array_equal(got.cpu().numpy() / 1000.0, g["b%d_pair_sims" % b])
+
+
+def test_gather_rows_packs_requested_rows():
+    """qrs_gather_rows (multi-GPU plumbing): arbitrary local rows, incl. empty ones and repeats, into one buffer."""
+    from query_recommendation_system_b200 import stages, synth
+    rowptr, colidx, val = synth.planted_csr(700, 900, 0.04, seed=3)
+    rowptr[5 + 1:] -= (rowptr[6] - rowptr[5])                       # make row 5 empty (drop its entries logically)
+    keep = torch.ones(colidx.numel(), dtype=torch.bool)
+    rp0, _, _ = synth.planted_csr(700, 900, 0.04, seed=3)
+    keep[rp0[5]:rp0[6]] = False
+    colidx, val = colidx[keep], val[keep]
+    rows = torch.tensor([699, 5, 0, 17, 17, 350], dtype=torch.int64)
+    lens = rowptr[rows + 1] - rowptr[rows]
+    off = torch.zeros(rows.numel() + 1, dtype=torch.int64)
+    off[1:] = torch.cumsum(lens, 0)
+    col, v = stages.gather_rows(cu(rowptr.numpy()), cu(colidx.numpy()), cu(val.numpy()), cu(rows.numpy()), cu(off.numpy()),
+                                int(off[-1]))
+    ref_c = torch.cat([colidx[rowptr[r]:rowptr[r + 1]] for r in rows.tolist()])
+    ref_v = torch.cat([val[rowptr[r]:rowptr[r + 1]] for r in rows.tolist()])
+    assert torch.equal(col.cpu(), ref_c) and torch.equal(v.cpu(), ref_v)
