@@ -331,7 +331,7 @@ def test_predict_dense_half_way_ties():
     assert np.array_equal(out.cpu().numpy().astype(np.int64), ref)
 
 
-def _sparse_case(n, m, k, seed, tie_heavy):
+def _sparse_case(n, m, k, seed, tie_heavy, pool=32):
     from query_recommendation_system_b200 import synth
     rowptr_t, colidx_t, val_t = synth.planted_csr(n, m, 0.05, seed=seed)
     rowptr, colidx, val = rowptr_t.numpy(), colidx_t.numpy(), val_t.numpy().copy()
@@ -344,8 +344,8 @@ def _sparse_case(n, m, k, seed, tie_heavy):
     sims = np.zeros((n, k))
     cnt = rng.integers(0, k + 1, n).astype(np.int32)
     for i in range(n):
-        g0 = (i // 32) * 32
-        cand = np.setdiff1d(np.arange(g0, g0 + 32), [i])
+        g0 = (i // pool) * pool
+        cand = np.setdiff1d(np.arange(g0, g0 + pool), [i])
         idx[i, :cnt[i]] = rng.choice(cand, cnt[i], replace=False)
         sims[i, :cnt[i]] = np.sort(rng.integers(0 if tie_heavy else 300, 1001, cnt[i]))[::-1] / 1000.0
     return rowptr, colidx, val, idx, sims, cnt
@@ -510,3 +510,23 @@ def test_gather_rows_packs_requested_rows():
     ref_c = torch.cat([colidx[rowptr[r]:rowptr[r + 1]] for r in rows.tolist()])
     ref_v = torch.cat([val[rowptr[r]:rowptr[r + 1]] for r in rows.tolist()])
     assert torch.equal(col.cpu(), ref_c) and torch.equal(v.cpu(), ref_v)
+
+
+@pytest.mark.parametrize("integer", [False, True])
+def test_predict_sparse_wide_tables_k50(integer):
+    """Neighbour tables wider than one warp (k = 50, the 10M-user config's top-k): two metadata rounds."""
+    from query_recommendation_system_b200 import stages
+    n, m, k = 512, 2000, 50
+    rowptr, colidx, val, idx, sims, cnt = _sparse_case(n, m, k, 5150, False, pool=64)
+    assert cnt.max() > 32
+    ref = spec.predict_user_branch_csr(rowptr, colidx, val, m, idx, sims, cnt)
+    total = sum(v[0].size for v in ref.values())
+    milli = cu(np.rint(sims * 1000).astype(np.int32)) if integer else None
+    rs, rc, cols, preds, cursor, nz = stages.predict_sparse(cu(rowptr), cu(colidx), cu(val), m, (cu(idx), cu(sims), cu(cnt)),
+                                                            0, n, 704, total + 3, u_milli=milli)
+    assert int(cursor.item()) == total
+    rs, rc, cols, preds = rs.cpu().numpy(), rc.cpu().numpy(), cols.cpu().numpy(), preds.cpu().numpy()
+    for t in range(n):
+        gc = np.concatenate([cols[rs[t, c]:rs[t, c] + rc[t, c]] for c in range(rs.shape[1])])
+        gp = np.concatenate([preds[rs[t, c]:rs[t, c] + rc[t, c]] for c in range(rs.shape[1])])
+        assert np.array_equal(gc, ref[t][0]) and np.array_equal(gp.astype(np.int64), ref[t][1])
