@@ -256,6 +256,26 @@ int qrs_recommend_topn(const int64_t *row_start, const int32_t *row_cnt, const v
                        const uint8_t *preds, int64_t n_users, int32_t nt, int32_t N,
                        int32_t *out_idx, uint8_t *out_val, int32_t *out_cnt, void *stream);
 
+/* ------------------------------------------------------ f-3: user-similarity branch at scale
+ * Replaces the scoring half of Recommender.compute_userSimilarities (recommender.py:256-269): the
+ * cosine of the mean-centred rating rows, np.around(., 3), negatives -> 0.  The reference centres an
+ * INTEGER block (recommender.py:263), so a centred value is trunc(r - mean) = (r * n - S) / n in C
+ * integer division (n rated cells summing to S); cells with rating 0 stay 0.  The candidate pairs
+ * come from the LSH stages over the users x queries rows instead of PCA + BIRCH clusters.
+ *
+ * qrs_center_rows: cval int16[nnz] (centred value of every CSR cell), norm2 int64[n_rows].
+ * qrs_pair_centered_cosine: sim_milli[p] = max(0, rint(1000 * cos)) for pairs[p] = i << 32 | j (row
+ * ids of this CSR); a zero-norm row scores 0.  flags: QRS_PAIRS_GROUPED = equal first ids are
+ * adjacent (e.g. after qrs_sort_u64 on bits [32, 64)), which lets row i be staged in shared memory
+ * (m <= 204800); otherwise, or with QRS_PAIRS_FORCE_SEARCH, the shorter row is searched in the longer. */
+#define QRS_PAIRS_GROUPED 1
+#define QRS_PAIRS_FORCE_SEARCH 2
+int qrs_center_rows(const int64_t *rowptr, const uint8_t *val, int64_t n_rows, int16_t *cval,
+                    int64_t *norm2, void *stream);
+int qrs_pair_centered_cosine(const int64_t *rowptr, const int32_t *colidx, const uint8_t *val,
+                             const int16_t *cval, const int64_t *norm2, const uint64_t *pairs,
+                             int64_t n_pairs, int32_t m, int32_t flags, int32_t *sim_milli, void *stream);
+
 /* ------------------------------------------------------ multi-GPU plumbing
  * Rows of the ratings CSR are sharded across GPUs; the prediction gathers neighbour rows
  * (recommender.py:320), so rows requested by other ranks are packed for sending:

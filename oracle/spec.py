@@ -211,6 +211,54 @@ def cosine_milli(sig: np.ndarray, pairs: np.ndarray) -> np.ndarray:
     return np.rint(dot.astype(np.float64) / den * 1000.0).astype(np.int32)
 
 
+# --------------------------------------------------------------------------- f-3
+def centered_rows(rowptr: np.ndarray, val: np.ndarray):
+    """Mean-centred rating rows as the reference really builds them
+    (recommender.py:263-267): the block is an INTEGER array, so assigning
+    `row[rated] - mean` back into it truncates toward zero.  With n rated cells
+    summing to S that is the C integer quotient `(r*n - S) / n` (when the exact
+    value is an integer, S/n is an integer too and the fp64 subtraction is exact;
+    otherwise it is >= 1/n from an integer, far beyond fp64 noise).
+
+    CSR in (ratings uint8, 0 = not rated) -> `cval int16[nnz]`, `n2 int64[rows]`
+    (squared norm of each centred row)."""
+    rowptr = np.asarray(rowptr, dtype=np.int64)
+    val = np.asarray(val).astype(np.int64)
+    rows = rowptr.size - 1
+    rid = np.repeat(np.arange(rows), np.diff(rowptr))
+    rated = val != 0
+    cnt = np.bincount(rid[rated], minlength=rows).astype(np.int64)
+    tot = np.bincount(rid[rated], weights=val[rated], minlength=rows).astype(np.int64)
+    num = val * cnt[rid] - tot[rid]
+    den = np.maximum(cnt[rid], 1)
+    q = np.abs(num) // den * np.sign(num)                 # truncating division
+    cval = np.where(rated, q, 0).astype(np.int16)
+    n2 = np.bincount(rid, weights=cval.astype(np.float64) ** 2, minlength=rows).astype(np.int64)
+    return cval, n2
+
+
+def centered_cosine_milli(rowptr, colidx, val, pairs) -> np.ndarray:
+    """`rint(1000 * cos)` of the centred rows of each pair, negatives clamped to 0
+    (recommender.py:267-269: `np.around(cosine_similarity(block), 3)`, `< 0 -> 0`);
+    a row of zero norm has similarity 0 with everything (sklearn's normalize leaves
+    it zero).  Exact int64 dot and norms, one fp64 sqrt and divide - the same
+    argument as `cosine_milli`."""
+    rowptr = np.asarray(rowptr, dtype=np.int64)
+    colidx = np.asarray(colidx, dtype=np.int64)
+    pairs = np.asarray(pairs, dtype=np.int64).reshape(-1, 2)
+    cval, n2 = centered_rows(rowptr, val)
+    out = np.zeros(pairs.shape[0], dtype=np.int32)
+    for p, (i, j) in enumerate(pairs):
+        a0, a1, b0, b1 = rowptr[i], rowptr[i + 1], rowptr[j], rowptr[j + 1]
+        _, ia, ib = np.intersect1d(colidx[a0:a1], colidx[b0:b1], assume_unique=True, return_indices=True)
+        dot = int((cval[a0:a1][ia].astype(np.int64) * cval[b0:b1][ib].astype(np.int64)).sum())
+        if n2[i] == 0 or n2[j] == 0:
+            continue
+        cos = float(dot) / math.sqrt(float(n2[i]) * float(n2[j]))
+        out[p] = max(0, int(np.rint(cos * 1000.0)))
+    return out
+
+
 # --------------------------------------------------------------------------- a7/a9
 def topk_tables(n: int, pairs: np.ndarray, sims: np.ndarray, k: int):
     """Neighbour tables (recommender.py:183-210) in CANONICAL order: per set, the

@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("QRS_B200_LIB", os.path.join(_HERE, "libqrs_b200.so"))
 
 QRS_OK = 0
 MINHASH_AUTO, MINHASH_DIRECT, MINHASH_FIRST_TOUCH = 0, 1, 2
+PAIRS_GROUPED, PAIRS_FORCE_SEARCH = 1, 2
 MAX_TOPK = 64
 MAX_BANDS = 256
 HASH_BITS = 24
@@ -52,6 +53,8 @@ SIGNATURES = {
     "qrs_answer_sets_fill": (C.c_int, [_p, _i64, _i32, _p, _i64, _p, _p, _p]),
     "qrs_recommend_topn": (C.c_int, [_p, _p, _p, _i32, _p, _i64, _i32, _i32, _p, _p, _p, _p]),
     "qrs_gather_rows": (C.c_int, [_p, _p, _p, _p, _i64, _p, _p, _p, _p]),
+    "qrs_center_rows": (C.c_int, [_p, _p, _i64, _p, _p, _p]),
+    "qrs_pair_centered_cosine": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _p, _p]),
     "qrs_predict_dense": (C.c_int, [_p, _p, _p, _i64, _i32, _p, _p, _p, _i32, _p, _p, _p, _i32, _i64, _i64, _p, _p]),
     "qrs_predict_max_tile": (_i32, [_i32]),
     "qrs_predict_sparse_workspace_bytes": (_sz, [_i64, _i32, _i32, _i64]),

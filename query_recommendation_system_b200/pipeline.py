@@ -104,6 +104,10 @@ class LshCfPipeline:
         self._pred_capacity = {}
         self.predict_chunks = 1             # > 1: predictions are produced (and can be shipped) chunk by chunk
         self.cols_mode = 0                  # prediction columns as int32 ids (0), uint16 ids (1) or a bitmap (2)
+        # how a candidate pair is scored: "signature" = rounded cosine of the MinHash signatures
+        # (recommender.py:203-204, the query branch); "ratings" = rounded, clamped cosine of the mean-centred
+        # rating rows (recommender.py:263-269, the user branch: LSH candidates stand in for PCA + BIRCH clusters)
+        self.similarity = "signature"
 
     # ------------------------------------------------------------------ distributed helpers
     @property
@@ -173,9 +177,24 @@ class LshCfPipeline:
         # a5 + a8: slots → verified, de-duplicated, scored pairs
         slot_off = st.pair_slots(flat)
         n_slots = int(slot_off[-1].item())
-        pairs, sims, counter = st.pairs_score(flat, slot_off, sig_all, norm2_all, self.b, n_slots, 0, True)
+        by_ratings = self.similarity == "ratings"
+        if by_ratings and G > 1:
+            raise _lib.QrsError("similarity='ratings' needs both rows of a pair on one rank: single-rank only")
+        if self.similarity not in ("signature", "ratings"):
+            raise ValueError("similarity must be 'signature' or 'ratings'")
+        pairs, sims, counter = st.pairs_score(flat, slot_off, sig_all, norm2_all, self.b, n_slots, 0, not by_ratings)
         n_pairs = int(counter.item())
-        pairs, sims = pairs[:n_pairs], sims[:n_pairs]
+        pairs = pairs[:n_pairs]
+        if by_ratings:
+            assert val is not None, "similarity='ratings' scores pairs on the ratings themselves"
+            if val_ready is not None:
+                torch.cuda.current_stream().wait_event(val_ready)
+            cval, norm2_c = st.center_rows(rowptr, val)
+            # equal first ids adjacent: the scoring kernel stages row i once per run
+            st.sort_u64(pairs, n_pairs, 1, 32, 32 + max(1, (n_total - 1).bit_length()))
+            sims = st.pair_centered_cosine(rowptr, colidx, val, cval, norm2_c, pairs, self.m, grouped=True)
+        else:
+            sims = sims[:n_pairs]
         out.pairs, out.sims, out.n_slots = pairs, sims, n_slots
         tm.mark("pairs+cosine")
 

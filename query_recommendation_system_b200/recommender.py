@@ -91,9 +91,16 @@ def _dict_to_table(sim: dict, n: int, device):
 
 
 class Recommender:
-    def __init__(self, device=None, bands=None, max_candidates=None, verbose: bool = True):
+    def __init__(self, device=None, bands=None, max_candidates=None, verbose: bool = True,
+                 user_branch: str = "cluster"):
         """`bands` / `max_candidates` override the reference's rules (needed when PERM has no
-        divisor that is a multiple of 10, recommender.py:156-165)."""
+        divisor that is a multiple of 10, recommender.py:156-165).  `user_branch`: "cluster" = the
+        reference's PCA + BIRCH pipeline on the host; "lsh" = LSH candidates over the users' rating rows
+        scored on the GPU with the same centred cosine (for shapes the dense pipeline
+        cannot reach)."""
+        if user_branch not in ("cluster", "lsh"):
+            raise ValueError("user_branch must be 'cluster' or 'lsh'")
+        self._user_branch = user_branch
         self.datasetFeatures = []
         self.tupleCount = {}
         self._device_arg = device
@@ -237,10 +244,55 @@ class Recommender:
         return _table_to_dict(idx, val, cnt, only_nonempty=True)
 
     # ------------------------------------------------------------------ user branch (host, out of scope)
+    def compute_userSimilarities_lsh(self):
+        """f-3: the user branch without the dense PCA + BIRCH step.  Users are the sets, their rated queries
+        the elements (Binding B); candidates = users sharing an LSH bucket; each candidate pair is scored
+        like the reference scores a pair inside a cluster (recommender.py:263-269: cosine of the
+        mean-centred, integer-truncated rating rows, 3 decimals, negatives -> 0); top-k as
+        recommender.py:274-286 in canonical order.  Every user gets an entry (possibly empty)."""
+        t0 = time.time()
+        dev = _device(self._device_arg)
+        R = np.asarray(self.ratings)
+        U, Q = R.shape
+        kmax = self._kmax if self._kmax is not None else round(math.log(U, 1.5))          # recommender.py:220
+        kmax = max(1, min(kmax, 64))
+        band = self._bands if self._bands is not None else choose_bands(PERM)
+        if band is None:
+            raise QrsError("no band count satisfies the reference rule for PERM=%d; pass bands=" % PERM)
+        rows, cols = np.nonzero(R)
+        rowptr = np.zeros(U + 1, dtype=np.int64)
+        np.cumsum(np.bincount(rows, minlength=U), out=rowptr[1:])
+        tab = np.empty((Q, PERM), dtype=np.int32)
+        for i in range(PERM):
+            tab[:, i] = np.random.permutation(Q)
+        rowptr_d = torch.from_numpy(rowptr).to(dev)
+        colidx_d = torch.from_numpy(cols.astype(np.int32)).to(dev)
+        val_d = torch.from_numpy(R[rows, cols].astype(np.uint8)).to(dev)
+        tab_d = torch.from_numpy(tab).to(dev)
+        head_ranks = stages.choose_head_ranks(Q, cols.size / max(U, 1))
+        head = stages.perm_head(tab_d, head_ranks) if head_ranks > 0 else None
+        sig, _, _ = stages.minhash(rowptr_d, colidx_d, Q, tab_d, head, b=0, want_norm2=False)
+        lsh = LSH(band, device=sig.device)
+        lsh.compute_buckets_batch(sig)
+        pairs, _ = lsh.candidates_scored(False)
+        P = pairs.numel()
+        cval, norm2 = stages.center_rows(rowptr_d, val_d)
+        if P:
+            stages.sort_u64(pairs, P, 1, 32, 32 + max(1, (U - 1).bit_length()))
+        sims = stages.pair_centered_cosine(rowptr_d, colidx_d, val_d, cval, norm2, pairs, Q, grouped=True)
+        idx, val, cnt = stages.topk_tables(pairs, sims, P, 0, U, kmax)
+        self._u_table = (idx, val, cnt)
+        self._log("Candidate user pairs: {}".format(P))
+        self._log("\n" + str(round(time.time() - t0, 3)) + "s for overall users_similarity scores")
+        return _table_to_dict(idx, val, cnt, only_nonempty=False)
+
     def compute_userSimilarities(self):
         """recommender.py:216-290 (StandardScaler → PCA(<=200) → BIRCH → per-cluster mean-centred cosine →
         top-k).  Dense sklearn pipeline kept on the host exactly as in the reference: it is not part
-        of the LSH path (SURVEY.md §2 #7); its output table feeds the GPU prediction kernel."""
+        of the LSH path; its output table feeds the GPU prediction kernel.
+        With user_branch="lsh" the GPU substitute compute_userSimilarities_lsh runs instead."""
+        if self._user_branch == "lsh":
+            return self.compute_userSimilarities_lsh()
         from sklearn.cluster import Birch
         from sklearn.decomposition import PCA
         from sklearn.metrics.pairwise import cosine_similarity

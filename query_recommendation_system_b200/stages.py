@@ -160,6 +160,31 @@ def pair_cosine(sig: torch.Tensor, norm2: torch.Tensor, pairs: torch.Tensor) -> 
     return sims
 
 
+# ------------------------------------------------------------------------ f-3
+def center_rows(rowptr: torch.Tensor, val: torch.Tensor):
+    """Mean-centred (truncated, recommender.py:263-267) rating rows: (cval int16[nnz], norm2 int64[rows])."""
+    _need_cuda(rowptr, val)
+    n_rows = rowptr.numel() - 1
+    cval = torch.empty(val.numel(), dtype=torch.int16, device=val.device)
+    norm2 = torch.empty(n_rows, dtype=torch.int64, device=val.device)
+    check(_lib.load().qrs_center_rows(ptr(rowptr), ptr(val), n_rows, ptr(cval), ptr(norm2), _stream()),
+          "qrs_center_rows")
+    return cval, norm2
+
+
+def pair_centered_cosine(rowptr: torch.Tensor, colidx: torch.Tensor, val: torch.Tensor, cval: torch.Tensor,
+                         norm2: torch.Tensor, pairs: torch.Tensor, m: int, grouped: bool = False,
+                         force_search: bool = False) -> torch.Tensor:
+    """int32 max(0, rint(1000 * cos)) of the centred rating rows of each pair (recommender.py:267-269)."""
+    _need_cuda(rowptr, colidx, val, cval, norm2, pairs)
+    sims = torch.empty(pairs.numel(), dtype=torch.int32, device=pairs.device)
+    flags = (_lib.PAIRS_GROUPED if grouped else 0) | (_lib.PAIRS_FORCE_SEARCH if force_search else 0)
+    check(_lib.load().qrs_pair_centered_cosine(ptr(rowptr), ptr(colidx), ptr(val), ptr(cval), ptr(norm2), ptr(pairs),
+                                               pairs.numel(), m, flags, ptr(sims), _stream()),
+          "qrs_pair_centered_cosine")
+    return sims
+
+
 # ------------------------------------------------------------------------ a7/a9
 def topk_tables(pairs: torch.Tensor, sims: torch.Tensor, n_pairs: int, row_base: int, n_rows: int, k: int,
                 want_milli: bool = False):

@@ -109,6 +109,19 @@ def pairs_score(records, slot_off, sig, norm2, b, capacity, sig_id_base=0, want_
     return pt, stt, torch.tensor([packed.size], dtype=torch.int64)
 
 
+def center_rows(rowptr, val):
+    cval, n2 = spec.centered_rows(rowptr.numpy(), val.numpy())
+    return torch.from_numpy(cval), torch.from_numpy(n2)
+
+
+def pair_centered_cosine(rowptr, colidx, val, cval, norm2, pairs, m, grouped=False, force_search=False):
+    p = pairs.numpy().view(np.uint64)
+    if grouped:
+        assert (np.diff((p >> np.uint64(32)).astype(np.int64)) >= 0).all(), "pairs are not grouped by first id"
+    pr = np.stack([(p >> np.uint64(32)).astype(np.int64), (p & np.uint64(0xFFFFFFFF)).astype(np.int64)], 1)
+    return torch.from_numpy(spec.centered_cosine_milli(rowptr.numpy(), colidx.numpy(), val.numpy(), pr))
+
+
 def topk_tables(pairs, sims, n_pairs, row_base, n_rows, k, want_milli=False):
     p = pairs.numpy().view(np.uint64)[:n_pairs]
     pr = np.stack([(p >> np.uint64(32)).astype(np.int64), (p & np.uint64(0xFFFFFFFF)).astype(np.int64)], 1)

@@ -172,3 +172,36 @@ def test_host_runner_chunked_matches_device_run(fmt):
             assert np.array_equal(mine_c, ref_c) and np.array_equal(mine_p, ref_p)
         seen += ch["n_users"]
     assert seen == n
+
+
+def test_user_branch_lsh_tables_and_hybrid_scores(golden_c1):
+    """f-3: Recommender(user_branch="lsh") — LSH candidates over the users' rating rows scored with the
+    reference's centred cosine; the tables match the oracle composition and compute_scores' hybrid rule runs
+    on them (the oracle's cell loop, oracle/port.py, on the same two tables)."""
+    from oracle import port, spec
+    from query_recommendation_system_b200.recommender import PERM, Recommender
+    g = golden_c1
+    R = g["ratings"].astype(np.int64)
+    U, Q = R.shape
+    rec = load_like_main()
+    rec._user_branch = "lsh"
+    rec._bands = 90                                         # r = 2: enough candidates among 100 users
+    np.random.seed(11)
+    us = rec.compute_userSimilarities()
+    tab = spec.permutation_table(Q, PERM, seed=11)
+    rows, cols = np.nonzero(R)
+    rowptr = np.zeros(U + 1, np.int64)
+    np.cumsum(np.bincount(rows, minlength=U), out=rowptr[1:])
+    val = R[rows, cols].astype(np.uint8)
+    sig = spec.signatures(rowptr, cols.astype(np.int32), tab)
+    cand = np.array(sorted(spec.candidates(sig, 90)), dtype=np.int64).reshape(-1, 2)
+    sims = spec.centered_cosine_milli(rowptr, cols, val, cand)
+    idx, v, cnt = spec.topk_tables(U, cand, sims / 1000.0, spec.max_candidates(U))
+    assert cand.shape[0] > 100 and sorted(us) == list(range(U))            # an entry for every user
+    for i in range(U):
+        assert np.array_equal(us[i]["indexes"], idx[i, :cnt[i]]) and np.array_equal(us[i]["values"], v[i, :cnt[i]])
+    q = {i: {"indexes": g["q_idx"][i, :g["q_cnt"][i]], "values": g["q_val"][i, :g["q_cnt"][i]]}
+         for i in range(int(g["n_sets"])) if g["q_cnt"][i] >= 0}
+    got = rec.predict_with_tables(q, us)
+    _, want, _ = port.compute_scores(R.astype(np.int32), q, us)
+    assert np.array_equal(got, np.asarray(want).astype(np.int64))

@@ -530,3 +530,120 @@ def test_predict_sparse_wide_tables_k50(integer):
         gc = np.concatenate([cols[rs[t, c]:rs[t, c] + rc[t, c]] for c in range(rs.shape[1])])
         gp = np.concatenate([preds[rs[t, c]:rs[t, c] + rc[t, c]] for c in range(rs.shape[1])])
         assert np.array_equal(gc, ref[t][0]) and np.array_equal(gp.astype(np.int64), ref[t][1])
+
+
+# ------------------------------------------------------------------------------ f-3
+def _ratings_csr(n, m, fill, seed):
+    """Random ratings rows incl. an empty row, a single-rating row, a constant row and explicit 0 cells."""
+    rng = np.random.default_rng(seed)
+    lens = rng.binomial(m, fill, n)
+    lens[0], lens[1] = 0, 1
+    rowptr = np.zeros(n + 1, np.int64)
+    rowptr[1:] = np.cumsum(lens)
+    colidx = np.concatenate([np.sort(rng.choice(m, l, replace=False)) for l in lens]).astype(np.int32)
+    val = rng.integers(1, 101, colidx.size).astype(np.uint8)
+    val[rowptr[2]:rowptr[3]] = 50                          # constant row: centres to zero norm
+    val[rng.random(val.size) < 0.02] = 0                   # stored but "not rated" cells
+    val[rowptr[4]:rowptr[5]] = np.where(np.arange(lens[4]) % 2 == 0, 1, 255)     # both ends of the uint8 range
+    return rowptr, colidx, val
+
+
+def test_center_rows_matches_oracle():
+    from query_recommendation_system_b200 import stages
+    rowptr, colidx, val = _ratings_csr(300, 900, 0.1, seed=2)
+    cval, n2 = stages.center_rows(cu(rowptr), cu(val))
+    want_c, want_n2 = spec.centered_rows(rowptr, val)
+    assert np.array_equal(cval.cpu().numpy(), want_c) and np.array_equal(n2.cpu().numpy(), want_n2)
+    assert want_n2[0] == 0 and want_n2[1] == 0 and want_n2[2] == 0 and want_c.min() < -100 and want_c.max() > 100
+
+
+@pytest.mark.parametrize("m,fill", [(300, 0.2), (70_000, 0.002), (250_000, 0.0006)])
+def test_pair_centered_cosine_matches_oracle(m, fill):
+    """m = 300 / 70 000: row i staged in shared memory; m = 250 000: beyond the staged limit, search kernel."""
+    from query_recommendation_system_b200 import stages
+    n = 200
+    rowptr, colidx, val = _ratings_csr(n, m, fill, seed=m)
+    rng = np.random.default_rng(5)
+    ii, jj = np.triu_indices(n, 1)
+    pick = rng.choice(ii.size, 6000, replace=False)
+    pr = np.stack([ii[pick], jj[pick]], 1)
+    pr = pr[np.argsort(pr[:, 0], kind="stable")]           # grouped by first id, seconds in random order
+    want = spec.centered_cosine_milli(rowptr, colidx, val, pr)
+    packed = cu(((pr[:, 0].astype(np.uint64) << np.uint64(32)) | pr[:, 1].astype(np.uint64)).view(np.int64))
+    d = [cu(rowptr), cu(colidx), cu(val)]
+    cval, n2 = stages.center_rows(d[0], d[2])
+    staged = stages.pair_centered_cosine(*d, cval, n2, packed, m, grouped=True)
+    search = stages.pair_centered_cosine(*d, cval, n2, packed, m, grouped=True, force_search=True)
+    shuffled = torch.randperm(packed.numel(), device=DEV)
+    anyorder = stages.pair_centered_cosine(*d, cval, n2, packed[shuffled].contiguous(), m, grouped=False)
+    assert np.array_equal(staged.cpu().numpy(), want)
+    assert np.array_equal(search.cpu().numpy(), want)
+    assert np.array_equal(anyorder.cpu().numpy(), want[shuffled.cpu().numpy()])
+    if m == 300:
+        assert (want > 0).sum() > 1000 and (want == 0).sum() > 1000
+
+
+def test_pair_centered_cosine_long_rows():
+    """Rows of ~2000 cells: the four-deep unrolled sweep of the staged kernel and its tail."""
+    from query_recommendation_system_b200 import stages
+    n, m = 40, 5000
+    rowptr, colidx, val = _ratings_csr(n, m, 0.4, seed=8)
+    ii, jj = np.triu_indices(n, 1)
+    pr = np.stack([ii, jj], 1)
+    want = spec.centered_cosine_milli(rowptr, colidx, val, pr)
+    packed = cu(((pr[:, 0].astype(np.uint64) << np.uint64(32)) | pr[:, 1].astype(np.uint64)).view(np.int64))
+    d = [cu(rowptr), cu(colidx), cu(val)]
+    cval, n2 = stages.center_rows(d[0], d[2])
+    got = stages.pair_centered_cosine(*d, cval, n2, packed, m, grouped=True)
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_pair_centered_cosine_reference_user_table_c1(golden_c1):
+    """The user neighbour table of the unmodified reference (recommender.py:256-286 on C1): every listed
+    similarity is reproduced by the kernel for that pair."""
+    from query_recommendation_system_b200 import stages
+    g = golden_c1
+    R = g["ratings"].astype(np.int64)
+    rows, cols = np.nonzero(R)
+    rowptr = np.zeros(R.shape[0] + 1, np.int64)
+    np.cumsum(np.bincount(rows, minlength=R.shape[0]), out=rowptr[1:])
+    pr = np.array([(i, int(g["u_idx"][i, t])) for i in range(R.shape[0]) for t in range(int(g["u_cnt"][i]))
+                   if int(g["u_idx"][i, t]) != i])
+    want = np.array([g["u_val"][i, t] for i in range(R.shape[0]) for t in range(int(g["u_cnt"][i]))
+                     if int(g["u_idx"][i, t]) != i])
+    packed = cu(((pr[:, 0].astype(np.uint64) << np.uint64(32)) | pr[:, 1].astype(np.uint64)).view(np.int64))
+    d = [cu(rowptr), cu(cols.astype(np.int32)), cu(R[rows, cols].astype(np.uint8))]
+    cval, n2 = stages.center_rows(d[0], d[2])
+    got = stages.pair_centered_cosine(*d, cval, n2, packed, R.shape[1], grouped=True)
+    assert np.array_equal(got.cpu().numpy(), np.rint(want * 1000).astype(np.int32)) and pr.shape[0] > 700
+
+
+def test_pipeline_ratings_similarity_matches_oracle():
+    """LshCfPipeline with similarity="ratings": LSH candidates, centred-cosine neighbour tables, predictions."""
+    from query_recommendation_system_b200 import synth
+    from query_recommendation_system_b200.pipeline import LshCfPipeline
+    n, m, K, b, k = 1024, 2000, 64, 16, 17
+    tab = spec.permutation_table(m, K, seed=7)
+    rowptr, colidx, val = synth.planted_csr(n, m, 0.05, seed=21)
+    pipe = LshCfPipeline(m=m, K=K, b=b, k=k, perm_tab=tab, device=DEV, distributed=False)
+    pipe.similarity = "ratings"
+    out = pipe.run(rowptr.to(DEV), colidx.to(DEV), val.to(DEV))
+    sig = spec.signatures(rowptr.numpy(), colidx.numpy(), tab)
+    cand = np.array(sorted(spec.candidates(sig, b)), dtype=np.int64).reshape(-1, 2)
+    want = spec.centered_cosine_milli(rowptr.numpy(), colidx.numpy(), val.numpy(), cand)
+    got_pairs = unpack(out.pairs)
+    order = np.lexsort((got_pairs[:, 1], got_pairs[:, 0]))
+    assert np.array_equal(got_pairs[order], cand) and np.array_equal(out.sims.cpu().numpy()[order], want)
+    idx, v, cnt = spec.topk_tables(n, cand, want / 1000.0, k)
+    assert np.array_equal(out.nbr_idx.cpu().numpy(), idx) and np.array_equal(out.nbr_val.cpu().numpy(), v)
+    assert np.array_equal(out.nbr_cnt.cpu().numpy(), cnt)
+    rows = np.arange(0, n, 37)
+    ref = spec.predict_user_branch_csr(rowptr.numpy(), colidx.numpy(), val.numpy(), m, idx, v, cnt, rows=rows)
+    rs, rc = out.pred_row_start.cpu().numpy(), out.pred_row_cnt.cpu().numpy()
+    pc, pv = out.pred_cols.cpu().numpy(), out.pred_vals.cpu().numpy()
+    assert (v[cnt > 0, 0] > 0.3).any() and (v == 0).any()
+    for u in rows:
+        gc = np.concatenate([pc[rs[u, x]:rs[u, x] + rc[u, x]] for x in range(rs.shape[1])])
+        gp = np.concatenate([pv[rs[u, x]:rs[u, x] + rc[u, x]] for x in range(rs.shape[1])])
+        rcols, rpreds = ref[u]
+        assert np.array_equal(gc, rcols) and np.array_equal(gp.astype(np.int64), rpreds), u
