@@ -345,6 +345,37 @@ def main():
         topn = {"ms": t0e.elapsed_time(t1e) / 5, "N": 10,
                 "note": "qrs_recommend_topn over the sparse predictions of the last step (outside the timed step)"}
 
+    # ---------------------------------------------------------------- f-3 extra: centred-cosine scoring of the step's pairs
+    usim = None
+    if world == 1 and out.pairs is not None and out.pairs.numel() > 0:
+        from query_recommendation_system_b200 import stages as _st
+        pr = out.pairs.clone()
+        P = pr.numel()
+        bits = 32 + max(1, (n - 1).bit_length())
+
+        def score_by_ratings():
+            cval, n2c = _st.center_rows(rowptr, val)
+            _st.sort_u64(pr, P, 1, 32, bits)
+            return _st.pair_centered_cosine(rowptr, colidx, val, cval, n2c, pr, m, grouped=True)
+        for _ in range(2):
+            score_by_ratings()
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0e.record()
+        for _ in range(5):
+            score_by_ratings()
+        t1e.record()
+        torch.cuda.synchronize()
+        ms_us = t0e.elapsed_time(t1e) / 5
+        lens = (rowptr[1:] - rowptr[:-1])
+        second = (pr & 0xFFFFFFFF)
+        # algorithmic bytes: the second row of every pair is streamed once (4 B column + 2 B centred value per
+        # cell), centring reads 1 B and writes 2 B per cell, the pair list is sorted (2 passes x 16 B) and read
+        usim_bytes = float(lens[second].sum().item()) * 6 + nnz * 3 + P * (16 * ((bits - 32 + 7) // 8) + 12)
+        usim = {"ms": ms_us, "pairs": P, "pairs_per_s": P / (ms_us * 1e-3),
+                "algorithmic_GBps": usim_bytes / (ms_us * 1e-3) / 1e9, "hbm_frac": usim_bytes / (ms_us * 1e-3) / 1e9 / peak,
+                "note": "qrs_center_rows + qrs_sort_u64 + qrs_pair_centered_cosine on the candidate pairs of the last "
+                        "step (user-branch scoring, recommender.py:263-269; outside the timed step)"}
+
     # ---------------------------------------------------------------- e2e: host buffers in, host results out
     runner = HostRunner(pipe)
     h_rowptr, h_colidx, h_val = [x.cpu().pin_memory() for x in (rowptr, colidx, val)]
@@ -388,7 +419,7 @@ def main():
                     "h2d_bytes_per_step": runner.h2d_bytes, "d2h_bytes_per_step": runner.d2h_bytes, "steps": e2e_steps,
                     "call": "pipeline.HostRunner(pipe, chunks=4, cols_format=auto)(rowptr, colidx, val) with pinned host tensors; returns pinned "
                             "sparse predictions + neighbour tables"},
-            "gpu_launches": int(launches), "clocks": clocks, "recommend_top_n": topn,
+            "gpu_launches": int(launches), "clocks": clocks, "recommend_top_n": topn, "user_similarity": usim,
         }
         if world == 1 and not args.no_cpu_baseline:
             tc, cc = run_cpu_port(args.config, args.cpu_sets)

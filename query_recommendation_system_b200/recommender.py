@@ -9,7 +9,8 @@ compute_userSimilarities` with their reference return types, and the module cons
 
 On the GPU: signatures (a1), banding + grouping + candidate pairs + cosine (a2-a8), top-k neighbour
 tables (a9), the per-cell weighted averages + hybrid rule (a10-a11) and — the first "next" row, f-1 —
-the predicate evaluation of compute_shingles on dictionary-encoded columns.  On the host, as in the
+the predicate evaluation of compute_shingles on dictionary-encoded columns; with user_branch="lsh" also the
+user-similarity tables (f-3: LSH candidates over the rating rows + the reference's centred cosine).  On the host, as in the
 reference and out of this path's scope: the PCA + BIRCH user clustering
 (compute_userSimilarities), CSV parsing and the interactive prompt.  The reference reads its tables through `datatable`, which is
 not installable here; `init` accepts anything with `.to_numpy()` (datatable Frames, pandas
