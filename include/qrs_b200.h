@@ -276,6 +276,31 @@ int qrs_pair_centered_cosine(const int64_t *rowptr, const int32_t *colidx, const
                              const int16_t *cval, const int64_t *norm2, const uint64_t *pairs,
                              int64_t n_pairs, int32_t m, int32_t flags, int32_t *sim_milli, void *stream);
 
+/* ------------------------------------------------------ f-4: CSV ingest of the utility matrix
+ * Replaces dt.fread of utility_matrix.csv (main.py:69-75) for the path: the file as the reference's
+ * generator writes it (generator.py:59-77, 329-332 - csv.writer: "\r\n" or "\n" rows, first line = the
+ * query ids WITHOUT a user field, then `user,r,r,,r,...`; empty field = not rated; integers, here 0..255
+ * with 0 = not rated) is parsed on the device into the ratings CSR (rowptr, colidx ascending, val).
+ * `text` is the whole file in device memory, 16-byte aligned.
+ *
+ * qrs_csv_line_ends: *n_lines = number of '\n' bytes; with capacity > 0 also line_end[k] = position of the
+ *   k-th one (k < capacity).  Call once with capacity 0 to size line_end.  If the text does not end with
+ *   '\n' the caller appends n_bytes as the end of the last line.
+ * qrs_csv_ratings_count: rows = lines first_line .. first_line + n_rows - 1 (first_line = 1 skips the
+ *   header).  rowptr int64[n_rows + 1] = exclusive scan of the rated cells per row; id_end[r] = position of
+ *   the comma closing row r's user id; err[0] = number of malformed rows (field count != Q + 1, a
+ *   non-digit in a rating field, a quote, a value > 255), err[1] = the first such row (INT32_MAX if none).
+ *   Malformed rows count 0 cells; qrs_csv_ratings_fill must only be called when err[0] == 0.
+ * ws: qrs_csv_workspace_bytes(n_bytes, n_rows) (either argument may be 0 for the call that does not use it). */
+size_t qrs_csv_workspace_bytes(int64_t n_bytes, int64_t n_rows);
+int qrs_csv_line_ends(const uint8_t *text, int64_t n_bytes, int64_t *line_end, int64_t capacity,
+                      uint64_t *n_lines, void *ws, size_t ws_bytes, void *stream);
+int qrs_csv_ratings_count(const uint8_t *text, const int64_t *line_end, int64_t first_line, int64_t n_rows,
+                          int32_t Q, int64_t *rowptr, int64_t *id_end, int32_t *err, void *ws, size_t ws_bytes,
+                          void *stream);
+int qrs_csv_ratings_fill(const uint8_t *text, const int64_t *line_end, int64_t first_line, int64_t n_rows,
+                         int32_t Q, const int64_t *rowptr, int32_t *colidx, uint8_t *val, void *stream);
+
 /* ------------------------------------------------------ multi-GPU plumbing
  * Rows of the ratings CSR are sharded across GPUs; the prediction gathers neighbour rows
  * (recommender.py:320), so rows requested by other ranks are packed for sending:

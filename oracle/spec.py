@@ -377,3 +377,22 @@ def predict_user_branch_csr(rowptr, colidx, val, Q, u_idx, u_val, u_cnt, rows=No
         keep = p != 0
         out[i] = (cols[keep].astype(np.int32), p[keep].astype(np.int64))
     return out
+
+
+# --------------------------------------------------------------------------- f-4
+def parse_utility_csv(data: bytes):
+    """utility_matrix.csv as main.py:69-75 reads it (the file of generator.py:59-77, 329-332: a header of
+    query ids without a user field, then `user,r,r,,r,...`; empty = not rated) with Python's own csv module
+    (the writer's counterpart) -> (query_ids, user_ids, dense int64[U, Q] with 0 = not rated)."""
+    import csv
+    import io
+    rows = list(csv.reader(io.StringIO(data.decode("utf-8"), newline="")))
+    query_ids = rows[0]
+    user_ids = [r[0] for r in rows[1:]]
+    dense = np.zeros((len(user_ids), len(query_ids)), dtype=np.int64)
+    for i, r in enumerate(rows[1:]):
+        assert len(r) == len(query_ids) + 1, "row %d: %d fields" % (i, len(r))
+        for j, f in enumerate(r[1:]):
+            if f != "":
+                dense[i, j] = int(f)
+    return query_ids, user_ids, dense

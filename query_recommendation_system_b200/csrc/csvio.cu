@@ -1,0 +1,252 @@
+// f-4: the wire format on the input side of the path.  utility_matrix.csv as
+// written by the reference's generator (generator.py:59-77, 329-332: csv.writer, "\r\n" rows,
+// header = query ids WITHOUT a user field, then `user,r,r,,r,...` with an empty field = not rated,
+// integers 1..100) is parsed on the GPU straight into the ratings CSR the path consumes — what
+// main.py:75 does with dt.fread into a dense frame.
+//
+//   qrs_csv_line_ends      positions of every '\n' (chunk counts -> scan -> ordered write)
+//   qrs_csv_ratings_count  per row: rated cells, end of the user-id field, format checks
+//   qrs_csv_ratings_fill   column ids + rating bytes at the scanned offsets
+//
+// A warp owns a row and walks it 32 bytes per step: one ballot marks the field terminators, its
+// prefix popcount is the field (= column) index of every byte, and the lane holding a terminator
+// assembles the up-to-3-digit integer from the bytes in front of it (shuffles + a 4-byte carry
+// across steps).  Emission order is ascending by construction, so rows come out sorted.
+#include "common.cuh"
+
+namespace qrs {
+
+constexpr int kCsvWarpBytes = 4096;        // bytes one warp scans for line ends (8 sweeps of 512)
+
+__device__ __forceinline__ uint4 load16_guarded(const uint8_t *text, int64_t p, int64_t n) {
+  if (p + 16 <= n) return *reinterpret_cast<const uint4 *>(text + p);
+  unsigned w[4] = {0u, 0u, 0u, 0u};
+  for (int k = 0; k < 16; ++k)
+    if (p + k < n) w[k >> 2] |= unsigned(text[p + k]) << (8 * (k & 3));
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// bit k of the result = byte k of the 16 loaded bytes is '\n'
+__device__ __forceinline__ unsigned newline_bits(uint4 v) {
+  const unsigned w[4] = {v.x, v.y, v.z, v.w};
+  unsigned bits = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const unsigned eq = __vcmpeq4(w[i], 0x0A0A0A0Au);           // 0xFF per matching byte
+    bits |= ((eq & 1u) | ((eq >> 7) & 2u) | ((eq >> 14) & 4u) | ((eq >> 21) & 8u)) << (4 * i);
+  }
+  return bits;
+}
+
+// WRITE = false: counts[chunk] = newlines in the chunk.  WRITE = true: line_end[offsets[chunk] + k] = position
+// of the chunk's k-th newline.  `text` is 16-byte aligned (checked by the entry point).
+template <bool WRITE>
+__global__ void __launch_bounds__(256)
+csv_newlines_kernel(const uint8_t *__restrict__ text, int64_t n, int64_t n_chunks, uint32_t *__restrict__ counts,
+                    const uint64_t *__restrict__ offsets, int64_t *__restrict__ line_end, int64_t capacity) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t ch = warp_global; ch < n_chunks; ch += nwarps) {
+    const int64_t base = ch * kCsvWarpBytes;
+    int64_t out = WRITE ? int64_t(offsets[ch]) : 0;
+    unsigned total = 0;
+#pragma unroll 2
+    for (int s = 0; s < kCsvWarpBytes / 512; ++s) {
+      const int64_t p = base + s * 512 + lane * 16;
+      unsigned bits = p < n ? newline_bits(load16_guarded(text, p, n)) : 0u;
+      const unsigned c = __popc(bits);
+      if (WRITE) {
+        unsigned incl = c;                                       // inclusive prefix of c over the lanes
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const unsigned up = __shfl_up_sync(kFull, incl, d);
+          if (lane >= d) incl += up;
+        }
+        const unsigned before = incl - c;
+        int64_t o = out + before;
+        while (bits) {
+          const int k = __ffs(bits) - 1;
+          bits &= bits - 1;
+          if (o < capacity) line_end[o] = p + k;
+          ++o;
+        }
+      }
+      unsigned sum = c;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(kFull, sum, o);
+      out += sum;
+      total += sum;
+    }
+    if (!WRITE && lane == 0) counts[ch] = total;
+  }
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+csv_ratings_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__ line_end, int64_t first_line,
+                   int64_t n_rows, int Q, uint32_t *__restrict__ row_cnt, int64_t *__restrict__ id_end,
+                   int *__restrict__ err, const int64_t *__restrict__ rowptr, int *__restrict__ colidx,
+                   uint8_t *__restrict__ val) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  const unsigned lt = lanemask_lt();
+  for (int64_t r = warp_global; r < n_rows; r += nwarps) {
+    const int64_t L = first_line + r;
+    const int64_t begin = L == 0 ? 0 : line_end[L - 1] + 1;
+    int64_t end = line_end[L];                                 // the '\n' (or one past the last byte of the text)
+    if (end > begin && text[end - 1] == '\r') --end;           // csv.writer's "\r\n"
+    const int64_t out_base = FILL ? rowptr[r] : 0;
+    int fields = 0, emitted = 0;
+    unsigned carry = 0;                                        // the 4 bytes in front of this step, nearest in bits 0-7
+    int64_t first_term = -1;
+    bool bad = false;
+    // the position `end` closes the last field: treated as one more terminator
+    for (int64_t s = begin; s <= end; s += 32) {
+      const int64_t p = s + lane;
+      const bool in = p <= end;
+      const int c = in ? (p < end ? int(text[p]) : int(',')) : 0;
+      const bool is_t = in && c == ',';
+      const bool is_d = unsigned(c - '0') < 10u;
+      const unsigned tmask = __ballot_sync(kFull, is_t);
+      const int f = fields + __popc(tmask & lt);               // field this byte belongs to (or terminates)
+      if (in && !is_t && f >= 1 && !is_d) bad = true;          // rating fields hold digits only
+      if (in && c == '"') bad = true;                          // quoted fields are not part of the format
+      int prev[4];
+#pragma unroll
+      for (int d = 1; d <= 4; ++d) {
+        const int up = __shfl_up_sync(kFull, c, d);
+        prev[d - 1] = lane >= d ? up : int((carry >> (8 * (d - lane - 1))) & 0xFFu);
+      }
+      bool emit = false;
+      int v = 0;
+      if (is_t && f >= 1) {
+        const unsigned d1 = unsigned(prev[0] - '0'), d2 = unsigned(prev[1] - '0'), d3 = unsigned(prev[2] - '0'),
+                       d4 = unsigned(prev[3] - '0');
+        if (d1 < 10u) {
+          v = int(d1);
+          if (d2 < 10u) {
+            v += 10 * int(d2);
+            if (d3 < 10u) {
+              v += 100 * int(d3);
+              if (d4 < 10u) bad = true;                        // four digits or more
+            }
+          }
+          if (v > 255) bad = true;
+          emit = v != 0;                                       // 0 = not rated, like an empty field
+        }
+      }
+      const unsigned emask = __ballot_sync(kFull, emit);
+      if (FILL && emit) {
+        const int64_t o = out_base + emitted + __popc(emask & lt);
+        colidx[o] = f - 1;
+        val[o] = uint8_t(v);
+      }
+      emitted += __popc(emask);
+      if (first_term < 0 && tmask != 0u) first_term = s + __ffs(tmask) - 1;
+      fields += __popc(tmask);
+      // the last four bytes of this step, for the next one
+      const unsigned b31 = __shfl_sync(kFull, c, 31), b30 = __shfl_sync(kFull, c, 30),
+                     b29 = __shfl_sync(kFull, c, 29), b28 = __shfl_sync(kFull, c, 28);
+      carry = (b31 & 0xFFu) | ((b30 & 0xFFu) << 8) | ((b29 & 0xFFu) << 16) | ((b28 & 0xFFu) << 24);
+    }
+    bad = __any_sync(kFull, bad) || fields != Q + 1;
+    if (!FILL && lane == 0) {
+      row_cnt[r] = bad ? 0u : unsigned(emitted);
+      id_end[r] = first_term < 0 ? end : first_term;
+      if (bad) {
+        atomicAdd(err, 1);
+        atomicMin(err + 1, int(r < 0x7FFFFFFF ? r : 0x7FFFFFFE));
+      }
+    }
+  }
+}
+
+}  // namespace qrs
+
+using namespace qrs;
+
+extern "C" {
+
+size_t qrs_csv_workspace_bytes(int64_t n_bytes, int64_t n_rows) {
+  if (n_bytes < 0 || n_rows < 0) return 0;
+  const int64_t chunks = ceil_div<int64_t>(n_bytes > 0 ? n_bytes : 1, kCsvWarpBytes);
+  const int64_t entries = chunks > n_rows ? chunks : n_rows;
+  return round_up<size_t>(size_t(entries) * 4, 256) + round_up<size_t>(size_t(chunks + 1) * 8, 256) +
+         scan_workspace_bytes(entries);
+}
+
+int qrs_csv_line_ends(const uint8_t *text, int64_t n_bytes, int64_t *line_end, int64_t capacity, uint64_t *n_lines,
+                      void *ws, size_t ws_bytes, void *stream) {
+  if (n_bytes < 0 || capacity < 0 || !n_lines || (n_bytes > 0 && !text) || (capacity > 0 && !line_end))
+    return QRS_ERR_INVALID_ARG;
+  if ((reinterpret_cast<uintptr_t>(text) & 15u) != 0) return QRS_ERR_INVALID_ARG;
+  cudaStream_t st = as_stream(stream);
+  if (n_bytes == 0) {
+    QRS_CUDA(cudaMemsetAsync(n_lines, 0, sizeof(uint64_t), st));
+    return QRS_OK;
+  }
+  if (!ws || ws_bytes < qrs_csv_workspace_bytes(n_bytes, 0)) return QRS_ERR_WORKSPACE;
+  const int64_t chunks = ceil_div<int64_t>(n_bytes, kCsvWarpBytes);
+  char *w = static_cast<char *>(ws);
+  uint32_t *counts = reinterpret_cast<uint32_t *>(w);
+  w += round_up<size_t>(size_t(chunks) * 4, 256);
+  uint64_t *offsets = reinterpret_cast<uint64_t *>(w);
+  w += round_up<size_t>(size_t(chunks + 1) * 8, 256);
+  int64_t blocks = ceil_div<int64_t>(chunks, 8);
+  const int64_t cap = int64_t(sm_count()) * 8;
+  if (blocks > cap) blocks = cap;
+  csv_newlines_kernel<false><<<unsigned(blocks), 256, 0, st>>>(text, n_bytes, chunks, counts, nullptr, nullptr, 0);
+  QRS_LAUNCH_CHECK();
+  int rc = exclusive_scan_u32_to_u64(counts, offsets, chunks, w, scan_workspace_bytes(chunks), st);
+  if (rc != QRS_OK) return rc;
+  QRS_CUDA(cudaMemcpyAsync(n_lines, offsets + chunks, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+  if (capacity > 0) {
+    csv_newlines_kernel<true><<<unsigned(blocks), 256, 0, st>>>(text, n_bytes, chunks, nullptr, offsets, line_end,
+                                                               capacity);
+    QRS_LAUNCH_CHECK();
+  }
+  return QRS_OK;
+}
+
+int qrs_csv_ratings_count(const uint8_t *text, const int64_t *line_end, int64_t first_line, int64_t n_rows, int32_t Q,
+                          int64_t *rowptr, int64_t *id_end, int32_t *err, void *ws, size_t ws_bytes, void *stream) {
+  if (n_rows < 0 || first_line < 0 || Q <= 0 || !rowptr || !err) return QRS_ERR_INVALID_ARG;
+  if (n_rows > 0 && (!text || !line_end || !id_end)) return QRS_ERR_INVALID_ARG;
+  if (!ws || ws_bytes < qrs_csv_workspace_bytes(0, n_rows)) return QRS_ERR_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  uint32_t *counts = static_cast<uint32_t *>(ws);
+  const int64_t chunks1 = 1;      // layout of qrs_csv_workspace_bytes(0, n_rows): counts | 1-chunk offsets | scan
+  char *w = static_cast<char *>(ws) + round_up<size_t>(size_t(n_rows > 1 ? n_rows : 1) * 4, 256) +
+            round_up<size_t>(size_t(chunks1 + 1) * 8, 256);
+  const int init[2] = {0, 0x7FFFFFFF};
+  QRS_CUDA(cudaMemcpyAsync(err, init, sizeof(init), cudaMemcpyHostToDevice, st));
+  if (n_rows > 0) {
+    int64_t blocks = ceil_div<int64_t>(n_rows, 8);
+    const int64_t cap = int64_t(sm_count()) * 8;
+    if (blocks > cap) blocks = cap;
+    csv_ratings_kernel<false><<<unsigned(blocks), 256, 0, st>>>(text, line_end, first_line, n_rows, Q, counts, id_end,
+                                                               err, nullptr, nullptr, nullptr);
+    QRS_LAUNCH_CHECK();
+  }
+  return exclusive_scan_u32_to_u64(counts, reinterpret_cast<uint64_t *>(rowptr), n_rows, w,
+                                   scan_workspace_bytes(n_rows), st);
+}
+
+int qrs_csv_ratings_fill(const uint8_t *text, const int64_t *line_end, int64_t first_line, int64_t n_rows, int32_t Q,
+                         const int64_t *rowptr, int32_t *colidx, uint8_t *val, void *stream) {
+  if (n_rows < 0 || first_line < 0 || Q <= 0 || !rowptr) return QRS_ERR_INVALID_ARG;
+  if (n_rows == 0) return QRS_OK;
+  if (!text || !line_end || !colidx || !val) return QRS_ERR_INVALID_ARG;
+  int64_t blocks = ceil_div<int64_t>(n_rows, 8);
+  const int64_t cap = int64_t(sm_count()) * 8;
+  if (blocks > cap) blocks = cap;
+  csv_ratings_kernel<true><<<unsigned(blocks), 256, 0, as_stream(stream)>>>(text, line_end, first_line, n_rows, Q,
+                                                                           nullptr, nullptr, nullptr, rowptr, colidx,
+                                                                           val);
+  QRS_LAUNCH_CHECK();
+  return QRS_OK;
+}
+
+}  // extern "C"

@@ -334,3 +334,50 @@ def gather_rows(rowptr, colidx, val, rows: torch.Tensor, out_off: torch.Tensor, 
     check(_lib.load().qrs_gather_rows(ptr(rowptr), ptr(colidx), ptr(val), ptr(rows), rows.numel(), ptr(out_off),
                                       ptr(col), ptr(v), _stream()), "qrs_gather_rows")
     return col[:total], v[:total]
+
+
+# ---------------------------------------------------------------------- f-4: CSV ingest
+def csv_line_ends(text: torch.Tensor) -> torch.Tensor:
+    """Positions of the line ends of a CSV text held on the device (uint8[n]); a last line without '\n' ends
+    at n.  int64[n_lines]."""
+    _need_cuda(text)
+    assert text.dtype == torch.uint8
+    lib = _lib.load()
+    n = text.numel()
+    dev = text.device
+    ws = _ws(lib.qrs_csv_workspace_bytes(n, 0), dev)
+    count = torch.zeros(1, dtype=torch.int64, device=dev)
+    check(lib.qrs_csv_line_ends(ptr(text), n, None, 0, ptr(count), ptr(ws), ws.numel(), _stream()), "qrs_csv_line_ends")
+    lines = int(count.item())
+    open_tail = n > 0 and int(text[-1].item()) != 10
+    ends = torch.empty(lines + (1 if open_tail else 0), dtype=torch.int64, device=dev)
+    if lines:
+        check(lib.qrs_csv_line_ends(ptr(text), n, ptr(ends), lines, ptr(count), ptr(ws), ws.numel(), _stream()),
+              "qrs_csv_line_ends")
+    if open_tail:
+        ends[-1] = n
+    return ends
+
+
+def csv_ratings(text: torch.Tensor, line_end: torch.Tensor, first_line: int, n_rows: int, Q: int):
+    """Rows `first_line ..` of the utility-matrix CSV → (rowptr int64[n_rows + 1], colidx int32[nnz],
+    val uint8[nnz], id_end int64[n_rows]); raises QrsError naming the first malformed row."""
+    _need_cuda(text, line_end)
+    lib = _lib.load()
+    dev = text.device
+    rowptr = torch.empty(n_rows + 1, dtype=torch.int64, device=dev)
+    id_end = torch.empty(max(n_rows, 1), dtype=torch.int64, device=dev)
+    err = torch.empty(2, dtype=torch.int32, device=dev)
+    ws = _ws(lib.qrs_csv_workspace_bytes(0, n_rows), dev)
+    check(lib.qrs_csv_ratings_count(ptr(text), ptr(line_end), first_line, n_rows, Q, ptr(rowptr), ptr(id_end), ptr(err),
+                                    ptr(ws), ws.numel(), _stream()), "qrs_csv_ratings_count")
+    tail = torch.cat([rowptr[-1:], err.to(torch.int64)]).cpu()
+    nnz, n_bad, first_bad = int(tail[0]), int(tail[1]), int(tail[2])
+    if n_bad:
+        raise _lib.QrsError("utility matrix CSV: %d malformed row(s), first at data row %d (expected %d fields, "
+                            "integer ratings 0..255, no quotes)" % (n_bad, first_bad, Q + 1))
+    colidx = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+    val = torch.empty(max(nnz, 1), dtype=torch.uint8, device=dev)
+    check(lib.qrs_csv_ratings_fill(ptr(text), ptr(line_end), first_line, n_rows, Q, ptr(rowptr), ptr(colidx), ptr(val),
+                                   _stream()), "qrs_csv_ratings_fill")
+    return rowptr, colidx[:nnz], val[:nnz], id_end[:n_rows]

@@ -168,3 +168,13 @@ def test_weighted_average_and_hybrid():
     for q, u, v in g["hybrid"]:
         assert spec.hybrid(q, u) == int(v)
     assert spec.hybrid(0.0, 5.0) == 22 and spec.hybrid(0.0, 5.0 - 1e-12) == 21
+
+
+def test_csv_reader_oracle_matches_reference_loaded_matrix(golden_c1):
+    """f-4: the oracle's reading of utility_matrix.csv equals what the unmodified reference loaded from it."""
+    import os
+    from conftest import GOLDEN
+    g = golden_c1
+    q, u, dense = spec.parse_utility_csv(open(os.path.join(GOLDEN, "c1", "utility_matrix.csv"), "rb").read())
+    assert q == g["queries_ids"].tolist() and u == g["users_ids"].tolist()
+    assert np.array_equal(dense, g["ratings"].astype(np.int64))
