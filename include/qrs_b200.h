@@ -301,6 +301,26 @@ int qrs_csv_ratings_count(const uint8_t *text, const int64_t *line_end, int64_t 
 int qrs_csv_ratings_fill(const uint8_t *text, const int64_t *line_end, int64_t first_line, int64_t n_rows,
                          int32_t Q, const int64_t *rowptr, int32_t *colidx, uint8_t *val, void *stream);
 
+/* ------------------------------------------------------ f-4: CSV export
+ * Replaces the export of main.py:97-111 (predictions.to_numpy().tolist() -> generator.write_csv,
+ * generator.py:59-77: csv.writer rows `user,v,v,...` + "\r\n"; the caller writes the header line of query
+ * ids).  A row is the union of the ratings CSR and, optionally, the sparse predictions of
+ * qrs_predict_sparse (row_start / row_cnt int[n_rows, nt], cols QRS_COLS_I32 or QRS_COLS_U16, preds) - the two
+ * never share a cell (recommender.py:302).  zero_as_empty = 0: final_predictions.csv (a 0 is printed);
+ * 1: the utility-matrix form (generator.py:329-332, empty field = not rated), which qrs_csv_ratings_* reads back.
+ * ids / ids_off int64[n_rows + 1]: the user ids as concatenated bytes.  Q <= 196608.
+ * count: text_off int64[n_rows + 1] = byte offset of every row (text_off[n_rows] = total size).
+ * fill: the text itself. */
+size_t qrs_csv_format_workspace_bytes(int64_t n_rows);
+int qrs_csv_format_count(const int64_t *ids_off, const int64_t *rowptr, const uint8_t *val,
+                         const int64_t *pred_start, const int32_t *pred_cnt, const uint8_t *preds, int32_t nt,
+                         int64_t n_rows, int32_t Q, int32_t zero_as_empty, int64_t *text_off, void *ws,
+                         size_t ws_bytes, void *stream);
+int qrs_csv_format_fill(const uint8_t *ids, const int64_t *ids_off, const int64_t *rowptr, const int32_t *colidx,
+                        const uint8_t *val, const int64_t *pred_start, const int32_t *pred_cnt,
+                        const void *pred_cols, int32_t cols_mode, const uint8_t *preds, int32_t nt, int64_t n_rows,
+                        int32_t Q, int32_t zero_as_empty, const int64_t *text_off, uint8_t *text, void *stream);
+
 /* ------------------------------------------------------ multi-GPU plumbing
  * Rows of the ratings CSR are sharded across GPUs; the prediction gathers neighbour rows
  * (recommender.py:320), so rows requested by other ranks are packed for sending:

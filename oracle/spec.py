@@ -396,3 +396,17 @@ def parse_utility_csv(data: bytes):
             if f != "":
                 dense[i, j] = int(f)
     return query_ids, user_ids, dense
+
+
+def format_matrix_csv(query_ids, user_ids, dense, zero_as_empty: bool) -> bytes:
+    """generator.write_csv (generator.py:59-77): `csv.writer(open(..., newline=""))`, header row, then one row
+    per user `[id, v, v, ...]`.  zero_as_empty=True is the utility matrix as create_utility_matrix builds it
+    (generator.py:329-332: "" = not rated); False is main.py:97-111's final_predictions (plain ints)."""
+    import csv
+    import io
+    buf = io.StringIO(newline="")
+    w = csv.writer(buf)
+    w.writerow(list(query_ids))
+    for u, row in zip(user_ids, np.asarray(dense)):
+        w.writerow([u] + [("" if (zero_as_empty and int(v) == 0) else int(v)) for v in row])
+    return buf.getvalue().encode("utf-8")

@@ -250,3 +250,192 @@ int qrs_csv_ratings_fill(const uint8_t *text, const int64_t *line_end, int64_t f
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// The output side: final_predictions.csv (main.py:97-111 -> generator.write_csv, generator.py:59-77:
+// csv.writer, header = query ids, rows `user,v,v,...` + "\r\n") and, with zero_as_empty, the
+// utility-matrix form itself (generator.py:329-332).  A row is the union of two sparse layers: the
+// ratings CSR and (optionally) the sparse predictions of qrs_predict_sparse — they never share a cell
+// (recommender.py:302 predicts only unrated cells).
+namespace qrs {
+
+constexpr int kFmtThreads = 256;
+constexpr int kFmtTile = 4096;                     // columns formatted per sweep: at most 16 KB of text
+constexpr int kFmtPerThread = kFmtTile / kFmtThreads;
+constexpr int kFmtMaxQ = 192 * 1024;
+
+__device__ __forceinline__ int digits_of(int v) { return v < 10 ? 1 : (v < 100 ? 2 : 3); }
+
+// warp per row: bytes of the row's text
+__global__ void __launch_bounds__(256)
+csv_format_count_kernel(const int64_t *__restrict__ ids_off, const int64_t *__restrict__ rowptr,
+                        const uint8_t *__restrict__ val, const int64_t *__restrict__ p_start,
+                        const int *__restrict__ p_cnt, const uint8_t *__restrict__ preds, int nt, int64_t n_rows, int Q,
+                        int zero_as_empty, uint32_t *__restrict__ row_bytes) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t r = warp_global; r < n_rows; r += nwarps) {
+    int dig = 0, cells = 0;
+    for (int64_t x = rowptr[r] + lane; x < rowptr[r + 1]; x += 32) {
+      const int v = val[x];
+      if (v != 0) { dig += digits_of(v); ++cells; }
+    }
+    if (p_start != nullptr)
+      for (int t = 0; t < nt; ++t) {
+        const int64_t a = p_start[r * nt + t];
+        const int c = p_cnt[r * nt + t];
+        for (int x = lane; x < c; x += 32) {
+          const int v = preds[a + x];
+          if (v != 0) { dig += digits_of(v); ++cells; }
+        }
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      dig += __shfl_xor_sync(kFull, dig, o);
+      cells += __shfl_xor_sync(kFull, cells, o);
+    }
+    if (lane == 0) {
+      const int64_t id_len = ids_off[r + 1] - ids_off[r];
+      row_bytes[r] = unsigned(id_len + Q + 2 + dig + (zero_as_empty ? 0 : Q - cells));
+    }
+  }
+}
+
+// CTA per row: the row's values by column in shared memory, then the text tile by tile
+__global__ void __launch_bounds__(kFmtThreads)
+csv_format_fill_kernel(const uint8_t *__restrict__ ids, const int64_t *__restrict__ ids_off,
+                       const int64_t *__restrict__ rowptr, const int *__restrict__ colidx,
+                       const uint8_t *__restrict__ val, const int64_t *__restrict__ p_start,
+                       const int *__restrict__ p_cnt, const void *__restrict__ p_cols, int cols_u16,
+                       const uint8_t *__restrict__ preds, int nt, int64_t n_rows, int Q, int q_pad, int zero_as_empty,
+                       const int64_t *__restrict__ text_off, uint8_t *__restrict__ text) {
+  extern __shared__ __align__(16) unsigned char fmt_smem[];
+  uint8_t *dense = fmt_smem;                                  // [q_pad]
+  uint8_t *tile_text = fmt_smem + q_pad;                      // [4 * kFmtTile]
+  __shared__ int warp_sum[kFmtThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int64_t r = blockIdx.x; r < n_rows; r += gridDim.x) {
+    for (int x = tid; x < q_pad / 4; x += kFmtThreads) reinterpret_cast<unsigned *>(dense)[x] = 0u;
+    __syncthreads();
+    for (int64_t x = rowptr[r] + tid; x < rowptr[r + 1]; x += kFmtThreads) dense[colidx[x]] = val[x];
+    if (p_start != nullptr)
+      for (int t = 0; t < nt; ++t) {
+        const int64_t a = p_start[r * nt + t];
+        const int c = p_cnt[r * nt + t];
+        for (int x = tid; x < c; x += kFmtThreads) {
+          const int col = cols_u16 ? int(static_cast<const uint16_t *>(p_cols)[a + x])
+                                   : static_cast<const int *>(p_cols)[a + x];
+          dense[col] = preds[a + x];
+        }
+      }
+    int64_t out = text_off[r];
+    const int64_t id_a = ids_off[r], id_len = ids_off[r + 1] - id_a;
+    for (int64_t x = tid; x < id_len; x += kFmtThreads) text[out + x] = ids[id_a + x];
+    out += id_len;
+    __syncthreads();
+    for (int q0 = 0; q0 < Q; q0 += kFmtTile) {
+      // bytes of this thread's kFmtPerThread consecutive columns: ',' + digits (or nothing for an empty cell)
+      const int c0 = q0 + tid * kFmtPerThread;
+      int len = 0;
+#pragma unroll
+      for (int u = 0; u < kFmtPerThread; ++u) {
+        const int col = c0 + u;
+        if (col < Q) {
+          const int v = dense[col];
+          len += 1 + (v == 0 ? (zero_as_empty ? 0 : 1) : digits_of(v));
+        }
+      }
+      int incl = len;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int up = __shfl_up_sync(kFull, incl, d);
+        if (lane >= d) incl += up;
+      }
+      if (lane == 31) warp_sum[warp] = incl;
+      __syncthreads();
+      int before = incl - len, total = 0;
+#pragma unroll
+      for (int w = 0; w < kFmtThreads / 32; ++w) {
+        if (w < warp) before += warp_sum[w];
+        total += warp_sum[w];
+      }
+      uint8_t *o = tile_text + before;
+#pragma unroll
+      for (int u = 0; u < kFmtPerThread; ++u) {
+        const int col = c0 + u;
+        if (col < Q) {
+          const int v = dense[col];
+          *o++ = ',';
+          if (v >= 100) *o++ = uint8_t('0' + v / 100);
+          if (v >= 10) *o++ = uint8_t('0' + (v / 10) % 10);
+          if (v != 0 || !zero_as_empty) *o++ = uint8_t('0' + v % 10);
+        }
+      }
+      __syncthreads();
+      for (int x = tid; x < total; x += kFmtThreads) text[out + x] = tile_text[x];
+      out += total;
+      __syncthreads();
+    }
+    if (tid == 0) { text[out] = '\r'; text[out + 1] = '\n'; }
+  }
+}
+
+}  // namespace qrs
+
+extern "C" {
+
+size_t qrs_csv_format_workspace_bytes(int64_t n_rows) {
+  if (n_rows < 0) return 0;
+  return round_up<size_t>(size_t(n_rows > 0 ? n_rows : 1) * 4, 256) + scan_workspace_bytes(n_rows);
+}
+
+int qrs_csv_format_count(const int64_t *ids_off, const int64_t *rowptr, const uint8_t *val, const int64_t *pred_start,
+                         const int32_t *pred_cnt, const uint8_t *preds, int32_t nt, int64_t n_rows, int32_t Q,
+                         int32_t zero_as_empty, int64_t *text_off, void *ws, size_t ws_bytes, void *stream) {
+  if (n_rows < 0 || Q <= 0 || !text_off || !ids_off || !rowptr) return QRS_ERR_INVALID_ARG;
+  if (pred_start && (!pred_cnt || !preds || nt <= 0)) return QRS_ERR_INVALID_ARG;
+  if (Q > kFmtMaxQ) return QRS_ERR_UNSUPPORTED;
+  if (!ws || ws_bytes < qrs_csv_format_workspace_bytes(n_rows)) return QRS_ERR_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  uint32_t *counts = static_cast<uint32_t *>(ws);
+  void *scan_ws = static_cast<char *>(ws) + round_up<size_t>(size_t(n_rows > 0 ? n_rows : 1) * 4, 256);
+  if (n_rows > 0) {
+    int64_t blocks = ceil_div<int64_t>(n_rows, 8);
+    const int64_t cap = int64_t(sm_count()) * 8;
+    if (blocks > cap) blocks = cap;
+    csv_format_count_kernel<<<unsigned(blocks), 256, 0, st>>>(ids_off, rowptr, val, pred_start, pred_cnt, preds, nt,
+                                                             n_rows, Q, zero_as_empty, counts);
+    QRS_LAUNCH_CHECK();
+  }
+  return exclusive_scan_u32_to_u64(counts, reinterpret_cast<uint64_t *>(text_off), n_rows, scan_ws,
+                                   scan_workspace_bytes(n_rows), st);
+}
+
+int qrs_csv_format_fill(const uint8_t *ids, const int64_t *ids_off, const int64_t *rowptr, const int32_t *colidx,
+                        const uint8_t *val, const int64_t *pred_start, const int32_t *pred_cnt, const void *pred_cols,
+                        int32_t cols_mode, const uint8_t *preds, int32_t nt, int64_t n_rows, int32_t Q,
+                        int32_t zero_as_empty, const int64_t *text_off, uint8_t *text, void *stream) {
+  if (n_rows < 0 || Q <= 0 || !text_off || !ids_off || !rowptr) return QRS_ERR_INVALID_ARG;
+  if (n_rows == 0) return QRS_OK;
+  if (!text || !ids) return QRS_ERR_INVALID_ARG;
+  if (pred_start && (!pred_cnt || !preds || !pred_cols || nt <= 0)) return QRS_ERR_INVALID_ARG;
+  if (cols_mode != QRS_COLS_I32 && cols_mode != QRS_COLS_U16) return QRS_ERR_UNSUPPORTED;
+  if (Q > kFmtMaxQ) return QRS_ERR_UNSUPPORTED;
+  const int q_pad = round_up(Q, 16);
+  const size_t smem = size_t(q_pad) + 4 * kFmtTile;
+  QRS_CUDA(cudaFuncSetAttribute(csv_format_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  int per_sm = 1;
+  QRS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, csv_format_fill_kernel, kFmtThreads, smem));
+  if (per_sm < 1) return QRS_ERR_UNSUPPORTED;
+  int64_t blocks = n_rows;
+  const int64_t cap = int64_t(sm_count()) * per_sm;
+  if (blocks > cap) blocks = cap;
+  csv_format_fill_kernel<<<unsigned(blocks), kFmtThreads, smem, as_stream(stream)>>>(
+      ids, ids_off, rowptr, colidx, val, pred_start, pred_cnt, pred_cols, cols_mode == QRS_COLS_U16, preds, nt, n_rows, Q,
+      q_pad, zero_as_empty, text_off, text);
+  QRS_LAUNCH_CHECK();
+  return QRS_OK;
+}
+
+}  // extern "C"

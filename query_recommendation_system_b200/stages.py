@@ -381,3 +381,31 @@ def csv_ratings(text: torch.Tensor, line_end: torch.Tensor, first_line: int, n_r
     check(lib.qrs_csv_ratings_fill(ptr(text), ptr(line_end), first_line, n_rows, Q, ptr(rowptr), ptr(colidx), ptr(val),
                                    _stream()), "qrs_csv_ratings_fill")
     return rowptr, colidx[:nnz], val[:nnz], id_end[:n_rows]
+
+
+def csv_format(ids: torch.Tensor, ids_off: torch.Tensor, rowptr: torch.Tensor, colidx: torch.Tensor, val: torch.Tensor,
+               Q: int, pred=None, zero_as_empty: bool = False) -> torch.Tensor:
+    """Rows `user,v,v,...\\r\\n` of the matrix (ratings CSR + optional sparse predictions
+    pred = (row_start int64[n, nt], row_cnt int32[n, nt], cols int32|int16, preds uint8)) as uint8 text."""
+    _need_cuda(ids, ids_off, rowptr, colidx, val)
+    lib = _lib.load()
+    dev = rowptr.device
+    n_rows = rowptr.numel() - 1
+    ps = pc = pcols = pv = None
+    nt, mode = 0, 0
+    if pred is not None:
+        ps, pc, pcols, pv = pred
+        _need_cuda(ps, pc, pcols, pv)
+        nt = ps.shape[1]
+        mode = 1 if pcols.dtype == torch.int16 else 0
+    text_off = torch.empty(n_rows + 1, dtype=torch.int64, device=dev)
+    ws = _ws(lib.qrs_csv_format_workspace_bytes(n_rows), dev)
+    z = 1 if zero_as_empty else 0
+    check(lib.qrs_csv_format_count(ptr(ids_off), ptr(rowptr), ptr(val), ptr(ps), ptr(pc), ptr(pv), nt, n_rows, Q, z,
+                                   ptr(text_off), ptr(ws), ws.numel(), _stream()), "qrs_csv_format_count")
+    total = int(text_off[-1].item())
+    text = torch.empty(max(total, 1), dtype=torch.uint8, device=dev)
+    check(lib.qrs_csv_format_fill(ptr(ids), ptr(ids_off), ptr(rowptr), ptr(colidx), ptr(val), ptr(ps), ptr(pc), ptr(pcols),
+                                  mode, ptr(pv), nt, n_rows, Q, z, ptr(text_off), ptr(text), _stream()),
+          "qrs_csv_format_fill")
+    return text[:total]

@@ -113,3 +113,91 @@ def test_parsed_file_feeds_the_recommender(golden_c1):
     assert queries_ids == q
     rec.init(np.array(u)[:, None], queries, queries_ids, dataset, csr_to_dense(rowptr, colidx, val, len(q)))
     assert np.array_equal(rec.ratings, golden_c1["ratings"].astype(np.int32))
+
+
+# ------------------------------------------------------------------------------ export
+def _csr(dense):
+    rows, cols = np.nonzero(dense)
+    rowptr = np.zeros(dense.shape[0] + 1, np.int64)
+    np.cumsum(np.bincount(rows, minlength=dense.shape[0]), out=rowptr[1:])
+    to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    return to(rowptr), to(cols.astype(np.int32)), to(dense[rows, cols].astype(np.uint8))
+
+
+def test_export_reproduces_the_reference_written_file(golden_c1):
+    """utility_matrix.csv of the golden set was written by the reference's generator: same bytes."""
+    from query_recommendation_system_b200 import io_csv
+    g = golden_c1
+    text = io_csv.format_matrix_csv(g["queries_ids"].tolist(), g["users_ids"].tolist(), *_csr(g["ratings"].astype(np.int64)),
+                                    zero_as_empty=True)
+    raw = open(os.path.join(GOLDEN, "c1", "utility_matrix.csv"), "rb").read()
+    assert text.cpu().numpy().tobytes() == raw
+    # and main.py:97-111's export of the reference's own final matrix
+    final = g["predictions"].astype(np.int64)
+    text = io_csv.format_matrix_csv(g["queries_ids"].tolist(), g["users_ids"].tolist(), *_csr(final), zero_as_empty=False)
+    assert text.cpu().numpy().tobytes() == spec.format_matrix_csv(g["queries_ids"].tolist(), g["users_ids"].tolist(),
+                                                                 final, False)
+
+
+@pytest.mark.parametrize("U,Q,fill", [(7, 1, 0.5), (40, 31, 0.5), (50, 4096, 0.1), (50, 4097, 0.1), (20, 9000, 0.6),
+                                      (3, 70_000, 0.01)])
+@pytest.mark.parametrize("zero_as_empty", [False, True])
+def test_export_matches_csv_writer_and_round_trips(U, Q, fill, zero_as_empty):
+    from query_recommendation_system_b200 import io_csv
+    rng = np.random.default_rng(Q + U)
+    dense = np.where(rng.random((U, Q)) < fill, rng.integers(1, 256, (U, Q)), 0)
+    dense[rng.random((U, Q)) < fill / 4] = 100
+    dense[0, :] = 0
+    dense[U - 1, :] = 255
+    users = ["user-%d" % (i * i) for i in range(U)]
+    users[1] = ""                                                       # an empty id is still a field
+    queries = ["Q%d" % (j + 1) for j in range(Q)]
+    rowptr, colidx, val = _csr(dense)
+    text = io_csv.format_matrix_csv(queries, users, rowptr, colidx, val, zero_as_empty=zero_as_empty)
+    data = text.cpu().numpy().tobytes()
+    assert data == spec.format_matrix_csv(queries, users, dense, zero_as_empty)
+    q, u, rp, ci, v = io_csv.parse_utility_matrix_bytes(np.frombuffer(data, dtype=np.uint8), DEV)
+    assert q == queries and u == users
+    assert torch.equal(rp, rowptr) and torch.equal(ci, colidx) and torch.equal(v, val)
+
+
+@pytest.mark.parametrize("cols_mode", [0, 1])
+def test_export_final_predictions_from_the_pipeline(cols_mode):
+    """Ratings CSR + the path's sparse predictions → final_predictions.csv, against the csv.writer oracle on the
+    densely assembled matrix (main.py:97-111)."""
+    from query_recommendation_system_b200 import io_csv, synth
+    from query_recommendation_system_b200.pipeline import LshCfPipeline
+    n, m, K, b, k = 512, 1500, 64, 16, 15
+    tab = spec.permutation_table(m, K, seed=7)
+    rowptr, colidx, val = [x.to(DEV) for x in synth.planted_csr(n, m, 0.05, seed=33)]
+    pipe = LshCfPipeline(m=m, K=K, b=b, k=k, perm_tab=tab, device=DEV, distributed=False)
+    pipe.cols_mode = cols_mode
+    out = pipe.run(rowptr, colidx, val)
+    users = ["U%d" % (i + 1) for i in range(n)]
+    queries = ["Q%d" % (j + 1) for j in range(m)]
+    pred = (out.pred_row_start, out.pred_row_cnt, out.pred_cols, out.pred_vals)
+    text = io_csv.format_matrix_csv(queries, users, rowptr, colidx, val, pred)
+    dense = csr_to_dense(rowptr, colidx, val, m)
+    rs, rc = out.pred_row_start.cpu().numpy(), out.pred_row_cnt.cpu().numpy()
+    pc, pv = out.pred_cols.cpu().numpy(), out.pred_vals.cpu().numpy()
+    if cols_mode == 1:
+        pc = pc.view(np.uint16)
+    filled = 0
+    for u in range(n):
+        for t in range(rs.shape[1]):
+            s, c = rs[u, t], rc[u, t]
+            assert (dense[u, pc[s:s + c]] == 0).all()                    # only unrated cells are predicted
+            dense[u, pc[s:s + c]] = pv[s:s + c]
+            filled += c
+    assert filled > 10_000
+    assert text.cpu().numpy().tobytes() == spec.format_matrix_csv(queries, users, dense, False)
+
+
+def test_export_rejects_too_many_columns():
+    from query_recommendation_system_b200 import io_csv
+    from query_recommendation_system_b200._lib import QrsError
+    dense = np.zeros((1, 4), dtype=np.int64)
+    rowptr, colidx, val = _csr(dense)
+    with pytest.raises(QrsError):
+        io_csv.format_matrix_csv(["Q"] * 200_000, ["U1"], rowptr, torch.zeros(1, dtype=torch.int32, device=DEV),
+                                 torch.zeros(1, dtype=torch.uint8, device=DEV))

@@ -178,3 +178,14 @@ def test_csv_reader_oracle_matches_reference_loaded_matrix(golden_c1):
     q, u, dense = spec.parse_utility_csv(open(os.path.join(GOLDEN, "c1", "utility_matrix.csv"), "rb").read())
     assert q == g["queries_ids"].tolist() and u == g["users_ids"].tolist()
     assert np.array_equal(dense, g["ratings"].astype(np.int64))
+
+
+def test_csv_writer_oracle_reproduces_reference_written_file(golden_c1):
+    """f-4: the oracle's writer gives the bytes the reference's generator wrote (tests/golden/c1)."""
+    import os
+    from conftest import GOLDEN
+    g = golden_c1
+    raw = open(os.path.join(GOLDEN, "c1", "utility_matrix.csv"), "rb").read()
+    assert spec.format_matrix_csv(g["queries_ids"].tolist(), g["users_ids"].tolist(), g["ratings"], True) == raw
+    q, u, dense = spec.parse_utility_csv(spec.format_matrix_csv(["a", "b"], ["x", ""], np.array([[0, 7], [100, 0]]), True))
+    assert (q, u, dense.tolist()) == (["a", "b"], ["x", ""], [[0, 7], [100, 0]])
