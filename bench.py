@@ -376,7 +376,53 @@ def main():
                 "note": "qrs_center_rows + qrs_sort_u64 + qrs_pair_centered_cosine on the candidate pairs of the last "
                         "step (user-branch scoring, recommender.py:263-269; outside the timed step)"}
 
-    # ---------------------------------------------------------------- e2e: host buffers in, host results out
+    # ---------------------------------------------------------------- f-4 extra: the CSV wire format either side of the path
+    csvio = None
+    if world == 1 and m <= 196608 and n * (2 * m + 16) + 4 * nnz < 8e9:
+        from query_recommendation_system_b200 import io_csv as _io, stages as _st
+        uids = ["U%d" % (i + 1) for i in range(n)]
+        qids = ["Q%d" % (j + 1) for j in range(m)]
+
+        def timed(fn, reps=3):
+            fn()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                r = fn()
+            b_.record()
+            torch.cuda.synchronize()
+            return r, a.elapsed_time(b_) / reps
+        enc = [u.encode() for u in uids]
+        ids_off = torch.from_numpy(np.concatenate([[0], np.cumsum([len(e) for e in enc])]).astype(np.int64)).to(dev)
+        ids = torch.from_numpy(np.frombuffer(b"".join(enc), dtype=np.uint8).copy()).to(dev)
+        body, ms_fmt = timed(lambda: _st.csv_format(ids, ids_off, rowptr, colidx, val, m, None, True))
+        header = torch.from_numpy(np.frombuffer((",".join(qids) + "\r\n").encode(), dtype=np.uint8).copy()).to(dev)
+        text = torch.cat([header, body])
+
+        def parse():
+            ends = _st.csv_line_ends(text, max_lines=text.numel() // (m + 1) + 2)
+            return _st.csv_ratings(text, ends, 1, ends.numel() - 1, m)
+        (rp2, ci2, v2, _), ms_parse = timed(parse)
+        same = bool(torch.equal(rp2, rowptr) and torch.equal(ci2, colidx) and torch.equal(v2, val))
+        pred_text_ms = None
+        if out.pred_row_start is not None:
+            pred = (out.pred_row_start, out.pred_row_cnt, out.pred_cols, out.pred_vals)
+            ptxt, pred_text_ms = timed(lambda: _st.csv_format(ids, ids_off, rowptr, colidx, val, m, pred, False), reps=2)
+            pred_bytes_txt = int(ptxt.numel())
+            del ptxt
+        tb = float(text.numel())
+        csvio = {"utility_matrix_bytes": int(tb), "round_trip_identical": same,
+                 "parse_ms": ms_parse, "parse_GBps": (tb + 5 * nnz + 8 * n) / (ms_parse * 1e-3) / 1e9,
+                 "format_ms": ms_fmt, "format_GBps": (tb + 5 * nnz + 8 * n) / (ms_fmt * 1e-3) / 1e9,
+                 "final_predictions_ms": pred_text_ms,
+                 "final_predictions_bytes": pred_bytes_txt if pred_text_ms is not None else None,
+                 "hbm_peak_GBps": peak,
+                 "note": "utility_matrix.csv text of this step's ratings formatted on the device "
+                         "(qrs_csv_format_*), parsed back (qrs_csv_line_ends + qrs_csv_ratings_*) and compared; "
+                         "final_predictions.csv text = ratings + the step's predictions; GB/s = (text + CSR bytes) / time; "
+                         "outside the timed step"}
+        del text, body
+
     runner = HostRunner(pipe)
     h_rowptr, h_colidx, h_val = [x.cpu().pin_memory() for x in (rowptr, colidx, val)]
     for _ in range(2):
@@ -419,7 +465,7 @@ def main():
                     "h2d_bytes_per_step": runner.h2d_bytes, "d2h_bytes_per_step": runner.d2h_bytes, "steps": e2e_steps,
                     "call": "pipeline.HostRunner(pipe, chunks=4, cols_format=auto)(rowptr, colidx, val) with pinned host tensors; returns pinned "
                             "sparse predictions + neighbour tables"},
-            "gpu_launches": int(launches), "clocks": clocks, "recommend_top_n": topn, "user_similarity": usim,
+            "gpu_launches": int(launches), "clocks": clocks, "recommend_top_n": topn, "user_similarity": usim, "csv_io": csvio,
         }
         if world == 1 and not args.no_cpu_baseline:
             tc, cc = run_cpu_port(args.config, args.cpu_sets)

@@ -295,11 +295,11 @@ int qrs_pair_centered_cosine(const int64_t *rowptr, const int32_t *colidx, const
 size_t qrs_csv_workspace_bytes(int64_t n_bytes, int64_t n_rows);
 int qrs_csv_line_ends(const uint8_t *text, int64_t n_bytes, int64_t *line_end, int64_t capacity,
                       uint64_t *n_lines, void *ws, size_t ws_bytes, void *stream);
-int qrs_csv_ratings_count(const uint8_t *text, const int64_t *line_end, int64_t first_line, int64_t n_rows,
-                          int32_t Q, int64_t *rowptr, int64_t *id_end, int32_t *err, void *ws, size_t ws_bytes,
+int qrs_csv_ratings_count(const uint8_t *text, int64_t n_bytes, const int64_t *line_end, int64_t first_line,
+                          int64_t n_rows, int32_t Q, int64_t *rowptr, int64_t *id_end, int32_t *err, void *ws, size_t ws_bytes,
                           void *stream);
-int qrs_csv_ratings_fill(const uint8_t *text, const int64_t *line_end, int64_t first_line, int64_t n_rows,
-                         int32_t Q, const int64_t *rowptr, int32_t *colidx, uint8_t *val, void *stream);
+int qrs_csv_ratings_fill(const uint8_t *text, int64_t n_bytes, const int64_t *line_end, int64_t first_line,
+                         int64_t n_rows, int32_t Q, const int64_t *rowptr, int32_t *colidx, uint8_t *val, void *stream);
 
 /* ------------------------------------------------------ f-4: CSV export
  * Replaces the export of main.py:97-111 (predictions.to_numpy().tolist() -> generator.write_csv,

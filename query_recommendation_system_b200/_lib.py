@@ -55,8 +55,8 @@ SIGNATURES = {
     "qrs_gather_rows": (C.c_int, [_p, _p, _p, _p, _i64, _p, _p, _p, _p]),
     "qrs_csv_workspace_bytes": (_sz, [_i64, _i64]),
     "qrs_csv_line_ends": (C.c_int, [_p, _i64, _p, _i64, _p, _p, _sz, _p]),
-    "qrs_csv_ratings_count": (C.c_int, [_p, _p, _i64, _i64, _i32, _p, _p, _p, _p, _sz, _p]),
-    "qrs_csv_ratings_fill": (C.c_int, [_p, _p, _i64, _i64, _i32, _p, _p, _p, _p]),
+    "qrs_csv_ratings_count": (C.c_int, [_p, _i64, _p, _i64, _i64, _i32, _p, _p, _p, _p, _sz, _p]),
+    "qrs_csv_ratings_fill": (C.c_int, [_p, _i64, _p, _i64, _i64, _i32, _p, _p, _p, _p]),
     "qrs_csv_format_workspace_bytes": (_sz, [_i64]),
     "qrs_csv_format_count": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _i64, _i32, _i32, _p, _p, _sz, _p]),
     "qrs_csv_format_fill": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _i32, _i64, _i32, _i32, _p, _p, _p]),

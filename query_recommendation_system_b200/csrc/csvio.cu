@@ -8,10 +8,6 @@
 //   qrs_csv_ratings_count  per row: rated cells, end of the user-id field, format checks
 //   qrs_csv_ratings_fill   column ids + rating bytes at the scanned offsets
 //
-// A warp owns a row and walks it 32 bytes per step: one ballot marks the field terminators, its
-// prefix popcount is the field (= column) index of every byte, and the lane holding a terminator
-// assembles the up-to-3-digit integer from the bytes in front of it (shuffles + a 4-byte carry
-// across steps).  Emission order is ascending by construction, so rows come out sorted.
 #include "common.cuh"
 
 namespace qrs {
@@ -82,12 +78,63 @@ csv_newlines_kernel(const uint8_t *__restrict__ text, int64_t n, int64_t n_chunk
   }
 }
 
+// exact per-byte tests on a 32-bit word: bit 7 of every byte that matches
+__device__ __forceinline__ unsigned bytes_equal(unsigned w, unsigned pattern) {
+  const unsigned x = w ^ pattern;
+  return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
+}
+__device__ __forceinline__ unsigned bytes_digit(unsigned w) {
+  const unsigned m7 = w & 0x7F7F7F7Fu;
+  const unsigned ge30 = m7 + 0x50505050u, ge3a = m7 + 0x46464646u;   // bit 7 <=> low 7 bits >= '0' / > '9'
+  return ge30 & ~ge3a & ~w & 0x80808080u;
+}
+
+// exclusive prefix over the lanes (and the warp total) of a per-lane count in 0..7: three bit-plane ballots
+__device__ __forceinline__ int prefix_small(int c, unsigned lt, int &total) {
+  const unsigned b0 = __ballot_sync(kFull, c & 1), b1 = __ballot_sync(kFull, c & 2), b2 = __ballot_sync(kFull, c & 4);
+  total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+  return __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
+}
+
+// the aligned word at position a of a row [begin, end]: bytes outside the row are blanked, the byte at `end`
+// (the '\r' / '\n' / end of text that closes the last field) reads as one more ','; vm flags the bytes inside
+__device__ __forceinline__ unsigned row_word(const uint8_t *__restrict__ text, int64_t n_bytes, int64_t a, int64_t begin,
+                                             int64_t end, unsigned &vm) {
+  vm = 0u;
+  if (a > end || a + 3 < begin) return 0u;
+  unsigned w = 0u;
+  if (a + 4 <= n_bytes) {
+    w = *reinterpret_cast<const unsigned *>(text + a);
+  } else {
+    for (int k = 0; k < 4; ++k)
+      if (a + k < n_bytes) w |= unsigned(text[a + k]) << (8 * k);
+  }
+  vm = 0x80808080u;
+  if (a < begin || a + 3 >= end) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int64_t pos = a + k;
+      const unsigned m = 0xFFu << (8 * k);
+      if (pos < begin || pos > end) { w &= ~m; vm &= ~m; }
+      else if (pos == end) w = (w & ~m) | (unsigned(',') << (8 * k));
+    }
+  }
+  return w;
+}
+
+// A warp owns a row and walks it 128 bytes per step (one aligned word per lane).  Comma and digit flags
+// come from word-wide byte tests; a comma right after a digit closes a rated cell, and only those (a few
+// per step) are parsed: the integer is read from the 4 bytes in front (own word + the previous lane's),
+// its column is the number of commas before it (per-lane counts -> bit-plane ballot prefix).  Emission
+// order is ascending by construction, so rows come out sorted.  The counting pass needs neither prefix:
+// it sums per lane and reduces once per row (only the steps up to the first comma, where the user id may
+// hold digits, take the indexed path).
 template <bool FILL>
 __global__ void __launch_bounds__(256)
-csv_ratings_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__ line_end, int64_t first_line,
-                   int64_t n_rows, int Q, uint32_t *__restrict__ row_cnt, int64_t *__restrict__ id_end,
-                   int *__restrict__ err, const int64_t *__restrict__ rowptr, int *__restrict__ colidx,
-                   uint8_t *__restrict__ val) {
+csv_ratings_kernel(const uint8_t *__restrict__ text, int64_t n_bytes, const int64_t *__restrict__ line_end,
+                   int64_t first_line, int64_t n_rows, int Q, uint32_t *__restrict__ row_cnt,
+                   int64_t *__restrict__ id_end, int *__restrict__ err, const int64_t *__restrict__ rowptr,
+                   int *__restrict__ colidx, uint8_t *__restrict__ val) {
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
@@ -98,58 +145,103 @@ csv_ratings_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__
     int64_t end = line_end[L];                                 // the '\n' (or one past the last byte of the text)
     if (end > begin && text[end - 1] == '\r') --end;           // csv.writer's "\r\n"
     const int64_t out_base = FILL ? rowptr[r] : 0;
-    int fields = 0, emitted = 0;
-    unsigned carry = 0;                                        // the 4 bytes in front of this step, nearest in bits 0-7
+    int fields = 0, emitted = 0;                               // FILL (and every row's first steps): warp-uniform totals
+    int my_fields = 0, my_emitted = 0;                         // counting pass: per-lane sums, reduced at the end
+    unsigned prev_w = 0u, prev_dg = 0u;                        // lane 31's word / digit flags of the previous step
     int64_t first_term = -1;
     bool bad = false;
-    // the position `end` closes the last field: treated as one more terminator
-    for (int64_t s = begin; s <= end; s += 32) {
-      const int64_t p = s + lane;
-      const bool in = p <= end;
-      const int c = in ? (p < end ? int(text[p]) : int(',')) : 0;
-      const bool is_t = in && c == ',';
-      const bool is_d = unsigned(c - '0') < 10u;
-      const unsigned tmask = __ballot_sync(kFull, is_t);
-      const int f = fields + __popc(tmask & lt);               // field this byte belongs to (or terminates)
-      if (in && !is_t && f >= 1 && !is_d) bad = true;          // rating fields hold digits only
-      if (in && c == '"') bad = true;                          // quoted fields are not part of the format
-      int prev[4];
-#pragma unroll
-      for (int d = 1; d <= 4; ++d) {
-        const int up = __shfl_up_sync(kFull, c, d);
-        prev[d - 1] = lane >= d ? up : int((carry >> (8 * (d - lane - 1))) & 0xFFu);
+    const int64_t a0 = begin & ~int64_t(3);
+    unsigned vm_next;
+    unsigned w_next = row_word(text, n_bytes, a0 + 4 * lane, begin, end, vm_next);
+    for (int64_t s = a0; s <= end; s += 128) {
+      const unsigned w = w_next, vm = vm_next;
+      w_next = row_word(text, n_bytes, s + 128 + 4 * lane, begin, end, vm_next);   // in flight during this step
+      const unsigned cm = bytes_equal(w, 0x2C2C2C2Cu) & vm;
+      const unsigned dg = bytes_digit(w);
+      const unsigned other = vm & ~(cm | dg);
+      unsigned pw = __shfl_up_sync(kFull, w, 1), pdg = __shfl_up_sync(kFull, dg, 1);
+      if (lane == 0) { pw = prev_w; pdg = prev_dg; }
+      prev_w = __shfl_sync(kFull, w, 31);
+      prev_dg = __shfl_sync(kFull, dg, 31);
+      // commas whose preceding byte is a digit: the cells that hold a number
+      unsigned cand = cm & unsigned((((unsigned long long)dg << 32) | pdg) >> 24);
+      const bool indexed = FILL || first_term < 0;             // warp-uniform
+      int f0 = 1, ctotal = 0;
+      if (indexed) {
+        f0 = fields + prefix_small(__popc(cm), lt, ctotal);    // field of this lane's first byte
+        if (first_term < 0 && ctotal > 0) {                    // the comma closing the user id
+          const int src = __ffs(__ballot_sync(kFull, cm != 0u)) - 1;
+          const unsigned cm_src = __shfl_sync(kFull, cm, src);
+          first_term = s + 4 * src + ((__ffs(cm_src) - 1) >> 3);
+        }
+        fields += ctotal;
+      } else {
+        my_fields += __popc(cm);
       }
-      bool emit = false;
-      int v = 0;
-      if (is_t && f >= 1) {
-        const unsigned d1 = unsigned(prev[0] - '0'), d2 = unsigned(prev[1] - '0'), d3 = unsigned(prev[2] - '0'),
-                       d4 = unsigned(prev[3] - '0');
-        if (d1 < 10u) {
-          v = int(d1);
-          if (d2 < 10u) {
-            v += 10 * int(d2);
-            if (d3 < 10u) {
-              v += 100 * int(d3);
-              if (d4 < 10u) bad = true;                        // four digits or more
-            }
+      if (other != 0u) {                                       // user-id text, or something that does not belong
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if ((other >> (8 * k + 7)) & 1u) {
+            const int fk = indexed ? f0 + __popc(cm & ((1u << (8 * k)) - 1u)) : 1;
+            if (fk >= 1 || ((w >> (8 * k)) & 0xFFu) == unsigned('"')) bad = true;
           }
-          if (v > 255) bad = true;
-          emit = v != 0;                                       // 0 = not rated, like an empty field
+      }
+      const unsigned long long win = (unsigned long long)pw | ((unsigned long long)w << 32);
+      int v4[4], c4[4];
+      unsigned emit4 = 0u;
+      while (cand != 0u) {                                     // a few lanes per step, one or two turns each
+        const int bit = __ffs(cand) - 1, k = bit >> 3;
+        cand &= cand - 1u;
+        const int fk = indexed ? f0 + __popc(cm & ((1u << (8 * k)) - 1u)) : 1;
+        if (fk < 1) continue;                                  // digits at the end of the user id
+        const unsigned before = unsigned(win >> (8 * k));      // the 4 bytes in front of byte k, nearest in bits 24-31
+        const unsigned d1 = (before >> 24) - '0', d2 = ((before >> 16) & 0xFFu) - '0',
+                       d3 = ((before >> 8) & 0xFFu) - '0', d4 = (before & 0xFFu) - '0';
+        int v = int(d1);
+        if (d2 < 10u) {
+          v += 10 * int(d2);
+          if (d3 < 10u) {
+            v += 100 * int(d3);
+            if (d4 < 10u) bad = true;                          // four digits or more
+          }
+        }
+        if (v > 255) bad = true;
+        if (v != 0) {                                          // 0 = not rated, like an empty field
+          emit4 |= 1u << k;
+          if (FILL) {
+            if (k == 0) { v4[0] = v; c4[0] = fk - 1; }
+            else if (k == 1) { v4[1] = v; c4[1] = fk - 1; }
+            else if (k == 2) { v4[2] = v; c4[2] = fk - 1; }
+            else { v4[3] = v; c4[3] = fk - 1; }
+          }
         }
       }
-      const unsigned emask = __ballot_sync(kFull, emit);
-      if (FILL && emit) {
-        const int64_t o = out_base + emitted + __popc(emask & lt);
-        colidx[o] = f - 1;
-        val[o] = uint8_t(v);
+      if (FILL) {
+        int etotal;
+        const int ebefore = prefix_small(__popc(emit4), lt, etotal);
+        if (emit4 != 0u) {
+          int64_t o = out_base + emitted + ebefore;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if ((emit4 >> k) & 1u) {
+              colidx[o] = c4[k];
+              val[o] = uint8_t(v4[k]);
+              ++o;
+            }
+        }
+        emitted += etotal;
+      } else {
+        my_emitted += __popc(emit4);
       }
-      emitted += __popc(emask);
-      if (first_term < 0 && tmask != 0u) first_term = s + __ffs(tmask) - 1;
-      fields += __popc(tmask);
-      // the last four bytes of this step, for the next one
-      const unsigned b31 = __shfl_sync(kFull, c, 31), b30 = __shfl_sync(kFull, c, 30),
-                     b29 = __shfl_sync(kFull, c, 29), b28 = __shfl_sync(kFull, c, 28);
-      carry = (b31 & 0xFFu) | ((b30 & 0xFFu) << 8) | ((b29 & 0xFFu) << 16) | ((b28 & 0xFFu) << 24);
+    }
+    if (!FILL) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        my_fields += __shfl_xor_sync(kFull, my_fields, o);
+        my_emitted += __shfl_xor_sync(kFull, my_emitted, o);
+      }
+      fields += my_fields;
+      emitted = my_emitted;
     }
     bad = __any_sync(kFull, bad) || fields != Q + 1;
     if (!FILL && lane == 0) {
@@ -210,9 +302,10 @@ int qrs_csv_line_ends(const uint8_t *text, int64_t n_bytes, int64_t *line_end, i
   return QRS_OK;
 }
 
-int qrs_csv_ratings_count(const uint8_t *text, const int64_t *line_end, int64_t first_line, int64_t n_rows, int32_t Q,
-                          int64_t *rowptr, int64_t *id_end, int32_t *err, void *ws, size_t ws_bytes, void *stream) {
-  if (n_rows < 0 || first_line < 0 || Q <= 0 || !rowptr || !err) return QRS_ERR_INVALID_ARG;
+int qrs_csv_ratings_count(const uint8_t *text, int64_t n_bytes, const int64_t *line_end, int64_t first_line,
+                          int64_t n_rows, int32_t Q, int64_t *rowptr, int64_t *id_end, int32_t *err, void *ws,
+                          size_t ws_bytes, void *stream) {
+  if (n_rows < 0 || n_bytes < 0 || first_line < 0 || Q <= 0 || !rowptr || !err) return QRS_ERR_INVALID_ARG;
   if (n_rows > 0 && (!text || !line_end || !id_end)) return QRS_ERR_INVALID_ARG;
   if (!ws || ws_bytes < qrs_csv_workspace_bytes(0, n_rows)) return QRS_ERR_WORKSPACE;
   cudaStream_t st = as_stream(stream);
@@ -226,7 +319,7 @@ int qrs_csv_ratings_count(const uint8_t *text, const int64_t *line_end, int64_t 
     int64_t blocks = ceil_div<int64_t>(n_rows, 8);
     const int64_t cap = int64_t(sm_count()) * 8;
     if (blocks > cap) blocks = cap;
-    csv_ratings_kernel<false><<<unsigned(blocks), 256, 0, st>>>(text, line_end, first_line, n_rows, Q, counts, id_end,
+    csv_ratings_kernel<false><<<unsigned(blocks), 256, 0, st>>>(text, n_bytes, line_end, first_line, n_rows, Q, counts, id_end,
                                                                err, nullptr, nullptr, nullptr);
     QRS_LAUNCH_CHECK();
   }
@@ -234,15 +327,15 @@ int qrs_csv_ratings_count(const uint8_t *text, const int64_t *line_end, int64_t 
                                    scan_workspace_bytes(n_rows), st);
 }
 
-int qrs_csv_ratings_fill(const uint8_t *text, const int64_t *line_end, int64_t first_line, int64_t n_rows, int32_t Q,
-                         const int64_t *rowptr, int32_t *colidx, uint8_t *val, void *stream) {
-  if (n_rows < 0 || first_line < 0 || Q <= 0 || !rowptr) return QRS_ERR_INVALID_ARG;
+int qrs_csv_ratings_fill(const uint8_t *text, int64_t n_bytes, const int64_t *line_end, int64_t first_line,
+                         int64_t n_rows, int32_t Q, const int64_t *rowptr, int32_t *colidx, uint8_t *val, void *stream) {
+  if (n_rows < 0 || n_bytes < 0 || first_line < 0 || Q <= 0 || !rowptr) return QRS_ERR_INVALID_ARG;
   if (n_rows == 0) return QRS_OK;
   if (!text || !line_end || !colidx || !val) return QRS_ERR_INVALID_ARG;
   int64_t blocks = ceil_div<int64_t>(n_rows, 8);
   const int64_t cap = int64_t(sm_count()) * 8;
   if (blocks > cap) blocks = cap;
-  csv_ratings_kernel<true><<<unsigned(blocks), 256, 0, as_stream(stream)>>>(text, line_end, first_line, n_rows, Q,
+  csv_ratings_kernel<true><<<unsigned(blocks), 256, 0, as_stream(stream)>>>(text, n_bytes, line_end, first_line, n_rows, Q,
                                                                            nullptr, nullptr, nullptr, rowptr, colidx,
                                                                            val);
   QRS_LAUNCH_CHECK();

@@ -35,7 +35,7 @@ def parse_utility_matrix_bytes(raw: np.ndarray, device="cuda"):
     Q = len(query_ids)
     host = torch.from_numpy(raw)
     text = (host.pin_memory() if torch.cuda.is_available() else host).to(device, non_blocking=True)
-    ends = stages.csv_line_ends(text)
+    ends = stages.csv_line_ends(text, max_lines=raw.size // (Q + 1) + 2)     # every line has >= Q + 1 bytes
     n_rows = ends.numel() - 1
     rowptr, colidx, val, id_end = stages.csv_ratings(text, ends, 1, n_rows, Q)
     begins = (ends[:-1] + 1).cpu().numpy()

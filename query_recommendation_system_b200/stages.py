@@ -337,26 +337,40 @@ def gather_rows(rowptr, colidx, val, rows: torch.Tensor, out_off: torch.Tensor, 
 
 
 # ---------------------------------------------------------------------- f-4: CSV ingest
-def csv_line_ends(text: torch.Tensor) -> torch.Tensor:
-    """Positions of the line ends of a CSV text held on the device (uint8[n]); a last line without '\n' ends
-    at n.  int64[n_lines]."""
+def csv_line_ends(text: torch.Tensor, max_lines: Optional[int] = None) -> torch.Tensor:
+    """Positions of the line ends of a CSV text held on the device (uint8[n]); a last line without '\\n' ends
+    at n.  int64[n_lines].  max_lines: an upper bound on the number of lines, if the caller has one (saves the
+    sizing pass; a text with more lines falls back to it)."""
     _need_cuda(text)
     assert text.dtype == torch.uint8
     lib = _lib.load()
     n = text.numel()
     dev = text.device
     ws = _ws(lib.qrs_csv_workspace_bytes(n, 0), dev)
-    count = torch.zeros(1, dtype=torch.int64, device=dev)
-    check(lib.qrs_csv_line_ends(ptr(text), n, None, 0, ptr(count), ptr(ws), ws.numel(), _stream()), "qrs_csv_line_ends")
-    lines = int(count.item())
-    open_tail = n > 0 and int(text[-1].item()) != 10
-    ends = torch.empty(lines + (1 if open_tail else 0), dtype=torch.int64, device=dev)
-    if lines:
-        check(lib.qrs_csv_line_ends(ptr(text), n, ptr(ends), lines, ptr(count), ptr(ws), ws.numel(), _stream()),
+    count = torch.zeros(2, dtype=torch.int64, device=dev)
+    if n:
+        count[1:] = text[-1:]                         # read back together with the line count
+    ends, lines = None, -1
+    if max_lines is not None and max_lines > 0:
+        ends = torch.empty(max_lines + 1, dtype=torch.int64, device=dev)
+        check(lib.qrs_csv_line_ends(ptr(text), n, ptr(ends), max_lines, ptr(count), ptr(ws), ws.numel(), _stream()),
               "qrs_csv_line_ends")
+        got = count.cpu()
+        lines, last = int(got[0]), int(got[1])
+        if lines > max_lines:
+            ends = None
+    if ends is None:
+        check(lib.qrs_csv_line_ends(ptr(text), n, None, 0, ptr(count), ptr(ws), ws.numel(), _stream()), "qrs_csv_line_ends")
+        got = count.cpu()
+        lines, last = int(got[0]), int(got[1])
+        ends = torch.empty(lines + 1, dtype=torch.int64, device=dev)
+        if lines:
+            check(lib.qrs_csv_line_ends(ptr(text), n, ptr(ends), lines, ptr(count), ptr(ws), ws.numel(), _stream()),
+                  "qrs_csv_line_ends")
+    open_tail = n > 0 and last != 10
     if open_tail:
-        ends[-1] = n
-    return ends
+        ends[lines] = n
+    return ends[:lines + (1 if open_tail else 0)]
 
 
 def csv_ratings(text: torch.Tensor, line_end: torch.Tensor, first_line: int, n_rows: int, Q: int):
@@ -369,7 +383,7 @@ def csv_ratings(text: torch.Tensor, line_end: torch.Tensor, first_line: int, n_r
     id_end = torch.empty(max(n_rows, 1), dtype=torch.int64, device=dev)
     err = torch.empty(2, dtype=torch.int32, device=dev)
     ws = _ws(lib.qrs_csv_workspace_bytes(0, n_rows), dev)
-    check(lib.qrs_csv_ratings_count(ptr(text), ptr(line_end), first_line, n_rows, Q, ptr(rowptr), ptr(id_end), ptr(err),
+    check(lib.qrs_csv_ratings_count(ptr(text), text.numel(), ptr(line_end), first_line, n_rows, Q, ptr(rowptr), ptr(id_end), ptr(err),
                                     ptr(ws), ws.numel(), _stream()), "qrs_csv_ratings_count")
     tail = torch.cat([rowptr[-1:], err.to(torch.int64)]).cpu()
     nnz, n_bad, first_bad = int(tail[0]), int(tail[1]), int(tail[2])
@@ -378,7 +392,7 @@ def csv_ratings(text: torch.Tensor, line_end: torch.Tensor, first_line: int, n_r
                             "integer ratings 0..255, no quotes)" % (n_bad, first_bad, Q + 1))
     colidx = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
     val = torch.empty(max(nnz, 1), dtype=torch.uint8, device=dev)
-    check(lib.qrs_csv_ratings_fill(ptr(text), ptr(line_end), first_line, n_rows, Q, ptr(rowptr), ptr(colidx), ptr(val),
+    check(lib.qrs_csv_ratings_fill(ptr(text), text.numel(), ptr(line_end), first_line, n_rows, Q, ptr(rowptr), ptr(colidx), ptr(val),
                                    _stream()), "qrs_csv_ratings_fill")
     return rowptr, colidx[:nnz], val[:nnz], id_end[:n_rows]
 

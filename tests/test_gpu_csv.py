@@ -77,8 +77,10 @@ def test_line_ends_across_chunk_boundaries():
                     continue
                 raw[-1] = 65
                 want = np.append(np.flatnonzero(raw == 10), n)
-            got = stages.csv_line_ends(torch.from_numpy(raw.copy()).to(DEV))
-            assert np.array_equal(got.cpu().numpy(), want), (n, tail_open)
+            t = torch.from_numpy(raw.copy()).to(DEV)
+            for bound in (None, want.size + 3, 1):              # sizing pass / one pass with a bound / bound too small
+                got = stages.csv_line_ends(t, max_lines=bound)
+                assert np.array_equal(got.cpu().numpy(), want), (n, tail_open, bound)
 
 
 @pytest.mark.parametrize("bad_row,text", [
