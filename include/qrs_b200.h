@@ -310,7 +310,7 @@ int qrs_csv_ratings_fill(const uint8_t *text, int64_t n_bytes, const int64_t *li
  * 1: the utility-matrix form (generator.py:329-332, empty field = not rated), which qrs_csv_ratings_* reads back.
  * ids / ids_off int64[n_rows + 1]: the user ids as concatenated bytes.  Q <= 196608.
  * count: text_off int64[n_rows + 1] = byte offset of every row (text_off[n_rows] = total size).
- * fill: the text itself. */
+ * fill: the text itself (`text` 16-byte aligned). */
 size_t qrs_csv_format_workspace_bytes(int64_t n_rows);
 int qrs_csv_format_count(const int64_t *ids_off, const int64_t *rowptr, const uint8_t *val,
                          const int64_t *pred_start, const int32_t *pred_cnt, const uint8_t *preds, int32_t nt,

@@ -395,7 +395,9 @@ csv_format_count_kernel(const int64_t *__restrict__ ids_off, const int64_t *__re
   }
 }
 
-// CTA per row: the row's values by column in shared memory, then the text tile by tile
+// CTA per row: the row's values by column in shared memory, then the text tile by tile.  A thread formats 16
+// consecutive columns (one 16-byte shared load); the tile's text is staged in shared memory at the same
+// 16-byte phase as its place in the output, so it leaves in aligned 16-byte stores.
 __global__ void __launch_bounds__(kFmtThreads)
 csv_format_fill_kernel(const uint8_t *__restrict__ ids, const int64_t *__restrict__ ids_off,
                        const int64_t *__restrict__ rowptr, const int *__restrict__ colidx,
@@ -404,12 +406,12 @@ csv_format_fill_kernel(const uint8_t *__restrict__ ids, const int64_t *__restric
                        const uint8_t *__restrict__ preds, int nt, int64_t n_rows, int Q, int q_pad, int zero_as_empty,
                        const int64_t *__restrict__ text_off, uint8_t *__restrict__ text) {
   extern __shared__ __align__(16) unsigned char fmt_smem[];
-  uint8_t *dense = fmt_smem;                                  // [q_pad]
-  uint8_t *tile_text = fmt_smem + q_pad;                      // [4 * kFmtTile]
+  uint8_t *dense = fmt_smem;                                  // [q_pad], q_pad % 16 == 0 and >= Q rounded up to a tile
+  uint8_t *tile_text = fmt_smem + q_pad;                      // [4 * kFmtTile + 16]
   __shared__ int warp_sum[kFmtThreads / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int64_t r = blockIdx.x; r < n_rows; r += gridDim.x) {
-    for (int x = tid; x < q_pad / 4; x += kFmtThreads) reinterpret_cast<unsigned *>(dense)[x] = 0u;
+    for (int x = tid; x < q_pad / 16; x += kFmtThreads) reinterpret_cast<uint4 *>(dense)[x] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
     for (int64_t x = rowptr[r] + tid; x < rowptr[r + 1]; x += kFmtThreads) dense[colidx[x]] = val[x];
     if (p_start != nullptr)
@@ -428,14 +430,17 @@ csv_format_fill_kernel(const uint8_t *__restrict__ ids, const int64_t *__restric
     out += id_len;
     __syncthreads();
     for (int q0 = 0; q0 < Q; q0 += kFmtTile) {
-      // bytes of this thread's kFmtPerThread consecutive columns: ',' + digits (or nothing for an empty cell)
+      // this thread's 16 consecutive columns: ',' + digits (or nothing for an empty cell)
       const int c0 = q0 + tid * kFmtPerThread;
+      uint4 dv = make_uint4(0u, 0u, 0u, 0u);
+      if (c0 < Q) dv = *reinterpret_cast<const uint4 *>(dense + c0);
+      const unsigned dw[4] = {dv.x, dv.y, dv.z, dv.w};
+      const int ncol = min(kFmtPerThread, Q - c0);            // <= 0 beyond the row
       int len = 0;
 #pragma unroll
       for (int u = 0; u < kFmtPerThread; ++u) {
-        const int col = c0 + u;
-        if (col < Q) {
-          const int v = dense[col];
+        if (u < ncol) {
+          const int v = int((dw[u >> 2] >> (8 * (u & 3))) & 0xFFu);
           len += 1 + (v == 0 ? (zero_as_empty ? 0 : 1) : digits_of(v));
         }
       }
@@ -453,12 +458,12 @@ csv_format_fill_kernel(const uint8_t *__restrict__ ids, const int64_t *__restric
         if (w < warp) before += warp_sum[w];
         total += warp_sum[w];
       }
-      uint8_t *o = tile_text + before;
+      const int phase = int(out & 15);
+      uint8_t *o = tile_text + phase + before;
 #pragma unroll
       for (int u = 0; u < kFmtPerThread; ++u) {
-        const int col = c0 + u;
-        if (col < Q) {
-          const int v = dense[col];
+        if (u < ncol) {
+          const int v = int((dw[u >> 2] >> (8 * (u & 3))) & 0xFFu);
           *o++ = ',';
           if (v >= 100) *o++ = uint8_t('0' + v / 100);
           if (v >= 10) *o++ = uint8_t('0' + (v / 10) % 10);
@@ -466,7 +471,17 @@ csv_format_fill_kernel(const uint8_t *__restrict__ ids, const int64_t *__restric
         }
       }
       __syncthreads();
-      for (int x = tid; x < total; x += kFmtThreads) text[out + x] = tile_text[x];
+      // buffer byte i <-> text[out - phase + i]; whole 16-byte vectors in the middle, bytes at the two ends
+      uint8_t *dst = text + (out - phase);
+      const int stop = phase + total;
+      const int v_lo = phase == 0 ? 0 : 1, v_hi = stop >> 4;  // full vectors [v_lo, v_hi)
+      for (int j = v_lo + tid; j < v_hi; j += kFmtThreads)
+        reinterpret_cast<uint4 *>(dst)[j] = reinterpret_cast<const uint4 *>(tile_text)[j];
+      if (tid < 16) {
+        if (phase != 0 && tid >= phase && tid < stop) dst[tid] = tile_text[tid];          // head of the first vector
+        const int x = (v_hi << 4) + tid;                                                  // tail after the last full one
+        if (x < stop && (v_hi >= v_lo) && x >= 16 * v_lo) dst[x] = tile_text[x];
+      }
       out += total;
       __syncthreads();
     }
@@ -511,12 +526,12 @@ int qrs_csv_format_fill(const uint8_t *ids, const int64_t *ids_off, const int64_
                         int32_t zero_as_empty, const int64_t *text_off, uint8_t *text, void *stream) {
   if (n_rows < 0 || Q <= 0 || !text_off || !ids_off || !rowptr) return QRS_ERR_INVALID_ARG;
   if (n_rows == 0) return QRS_OK;
-  if (!text || !ids) return QRS_ERR_INVALID_ARG;
+  if (!text || !ids || (reinterpret_cast<uintptr_t>(text) & 15u) != 0) return QRS_ERR_INVALID_ARG;
   if (pred_start && (!pred_cnt || !preds || !pred_cols || nt <= 0)) return QRS_ERR_INVALID_ARG;
   if (cols_mode != QRS_COLS_I32 && cols_mode != QRS_COLS_U16) return QRS_ERR_UNSUPPORTED;
   if (Q > kFmtMaxQ) return QRS_ERR_UNSUPPORTED;
   const int q_pad = round_up(Q, 16);
-  const size_t smem = size_t(q_pad) + 4 * kFmtTile;
+  const size_t smem = size_t(q_pad) + 4 * kFmtTile + 16;
   QRS_CUDA(cudaFuncSetAttribute(csv_format_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   int per_sm = 1;
   QRS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, csv_format_fill_kernel, kFmtThreads, smem));
