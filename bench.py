@@ -323,7 +323,7 @@ def main():
         v["frac"] = v["achieved"] / peak
     dominant = max(("signatures+banding", "predict"), key=lambda s: stage_ms.get(s, 0.0))
     roofline = dict(rl[dominant])
-    kernel_name = "predict_sparse_kernel" if dominant == "predict" else "minhash_kernel"
+    kernel_name = "predict_sparse_kernel" if dominant == "predict" else ("minhash_tile_kernel" if m <= 32768 else "minhash_kernel")
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")     # DRAM bytes per launch from the committed ncu capture
     if world == 1 and args.config == "C2" and os.path.exists(tpath):

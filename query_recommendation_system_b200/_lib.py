@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("QRS_B200_LIB", os.path.join(_HERE, "libqrs_b200.so"))   # override: debugging builds only
 
 QRS_OK = 0
-MINHASH_AUTO, MINHASH_DIRECT, MINHASH_FIRST_TOUCH = 0, 1, 2
+MINHASH_AUTO, MINHASH_DIRECT, MINHASH_FIRST_TOUCH, MINHASH_TILE = 0, 1, 2, 3
 PAIRS_GROUPED, PAIRS_FORCE_SEARCH = 1, 2
 MAX_TOPK = 64
 MAX_BANDS = 256

@@ -178,6 +178,229 @@ minhash_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ colid
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tile scan (QRS_MINHASH_TILE): the same first-touch walk for 32 consecutive sets at once.
+//
+// Shared memory holds one 32-bit word per element: bit j of word e says "element e belongs
+// to set s0 + j".  A lane owns one hash and walks its permutation in rank order; each rank
+// costs ONE word load that answers the membership question for all 32 sets, and the sets
+// that meet their first element at this rank get the rank as their signature value.  The walk
+// ends when every (set, hash) of the warp is resolved: about ln(1024) * m / |set| ranks, so a
+// (set, hash) costs ~1.5 warp instructions instead of the ~40 of the per-set scan above.
+//   * the word map is built without atomics: warp w owns the sets 8w .. 8w+7, i.e. byte w of
+//     every word, and adds its sets one after the other with byte read-modify-writes;
+//   * order_head is hash-major (32 ranks of one hash = one 128-byte line), the walk wants
+//     lane = hash: every warp stages 32 ranks x 32 hashes through a padded shared tile;
+//   * short sets (len*len < m, AUTO only) are left out of the map and take the direct
+//     gather-min; a (set, hash) still open after R ranks takes direct_min_one_hash.
+//   dynamic smem: long long rp[40] | unsigned bm[m] | int sigt[32][Kp] | int xpose[NW][32*33]
+constexpr int kTileSets = 32;
+constexpr int kTileThreads = 128;
+constexpr int kTileMaxMapBytes = 128 * 1024;
+constexpr int kTileMaxSmemBytes = 227 * 1024;
+constexpr bool kAutoUsesTile = true;   // AUTO takes the tile scan whenever the word map fits
+
+__host__ __device__ constexpr int tile_sig_stride(int K) { return round_up(K, 32) + 1; }
+
+__global__ void __launch_bounds__(kTileThreads)
+minhash_tile_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ colidx, int64_t n, int m,
+                    const int *__restrict__ perm_tab, const int *__restrict__ order_head, int R, int K, int b,
+                    int64_t id_base, int *__restrict__ sig, long long *__restrict__ norm2,
+                    uint64_t *__restrict__ records, int64_t rec_stride, int mode, int map_words) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int NW = kTileThreads / 32;
+  static_assert(NW * 8 == kTileSets, "warp w owns byte w of every map word");
+  const int Kp = tile_sig_stride(K);
+  long long *rp = reinterpret_cast<long long *>(smem_raw);
+  unsigned *bm = reinterpret_cast<unsigned *>(rp + 40);   // 16-byte aligned: map_words % 4 == 0
+  int *sigt = reinterpret_cast<int *>(bm + map_words);
+  int *xpose = sigt + kTileSets * Kp;
+  unsigned char *bmb = reinterpret_cast<unsigned char *>(bm);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r_band = b > 0 ? K / b : 0;
+  const int64_t tiles = ceil_div<int64_t>(n, kTileSets);
+  int *xp = xpose + warp * (32 * 33);
+
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int64_t s0 = tile * kTileSets;
+    const int nsets = int(min(int64_t(kTileSets), n - s0));
+
+    // ---- stage the row bounds, clear the map
+    if (tid <= kTileSets) rp[tid] = rowptr[s0 + min(tid, nsets)];
+    for (int t = tid * 4; t < map_words; t += kTileThreads * 4)
+      *reinterpret_cast<uint4 *>(bm + t) = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+
+    // scanmask: sets that take part in the walk; the others are empty (-1 row), absent, or short
+    unsigned scanmask = 0;
+    {
+      bool scan = false;
+      if (lane < nsets) {
+        const long long len = rp[lane + 1] - rp[lane];
+        scan = len > 0 && (mode == QRS_MINHASH_TILE || len * len >= m);
+      }
+      scanmask = __ballot_sync(kFull, scan);
+    }
+
+    // ---- build: warp w adds its 8 sets to byte w of the words, one set after the other
+    for (int jj = 0; jj < 8; ++jj) {
+      const int j = warp * 8 + jj;
+      if (j >= nsets) break;
+      const int64_t lo = rp[j];
+      const int len = int(rp[j + 1] - lo);
+      if (len == 0) {
+        for (int i = lane; i < K; i += 32) sigt[j * Kp + i] = -1;
+        continue;
+      }
+      if (!((scanmask >> j) & 1u)) continue;
+      const unsigned char bit = (unsigned char)(1u << jj);
+      int t = lane;
+      for (; t + 96 < len; t += 128) {
+        int e0 = ld_stream_s32(colidx + lo + t), e1 = ld_stream_s32(colidx + lo + t + 32);
+        int e2 = ld_stream_s32(colidx + lo + t + 64), e3 = ld_stream_s32(colidx + lo + t + 96);
+        unsigned char *p0 = bmb + e0 * 4 + warp, *p1 = bmb + e1 * 4 + warp;
+        unsigned char *p2 = bmb + e2 * 4 + warp, *p3 = bmb + e3 * 4 + warp;
+        unsigned char v0 = *p0, v1 = *p1, v2 = *p2, v3 = *p3;   // distinct elements: no aliasing
+        *p0 = v0 | bit; *p1 = v1 | bit; *p2 = v2 | bit; *p3 = v3 | bit;
+      }
+      for (; t < len; t += 32) {
+        unsigned char *p0 = bmb + ld_stream_s32(colidx + lo + t) * 4 + warp;
+        *p0 = *p0 | bit;
+      }
+      __syncwarp();   // the next set of this warp may touch the bytes other lanes just wrote
+    }
+    __syncthreads();
+
+    // ---- walk: lane = hash, 32 ranks staged per round
+    for (int i0 = warp * 32; i0 < K; i0 += NW * 32) {
+      const int i = i0 + lane;
+      unsigned found = (i < K) ? ~scanmask : kFull;
+      int *srow = sigt + i;   // column i of the signature tile (only written by lanes with i < K)
+      for (int r0 = 0; r0 < R; r0 += 32) {
+        if (__all_sync(kFull, found == kFull)) break;
+        // 16-byte loads: 8 lanes cover the 32 ranks of one hash, a warp load covers 4 hashes;
+        // lane (hq, rq4) stores to banks hq + rq4 + c: conflict-free with the 33-word pitch
+#pragma unroll
+        for (int s4 = 0; s4 < 32; s4 += 4) {
+          const int hh = s4 + (lane >> 3), rq4 = (lane & 7) * 4;
+          const int ih = min(i0 + hh, K - 1);
+          const int4 v = __ldg(reinterpret_cast<const int4 *>(order_head + int64_t(ih) * R + r0 + rq4));
+          int *dst = xp + hh * 33 + rq4;
+          dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+        }
+        __syncwarp();
+        for (int rq = 0; rq < 32; rq += 8) {
+          int e[8];
+          unsigned w[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) e[u] = xp[lane * 33 + rq + u];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) w[u] = bm[e[u]];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            unsigned nw = w[u] & ~found;
+            found |= w[u];
+            while (nw) {
+              const int j = __ffs(nw) - 1;
+              nw &= nw - 1;
+              srow[j * Kp] = r0 + rq + u;
+            }
+          }
+          if (__all_sync(kFull, found == kFull)) break;
+        }
+        __syncwarp();   // xp is rewritten by the next round
+      }
+      // still open after the head: gather-min per (set, hash), the whole warp on each
+      unsigned miss = ~found;
+      unsigned lanes_open = __ballot_sync(kFull, miss != 0);
+      while (lanes_open) {
+        const int src = __ffs(lanes_open) - 1;
+        lanes_open &= lanes_open - 1;
+        unsigned mm = __shfl_sync(kFull, miss, src);
+        while (mm) {
+          const int j = __ffs(mm) - 1;
+          mm &= mm - 1;
+          const int64_t lo = rp[j];
+          const int v = direct_min_one_hash(colidx, lo, int(rp[j + 1] - lo), perm_tab, K, i0 + src, lane);
+          if (lane == 0) sigt[j * Kp + i0 + src] = v;
+        }
+      }
+    }
+
+    // ---- short sets (AUTO): direct gather-min, lane owns a hash, elements broadcast 32 at a time
+    for (int jj = 0; jj < 8; ++jj) {
+      const int j = warp * 8 + jj;
+      if (j >= nsets) break;
+      const int64_t lo = rp[j];
+      const int len = int(rp[j + 1] - lo);
+      if (len == 0 || ((scanmask >> j) & 1u)) continue;
+      for (int i0 = 0; i0 < K; i0 += 32) {
+        const int i = min(i0 + lane, K - 1);
+        int v = 0x7FFFFFFF;
+        for (int t0 = 0; t0 < len; t0 += 32) {
+          const int mine = (t0 + lane < len) ? __ldg(colidx + lo + t0 + lane) : -1;
+          const int cnt = min(32, len - t0);
+          for (int t = 0; t < cnt; ++t) {
+            const int e0 = __shfl_sync(kFull, mine, t);
+            v = min(v, __ldg(perm_tab + int64_t(e0) * K + i));
+          }
+        }
+        if (i0 + lane < K) sigt[j * Kp + i0 + lane] = v;
+      }
+    }
+    __syncthreads();
+
+    // ---- epilogue: rows to global (+ norm2), bucket records with lane = set
+    for (int j = warp; j < nsets; j += NW) {
+      long long acc = 0;
+      for (int i = lane; i < K; i += 32) {
+        const int x = sigt[j * Kp + i];
+        sig[(s0 + j) * K + i] = x;
+        acc += (long long)x * x;
+      }
+      if (norm2 != nullptr) {
+        acc = warp_sum_ll(acc);
+        if (lane == 0) norm2[s0 + j] = acc;
+      }
+    }
+    if (records != nullptr) {
+      for (int idx = tid; idx < b * kTileSets; idx += kTileThreads) {
+        const int band = idx >> 5, j = idx & 31;
+        if (j < nsets)
+          records[int64_t(band) * rec_stride + s0 + j] =
+              band_record(sigt + j * Kp + band * r_band, r_band, uint32_t(band), uint32_t(id_base + s0 + j));
+      }
+    }
+    __syncthreads();   // rp / sigt / bm are rewritten by the next tile
+  }
+}
+
+static size_t tile_smem_bytes(int K, int map_words) {
+  return 40 * 8 + size_t(map_words) * 4 +
+         (size_t(kTileSets) * tile_sig_stride(K) + size_t(kTileThreads / 32) * 32 * 33) * 4;
+}
+
+static int launch_minhash_tile(const int64_t *rowptr, const int *colidx, int64_t n, int m, const int *perm_tab,
+                               const int *order_head, int R, int K, int b, int64_t id_base, int *sig,
+                               long long *norm2, uint64_t *records, int64_t rec_stride, int mode,
+                               cudaStream_t stream) {
+  const int map_words = round_up(m, 4);
+  const size_t smem = tile_smem_bytes(K, map_words);
+  QRS_CUDA(cudaFuncSetAttribute(minhash_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  int per_sm = 0;
+  QRS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, minhash_tile_kernel, kTileThreads, smem));
+  if (per_sm < 1) return QRS_ERR_UNSUPPORTED;
+  int64_t grid = int64_t(sm_count()) * per_sm;
+  const int64_t tiles = ceil_div<int64_t>(n, kTileSets);
+  if (grid > tiles) grid = tiles;
+  minhash_tile_kernel<<<unsigned(grid), kTileThreads, smem, stream>>>(rowptr, colidx, n, m, perm_tab, order_head, R,
+                                                                      K, b, id_base, sig, norm2, records, rec_stride,
+                                                                      mode, map_words);
+  QRS_LAUNCH_CHECK();
+  return QRS_OK;
+}
+
 template <bool BYTEMAP, int THREADS>
 static int launch_minhash(const int64_t *rowptr, const int *colidx, int64_t n, int m, const int *perm_tab,
                           const int *order_head, int R, int K, int b, int64_t id_base, int *sig,
@@ -223,7 +446,7 @@ int qrs_minhash_perm(const int64_t *rowptr, const int32_t *colidx, int64_t n, in
                      int32_t mode, void *stream) {
   if (n < 0 || m <= 0 || K <= 0 || !rowptr || !perm_tab || !sig) return QRS_ERR_INVALID_ARG;
   if (n > 0 && !colidx) return QRS_ERR_INVALID_ARG;
-  if (mode < QRS_MINHASH_AUTO || mode > QRS_MINHASH_FIRST_TOUCH) return QRS_ERR_INVALID_ARG;
+  if (mode < QRS_MINHASH_AUTO || mode > QRS_MINHASH_TILE) return QRS_ERR_INVALID_ARG;
   if (records) {
     if (b <= 0 || b > QRS_MAX_BANDS || K % b != 0 || rec_stride < n) return QRS_ERR_INVALID_ARG;
     if (id_base < 0 || id_base + n > (int64_t(1) << 32)) return QRS_ERR_UNSUPPORTED;
@@ -236,8 +459,15 @@ int qrs_minhash_perm(const int64_t *rowptr, const int32_t *colidx, int64_t n, in
   if (R % 32 != 0 || R > m) return QRS_ERR_INVALID_ARG;
   bool ft_possible = R >= 32 && mode != QRS_MINHASH_DIRECT && m <= kMaxElemsFirstTouch;
   if (mode == QRS_MINHASH_FIRST_TOUCH && !ft_possible) return QRS_ERR_UNSUPPORTED;
+  const bool tile_possible = R >= 32 && int64_t(m) * 4 <= kTileMaxMapBytes &&
+                             (reinterpret_cast<uintptr_t>(order_head) & 15) == 0 &&
+                             tile_smem_bytes(K, round_up(m, 4)) <= size_t(kTileMaxSmemBytes);
+  if (mode == QRS_MINHASH_TILE && !tile_possible) return QRS_ERR_UNSUPPORTED;
   cudaStream_t st = as_stream(stream);
   long long *n2 = reinterpret_cast<long long *>(norm2);
+  if (tile_possible && (mode == QRS_MINHASH_TILE || (mode == QRS_MINHASH_AUTO && kAutoUsesTile)))
+    return launch_minhash_tile(rowptr, colidx, n, m, perm_tab, order_head, R, K, b, id_base, sig, n2, records,
+                               rec_stride, mode, st);
   if (!ft_possible)
     return launch_minhash<true, 128>(rowptr, colidx, n, m, perm_tab, order_head, 0, K, b, id_base, sig, n2,
                                      records, rec_stride, QRS_MINHASH_DIRECT, 0, st);

@@ -38,7 +38,10 @@ def gpu_signatures(g_rowptr, g_colidx, tab, b=0, mode=0, R=None):
 
 
 # ------------------------------------------------------------------------------ a1
-@pytest.mark.parametrize("mode", [0, 1, 2])
+TILE_MAX_ELEMENTS = 32768   # QRS_MINHASH_TILE: one 32-bit word per element, 128 KB of shared memory
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
 def test_minhash_c1_bit_exact(golden_c1, mode):
     g = golden_c1
     tab = g["perm_tab"].astype(np.int32)
@@ -48,9 +51,11 @@ def test_minhash_c1_bit_exact(golden_c1, mode):
     assert np.array_equal(norm2.cpu().numpy(), (ref * ref).sum(axis=1))
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
 def test_minhash_synth_bit_exact(golden_synth, mode):
     g = golden_synth
+    if mode == 3 and int(g["m"]) > TILE_MAX_ELEMENTS:
+        pytest.skip("the tile scan's word map does not fit shared memory (covered by test_minhash_tile_refuses_large_m)")
     tab = spec.permutation_table(int(g["m"]), int(g["K"]), seed=int(g["perm_seed"]))
     sig, norm2, _ = gpu_signatures(g["rowptr"], g["colidx"], tab, mode=mode)
     ref = g["sig"].astype(np.int64)
@@ -68,9 +73,68 @@ def test_minhash_head_exhaustion_falls_back_to_direct():
     colidx = np.concatenate(rows).astype(np.int32)
     tab = spec.permutation_table(m, K, seed=3)
     ref = spec.signatures(rowptr, colidx, tab)
-    for mode in (0, 1, 2):
+    for mode in (0, 1, 2, 3):
         sig, _, _ = gpu_signatures(rowptr, colidx, tab, mode=mode, R=32)
         assert np.array_equal(sig.cpu().numpy().astype(np.int64), ref)
+
+
+def _ragged_rows(rng, n, m, lens):
+    rows = [np.sort(rng.choice(m, size=int(l), replace=False)).astype(np.int32) for l in lens]
+    rowptr = np.zeros(n + 1, np.int64)
+    rowptr[1:] = np.cumsum([r.size for r in rows])
+    colidx = np.concatenate(rows).astype(np.int32) if rowptr[-1] else np.zeros(0, np.int32)
+    return rowptr, colidx
+
+
+@pytest.mark.parametrize("mode", [0, 3])
+@pytest.mark.parametrize("n,m,K,b", [(1, 64, 32, 8), (31, 900, 96, 24), (33, 900, 100, 25), (517, 3000, 180, 60),
+                                       (1000, 10000, 128, 32), (200, 32768, 64, 16)])
+def test_minhash_tile_ragged_tiles(mode, n, m, K, b):
+    """Tile scan (32 sets per CTA step): partial last tile, K not a multiple of 32, empty / one-element /
+    short / long sets side by side in one tile (AUTO sends the short ones to the direct path), and the
+    fused norm2 + bucket records."""
+    from query_recommendation_system_b200 import stages
+    rng = np.random.default_rng(n * 7 + K)
+    kinds = rng.integers(0, 5, size=n)
+    hi = max(2, min(m // 8, 600))
+    lens = np.where(kinds == 0, 0, np.where(kinds == 1, 1, np.where(kinds == 2, rng.integers(2, 12, size=n),
+                                                                   rng.integers(hi // 2, hi, size=n))))
+    if lens.sum() == 0:
+        lens[0] = 3          # an all-empty CSR has no colidx buffer to pass
+    rowptr, colidx = _ragged_rows(rng, n, m, lens)
+    tab = spec.permutation_table(m, K, seed=11)
+    ref = spec.signatures(rowptr, colidx, tab)
+    sig, norm2, rec = gpu_signatures(rowptr, colidx, tab, b=b, mode=mode)
+    assert np.array_equal(sig.cpu().numpy().astype(np.int64), ref)
+    assert np.array_equal(norm2.cpu().numpy(), (ref * ref).sum(axis=1))
+    rec2, norm2b = stages.band_records(sig, b, 0)
+    assert torch.equal(rec, rec2) and torch.equal(norm2, norm2b)
+
+
+def test_minhash_tile_equals_first_touch_at_bench_density():
+    """C2-like rows (5 % of 10 000 elements, planted groups): the three scans agree, records included."""
+    from query_recommendation_system_b200 import synth
+    n, m, K, b = 4096 + 17, 10000, 128, 32
+    rowptr, colidx, _ = synth.planted_csr(n, m, 0.05, seed=5)
+    rowptr, colidx = rowptr.numpy(), colidx.numpy()
+    tab = spec.permutation_table(m, K, seed=7)
+    outs = [gpu_signatures(rowptr, colidx, tab, b=b, mode=mode) for mode in (2, 3, 0)]
+    for sig, norm2, rec in outs[1:]:
+        assert torch.equal(sig, outs[0][0]) and torch.equal(norm2, outs[0][1]) and torch.equal(rec, outs[0][2])
+    ref = spec.signatures(rowptr[:257], colidx[:rowptr[256]], tab)
+    assert np.array_equal(outs[1][0][:256].cpu().numpy().astype(np.int64), ref)
+
+
+def test_minhash_tile_refuses_large_m():
+    from query_recommendation_system_b200 import _lib
+    rng = np.random.default_rng(2)
+    n, m, K = 40, TILE_MAX_ELEMENTS + 1, 32
+    rowptr, colidx = _ragged_rows(rng, n, m, rng.integers(50, 400, size=n))
+    tab = spec.permutation_table(m, K, seed=1)
+    with pytest.raises(_lib.QrsError):
+        gpu_signatures(rowptr, colidx, tab, mode=3)
+    sig, _, _ = gpu_signatures(rowptr, colidx, tab, mode=0)     # AUTO falls back to the per-set scan
+    assert np.array_equal(sig.cpu().numpy().astype(np.int64), spec.signatures(rowptr, colidx, tab))
 
 
 def test_minhash_seeded_5000x2000_and_fused_records():
