@@ -199,6 +199,22 @@ constexpr int kTileThreads = 128;
 constexpr int kTileMaxMapBytes = 128 * 1024;
 constexpr int kTileMaxSmemBytes = 227 * 1024;
 constexpr bool kAutoUsesTile = true;   // AUTO takes the tile scan whenever the word map fits
+constexpr int kTileCoopBits = 6;       // new sets of one lane in one 8-rank step from which the warp records them
+#ifndef QRS_TILE_COOP
+#define QRS_TILE_COOP 1
+#endif
+
+__device__ __forceinline__ unsigned bfind(unsigned x) {   // index of the most significant set bit
+  unsigned r;
+  asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
+  return r;
+}
+__device__ __forceinline__ void st_shared_s32(unsigned addr, int v) {
+  asm volatile("st.shared.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 
 __host__ __device__ constexpr int tile_sig_stride(int K) { return round_up(K, 32) + 1; }
 
@@ -255,28 +271,36 @@ minhash_tile_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ 
       }
       if (!((scanmask >> j) & 1u)) continue;
       const unsigned char bit = (unsigned char)(1u << jj);
-      int t = lane;
-      for (; t + 96 < len; t += 128) {
-        int e0 = ld_stream_s32(colidx + lo + t), e1 = ld_stream_s32(colidx + lo + t + 32);
-        int e2 = ld_stream_s32(colidx + lo + t + 64), e3 = ld_stream_s32(colidx + lo + t + 96);
-        unsigned char *p0 = bmb + e0 * 4 + warp, *p1 = bmb + e1 * 4 + warp;
-        unsigned char *p2 = bmb + e2 * 4 + warp, *p3 = bmb + e3 * 4 + warp;
-        unsigned char v0 = *p0, v1 = *p1, v2 = *p2, v3 = *p3;   // distinct elements: no aliasing
-        *p0 = v0 | bit; *p1 = v1 | bit; *p2 = v2 | bit; *p3 = v3 | bit;
-      }
-      for (; t < len; t += 32) {
-        unsigned char *p0 = bmb + ld_stream_s32(colidx + lo + t) * 4 + warp;
-        *p0 = *p0 | bit;
+      for (int t = lane; t < len; t += 256) {
+        int e[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) e[u] = (t + 32 * u < len) ? ld_stream_s32(colidx + lo + t + 32 * u) : -1;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (e[u] >= 0) {                 // distinct elements of one row: no two lanes share a byte
+            unsigned char *p = bmb + e[u] * 4 + warp;
+            *p = *p | bit;
+          }
       }
       __syncwarp();   // the next set of this warp may touch the bytes other lanes just wrote
     }
     __syncthreads();
 
+    // the next tile's column indices (one contiguous CSR span, read once) on their way into L2
+    if (tile + gridDim.x < tiles) {
+      const int64_t sn = (tile + gridDim.x) * kTileSets;
+      const int64_t a = rowptr[sn], e = rowptr[min(sn + kTileSets, n)];
+      const char *base = reinterpret_cast<const char *>(colidx + a);
+      for (int64_t off = int64_t(tid) * 128; off < (e - a) * 4; off += kTileThreads * 128) prefetch_l2(base + off);
+    }
+
     // ---- walk: lane = hash, 32 ranks staged per round
     for (int i0 = warp * 32; i0 < K; i0 += NW * 32) {
       const int i = i0 + lane;
       unsigned found = (i < K) ? ~scanmask : kFull;
-      int *srow = sigt + i;   // column i of the signature tile (only written by lanes with i < K)
+      // column i of the signature tile as a shared-window byte address (only lanes with i < K write)
+      const unsigned srow_s = unsigned(__cvta_generic_to_shared(sigt + i));
+      const unsigned Kp4 = unsigned(Kp) * 4u;
       for (int r0 = 0; r0 < R; r0 += 32) {
         if (__all_sync(kFull, found == kFull)) break;
         // 16-byte loads: 8 lanes cover the 32 ranks of one hash, a warp load covers 4 hashes;
@@ -290,24 +314,60 @@ minhash_tile_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ 
           dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
         }
         __syncwarp();
+        // 8 ranks per step; the NEXT step's elements and words are loaded before this step's hits are recorded
+        int e[8];
+        unsigned w[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) e[u] = xp[lane * 33 + u];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) w[u] = bm[e[u]];
         for (int rq = 0; rq < 32; rq += 8) {
-          int e[8];
-          unsigned w[8];
+          unsigned wn[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+          if (rq + 8 < 32) {
 #pragma unroll
-          for (int u = 0; u < 8; ++u) e[u] = xp[lane * 33 + rq + u];
+            for (int u = 0; u < 8; ++u) e[u] = xp[lane * 33 + rq + 8 + u];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) w[u] = bm[e[u]];
+            for (int u = 0; u < 8; ++u) wn[u] = bm[e[u]];
+          }
+          unsigned nw[8], all_new = 0;
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            unsigned nw = w[u] & ~found;
+            nw[u] = w[u] & ~found;
             found |= w[u];
-            while (nw) {
-              const int j = __ffs(nw) - 1;
-              nw &= nw - 1;
-              srow[j * Kp] = r0 + rq + u;
+            all_new |= nw[u];
+          }
+#if QRS_TILE_COOP
+          // a lane that meets many of its sets in this step (a shared element of a taste group) hands the
+          // recording to the warp: lane j looks for its own bit and writes one word, no per-bit loop
+          unsigned big = __ballot_sync(kFull, __popc(all_new) >= kTileCoopBits);
+          if (big) {
+            if ((big >> lane) & 1u) all_new = 0;
+            do {
+              const int src = __ffs(big) - 1;
+              big &= big - 1;
+              int rk = -1;
+#pragma unroll
+              for (int u = 0; u < 8; ++u)
+                if ((__shfl_sync(kFull, nw[u], src) >> lane) & 1u) rk = u;
+              if (rk >= 0) sigt[lane * Kp + i0 + src] = r0 + rq + rk;
+            } while (big);
+          }
+          if (__any_sync(kFull, all_new != 0))
+#endif
+          {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              unsigned x = nw[u] & all_new;
+              while (x) {
+                const unsigned j = bfind(x);
+                x ^= 1u << j;
+                st_shared_s32(srow_s + j * Kp4, r0 + rq + u);
+              }
             }
           }
           if (__all_sync(kFull, found == kFull)) break;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) w[u] = wn[u];
         }
         __syncwarp();   // xp is rewritten by the next round
       }

@@ -269,6 +269,7 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
     const bool bitmap = cols_mode == 2;
     const int j_lo = warp * range, j_hi = min(width, j_lo + range);
     uint16_t *wj = jlist + j_lo;
+    unsigned *const bitmap_row = reinterpret_cast<unsigned *>(cols) + item * (tile >> 5);
     int touched = 0;
 #pragma unroll 2
     for (int j0 = j_lo; j0 < j_hi; j0 += 64) {
@@ -292,8 +293,7 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
         if (jb < j_hi) { const Acc x = acc[jb]; hit1 = x.den != 0.0 || x.num != 0.0; }
       }
       const unsigned m0 = __ballot_sync(kFull, hit0), m1 = __ballot_sync(kFull, hit1);
-      if (bitmap && lane < 2 && j0 + 32 * lane < j_hi)
-        reinterpret_cast<unsigned *>(cols)[item * (tile >> 5) + (j0 >> 5) + lane] = lane == 0 ? m0 : m1;
+      if (bitmap && lane < 2 && j0 + 32 * lane < j_hi) bitmap_row[(j0 >> 5) + lane] = lane == 0 ? m0 : m1;
       const int n0 = __popc(m0);
       if (hit0) wj[touched + __popc(m0 & lt)] = uint16_t(ja);
       if (hit1) wj[touched + n0 + __popc(m1 & lt)] = uint16_t(jb);
@@ -315,7 +315,13 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
     // ---- pass 2: one prediction byte per listed column, written straight into the reserved slice (ascending:
     //      warp ranges are ascending, lists are ascending); accumulators back to zero
     {
+      // this warp's part of the slice: 64-bit bases once, 32-bit offsets per prediction
       const int64_t wbase = int64_t(*s_base) + w_off[warp];
+      const int64_t gbase = region_base + wbase;
+      const int fit = int(max(int64_t(0), min(int64_t(touched), region_cap - wbase)));   // region overflow: dropped
+      uint8_t *const w_preds = preds + gbase;
+      int *const w_cols32 = cols + gbase;
+      uint16_t *const w_cols16 = reinterpret_cast<uint16_t *>(cols) + gbase;
       int nz = 0;
 #pragma unroll 2
       for (int x0 = 0; x0 < touched; x0 += 32) {
@@ -329,38 +335,39 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
           if constexpr (MILLI) {
             const unsigned lo = unsigned(a), hi = unsigned(a >> 32);
             const unsigned D = lo & 0xFFFFFu, raters = lo >> 20;
-            if (raters == 1u) {
-              // one rater: x = (7r + 180) / 10 exactly; half-way cases take the fp64 chain's bit
-              const unsigned r1 = hi >> 24, x10 = 7u * r1 + 180u, q = x10 / 10u, rem = x10 - 10u * q;
-              p = int(q) + (rem > 5u ? 1 : 0);
-              if (rem == 5u) p += int((tie_bits[(r1 / 10u) * 32u + (D >> 5)] >> (D & 31u)) & 1u);
-            } else {
-              const unsigned N = hi & 0xFFFFFFu;
-              const unsigned X = 7u * N + 180u * D, Y = 10u * D;    // x = X / Y = 0.7 * N / D + 18
-              // q = X / Y via a float estimate (q < 256, estimate off by at most one) corrected exactly
-              unsigned q = unsigned(__fdividef(float(X), float(Y)));
-              int rem = int(X - q * Y);
-              if (rem < 0) { --q; rem += int(Y); } else if (rem >= int(Y)) { ++q; rem -= int(Y); }
-              const unsigned rem2 = 2u * unsigned(rem);
-              p = int(q) + (rem2 > Y ? 1 : 0);
-              tie = rem2 == Y;          // exact half-way: the reference's fp64 rounding noise decides (fix-up kernel)
+            const unsigned N = hi & 0xFFFFFFu;
+            const unsigned X = 7u * N + 180u * D, Y = 10u * D;    // x = X / Y = 0.7 * N / D + 18
+            // q = X / Y via a float estimate (q < 256, estimate off by at most one) corrected exactly
+            unsigned q = unsigned(__fdividef(float(X), float(Y)));
+            int rem = int(X - q * Y);
+            if (rem < 0) { --q; rem += int(Y); } else if (rem >= int(Y)) { ++q; rem -= int(Y); }
+            const unsigned rem2 = 2u * unsigned(rem);
+            p = int(q) + (rem2 > Y ? 1 : 0);
+            if (rem2 == Y) {
+              // exact half-way: the reference's fp64 rounding noise decides.  One rater (N = r * D, so
+              // x = (7r + 180) / 10): the fp64 chain's bit from the table; several: the fix-up kernel
+              if (raters == 1u) {
+                const unsigned r1 = hi >> 24;
+                p += int((tie_bits[(r1 / 10u) * 32u + (D >> 5)] >> (D & 31u)) & 1u);
+              } else {
+                tie = true;
+              }
             }
           } else {
             p = predict_from(a.num, a.den);
           }
-          const int64_t pos = wbase + x;
-          if (pos < region_cap) {
+          if (x < fit) {
             if (MILLI && tie) {
               const unsigned long long slot = atomicAdd(tie_count, 1ull);
               if (int64_t(slot) < tie_capacity)
-                tie_list[slot] = make_ulonglong2((unsigned long long)(region_base + pos),
+                tie_list[slot] = make_ulonglong2((unsigned long long)(gbase + x),
                                                  ((unsigned long long)(unsigned)ul << 32) | unsigned(q0 + j));
               else
                 p = resolve_tie(colidx, val, meta4, m_s, c, q0 + j);   // list full: settle here
             }
-            if (cols_mode == 1) reinterpret_cast<uint16_t *>(cols)[region_base + pos] = uint16_t(q0 + j);
-            else if (cols_mode == 0) cols[region_base + pos] = q0 + j;
-            preds[region_base + pos] = uint8_t(p);
+            if (cols_mode == 1) w_cols16[x] = uint16_t(q0 + j);
+            else if (cols_mode == 0) w_cols32[x] = q0 + j;
+            w_preds[x] = uint8_t(p);
           }
         }
         nz += __popc(__ballot_sync(kFull, p != 0));
