@@ -69,8 +69,9 @@ __host__ __device__ __forceinline__ uint32_t rec_hash(uint64_t rec) { return uin
 __host__ __device__ __forceinline__ uint32_t rec_band(uint64_t rec) { return uint32_t(rec >> 32) & 0xFFu; }
 __host__ __device__ __forceinline__ uint32_t rec_id(uint64_t rec) { return uint32_t(rec); }
 
-// record of (set, band) from r consecutive signature values
-__device__ __forceinline__ uint64_t band_record(const int *lanes, int r, uint32_t band, uint32_t id) {
+// record of (set, band) from r consecutive signature values (int rows, or the 16-bit rows of the tile scan)
+template <typename T>
+__device__ __forceinline__ uint64_t band_record(const T *lanes, int r, uint32_t band, uint32_t id) {
   uint32_t h = band_hash_init(band);
   bool all_neg = true;
   for (int c = 0; c < r; ++c) {

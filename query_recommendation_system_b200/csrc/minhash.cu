@@ -193,30 +193,35 @@ minhash_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ colid
 //     lane = hash: every warp stages 32 ranks x 32 hashes through a padded shared tile;
 //   * short sets (len*len < m, AUTO only) are left out of the map and take the direct
 //     gather-min; a (set, hash) still open after R ranks takes direct_min_one_hash.
-//   dynamic smem: long long rp[40] | unsigned bm[m] | int sigt[32][Kp] | int xpose[NW][32*33]
+//   * everything staged in shared memory is 16 bits wide (m <= 32768 bounds element ids, ranks and
+//     signature values), which is what lets four CTAs share an SM at the bench shape.
+//   dynamic smem: long long rp[40] | unsigned bm[m] | short sigt[32][Kp] | u16 xpose[NW][32][24]
 constexpr int kTileSets = 32;
 constexpr int kTileThreads = 128;
-constexpr int kTileMaxMapBytes = 128 * 1024;
+constexpr int kTileMaxElems = 32768;           // one 32-bit word per element: 128 KB at most; ids fit 15 bits
 constexpr int kTileMaxSmemBytes = 227 * 1024;
 constexpr bool kAutoUsesTile = true;   // AUTO takes the tile scan whenever the word map fits
-constexpr int kTileCoopBits = 6;       // new sets of one lane in one 8-rank step from which the warp records them
-#ifndef QRS_TILE_COOP
-#define QRS_TILE_COOP 1
+#ifndef QRS_TILE_COOP_BITS
+#define QRS_TILE_COOP_BITS 6
 #endif
+constexpr int kTileCoopBits = QRS_TILE_COOP_BITS;   // new sets of one lane in one 8-rank step from which the warp records them
+constexpr int kTileChunk = 16;         // ranks staged per round
+constexpr int kTilePitch = 24;         // u16 per staged hash row: 48-byte rows keep the 16-byte reads conflict-free
 
 __device__ __forceinline__ unsigned bfind(unsigned x) {   // index of the most significant set bit
   unsigned r;
   asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
   return r;
 }
-__device__ __forceinline__ void st_shared_s32(unsigned addr, int v) {
-  asm volatile("st.shared.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+__device__ __forceinline__ void st_shared_s16(unsigned addr, int v) {
+  asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(short(v)) : "memory");
 }
 __device__ __forceinline__ void prefetch_l2(const void *p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
-__host__ __device__ constexpr int tile_sig_stride(int K) { return round_up(K, 32) + 1; }
+// signature-tile pitch in shorts: (pitch / 2) odd, so the 32 rows start in 32 different banks
+__host__ __device__ constexpr int tile_sig_stride(int K) { return round_up(K, 32) + 2; }
 
 __global__ void __launch_bounds__(kTileThreads)
 minhash_tile_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ colidx, int64_t n, int m,
@@ -229,14 +234,14 @@ minhash_tile_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ 
   const int Kp = tile_sig_stride(K);
   long long *rp = reinterpret_cast<long long *>(smem_raw);
   unsigned *bm = reinterpret_cast<unsigned *>(rp + 40);   // 16-byte aligned: map_words % 4 == 0
-  int *sigt = reinterpret_cast<int *>(bm + map_words);
-  int *xpose = sigt + kTileSets * Kp;
+  short *sigt = reinterpret_cast<short *>(bm + map_words);
+  unsigned short *xpose = reinterpret_cast<unsigned short *>(sigt + kTileSets * Kp);   // Kp % 8 == 2: see tile_smem_bytes
   unsigned char *bmb = reinterpret_cast<unsigned char *>(bm);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int r_band = b > 0 ? K / b : 0;
   const int64_t tiles = ceil_div<int64_t>(n, kTileSets);
-  int *xp = xpose + warp * (32 * 33);
+  unsigned short *xp = xpose + warp * (32 * kTilePitch);
 
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int64_t s0 = tile * kTileSets;
@@ -259,30 +264,53 @@ minhash_tile_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ 
       scanmask = __ballot_sync(kFull, scan);
     }
 
-    // ---- build: warp w adds its 8 sets to byte w of the words, one set after the other
+    // ---- empty sets: a row of -1
     for (int jj = 0; jj < 8; ++jj) {
       const int j = warp * 8 + jj;
-      if (j >= nsets) break;
-      const int64_t lo = rp[j];
-      const int len = int(rp[j + 1] - lo);
-      if (len == 0) {
+      if (j < nsets && rp[j + 1] == rp[j])
         for (int i = lane; i < K; i += 32) sigt[j * Kp + i] = -1;
-        continue;
-      }
-      if (!((scanmask >> j) & 1u)) continue;
-      const unsigned char bit = (unsigned char)(1u << jj);
-      for (int t = lane; t < len; t += 256) {
-        int e[8];
+    }
+
+    // ---- build: warp w adds its (up to) 8 sets to byte w of the words, one set after the other, 256 entries
+    //      per step; the NEXT step's column indices are loaded before this step's bytes are updated
+    {
+      unsigned todo = (scanmask >> (warp * 8)) & 0xFFu;
+      int jj = todo ? __ffs(todo) - 1 : -1;
+      int t0 = 0;
+      int e[8];
+      auto load8 = [&](int (&dst)[8], int set, int first) {
+        const int64_t lo = rp[warp * 8 + set];
+        const int len = int(rp[warp * 8 + set + 1] - lo);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) e[u] = (t + 32 * u < len) ? ld_stream_s32(colidx + lo + t + 32 * u) : -1;
+        for (int u = 0; u < 8; ++u) {
+          const int t = first + lane + 32 * u;
+          dst[u] = t < len ? ld_stream_s32(colidx + lo + t) : -1;
+        }
+      };
+      if (jj >= 0) load8(e, jj, 0);
+      while (jj >= 0) {
+        const int len = int(rp[warp * 8 + jj + 1] - rp[warp * 8 + jj]);
+        int njj = jj, nt0 = t0 + 256;
+        if (nt0 >= len) {
+          todo &= todo - 1;
+          njj = todo ? __ffs(todo) - 1 : -1;
+          nt0 = 0;
+        }
+        int en[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
+        if (njj >= 0) load8(en, njj, nt0);
+        const unsigned char bit = (unsigned char)(1u << jj);
 #pragma unroll
         for (int u = 0; u < 8; ++u)
           if (e[u] >= 0) {                 // distinct elements of one row: no two lanes share a byte
             unsigned char *p = bmb + e[u] * 4 + warp;
             *p = *p | bit;
           }
+        if (njj != jj) __syncwarp();       // the next set may touch the bytes other lanes just wrote
+#pragma unroll
+        for (int u = 0; u < 8; ++u) e[u] = en[u];
+        jj = njj;
+        t0 = nt0;
       }
-      __syncwarp();   // the next set of this warp may touch the bytes other lanes just wrote
     }
     __syncthreads();
 
@@ -294,40 +322,38 @@ minhash_tile_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ 
       for (int64_t off = int64_t(tid) * 128; off < (e - a) * 4; off += kTileThreads * 128) prefetch_l2(base + off);
     }
 
-    // ---- walk: lane = hash, 32 ranks staged per round
+    // ---- walk: lane = hash, 16 ranks staged per round
     for (int i0 = warp * 32; i0 < K; i0 += NW * 32) {
       const int i = i0 + lane;
       unsigned found = (i < K) ? ~scanmask : kFull;
       // column i of the signature tile as a shared-window byte address (only lanes with i < K write)
       const unsigned srow_s = unsigned(__cvta_generic_to_shared(sigt + i));
-      const unsigned Kp4 = unsigned(Kp) * 4u;
-      for (int r0 = 0; r0 < R; r0 += 32) {
+      const unsigned Kp2 = unsigned(Kp) * 2u;
+      for (int r0 = 0; r0 < R; r0 += kTileChunk) {
         if (__all_sync(kFull, found == kFull)) break;
-        // 16-byte loads: 8 lanes cover the 32 ranks of one hash, a warp load covers 4 hashes;
-        // lane (hq, rq4) stores to banks hq + rq4 + c: conflict-free with the 33-word pitch
+        // 16-byte loads: 4 lanes cover the 16 ranks of one hash, a warp load covers 8 hashes; ids packed to u16
 #pragma unroll
-        for (int s4 = 0; s4 < 32; s4 += 4) {
-          const int hh = s4 + (lane >> 3), rq4 = (lane & 7) * 4;
+        for (int s8 = 0; s8 < 32; s8 += 8) {
+          const int hh = s8 + (lane >> 2), rq4 = (lane & 3) * 4;
           const int ih = min(i0 + hh, K - 1);
           const int4 v = __ldg(reinterpret_cast<const int4 *>(order_head + int64_t(ih) * R + r0 + rq4));
-          int *dst = xp + hh * 33 + rq4;
-          dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+          *reinterpret_cast<uint2 *>(xp + hh * kTilePitch + rq4) =
+              make_uint2(unsigned(v.x) | (unsigned(v.y) << 16), unsigned(v.z) | (unsigned(v.w) << 16));
         }
         __syncwarp();
-        // 8 ranks per step; the NEXT step's elements and words are loaded before this step's hits are recorded
-        int e[8];
-        unsigned w[8];
+        // 8 ranks per step; the second step's words are loaded before the first step's hits are recorded
+        unsigned w[8], wn[8];
+        {
+          const uint4 q = *reinterpret_cast<const uint4 *>(xp + lane * kTilePitch);
+          w[0] = bm[q.x & 0xFFFFu]; w[1] = bm[q.x >> 16]; w[2] = bm[q.y & 0xFFFFu]; w[3] = bm[q.y >> 16];
+          w[4] = bm[q.z & 0xFFFFu]; w[5] = bm[q.z >> 16]; w[6] = bm[q.w & 0xFFFFu]; w[7] = bm[q.w >> 16];
+        }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) e[u] = xp[lane * 33 + u];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) w[u] = bm[e[u]];
-        for (int rq = 0; rq < 32; rq += 8) {
-          unsigned wn[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-          if (rq + 8 < 32) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) e[u] = xp[lane * 33 + rq + 8 + u];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) wn[u] = bm[e[u]];
+        for (int rq = 0; rq < kTileChunk; rq += 8) {
+          if (rq == 0) {
+            const uint4 q = *reinterpret_cast<const uint4 *>(xp + lane * kTilePitch + 8);
+            wn[0] = bm[q.x & 0xFFFFu]; wn[1] = bm[q.x >> 16]; wn[2] = bm[q.y & 0xFFFFu]; wn[3] = bm[q.y >> 16];
+            wn[4] = bm[q.z & 0xFFFFu]; wn[5] = bm[q.z >> 16]; wn[6] = bm[q.w & 0xFFFFu]; wn[7] = bm[q.w >> 16];
           }
           unsigned nw[8], all_new = 0;
 #pragma unroll
@@ -336,9 +362,8 @@ minhash_tile_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ 
             found |= w[u];
             all_new |= nw[u];
           }
-#if QRS_TILE_COOP
           // a lane that meets many of its sets in this step (a shared element of a taste group) hands the
-          // recording to the warp: lane j looks for its own bit and writes one word, no per-bit loop
+          // recording to the warp: lane j looks for its own bit and writes one value, no per-bit loop
           unsigned big = __ballot_sync(kFull, __popc(all_new) >= kTileCoopBits);
           if (big) {
             if ((big >> lane) & 1u) all_new = 0;
@@ -349,19 +374,17 @@ minhash_tile_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ 
 #pragma unroll
               for (int u = 0; u < 8; ++u)
                 if ((__shfl_sync(kFull, nw[u], src) >> lane) & 1u) rk = u;
-              if (rk >= 0) sigt[lane * Kp + i0 + src] = r0 + rq + rk;
+              if (rk >= 0) sigt[lane * Kp + i0 + src] = short(r0 + rq + rk);
             } while (big);
           }
-          if (__any_sync(kFull, all_new != 0))
-#endif
-          {
+          if (__any_sync(kFull, all_new != 0)) {
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
               unsigned x = nw[u] & all_new;
               while (x) {
                 const unsigned j = bfind(x);
                 x ^= 1u << j;
-                st_shared_s32(srow_s + j * Kp4, r0 + rq + u);
+                st_shared_s16(srow_s + j * Kp2, r0 + rq + u);
               }
             }
           }
@@ -383,7 +406,7 @@ minhash_tile_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ 
           mm &= mm - 1;
           const int64_t lo = rp[j];
           const int v = direct_min_one_hash(colidx, lo, int(rp[j + 1] - lo), perm_tab, K, i0 + src, lane);
-          if (lane == 0) sigt[j * Kp + i0 + src] = v;
+          if (lane == 0) sigt[j * Kp + i0 + src] = short(v);
         }
       }
     }
@@ -406,7 +429,7 @@ minhash_tile_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ 
             v = min(v, __ldg(perm_tab + int64_t(e0) * K + i));
           }
         }
-        if (i0 + lane < K) sigt[j * Kp + i0 + lane] = v;
+        if (i0 + lane < K) sigt[j * Kp + i0 + lane] = short(v);
       }
     }
     __syncthreads();
@@ -437,8 +460,9 @@ minhash_tile_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ 
 }
 
 static size_t tile_smem_bytes(int K, int map_words) {
-  return 40 * 8 + size_t(map_words) * 4 +
-         (size_t(kTileSets) * tile_sig_stride(K) + size_t(kTileThreads / 32) * 32 * 33) * 4;
+  // sigt: 32 * Kp shorts with Kp % 8 == 2 -> 64 * Kp bytes, a multiple of 16: xpose stays 16-byte aligned
+  return 40 * 8 + size_t(map_words) * 4 + size_t(kTileSets) * tile_sig_stride(K) * 2 +
+         size_t(kTileThreads / 32) * 32 * kTilePitch * 2;
 }
 
 static int launch_minhash_tile(const int64_t *rowptr, const int *colidx, int64_t n, int m, const int *perm_tab,
@@ -519,7 +543,7 @@ int qrs_minhash_perm(const int64_t *rowptr, const int32_t *colidx, int64_t n, in
   if (R % 32 != 0 || R > m) return QRS_ERR_INVALID_ARG;
   bool ft_possible = R >= 32 && mode != QRS_MINHASH_DIRECT && m <= kMaxElemsFirstTouch;
   if (mode == QRS_MINHASH_FIRST_TOUCH && !ft_possible) return QRS_ERR_UNSUPPORTED;
-  const bool tile_possible = R >= 32 && int64_t(m) * 4 <= kTileMaxMapBytes &&
+  const bool tile_possible = R >= 32 && m <= kTileMaxElems &&
                              (reinterpret_cast<uintptr_t>(order_head) & 15) == 0 &&
                              tile_smem_bytes(K, round_up(m, 4)) <= size_t(kTileMaxSmemBytes);
   if (mode == QRS_MINHASH_TILE && !tile_possible) return QRS_ERR_UNSUPPORTED;
