@@ -60,7 +60,7 @@ struct __align__(16) Acc { double num, den; };
 //  F64  : {num, den} in fp64, updated in table order — the reference's arithmetic verbatim.
 //  MILLI: similarities are multiples of 0.001 (np.around(., 3), recommender.py:204/270), so
 //         N = sum r*milli, D = sum milli and the rater count are exact integers packed in one
-//         u64 (N << 32 | cnt << 20 | D).  round(0.7*N/D + 18) is then decided in exact integer
+//         u64 (r << 56 | N << 32 | cnt << 24 | D).  round(0.7*N/D + 18) is then decided in exact integer
 //         arithmetic; it can differ from the reference's fp64 evaluation only when
 //         (7N + 180D) / (10D) is EXACTLY half-way between two integers (the fp64 rounding noise
 //         of ~1e-12 is far below the next possible distance 1/(20D) >= 7e-7), and exactly those
@@ -82,6 +82,16 @@ __host__ __device__ constexpr int sparse_warp_range(int tile) { return round_up(
 __host__ __device__ constexpr size_t sparse_cta_bytes(int tile, bool milli) {
   return round_up<size_t>(size_t(tile) * (milli ? 8 : 16), 16) +
          round_up<size_t>(size_t(sparse_warp_range(tile)) * kSpWarpsCta * 2, 16) + 64 * 8 + 256 + 26 * 32 * 4 + 64 * 16;
+}
+
+// predicated 8-byte shared-memory load / store (cond != 0), by shared-window byte address
+__device__ __forceinline__ void lds_u64_if(unsigned long long &x, unsigned addr, unsigned cond) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.shared.u64 %0, [%1];\n\t}"
+               : "=l"(x) : "r"(addr), "r"(cond) : "memory");
+}
+__device__ __forceinline__ void sts_u64_if(unsigned addr, unsigned long long x, unsigned cond) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.u64 [%0], %1;\n\t}"
+               :: "r"(addr), "l"(x), "r"(cond) : "memory");
 }
 
 constexpr int kTieBitWords = 26 * 32;   // single-rater half-way bits: 26 ratings (5, 15, .., 255) x 1024 milli
@@ -154,6 +164,7 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
   __syncthreads();
 
   const unsigned lt = lanemask_lt();
+  const unsigned acc_s = unsigned(__cvta_generic_to_shared(acc));   // shared-window byte address of acc[0]
   const int stride = nt + 1;
   // output slices are reserved from one of n_regions cursors (a single cursor would serialise
   // millions of same-address atomics in L2); region r owns [r * region_cap, (r + 1) * region_cap)
@@ -161,11 +172,11 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
   unsigned long long *cursor = cursors + region;
   const int64_t region_base = int64_t(region) * region_cap;
 
-  // one rating r of a neighbour into column slot j (inc: MILLI increment milli | 1 << 20; g: neighbour slot)
+  // one rating r of a neighbour into column slot j (inc: MILLI increment milli | 1 << 24; g: neighbour slot)
   auto add = [&](int j, int r, unsigned inc, int g) {
     if constexpr (MILLI) {
       // u64 = r (8 bits, meaningful for a single rater) | N = sum r*milli (24) | raters (12) | D = sum milli (20)
-      acc[j] += (static_cast<unsigned long long>((unsigned(r) << 24) + unsigned(r) * (inc & 0xFFFFFu)) << 32) | inc;
+      acc[j] += (static_cast<unsigned long long>(unsigned(r) * inc) << 32) | inc;
     } else {
       const double s = m_s[g];
       Acc x = acc[j];
@@ -196,7 +207,7 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
         if constexpr (MILLI) {
           const int milli = u_milli[ul * ku + tid];
           m_s[tid] = double(milli) / 1000.0;        // == the table's double (u_val == u_milli / 1000.0)
-          inc = unsigned(milli) | (1u << 20);
+          inc = unsigned(milli) | (1u << 24);
         } else {
           m_s[tid] = u_val[ul * ku + tid];
         }
@@ -232,9 +243,24 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
     auto process_group = [&](const Group &G, int g0) {
 #pragma unroll
       for (int g = 0; g < kSpAhead; ++g) {
-        if (G.rat[g] & 0xFFu) add(G.col[g].x - q0, int(G.rat[g] & 0xFFu), G.inc[g], g0 + g);
-        if (G.rat[g] >> 8) add(G.col[g].y - q0, int(G.rat[g] >> 8), G.inc[g], g0 + g);
-        if (any_long) {                             // block-uniform; the rest of a long segment straight from memory
+        if constexpr (MILLI) {
+          // both read-modify-writes of the thread at once, predicated instead of branched (the two entries
+          // of one neighbour are different columns).  inc = milli | 1 << 24 is the low word's increment (D and
+          // the rater count) AND the high word's multiplier: r * inc = r << 24 | r * milli, as r * milli < 2^24
+          const unsigned r0 = G.rat[g] & 0xFFu, r1 = G.rat[g] >> 8;
+          const unsigned a0 = acc_s + unsigned(G.col[g].x - q0) * 8u, a1 = acc_s + unsigned(G.col[g].y - q0) * 8u;
+          unsigned long long x0, x1;
+          lds_u64_if(x0, a0, r0);
+          lds_u64_if(x1, a1, r1);
+          x0 += (static_cast<unsigned long long>(r0 * G.inc[g]) << 32) | G.inc[g];
+          x1 += (static_cast<unsigned long long>(r1 * G.inc[g]) << 32) | G.inc[g];
+          sts_u64_if(a0, x0, r0);
+          sts_u64_if(a1, x1, r1);
+        } else {
+          if (G.rat[g] & 0xFFu) add(G.col[g].x - q0, int(G.rat[g] & 0xFFu), G.inc[g], g0 + g);
+          if (G.rat[g] >> 8) add(G.col[g].y - q0, int(G.rat[g] >> 8), G.inc[g], g0 + g);
+        }
+        if (!MILLI && any_long) {                   // block-uniform; the rest of a long segment straight from memory
           const int4 mt = meta4[g0 + g];
 #pragma unroll 1
           for (int x = mt.x + kSpSpan + tid; x < mt.z; x += kSpThreads) {
@@ -259,6 +285,21 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
       }
     }
 
+    // ---- MILLI: the sums are exact integers, so the order of the additions is free — the rest of the segments
+    //      longer than one CTA pass is added here, neighbour by neighbour (a barrier between two neighbours: they
+    //      may share columns), which keeps the test out of the loop above
+    if (MILLI && any_long) {
+      for (int g = 0; g < c; ++g) {
+        const int4 mt = meta4[g];
+#pragma unroll 1
+        for (int x = mt.x + kSpSpan + tid; x < mt.z; x += kSpThreads) {
+          const int r = val[x];
+          if (r != 0) add(__ldg(colidx + x) - q0, r, unsigned(mt.w), g);
+        }
+        __syncthreads();
+      }
+    }
+
     // ---- the user's own rated cells are not predicted (recommender.py:302): drop what landed there
     for (int64_t x = own_a + tid; x < own_e; x += kSpThreads)
       if (val[x] != 0) acc[__ldg(colidx + x) - q0] = zero;
@@ -280,12 +321,12 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
         // cleared right here and predicts nothing (weightSum == 0, recommender.py:44)
         if (ja < j_hi) {
           const unsigned long long x = acc[ja];
-          hit0 = (unsigned(x) & 0xFFFFFu) != 0u;
+          hit0 = (unsigned(x) & 0xFFFFFFu) != 0u;
           if (!hit0 && x != 0ull) acc[ja] = 0ull;
         }
         if (jb < j_hi) {
           const unsigned long long x = acc[jb];
-          hit1 = (unsigned(x) & 0xFFFFFu) != 0u;
+          hit1 = (unsigned(x) & 0xFFFFFFu) != 0u;
           if (!hit1 && x != 0ull) acc[jb] = 0ull;
         }
       } else {
@@ -317,11 +358,9 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
     {
       // this warp's part of the slice: 64-bit bases once, 32-bit offsets per prediction
       const int64_t wbase = int64_t(*s_base) + w_off[warp];
-      const int64_t gbase = region_base + wbase;
       const int fit = int(max(int64_t(0), min(int64_t(touched), region_cap - wbase)));   // region overflow: dropped
-      uint8_t *const w_preds = preds + gbase;
-      int *const w_cols32 = cols + gbase;
-      uint16_t *const w_cols16 = reinterpret_cast<uint16_t *>(cols) + gbase;
+      uint8_t *const w_preds = preds + (region_base + wbase);
+      char *const w_cols = reinterpret_cast<char *>(cols) + (region_base + wbase) * (cols_mode == 1 ? 2 : 4);
       int nz = 0;
 #pragma unroll 2
       for (int x0 = 0; x0 < touched; x0 += 32) {
@@ -334,7 +373,7 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
           bool tie = false;
           if constexpr (MILLI) {
             const unsigned lo = unsigned(a), hi = unsigned(a >> 32);
-            const unsigned D = lo & 0xFFFFFu, raters = lo >> 20;
+            const unsigned D = lo & 0xFFFFFFu, raters = lo >> 24;
             const unsigned N = hi & 0xFFFFFFu;
             const unsigned X = 7u * N + 180u * D, Y = 10u * D;    // x = X / Y = 0.7 * N / D + 18
             // q = X / Y via a float estimate (q < 256, estimate off by at most one) corrected exactly
@@ -360,13 +399,13 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
             if (MILLI && tie) {
               const unsigned long long slot = atomicAdd(tie_count, 1ull);
               if (int64_t(slot) < tie_capacity)
-                tie_list[slot] = make_ulonglong2((unsigned long long)(gbase + x),
+                tie_list[slot] = make_ulonglong2((unsigned long long)(w_preds + x - preds),   // position in preds
                                                  ((unsigned long long)(unsigned)ul << 32) | unsigned(q0 + j));
               else
                 p = resolve_tie(colidx, val, meta4, m_s, c, q0 + j);   // list full: settle here
             }
-            if (cols_mode == 1) w_cols16[x] = uint16_t(q0 + j);
-            else if (cols_mode == 0) w_cols32[x] = q0 + j;
+            if (cols_mode == 1) reinterpret_cast<uint16_t *>(w_cols)[x] = uint16_t(q0 + j);
+            else if (cols_mode == 0) reinterpret_cast<int *>(w_cols)[x] = q0 + j;
             w_preds[x] = uint8_t(p);
           }
         }
