@@ -1,0 +1,14 @@
+#!/bin/bash
+# Round-end evidence in one gpurun call: the default bench line, then (after it exited 0 without ncu) the ncu
+# launch list of the bench command and one full capture of the dominant kernel.  Outputs → gpurun_out/.
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+mkdir -p gpurun_out
+t0=$SECONDS
+timeout 60 python bench.py > gpurun_out/bench_c2.json 2> gpurun_out/bench.err
+echo "bench rc=$? t=$((SECONDS-t0))"; head -c 300 gpurun_out/bench_c2.json; echo
+timeout 75 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:qrs:: --csv \
+  --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu1.log 2>&1
+echo "ncu launches rc=$? t=$((SECONDS-t0))"
+timeout 60 ncu --set full --clock-control none --import-source on -k regex:predict_sparse_kernel -s 3 -c 1 -f \
+  -o gpurun_out/predict python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu2.log 2>&1
+echo "ncu full rc=$? t=$((SECONDS-t0))"
