@@ -224,6 +224,9 @@ int qrs_predict_dense(const int64_t *rowptr, const int32_t *colidx, const uint8_
 #define QRS_COLS_U16 1
 #define QRS_COLS_BITMAP 2
 int32_t qrs_predict_max_tile(int32_t integer_tables /* 1 when u_milli is used */);
+/* CSR positions of one neighbour's segment (its entries inside one column tile) that a CTA takes in one pass;
+ * pick `tile` so that an average segment stays below ~0.9 of it (longer segments are correct but slower). */
+int32_t qrs_predict_segment_span(void);
 size_t qrs_predict_sparse_workspace_bytes(int64_t U, int32_t Q, int32_t tile, int64_t capacity);
 /* u_milli (optional): the same similarities as integers, u_val[t] == u_milli[t] / 1000.0 exactly
  * (what np.around(., 3) produces, recommender.py:204, 270; qrs_topk_tables emits it).  When given,

@@ -70,7 +70,19 @@ struct AccOf { using type = Acc; };
 template <>
 struct AccOf<true> { using type = unsigned long long; };
 
-constexpr int kSpThreads = 384;   // 12 warps: two entries per thread cover a 768-entry neighbour segment
+// CTA shape of the sparse predictor.  Shipped: 384 threads (12 warps: two entries per thread cover a 768-entry
+// neighbour segment), two CTAs per SM.  Both are build-time parameters so that other shapes (e.g. 192 threads x 4
+// CTAs over half-width column tiles) can be measured as separate libraries (QRS_B200_LIB); the host side derives
+// its tile choice from qrs_predict_segment_span() / qrs_predict_max_tile(), never from these numbers.
+#ifndef QRS_SP_THREADS
+#define QRS_SP_THREADS 384
+#endif
+#ifndef QRS_SP_MIN_CTAS
+#define QRS_SP_MIN_CTAS 2
+#endif
+constexpr int kSpThreads = QRS_SP_THREADS;
+constexpr int kSpMinCtas = QRS_SP_MIN_CTAS;
+static_assert(kSpThreads % 32 == 0 && kSpThreads >= 64 && kSpThreads <= 512, "meta setup uses 64 threads, w_cnt holds 16 warps");
 constexpr int kSpWarpsCta = kSpThreads / 32;
 constexpr int kSpAhead = 4;    // neighbours whose segment loads are in flight together (x2: double-buffered)
 constexpr int kSpSpan = 2 * kSpThreads;   // CSR positions one CTA pass covers: two consecutive entries per thread
@@ -129,7 +141,7 @@ __device__ __noinline__ int resolve_tie(const int *__restrict__ colidx, const ui
 // register set while the current group is accumulated.  The output sweep is per warp over its own
 // column range: list the touched columns, reserve one slice for the CTA, predict into the slice.
 template <bool MILLI>
-__global__ void __launch_bounds__(kSpThreads, 2)
+__global__ void __launch_bounds__(kSpThreads, kSpMinCtas)
 predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict__ val, int Q,
                       const int *__restrict__ u_idx, const double *__restrict__ u_val,
                       const int *__restrict__ u_milli, const int *__restrict__ u_cnt, int ku, int64_t user_base,
@@ -586,8 +598,19 @@ using namespace qrs;
 
 extern "C" {
 
-/* largest column tile that still lets two CTAs share an SM (<= ~112 KB of shared memory each) */
-int32_t qrs_predict_max_tile(int32_t integer_tables) { return integer_tables ? 10016 : 5824; }
+/* largest column tile that still lets kSpMinCtas CTAs share an SM (two CTAs of <= ~112 KB of shared memory each as
+ * shipped) */
+int32_t qrs_predict_max_tile(int32_t integer_tables) {
+  if (kSpThreads == 384 && kSpMinCtas == 2) return integer_tables ? 10016 : 5824;
+  const size_t budget = size_t(228) * 1024 / kSpMinCtas - 1024;   // 1 KB per CTA is reserved by the system
+  int tile = 32;
+  while (sparse_cta_bytes(tile + 32, integer_tables != 0) <= budget) tile += 32;
+  return tile;
+}
+
+/* CSR positions of one neighbour segment that one CTA pass covers (two per thread); longer segments take a slower
+ * tail loop, so the host picks the column tile that keeps an average segment below ~0.9 of this */
+int32_t qrs_predict_segment_span(void) { return kSpSpan; }
 
 static int64_t tie_list_capacity(int64_t capacity) { return capacity / 32 + 65536; }
 constexpr size_t kSingleTabBytes = round_up<size_t>(26 * 32 * 4, 256);

@@ -233,17 +233,19 @@ def predict_dense(rowptr, colidx, val, Q: int, q_tab: Optional[Table], u_tab: Op
     return out
 
 
-PREDICT_SEGMENT_TARGET = 690.0     # ~0.9 x the 768 entries one CTA pass covers (csrc/predict.cu kSpSpan)
+PREDICT_SEGMENT_FILL = 690.0 / 768.0   # an average neighbour segment should fill <= ~0.9 of one CTA pass
 
 
 def choose_predict_tile(Q: int, avg_len: float = 0.0, integer_tables: bool = True) -> int:
-    """Column tile of the sparse predictor.  One CTA of 384 threads accumulates one (user, tile) and takes two
-    consecutive entries of a neighbour's segment per thread (768 per pass; longer segments take a slower tail
-    loop): the fewest equal tiles such that a tile fits one CTA's shared memory and an average row leaves
-    <= ~690 entries in it."""
-    max_tile = _lib.load().qrs_predict_max_tile(1 if integer_tables else 0)
+    """Column tile of the sparse predictor.  One CTA accumulates one (user, tile) and takes two consecutive
+    entries of a neighbour's segment per thread (qrs_predict_segment_span() per pass — 768 with the shipped
+    384-thread CTAs; longer segments take a slower tail loop): the fewest equal tiles such that a tile fits one
+    CTA's shared memory and an average row leaves <= ~0.9 of a pass (690 entries) in it."""
+    lib = _lib.load()
+    max_tile = lib.qrs_predict_max_tile(1 if integer_tables else 0)
+    target = PREDICT_SEGMENT_FILL * lib.qrs_predict_segment_span()
     nt = max(1, math.ceil(Q / max_tile))
-    while avg_len > 0 and avg_len / nt > PREDICT_SEGMENT_TARGET and math.ceil(Q / nt) > 256:
+    while avg_len > 0 and avg_len / nt > target and math.ceil(Q / nt) > 256:
         nt += 1
     return int(min(max_tile, max(32, math.ceil(math.ceil(Q / nt) / 32.0) * 32)))
 
