@@ -29,6 +29,13 @@ def test_launch_heuristics():
     for q, avg in ((10_000, 500), (100_000, 1000), (1_000, 50), (37, 3)):
         t = stages.choose_predict_tile(q, avg)
         assert t % 32 == 0 and t <= 10_016 and -(-q // t) * t >= q
+    # the tile choice follows the library's CTA shape (shipped: 384 threads x 2 entries, two CTAs per SM)
+    from query_recommendation_system_b200 import _lib
+    lib = _lib.load()
+    assert lib.qrs_predict_segment_span() == 768 and lib.qrs_predict_max_tile(1) == 10_016
+    assert stages.choose_predict_tile(10_000, 495.0) == 10_016          # C2: the whole query axis in one tile
+    assert stages.choose_predict_tile(100_000, 1000.0) == 10_016        # C3: 10 tiles of an average 100 entries
+    assert stages.choose_predict_tile(10_000, 5000.0) < 1500            # dense rows: tiles keep a segment in one pass
 
 
 def test_synth_is_deterministic_and_shardable():
