@@ -160,6 +160,14 @@ def reference_arm(args):
     print(json.dumps(line))
 
 
+def onchip_roofline(wavefronts, ms, sm_count, sm_mhz):
+    """Second roof of a shared-memory-bound kernel: `wavefronts` shared-memory wavefronts per launch (ncu:
+    l1tex__data_pipe_lsu_wavefronts_mem_shared.sum) at one wavefront per SM per clock, against the measured time."""
+    floor_ms = wavefronts / (sm_count * sm_mhz * 1e6) * 1e3
+    return {"bound": "shared-memory data pipe", "achieved": wavefronts / (ms * 1e-3) / 1e9, "peak": sm_count * sm_mhz * 1e-3,
+            "unit": "Gwavefront/s", "frac": floor_ms / ms, "wavefronts_per_launch": int(wavefronts), "floor_ms": floor_ms}
+
+
 def workload_config(config, n_gpus, l2_note):
     from query_recommendation_system_b200 import synth
     n, m, density, K, b, k = synth.config_shape(config)
@@ -330,6 +338,13 @@ def main():
         traffic = json.load(open(tpath)).get(kernel_name)
     roofline.update({"kernel": kernel_name, "stage": dominant, "peak_source": peak_src + " (of measured)",
                      "traffic": traffic, "traffic_source": "profiles/r1_traffic.json (ncu --set full, same command)"})
+    try:    # the on-chip roof the dominant kernel is actually close to (counter from the same committed capture)
+        wf = json.load(open(tpath)).get(kernel_name + ":smem_wavefronts") if traffic is not None else None
+        if wf:
+            roofline["onchip"] = onchip_roofline(float(wf), roofline["ms"], torch.cuda.get_device_properties(dev).multi_processor_count,
+                                                 float(clocks.get("sm_mhz") or 1965.0))
+    except Exception:
+        pass
 
     # ---------------------------------------------------------------- f-2 extra: per-user top-10 recommendations
     topn = None

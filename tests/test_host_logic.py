@@ -68,3 +68,10 @@ def test_recommender_io_glue_on_golden_files(golden_c1):
     rec.init(users, queries, ids, dataset, ratings)                           # recommender.py:51-64
     assert rec.ratings.dtype == np.int32 and np.array_equal(rec.ratings, golden_c1["ratings"])
     assert rec.dataset.shape[0] == int(golden_c1["m"]) and rec.usersIDs[0] == "U1"
+
+
+def test_bench_onchip_roofline_arithmetic():
+    import bench
+    r = bench.onchip_roofline(9.0e8, 6.0, 148, 2000.0)        # 9e8 wavefronts / (148 SMs x 2 GHz) = 3.04 ms
+    assert abs(r["floor_ms"] - 9.0e8 / (148 * 2.0e9) * 1e3) < 1e-12 and abs(r["frac"] - r["floor_ms"] / 6.0) < 1e-12
+    assert abs(r["achieved"] / r["peak"] - r["frac"]) < 1e-12
