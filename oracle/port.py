@@ -89,6 +89,13 @@ def query_similarities(signatures, b, k):
     for s in signatures:
         lsh.compute_buckets(s)
     cand = lsh.get_candidates(signatures)
+    return similarities_from_candidates(signatures, cand, k), cand
+
+
+def similarities_from_candidates(signatures, cand, k, cosine_row0=_cosine_row0):
+    """recommender.py:183-210 alone (the block after `get_candidates`): adjacency in the
+    candidate set's iteration order, rounded cosine of each set against its neighbours,
+    top-k by `argsort()[::-1]`.  `cosine_row0(vectors)` = row 0 of the cosine matrix."""
     sim = {}
     for i, j in cand:
         for a in (i, j):
@@ -99,11 +106,11 @@ def query_similarities(signatures, b, k):
         sim[i]["signatures"].append(signatures[j])
         sim[j]["signatures"].append(signatures[i])
     for i in sim:
-        vals = np.around(_cosine_row0(sim[i].pop("signatures"))[1:], 3)
+        vals = np.around(cosine_row0(sim[i].pop("signatures"))[1:], 3)
         keep = np.argsort(vals)[::-1][:k]
         sim[i]["indexes"] = np.array(sim[i]["indexes"])[keep]
         sim[i]["values"] = vals[keep]
-    return sim, cand
+    return sim
 
 
 def weighted_average(ratings_vec, indexes, sims):

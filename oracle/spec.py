@@ -154,6 +154,44 @@ def candidates_packed(sig: np.ndarray, b: int) -> np.ndarray:
     return np.unique(np.concatenate(chunks))
 
 
+def candidates_packed_fast(sig: np.ndarray, b: int) -> np.ndarray:
+    """Same result as `candidates_packed` (lsh.py:40-54) without a Python loop per bucket, for the
+    full-size parity check of bench.py: band lanes packed into one integer key, one stable sort per
+    band, and every member of a bucket paired with the earlier members of its run by index
+    arithmetic.  Exact for r <= 4 (the r 16-bit lanes fit one u64); other r fall back."""
+    n, K = sig.shape
+    r = K // b
+    if K % b != 0:
+        raise AssertionError("signature length %d is not a multiple of b=%d" % (K, b))
+    if r > 4:
+        return candidates_packed(sig, b)
+    lanes = (sig.astype(np.int64) & 0xFFFF).astype(np.uint64).reshape(n, b, r)
+    chunks = []
+    for band in range(b):
+        key = np.zeros(n, dtype=np.uint64)
+        for c in range(r):
+            key = (key << np.uint64(16)) | lanes[:, band, c]
+        keep = np.flatnonzero(~(lanes[:, band, :] == 0xFFFF).all(axis=1))      # all lanes == -1: skipped (lsh.py:47)
+        if keep.size < 2:
+            continue
+        order = np.argsort(key[keep], kind="stable")
+        ids = keep[order]                                  # ascending ids inside a run (stable sort of ascending ids)
+        ks = key[keep][order]
+        start = np.flatnonzero(np.r_[True, ks[1:] != ks[:-1]])
+        run_of = np.cumsum(np.r_[True, ks[1:] != ks[:-1]]) - 1
+        off = np.arange(ids.size) - start[run_of]          # earlier members of the same bucket
+        tot = int(off.sum())
+        if tot == 0:
+            continue
+        second = np.repeat(np.arange(ids.size), off)       # position of the later member, `off` times
+        first_rel = np.arange(tot) - np.repeat(np.cumsum(off) - off, off)
+        first = start[run_of[second]] + first_rel
+        chunks.append((ids[first].astype(np.uint64) << np.uint64(32)) | ids[second].astype(np.uint64))
+    if not chunks:
+        return np.zeros(0, dtype=np.uint64)
+    return np.unique(np.concatenate(chunks))
+
+
 def candidates(sig: np.ndarray, b: int) -> set:
     """`set[(i, j)]`, i < j — the return value of `LSH.get_candidates` (lsh.py:40-54)."""
     p = candidates_packed(sig, b)
