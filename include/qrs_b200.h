@@ -199,10 +199,11 @@ int qrs_predict_dense(const int64_t *rowptr, const int32_t *colidx, const uint8_
 
 /* Sparse form for the scaled configurations (user branch only, query branch
  * absent ⇒ q = 0): per user the non-zero predictions over unrated queries.
- * The CSR must hold fewer than 2^31 entries (positions are 32-bit inside the kernel).
- * The query axis is cut into nt = ceil(Q / tile) tiles of `tile` columns
- * (a multiple of 32, <= qrs_predict_max_tile(): as large as fits, one CTA
- * accumulates one (user, tile) in shared memory).  For user t and tile c,
+ * The query axis is cut into nt = ceil(Q / tile) windows of `tile` columns
+ * (a multiple of 32, <= qrs_predict_max_tile()); one WARP accumulates one
+ * (user, window) in its slice of shared memory, so smaller windows put more
+ * independent warps on an SM (qrs_predict_warps_per_sm) and larger ones fill
+ * the 32-entry steps better.  For user t and window c,
  *   row_start int64[n_users*nt], row_cnt int32[n_users*nt] (index t*nt + c)
  * locate a contiguous slice of (cols int32[], preds uint8[]), ascending in
  * col.  Slices are placed by atomic cursors, so their order in the buffer is
@@ -219,26 +220,34 @@ int qrs_predict_dense(const int64_t *rowptr, const int32_t *colidx, const uint8_
  * cursors[n_regions] (one extra u64) receives the number of non-zero ones.  How the columns are reported:
  *   QRS_COLS_I32 / QRS_COLS_U16: cols is int32[capacity] / uint16[capacity] (Q <= 65536), aligned with preds;
  *   QRS_COLS_BITMAP: cols is uint32[n_users * nt * tile / 32], zeroed by the caller: bit c of word
- *       (t*nt + tile_index) * tile/32 + c/32 marks column tile_index*tile + c as having a byte in preds. */
+ *       (t*nt + window) * tile/32 + c/32 marks column window*tile + c as having a byte in preds. */
 #define QRS_COLS_I32 0
 #define QRS_COLS_U16 1
 #define QRS_COLS_BITMAP 2
 int32_t qrs_predict_max_tile(int32_t integer_tables /* 1 when u_milli is used */);
-/* CSR positions of one neighbour's segment (its entries inside one column tile) that a CTA takes in one pass;
- * pick `tile` so that an average segment stays below ~0.9 of it (longer segments are correct but slower). */
-int32_t qrs_predict_segment_span(void);
-size_t qrs_predict_sparse_workspace_bytes(int64_t U, int32_t Q, int32_t tile, int64_t capacity);
+/* warps (= (user, window) items in flight) per SM for a window width; 0 if the width is invalid or does not fit */
+int32_t qrs_predict_warps_per_sm(int32_t tile, int32_t integer_tables);
+size_t qrs_predict_sparse_workspace_bytes(int64_t U, int64_t nnz, int32_t Q, int32_t tile, int64_t capacity);
+/* Row preparation, once per ratings CSR and window width: cuts every row at the window bounds and writes the
+ * (row, window) sub-segments as 32-bit words (column - window start) << 8 | rating, zero-padded to whole
+ * 128-byte steps, into the workspace (at most 4 * (nnz + 32 * U * nt) bytes of it).  The predictor reads only
+ * this copy in its loop, so colidx / val need no particular alignment or padding.  qrs_predict_sparse calls it
+ * itself unless `prepared` != 0 says the workspace already holds the preparation of the same CSR, Q and tile
+ * (several user ranges predicted from one preparation). */
+int qrs_predict_prepare(const int64_t *rowptr, const int32_t *colidx, const uint8_t *val,
+                        int64_t U, int64_t nnz, int32_t Q, int32_t tile, int64_t capacity,
+                        void *ws, size_t ws_bytes, void *stream);
 /* u_milli (optional): the same similarities as integers, u_val[t] == u_milli[t] / 1000.0 exactly
  * (what np.around(., 3) produces, recommender.py:204, 270; qrs_topk_tables emits it).  When given,
  * the kernel accumulates exact integers (half the shared memory, no fp64 in the inner loop) and
  * falls back to the reference's sequential fp64 arithmetic only for cells whose value is exactly
  * half-way between two integers — the results are identical to the u_val path bit for bit. */
 int qrs_predict_sparse(const int64_t *rowptr, const int32_t *colidx, const uint8_t *val,
-                       int64_t U, int32_t Q,
+                       int64_t U, int64_t nnz, int32_t Q,
                        const int32_t *u_idx, const double *u_val, const int32_t *u_milli,
                        const int32_t *u_cnt, int32_t ku,
                        int64_t user_base, int64_t n_users, int32_t tile,
-                       void *ws, size_t ws_bytes,
+                       void *ws, size_t ws_bytes, int32_t prepared,
                        int64_t *row_start, int32_t *row_cnt,
                        void *cols, int32_t cols_mode /* QRS_COLS_* */, uint8_t *preds,
                        int64_t capacity, int32_t n_regions, unsigned long long *cursors, void *stream);

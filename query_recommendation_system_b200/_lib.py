@@ -64,9 +64,10 @@ SIGNATURES = {
     "qrs_pair_centered_cosine": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _p, _p]),
     "qrs_predict_dense": (C.c_int, [_p, _p, _p, _i64, _i32, _p, _p, _p, _i32, _p, _p, _p, _i32, _i64, _i64, _p, _p]),
     "qrs_predict_max_tile": (_i32, [_i32]),
-    "qrs_predict_segment_span": (_i32, []),
-    "qrs_predict_sparse_workspace_bytes": (_sz, [_i64, _i32, _i32, _i64]),
-    "qrs_predict_sparse": (C.c_int, [_p, _p, _p, _i64, _i32, _p, _p, _p, _p, _i32, _i64, _i64, _i32, _p, _sz,
+    "qrs_predict_warps_per_sm": (_i32, [_i32, _i32]),
+    "qrs_predict_sparse_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32, _i64]),
+    "qrs_predict_prepare": (C.c_int, [_p, _p, _p, _i64, _i64, _i32, _i32, _i64, _p, _sz, _p]),
+    "qrs_predict_sparse": (C.c_int, [_p, _p, _p, _i64, _i64, _i32, _p, _p, _p, _p, _i32, _i64, _i64, _i32, _p, _sz, _i32,
                                      _p, _p, _p, _i32, _p, _i64, _i32, _p, _p]),
 }
 

@@ -288,7 +288,9 @@ int qrs_pairs_score(const uint64_t *records, int64_t n_records, const uint64_t *
   if (K > kMaxSigWords * 32 || K / b > 32 || b > QRS_MAX_BANDS) return QRS_ERR_UNSUPPORTED;
   if (n_records == 0) return QRS_OK;
   const int grid = sm_count() * 8;
-  if (K / b == 4 && K % 128 == 0) {
+  // the r = 4 kernel reads signature rows with 16-byte loads: only for a 16-byte aligned matrix (rows are K * 4 bytes,
+  // K % 128 == 0); anything else takes the generic kernel's 4-byte loads
+  if (K / b == 4 && K % 128 == 0 && (reinterpret_cast<uintptr_t>(sig) & 15) == 0) {
     pairs_score_r4_kernel<<<grid, kPairThreads, 0, as_stream(stream)>>>(
         records, n_records, slot_off, sig, reinterpret_cast<const long long *>(norm2), sig_id_base, K, pairs, sim_milli,
         capacity, n_pairs);

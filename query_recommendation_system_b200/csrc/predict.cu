@@ -7,11 +7,12 @@
 // reproduces, per cell, exactly the reference's left-to-right fp64 sums — cells no
 // neighbour rated keep den == 0 and are "missed" (prediction 0) without being visited.
 //
-//   sparse form : one CTA per (user, column tile); accumulators for the tile live in shared
-//                 memory (exact integers when the similarities are multiples of 0.001, fp64
-//                 otherwise), neighbour row segments are located through a per-row tile index
-//                 and loaded a group of neighbours ahead of the accumulation; only the columns
-//                 a neighbour touched are swept, predicted and written.
+//   sparse form : one WARP per (user, column window); accumulators for the window live in the
+//                 warp's slice of shared memory (exact integers when the similarities are
+//                 multiples of 0.001, fp64 otherwise), neighbour rows are read from a packed,
+//                 window-major copy of the ratings built once per CSR (qrs_predict_prepare),
+//                 a few steps ahead of the accumulation; only the columns a neighbour touched
+//                 are predicted and written.  No block barrier in the loop.
 //   dense form  : one CTA per user at reference scale, adds the query branch.
 #include "common.cuh"
 
@@ -31,9 +32,17 @@ __device__ __forceinline__ int hybrid_rule(double q, double u) {
   return int(rint(x));
 }
 
-// ------------------------------------------------------------------ tile index
-// tilepos[v*(nt+1) + t] = rowptr[v] + number of entries of row v with col < t*tile (t = 0..nt):
-// the absolute CSR position where tile t of row v starts; tile t ends where tile t+1 starts.
+// ------------------------------------------------------------------ row preparation (once per ratings CSR)
+// The predictor streams, for user i and column window t, the entries of every neighbour row that fall into the
+// window.  qrs_predict_prepare lays the rows out for exactly that access: row v is cut at the window bounds
+// (binary searches, rows are ascending) and every (row, window) sub-segment is written as 32-bit words
+//   (column - t * tile) << 8 | rating
+// padded with zero words to a multiple of 32, so that one warp step is ONE aligned 128-byte line, needs no bounds
+// or alignment handling, and costs one load per entry instead of a column and a rating load.  seg_off[v * nt + t]
+// is the sub-segment's first step (units of 32 words); sub-segments are consecutive in (v, t) order, so the next
+// entry is its end.  The caller's colidx / val need no alignment or padding.
+
+// tilepos[v*(nt+1) + t] = rowptr[v] + number of entries of row v with col < t*tile (t = 0..nt)
 __global__ void __launch_bounds__(256)
 tile_index_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ colidx, int64_t U, int tile, int nt,
                   int64_t *__restrict__ tilepos) {
@@ -50,6 +59,39 @@ tile_index_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ co
       if (int64_t(__ldg(colidx + lo + mid)) < bound) a = mid + 1; else e = mid;
     }
     tilepos[x] = lo + a;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+seg_steps_kernel(const int64_t *__restrict__ tilepos, int64_t U, int nt, uint32_t *__restrict__ steps) {
+  const int64_t total = U * nt;
+  for (int64_t x = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; x < total; x += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t v = x / nt;
+    const int64_t *tp = tilepos + v * (nt + 1) + (x - v * nt);
+    steps[x] = uint32_t((tp[1] - tp[0] + 31) >> 5);
+  }
+}
+
+// one warp per (row, window) sub-segment
+__global__ void __launch_bounds__(256)
+pack_rows_kernel(const int *__restrict__ colidx, const uint8_t *__restrict__ val, const int64_t *__restrict__ tilepos,
+                 const uint64_t *__restrict__ seg_off, int64_t U, int nt, int tile, uint32_t *__restrict__ packed) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  const int64_t total = U * nt;
+  for (int64_t x = warp_global; x < total; x += nwarps) {
+    const int64_t v = x / nt;
+    const int t = int(x - v * nt);
+    const int64_t a = tilepos[v * (nt + 1) + t], e = tilepos[v * (nt + 1) + t + 1];
+    const uint64_t o = seg_off[x], n = seg_off[x + 1] - o;
+    const int q0 = t * tile;
+    for (uint64_t s = 0; s < n; ++s) {
+      const int64_t i = a + int64_t(s) * 32 + lane;
+      uint32_t w = 0;
+      if (i < e) w = (uint32_t(ld_stream_s32(colidx + i) - q0) << 8) | uint32_t(val[i]);
+      packed[((o + s) << 5) + lane] = w;
+    }
   }
 }
 
@@ -70,54 +112,54 @@ struct AccOf { using type = Acc; };
 template <>
 struct AccOf<true> { using type = unsigned long long; };
 
-// CTA shape of the sparse predictor.  Shipped: 384 threads (12 warps: two entries per thread cover a 768-entry
-// neighbour segment), two CTAs per SM.  Both are build-time parameters so that other shapes (e.g. 192 threads x 4
-// CTAs over half-width column tiles) can be measured as separate libraries (QRS_B200_LIB); the host side derives
-// its tile choice from qrs_predict_segment_span() / qrs_predict_max_tile(), never from these numbers.
-#ifndef QRS_SP_THREADS
-#define QRS_SP_THREADS 384
-#endif
-#ifndef QRS_SP_MIN_CTAS
-#define QRS_SP_MIN_CTAS 2
-#endif
-constexpr int kSpThreads = QRS_SP_THREADS;
-constexpr int kSpMinCtas = QRS_SP_MIN_CTAS;
-static_assert(kSpThreads % 32 == 0 && kSpThreads >= 64 && kSpThreads <= 512, "meta setup uses 64 threads, w_cnt holds 16 warps");
-constexpr int kSpWarpsCta = kSpThreads / 32;
-constexpr int kSpAhead = 4;    // neighbours whose segment loads are in flight together (x2: double-buffered)
-constexpr int kSpSpan = 2 * kSpThreads;   // CSR positions one CTA pass covers: two consecutive entries per thread
+// A WARP owns one (user, column window) at a time: accumulators for the window's `tile` columns in its own slice
+// of shared memory, the neighbours' sub-segments streamed in table order (entries of one neighbour hit distinct
+// columns, so the read-modify-writes need no atomics; neighbours are serialised by the warp's own program order
+// — no block barrier anywhere in the loop), then the window is swept by the same warp.  Warps never talk to each
+// other; a CTA is just as many warps as fit one SM's shared memory.
+constexpr int kPwListCap = 128;             // step-list entries built per round
+constexpr unsigned kPwSingle = 1u << 30;    // entry covers ONE 32-word step (else two consecutive steps of one neighbour)
+constexpr int kPwBatch = 4;                 // list entries whose loads are in flight together (x2: double-buffered)
+constexpr int kPwMaxWarps = 20;             // 640 threads: up to 96 registers per thread, no spills
+constexpr int kTieBitWords = 26 * 32;       // single-rater half-way bits: 26 ratings (5, 15, .., 255) x 1024 milli
+constexpr size_t kPwCtaBytes = round_up<size_t>(kTieBitWords * 4, 16);
 
-// columns each warp sweeps in the output passes; the per-warp lists live at [w * range, (w + 1) * range)
-__host__ __device__ constexpr int sparse_warp_range(int tile) { return round_up(ceil_div(tile, kSpWarpsCta), 32); }
-
-// shared memory of one CTA: acc[tile] | u16 jlist[warps*range] | metadata
-__host__ __device__ constexpr size_t sparse_cta_bytes(int tile, bool milli) {
-  return round_up<size_t>(size_t(tile) * (milli ? 8 : 16), 16) +
-         round_up<size_t>(size_t(sparse_warp_range(tile)) * kSpWarpsCta * 2, 16) + 64 * 8 + 256 + 26 * 32 * 4 + 64 * 16;
+// shared memory of one warp: acc[tile] | u16 jlist[tile] | step list | (F64) similarity of each neighbour
+__host__ __device__ constexpr size_t pw_warp_bytes(int tile, bool milli) {
+  return round_up<size_t>(size_t(tile) * (milli ? 8 : 16), 16) + round_up<size_t>(size_t(tile) * 2, 16) +
+         size_t(kPwListCap) * 8 + (milli ? 0 : 64 * 8);
 }
 
 // predicated 8-byte shared-memory load / store (cond != 0), by shared-window byte address
 __device__ __forceinline__ void lds_u64_if(unsigned long long &x, unsigned addr, unsigned cond) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.shared.u64 %0, [%1];\n\t}"
-               : "=l"(x) : "r"(addr), "r"(cond) : "memory");
+               : "+l"(x) : "r"(addr), "r"(cond) : "memory");
 }
 __device__ __forceinline__ void sts_u64_if(unsigned addr, unsigned long long x, unsigned cond) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.u64 [%0], %1;\n\t}"
                :: "r"(addr), "l"(x), "r"(cond) : "memory");
 }
-
-constexpr int kTieBitWords = 26 * 32;   // single-rater half-way bits: 26 ratings (5, 15, .., 255) x 1024 milli
+__device__ __forceinline__ unsigned ld_stream_u32(const uint32_t *p) {
+  unsigned v;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
 
 __device__ __forceinline__ int predict_from(double num, double den) {
   return den != 0.0 ? hybrid_rule(0.0, num / den) : 0;
 }
 
-// the reference's sequential fp64 evaluation of one cell, re-gathered from the neighbour segments
-__device__ __noinline__ int resolve_tie(const int *__restrict__ colidx, const uint8_t *__restrict__ val,
-                                        const int4 *meta4, const double *m_s, int c, int col) {
+// the reference's sequential fp64 evaluation of one cell, re-gathered from the neighbours' CSR rows (rare path:
+// only when the list of half-way cells is full)
+__device__ __noinline__ int resolve_tie(const int64_t *__restrict__ rowptr, const int *__restrict__ colidx,
+                                        const uint8_t *__restrict__ val, const int *__restrict__ u_idx,
+                                        const int *__restrict__ u_milli, int64_t ul, int ku, int c, int col) {
   double num = 0.0, den = 0.0;
   for (int t = 0; t < c; ++t) {
-    const int a = meta4[t].y, n = meta4[t].z - a;
+    const int v = u_idx[ul * ku + t];
+    const double s = double(u_milli[ul * ku + t]) / 1000.0;
+    const int64_t a = rowptr[v];
+    const int n = int(rowptr[v + 1] - a);
     int lo = 0, hi = n;
     while (lo < hi) {
       const int mid = (lo + hi) >> 1;
@@ -126,26 +168,22 @@ __device__ __noinline__ int resolve_tie(const int *__restrict__ colidx, const ui
     if (lo < n && __ldg(colidx + a + lo) == col) {
       const int r = val[a + lo];
       if (r != 0) {
-        num = __dadd_rn(num, __dmul_rn(double(r), m_s[t]));
-        den = __dadd_rn(den, m_s[t]);
+        num = __dadd_rn(num, __dmul_rn(double(r), s));
+        den = __dadd_rn(den, s);
       }
     }
   }
   return predict_from(num, den);
 }
 
-// One CTA per (user, column tile).  The neighbours' segments are streamed one after the other (table
-// order) by all threads — entries of one neighbour hit distinct columns, so the shared-memory
-// read-modify-writes need no atomics, and a block barrier between neighbours keeps the reference's
-// left-to-right order per column.  The next group of neighbours is being loaded into a second
-// register set while the current group is accumulated.  The output sweep is per warp over its own
-// column range: list the touched columns, reserve one slice for the CTA, predict into the slice.
 template <bool MILLI>
-__global__ void __launch_bounds__(kSpThreads, kSpMinCtas)
-predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict__ val, int Q,
+__global__ void __launch_bounds__(kPwMaxWarps * 32, 1)
+predict_sparse_kernel(const uint32_t *__restrict__ packed, const uint64_t *__restrict__ seg_off,
+                      const int64_t *__restrict__ rowptr, const int *__restrict__ colidx,
+                      const uint8_t *__restrict__ val, int Q,
                       const int *__restrict__ u_idx, const double *__restrict__ u_val,
                       const int *__restrict__ u_milli, const int *__restrict__ u_cnt, int ku, int64_t user_base,
-                      int64_t n_users, int tile, int nt, const int64_t *__restrict__ tilepos,
+                      int64_t n_users, int tile, int nt,
                       int64_t *__restrict__ row_start, int *__restrict__ row_cnt, int *__restrict__ cols,
                       uint8_t *__restrict__ preds, int64_t region_cap, int n_regions,
                       unsigned long long *__restrict__ cursors, unsigned long long *__restrict__ tie_count,
@@ -154,42 +192,32 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
   using acc_t = typename AccOf<MILLI>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int range = sparse_warp_range(tile);
-  acc_t *acc = reinterpret_cast<acc_t *>(smem_raw);
-  unsigned char *ptr = smem_raw + round_up<size_t>(size_t(tile) * (MILLI ? 8 : 16), 16);
-  uint16_t *jlist = reinterpret_cast<uint16_t *>(ptr);
-  unsigned char *meta = ptr + round_up<size_t>(size_t(range) * kSpWarpsCta * 2, 16);
-  double *m_s = reinterpret_cast<double *>(meta);                    // [64] similarity of each neighbour
-  int *w_cnt = reinterpret_cast<int *>(meta + 64 * 8);              // [16] prediction bytes per warp
-  int *w_off = w_cnt + 16;                                          // [16] exclusive prefix of w_cnt
-  unsigned long long *s_base = reinterpret_cast<unsigned long long *>(w_cnt + 48);
-  unsigned *tie_bits = reinterpret_cast<unsigned *>(w_cnt + 64);    // [26 * 32] MILLI: single-rater half-way bits
-  // [64] per neighbour, one 16-byte broadcast load: {even-aligned first position, first position, end position,
-  // MILLI increment}; positions are 32-bit (nnz < 2^31, checked by the host side)
-  int4 *meta4 = reinterpret_cast<int4 *>(w_cnt + 64 + kTieBitWords);
+  const int warps_cta = blockDim.x >> 5;
+  unsigned *tie_bits = reinterpret_cast<unsigned *>(smem_raw);           // [26 * 32] MILLI: single-rater half-way bits
+  unsigned char *mine = smem_raw + kPwCtaBytes + size_t(warp) * pw_warp_bytes(tile, MILLI);
+  acc_t *acc = reinterpret_cast<acc_t *>(mine);
+  uint16_t *jlist = reinterpret_cast<uint16_t *>(mine + round_up<size_t>(size_t(tile) * (MILLI ? 8 : 16), 16));
+  uint2 *steps = reinterpret_cast<uint2 *>(reinterpret_cast<unsigned char *>(jlist) + round_up<size_t>(size_t(tile) * 2, 16));
+  double *m_s = reinterpret_cast<double *>(steps + kPwListCap);          // [64] F64 only: similarity of each neighbour
+
   acc_t zero;
   if constexpr (MILLI) zero = 0ull; else zero = Acc{0.0, 0.0};
-  for (int j = tid; j < tile; j += kSpThreads) acc[j] = zero;
+  for (int j = lane; j < tile; j += 32) acc[j] = zero;
   if constexpr (MILLI)
-    for (int w = tid; w < kTieBitWords; w += kSpThreads) tie_bits[w] = tie_bits_g[w];
-  if (tid < 64) meta4[tid] = make_int4(0, 0, 0, 0);
-  __syncthreads();
+    for (int w = tid; w < kTieBitWords; w += blockDim.x) tie_bits[w] = tie_bits_g[w];
+  __syncthreads();          // the only block barrier: the table every warp reads
 
   const unsigned lt = lanemask_lt();
   const unsigned acc_s = unsigned(__cvta_generic_to_shared(acc));   // shared-window byte address of acc[0]
-  const int stride = nt + 1;
   // output slices are reserved from one of n_regions cursors (a single cursor would serialise
   // millions of same-address atomics in L2); region r owns [r * region_cap, (r + 1) * region_cap)
   const int region = int(blockIdx.x % n_regions);
   unsigned long long *cursor = cursors + region;
   const int64_t region_base = int64_t(region) * region_cap;
 
-  // one rating r of a neighbour into column slot j (inc: MILLI increment milli | 1 << 24; g: neighbour slot)
-  auto add = [&](int j, int r, unsigned inc, int g) {
-    if constexpr (MILLI) {
-      // u64 = r (8 bits, meaningful for a single rater) | N = sum r*milli (24) | raters (12) | D = sum milli (20)
-      acc[j] += (static_cast<unsigned long long>(unsigned(r) * inc) << 32) | inc;
-    } else {
+  // one rating r of a neighbour into column slot j (F64 flavour; g: neighbour slot)
+  auto add_f64 = [&](int j, int r, int g) {
+    if constexpr (!MILLI) {
       const double s = m_s[g];
       Acc x = acc[j];
       x.num = __dadd_rn(x.num, __dmul_rn(double(r), s));
@@ -198,178 +226,187 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
     }
   };
 
+  struct Batch { unsigned p0[kPwBatch], p1[kPwBatch], tag[kPwBatch]; };
+
   const int64_t items = n_users * nt;
+  const int64_t warp_global = int64_t(blockIdx.x) * warps_cta + warp;
+  const int64_t nwarps = int64_t(gridDim.x) * warps_cta;
   long long nz_total = 0;
-  for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+  for (int64_t item = warp_global; item < items; item += nwarps) {
     const int64_t ul = item / nt;                 // local user
     const int t = int(item - ul * nt);
     const int64_t ug = user_base + ul;            // global user = CSR row
     const int q0 = t * tile;
     const int width = min(tile, Q - q0);
     const int c = min(u_cnt[ul], ku);
-    const int c4 = round_up(c, kSpAhead);         // padded with empty neighbours: no bounds checks in the loop
-    bool is_long = false;
-    if (tid < c4) {
-      int4 mt = make_int4(0, 0, 0, 0);
-      if (tid < c) {
-        const int v = u_idx[ul * ku + tid];
-        const int64_t *tp = tilepos + int64_t(v) * stride + t;
-        const int64_t a = __ldg(tp), e = __ldg(tp + 1);
-        unsigned inc = 0;
-        if constexpr (MILLI) {
-          const int milli = u_milli[ul * ku + tid];
-          m_s[tid] = double(milli) / 1000.0;        // == the table's double (u_val == u_milli / 1000.0)
-          inc = unsigned(milli) | (1u << 24);
-        } else {
-          m_s[tid] = u_val[ul * ku + tid];
-        }
-        mt = make_int4(int(a) & ~1, int(a), int(e), int(inc));
-        is_long = (int(a) & ~1) + kSpSpan < int(e);
-      }
-      meta4[tid] = mt;
-    }
-    const int64_t own_a = __ldg(tilepos + ug * stride + t), own_e = __ldg(tilepos + ug * stride + t + 1);
-    const bool any_long = __syncthreads_or(is_long);
 
-    // ---- neighbours in table order, kSpAhead at a time, two register sets in ping-pong: the NEXT group's
-    //      entries are being loaded while the current group is accumulated.  A thread takes two consecutive
-    //      CSR positions of a segment (one 8-byte column load + one 2-byte rating load from an even position).
-    struct Group { int2 col[kSpAhead]; unsigned rat[kSpAhead]; unsigned inc[kSpAhead]; };
-    auto load_group = [&](Group &G, int g0) {
+    // ---- the neighbours' sub-segments of this window: lane <-> table slots lane and lane + 32
+    unsigned o0 = 0, n0 = 0, tag0 = 0, o1 = 0, n1 = 0, tag1 = 0;
+    if (lane < c) {
+      const int v = u_idx[ul * ku + lane];
+      const uint64_t *so = seg_off + int64_t(v) * nt + t;
+      const uint64_t a = __ldg(so);
+      o0 = unsigned(a);
+      n0 = unsigned(__ldg(so + 1) - a);
+      if constexpr (MILLI) tag0 = unsigned(u_milli[ul * ku + lane]) | (1u << 24);
+      else { tag0 = unsigned(lane); m_s[lane] = u_val[ul * ku + lane]; }
+    }
+    if (lane + 32 < c) {
+      const int v = u_idx[ul * ku + lane + 32];
+      const uint64_t *so = seg_off + int64_t(v) * nt + t;
+      const uint64_t a = __ldg(so);
+      o1 = unsigned(a);
+      n1 = unsigned(__ldg(so + 1) - a);
+      if constexpr (MILLI) tag1 = unsigned(u_milli[ul * ku + lane + 32]) | (1u << 24);
+      else { tag1 = unsigned(lane + 32); m_s[lane + 32] = u_val[ul * ku + lane + 32]; }
+    }
+    // list entries (one or two steps each) in table order: slots 0..31, then 32..63
+    const unsigned d0 = (n0 + 1) >> 1, d1 = (n1 + 1) >> 1;
+    unsigned ex0 = d0, ex1 = d1;
 #pragma unroll
-      for (int g = 0; g < kSpAhead; ++g) {
-        const int4 mt = meta4[g0 + g];
-        const int p0 = mt.x + 2 * tid;
-        G.inc[g] = unsigned(mt.w);
-        G.rat[g] = 0u;
-        G.col[g] = make_int2(0, 0);
-        if (p0 < mt.z) {
-          G.col[g] = *reinterpret_cast<const int2 *>(colidx + p0);
-          unsigned rr = *reinterpret_cast<const unsigned short *>(val + p0);
-          if (p0 < mt.y) rr &= 0xFF00u;                           // position before the segment
-          if (p0 + 1 >= mt.z) rr &= 0x00FFu;                      // position after the segment
-          G.rat[g] = rr;
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned y0 = __shfl_up_sync(kFull, ex0, o), y1 = __shfl_up_sync(kFull, ex1, o);
+      if (lane >= o) { ex0 += y0; ex1 += y1; }
+    }
+    const unsigned tot0 = __shfl_sync(kFull, ex0, 31);
+    const unsigned total = tot0 + __shfl_sync(kFull, ex1, 31);
+    ex0 -= d0;
+    ex1 = ex1 - d1 + tot0;
+
+    if (total == 0) {       // nothing gathered: no prediction in this window (the bitmap rows are zeroed by the caller)
+      if (lane == 0) { row_start[item] = region_base; row_cnt[item] = 0; }
+      continue;
+    }
+
+    for (unsigned R0 = 0; R0 < total; R0 += kPwListCap) {
+      __syncwarp();          // the previous round's list has been consumed (and m_s is written)
+      {
+        const unsigned hi = R0 + kPwListCap;
+        for (unsigned k = max(ex0, R0); k < min(ex0 + d0, hi); ++k) {
+          const unsigned j = k - ex0;
+          steps[k - R0] = make_uint2(o0 + 2 * j, tag0 | ((2 * j + 1 >= n0) ? kPwSingle : 0u));
+        }
+        for (unsigned k = max(ex1, R0); k < min(ex1 + d1, hi); ++k) {
+          const unsigned j = k - ex1;
+          steps[k - R0] = make_uint2(o1 + 2 * j, tag1 | ((2 * j + 1 >= n1) ? kPwSingle : 0u));
         }
       }
-    };
-    auto process_group = [&](const Group &G, int g0) {
+      __syncwarp();
+      const int cnt = int(min(unsigned(kPwListCap), total - R0));
+
+      // ---- list entries in order, kPwBatch at a time, two register sets in ping-pong: the NEXT batch's words are
+      //      being loaded while the current batch is accumulated.  A lane takes word `lane` of each step.
+      auto load_batch = [&](Batch &B, int f0) {
 #pragma unroll
-      for (int g = 0; g < kSpAhead; ++g) {
-        if constexpr (MILLI) {
-          // both read-modify-writes of the thread at once, predicated instead of branched (the two entries
-          // of one neighbour are different columns).  inc = milli | 1 << 24 is the low word's increment (D and
-          // the rater count) AND the high word's multiplier: r * inc = r << 24 | r * milli, as r * milli < 2^24
-          const unsigned r0 = G.rat[g] & 0xFFu, r1 = G.rat[g] >> 8;
-          const unsigned a0 = acc_s + unsigned(G.col[g].x - q0) * 8u, a1 = acc_s + unsigned(G.col[g].y - q0) * 8u;
-          unsigned long long x0, x1;
-          lds_u64_if(x0, a0, r0);
-          lds_u64_if(x1, a1, r1);
-          x0 += (static_cast<unsigned long long>(r0 * G.inc[g]) << 32) | G.inc[g];
-          x1 += (static_cast<unsigned long long>(r1 * G.inc[g]) << 32) | G.inc[g];
-          sts_u64_if(a0, x0, r0);
-          sts_u64_if(a1, x1, r1);
-        } else {
-          if (G.rat[g] & 0xFFu) add(G.col[g].x - q0, int(G.rat[g] & 0xFFu), G.inc[g], g0 + g);
-          if (G.rat[g] >> 8) add(G.col[g].y - q0, int(G.rat[g] >> 8), G.inc[g], g0 + g);
+        for (int i = 0; i < kPwBatch; ++i) {
+          unsigned a = 0, b2 = 0, tg = 0;
+          if (f0 + i < cnt) {                       // warp-uniform
+            const uint2 e = steps[f0 + i];
+            tg = e.y;
+            const uint32_t *src = packed + (size_t(e.x) << 5) + lane;
+            a = ld_stream_u32(src);
+            if (!(tg & kPwSingle)) b2 = ld_stream_u32(src + 32);
+          }
+          B.p0[i] = a; B.p1[i] = b2; B.tag[i] = tg;
         }
-        if (!MILLI && any_long) {                   // block-uniform; the rest of a long segment straight from memory
-          const int4 mt = meta4[g0 + g];
-#pragma unroll 1
-          for (int x = mt.x + kSpSpan + tid; x < mt.z; x += kSpThreads) {
-            const int r = val[x];
-            if (r != 0) add(__ldg(colidx + x) - q0, r, unsigned(mt.w), g0 + g);
+      };
+      auto process_batch = [&](const Batch &B) {
+#pragma unroll
+        for (int i = 0; i < kPwBatch; ++i) {
+          const unsigned r0 = B.p0[i] & 0xFFu, r1 = B.p1[i] & 0xFFu;
+          if constexpr (MILLI) {
+            // both read-modify-writes of the lane at once, predicated instead of branched (the two entries belong
+            // to one neighbour: different columns).  inc = milli | 1 << 24 is the low word's increment (D and the
+            // rater count) AND the high word's multiplier: r * inc = r << 24 | r * milli, as r * milli < 2^24
+            const unsigned inc = B.tag[i] & 0x1FFFFFFu;
+            const unsigned a0 = acc_s + ((B.p0[i] >> 5) & ~7u), a1 = acc_s + ((B.p1[i] >> 5) & ~7u);
+            unsigned long long x0 = 0, x1 = 0;
+            lds_u64_if(x0, a0, r0);
+            lds_u64_if(x1, a1, r1);
+            x0 += (static_cast<unsigned long long>(r0 * inc) << 32) | inc;
+            x1 += (static_cast<unsigned long long>(r1 * inc) << 32) | inc;
+            sts_u64_if(a0, x0, r0);
+            sts_u64_if(a1, x1, r1);
+          } else {
+            const int g = int(B.tag[i] & 63u);
+            if (r0) add_f64(int(B.p0[i] >> 8), int(r0), g);
+            if (r1) add_f64(int(B.p1[i] >> 8), int(r1), g);
+          }
+          __syncwarp();      // the next entry may be another neighbour: same columns from other lanes
+        }
+      };
+      {
+        Batch A, B;
+        load_batch(A, 0);
+        for (int f0 = 0; f0 < cnt; f0 += 2 * kPwBatch) {
+          const bool more = f0 + kPwBatch < cnt;
+          if (more) load_batch(B, f0 + kPwBatch);
+          process_batch(A);
+          if (more) {
+            if (f0 + 2 * kPwBatch < cnt) load_batch(A, f0 + 2 * kPwBatch);
+            process_batch(B);
           }
         }
-        __syncthreads();
-      }
-    };
-    {
-      Group A, B;
-      if (c4 > 0) load_group(A, 0);
-      for (int g0 = 0; g0 < c4; g0 += 2 * kSpAhead) {
-        const bool more = g0 + kSpAhead < c4;
-        if (more) load_group(B, g0 + kSpAhead);
-        process_group(A, g0);
-        if (more) {
-          if (g0 + 2 * kSpAhead < c4) load_group(A, g0 + 2 * kSpAhead);
-          process_group(B, g0 + kSpAhead);
-        }
-      }
-    }
-
-    // ---- MILLI: the sums are exact integers, so the order of the additions is free — the rest of the segments
-    //      longer than one CTA pass is added here, neighbour by neighbour (a barrier between two neighbours: they
-    //      may share columns), which keeps the test out of the loop above
-    if (MILLI && any_long) {
-      for (int g = 0; g < c; ++g) {
-        const int4 mt = meta4[g];
-#pragma unroll 1
-        for (int x = mt.x + kSpSpan + tid; x < mt.z; x += kSpThreads) {
-          const int r = val[x];
-          if (r != 0) add(__ldg(colidx + x) - q0, r, unsigned(mt.w), g);
-        }
-        __syncthreads();
       }
     }
 
     // ---- the user's own rated cells are not predicted (recommender.py:302): drop what landed there
-    for (int64_t x = own_a + tid; x < own_e; x += kSpThreads)
-      if (val[x] != 0) acc[__ldg(colidx + x) - q0] = zero;
-    __syncthreads();
+    {
+      const uint64_t *so = seg_off + ug * nt + t;
+      const uint64_t a = __ldg(so), e = __ldg(so + 1);
+      for (uint64_t s = a; s < e; ++s) {
+        const unsigned p = ld_stream_u32(packed + (s << 5) + lane);
+        if (p & 0xFFu) acc[p >> 8] = zero;
+      }
+    }
+    __syncwarp();
 
-    // ---- pass 1 (per warp, its own column range): ascending list of the columns that get a prediction byte.
-    //      A lane looks at columns j0 + lane and j0 + 32 + lane, so the two ballots ARE the bitmap words.
+    // ---- pass 1: ascending list of the window's columns that get a prediction byte.  A lane looks at columns
+    //      j0 + lane and j0 + 32 + lane, so the two ballots ARE the bitmap words.
     const bool bitmap = cols_mode == 2;
-    const int j_lo = warp * range, j_hi = min(width, j_lo + range);
-    uint16_t *wj = jlist + j_lo;
     unsigned *const bitmap_row = reinterpret_cast<unsigned *>(cols) + item * (tile >> 5);
     int touched = 0;
 #pragma unroll 2
-    for (int j0 = j_lo; j0 < j_hi; j0 += 64) {
+    for (int j0 = 0; j0 < width; j0 += 64) {
       const int ja = j0 + lane, jb = ja + 32;
       bool hit0 = false, hit1 = false;
       if constexpr (MILLI) {
         // listed iff D != 0 (then the prediction is >= 18); an accumulator whose similarities are all 0 is
         // cleared right here and predicts nothing (weightSum == 0, recommender.py:44)
-        if (ja < j_hi) {
+        if (ja < width) {
           const unsigned long long x = acc[ja];
           hit0 = (unsigned(x) & 0xFFFFFFu) != 0u;
           if (!hit0 && x != 0ull) acc[ja] = 0ull;
         }
-        if (jb < j_hi) {
+        if (jb < width) {
           const unsigned long long x = acc[jb];
           hit1 = (unsigned(x) & 0xFFFFFFu) != 0u;
           if (!hit1 && x != 0ull) acc[jb] = 0ull;
         }
       } else {
-        if (ja < j_hi) { const Acc x = acc[ja]; hit0 = x.den != 0.0 || x.num != 0.0; }
-        if (jb < j_hi) { const Acc x = acc[jb]; hit1 = x.den != 0.0 || x.num != 0.0; }
+        if (ja < width) { const Acc x = acc[ja]; hit0 = x.den != 0.0 || x.num != 0.0; }
+        if (jb < width) { const Acc x = acc[jb]; hit1 = x.den != 0.0 || x.num != 0.0; }
       }
       const unsigned m0 = __ballot_sync(kFull, hit0), m1 = __ballot_sync(kFull, hit1);
-      if (bitmap && lane < 2 && j0 + 32 * lane < j_hi) bitmap_row[(j0 >> 5) + lane] = lane == 0 ? m0 : m1;
-      const int n0 = __popc(m0);
-      if (hit0) wj[touched + __popc(m0 & lt)] = uint16_t(ja);
-      if (hit1) wj[touched + n0 + __popc(m1 & lt)] = uint16_t(jb);
-      touched += n0 + __popc(m1);
+      if (bitmap && lane < 2 && j0 + 32 * lane < width) bitmap_row[(j0 >> 5) + lane] = lane == 0 ? m0 : m1;
+      const int c0 = __popc(m0);
+      if (hit0) jlist[touched + __popc(m0 & lt)] = uint16_t(ja);
+      if (hit1) jlist[touched + c0 + __popc(m1 & lt)] = uint16_t(jb);
+      touched += c0 + __popc(m1);
     }
-    if (lane == 0) w_cnt[warp] = touched;
-    __syncthreads();
-    if (tid == 0) {
-      int sum = 0;
-#pragma unroll
-      for (int w = 0; w < kSpWarpsCta; ++w) { w_off[w] = sum; sum += w_cnt[w]; }
-      unsigned long long base = 0;
-      if (sum > 0) base = atomicAdd(cursor, (unsigned long long)sum);
+    unsigned long long base = 0;
+    if (lane == 0) {
+      if (touched > 0) base = atomicAdd(cursor, (unsigned long long)touched);
       row_start[item] = region_base + int64_t(base);
-      row_cnt[item] = sum;
-      *s_base = base;
+      row_cnt[item] = touched;
     }
-    __syncthreads();
-    // ---- pass 2: one prediction byte per listed column, written straight into the reserved slice (ascending:
-    //      warp ranges are ascending, lists are ascending); accumulators back to zero
+    base = __shfl_sync(kFull, base, 0);
+    __syncwarp();            // jlist is read by other lanes than those that wrote it
+
+    // ---- pass 2: one prediction byte per listed column, written straight into the reserved slice (ascending);
+    //      accumulators back to zero
     {
-      // this warp's part of the slice: 64-bit bases once, 32-bit offsets per prediction
-      const int64_t wbase = int64_t(*s_base) + w_off[warp];
+      const int64_t wbase = int64_t(base);
       const int fit = int(max(int64_t(0), min(int64_t(touched), region_cap - wbase)));   // region overflow: dropped
       uint8_t *const w_preds = preds + (region_base + wbase);
       char *const w_cols = reinterpret_cast<char *>(cols) + (region_base + wbase) * (cols_mode == 1 ? 2 : 4);
@@ -379,7 +416,7 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
         const int x = x0 + lane;
         int p = 0;
         if (x < touched) {
-          const int j = wj[x];
+          const int j = jlist[x];
           const acc_t a = acc[j];
           acc[j] = zero;
           bool tie = false;
@@ -414,7 +451,7 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
                 tie_list[slot] = make_ulonglong2((unsigned long long)(w_preds + x - preds),   // position in preds
                                                  ((unsigned long long)(unsigned)ul << 32) | unsigned(q0 + j));
               else
-                p = resolve_tie(colidx, val, meta4, m_s, c, q0 + j);   // list full: settle here
+                p = resolve_tie(rowptr, colidx, val, u_idx, u_milli, ul, ku, c, q0 + j);   // list full: settle here
             }
             if (cols_mode == 1) reinterpret_cast<uint16_t *>(w_cols)[x] = uint16_t(q0 + j);
             else if (cols_mode == 0) reinterpret_cast<int *>(w_cols)[x] = q0 + j;
@@ -425,7 +462,7 @@ predict_sparse_kernel(const int *__restrict__ colidx, const uint8_t *__restrict_
       }
       nz_total += nz;
     }
-    __syncthreads();
+    __syncwarp();
   }
   // non-zero predictions of this launch (statistics): one atomic per warp
   if (lane == 0 && nz_total > 0) atomicAdd(cursors + n_regions, (unsigned long long)nz_total);
@@ -566,28 +603,34 @@ predict_tie_fixup_kernel(const int64_t *__restrict__ rowptr, const int *__restri
   }
 }
 
-static size_t sparse_smem_bytes(int tile, bool milli) { return sparse_cta_bytes(tile, milli); }
+// warps (each with its own window) that fit one CTA = one SM: 227 KB minus the CTA's table and 1 KB the system keeps
+static int predict_warps_per_cta(int tile, bool milli) {
+  const size_t budget = size_t(227) * 1024 - 1024 - kPwCtaBytes;
+  const size_t per = pw_warp_bytes(tile, milli);
+  const size_t w = budget / per;
+  return int(w > size_t(kPwMaxWarps) ? size_t(kPwMaxWarps) : w);
+}
 
 template <bool MILLI>
-static int launch_predict_sparse(const int *colidx, const uint8_t *val, int Q, const int *u_idx, const double *u_val,
+static int launch_predict_sparse(const uint32_t *packed, const uint64_t *seg_off, const int64_t *rowptr,
+                                 const int *colidx, const uint8_t *val, int Q, const int *u_idx, const double *u_val,
                                  const int *u_milli, const int *u_cnt, int ku, int64_t user_base, int64_t n_users,
-                                 int tile, int nt, const int64_t *tilepos, int64_t *row_start, int *row_cnt, int *cols,
+                                 int tile, int nt, int64_t *row_start, int *row_cnt, int *cols,
                                  uint8_t *preds, int64_t region_cap, int n_regions, unsigned long long *cursors,
                                  unsigned long long *tie_count, ulonglong2 *tie_list, int64_t tie_capacity,
                                  int cols_mode, const unsigned *single_tab, cudaStream_t st) {
   auto kern = predict_sparse_kernel<MILLI>;
-  const size_t smem = sparse_smem_bytes(tile, MILLI);
+  const int warps = predict_warps_per_cta(tile, MILLI);
+  if (warps < 1) return QRS_ERR_UNSUPPORTED;
+  const size_t smem = kPwCtaBytes + size_t(warps) * pw_warp_bytes(tile, MILLI);
   QRS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  int per_sm = 0;
-  QRS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSpThreads, smem));
-  if (per_sm < 1) return QRS_ERR_UNSUPPORTED;
-  int64_t grid = int64_t(sm_count()) * per_sm;
-  const int64_t need = n_users * nt;
+  int64_t grid = sm_count();                     // one CTA per SM: as many independent warps as its shared memory holds
+  const int64_t need = ceil_div<int64_t>(n_users * nt, warps);
   if (grid > need) grid = need;
-  kern<<<unsigned(grid), kSpThreads, smem, st>>>(colidx, val, Q, u_idx, u_val, u_milli, u_cnt, ku, user_base,
-                                                    n_users, tile, nt, tilepos, row_start, row_cnt, cols, preds,
-                                                    region_cap, n_regions, cursors, tie_count, tie_list, tie_capacity,
-                                                    cols_mode, single_tab);
+  kern<<<unsigned(grid), warps * 32, smem, st>>>(packed, seg_off, rowptr, colidx, val, Q, u_idx, u_val, u_milli, u_cnt,
+                                                  ku, user_base, n_users, tile, nt, row_start, row_cnt, cols, preds,
+                                                  region_cap, n_regions, cursors, tie_count, tie_list, tie_capacity,
+                                                  cols_mode, single_tab);
   QRS_LAUNCH_CHECK();
   return QRS_OK;
 }
@@ -596,85 +639,157 @@ static int launch_predict_sparse(const int *colidx, const uint8_t *val, int Q, c
 
 using namespace qrs;
 
+namespace {
+
+int64_t tie_list_capacity(int64_t capacity) { return capacity / 32 + 65536; }
+constexpr size_t kSingleTabBytes = round_up<size_t>(26 * 32 * 4, 256);
+
+// workspace: tile index | steps per sub-segment | seg_off | scan scratch | tie counter | single-rater table |
+// packed rows | tie list
+struct PredictWs {
+  int64_t *tilepos;
+  uint32_t *steps;
+  uint64_t *seg_off;
+  void *scan_ws;
+  size_t scan_bytes;
+  unsigned long long *tie_count;
+  unsigned *single_tab;
+  ulonglong2 *tie_list;
+  int64_t tie_cap;
+  uint32_t *packed;
+  size_t total;
+};
+
+PredictWs carve_predict_ws(void *ws, int64_t U, int64_t nt, int64_t nnz, int64_t capacity) {
+  PredictWs w;
+  char *p = static_cast<char *>(ws);
+  const size_t segs = size_t(U > 0 ? U : 1) * size_t(nt);
+  w.tilepos = reinterpret_cast<int64_t *>(p);
+  p += round_up<size_t>(size_t(U > 0 ? U : 1) * size_t(nt + 1) * 8, 256);
+  w.steps = reinterpret_cast<uint32_t *>(p);
+  p += round_up<size_t>(segs * 4, 256);
+  w.seg_off = reinterpret_cast<uint64_t *>(p);
+  p += round_up<size_t>((segs + 1) * 8, 256);
+  w.scan_ws = p;
+  w.scan_bytes = scan_workspace_bytes(int64_t(segs));
+  p += round_up<size_t>(w.scan_bytes, 256);
+  w.tie_count = reinterpret_cast<unsigned long long *>(p);
+  p += 256;
+  w.single_tab = reinterpret_cast<unsigned *>(p);
+  p += kSingleTabBytes;
+  w.packed = reinterpret_cast<uint32_t *>(p);
+  // every sub-segment is padded to whole 32-word steps: at most nnz + 31 words per sub-segment
+  p += round_up<size_t>((size_t(nnz > 0 ? nnz : 0) + 32 * segs) * 4, 256);
+  // last, so that everything the preparation wrote sits at offsets that do not depend on `capacity`
+  w.tie_cap = tie_list_capacity(capacity);
+  w.tie_list = reinterpret_cast<ulonglong2 *>(p);
+  p += round_up<size_t>(size_t(w.tie_cap) * 16, 256);
+  w.total = size_t(p - static_cast<char *>(ws));
+  return w;
+}
+
+}  // namespace
+
 extern "C" {
 
-/* largest column tile that still lets kSpMinCtas CTAs share an SM (two CTAs of <= ~112 KB of shared memory each as
- * shipped) */
+/* widest column window one warp can own (its accumulators + column list must fit one SM's shared memory) */
 int32_t qrs_predict_max_tile(int32_t integer_tables) {
-  if (kSpThreads == 384 && kSpMinCtas == 2) return integer_tables ? 10016 : 5824;
-  const size_t budget = size_t(228) * 1024 / kSpMinCtas - 1024;   // 1 KB per CTA is reserved by the system
   int tile = 32;
-  while (sparse_cta_bytes(tile + 32, integer_tables != 0) <= budget) tile += 32;
+  while (tile + 32 <= 65536 && predict_warps_per_cta(tile + 32, integer_tables != 0) >= 1) tile += 32;
   return tile;
 }
 
-/* CSR positions of one neighbour segment that one CTA pass covers (two per thread); longer segments take a slower
- * tail loop, so the host picks the column tile that keeps an average segment below ~0.9 of this */
-int32_t qrs_predict_segment_span(void) { return kSpSpan; }
-
-static int64_t tie_list_capacity(int64_t capacity) { return capacity / 32 + 65536; }
-constexpr size_t kSingleTabBytes = round_up<size_t>(26 * 32 * 4, 256);
-
-size_t qrs_predict_sparse_workspace_bytes(int64_t U, int32_t Q, int32_t tile, int64_t capacity) {
-  if (U < 0 || Q <= 0 || tile <= 0 || capacity < 0) return 0;
-  const int64_t nt = ceil_div<int64_t>(Q, tile);
-  // tile index | tie counter | single-rater table | list of exact half-way cells awaiting their fp64 replay
-  return round_up<size_t>(size_t(U > 0 ? U : 1) * size_t(nt + 1) * 8, 256) + 256 + kSingleTabBytes +
-         round_up<size_t>(size_t(tie_list_capacity(capacity)) * 16, 256);
+/* independent warps (each owning one (user, window) at a time) that share an SM for this window width */
+int32_t qrs_predict_warps_per_sm(int32_t tile, int32_t integer_tables) {
+  if (tile <= 0 || tile % 32 != 0) return 0;
+  return predict_warps_per_cta(tile, integer_tables != 0);
 }
 
-int qrs_predict_sparse(const int64_t *rowptr, const int32_t *colidx, const uint8_t *val, int64_t U, int32_t Q,
-                       const int32_t *u_idx, const double *u_val, const int32_t *u_milli, const int32_t *u_cnt,
-                       int32_t ku, int64_t user_base, int64_t n_users, int32_t tile, void *ws, size_t ws_bytes,
-                       int64_t *row_start, int32_t *row_cnt, void *cols_any, int32_t cols_mode, uint8_t *preds,
-                       int64_t capacity, int32_t n_regions, unsigned long long *cursors, void *stream) {
+size_t qrs_predict_sparse_workspace_bytes(int64_t U, int64_t nnz, int32_t Q, int32_t tile, int64_t capacity) {
+  if (U < 0 || nnz < 0 || Q <= 0 || tile <= 0 || capacity < 0) return 0;
+  return carve_predict_ws(nullptr, U, ceil_div<int64_t>(Q, tile), nnz, capacity).total;
+}
+
+int qrs_predict_prepare(const int64_t *rowptr, const int32_t *colidx, const uint8_t *val, int64_t U, int64_t nnz,
+                        int32_t Q, int32_t tile, int64_t capacity, void *ws, size_t ws_bytes, void *stream) {
+  if (!rowptr || U < 0 || nnz < 0 || Q <= 0 || capacity < 0) return QRS_ERR_INVALID_ARG;
+  if (tile <= 0 || tile % 32 != 0) return QRS_ERR_INVALID_ARG;
+  if (nnz >= (int64_t(1) << 36)) return QRS_ERR_UNSUPPORTED;
+  const int64_t nt64 = ceil_div<int64_t>(Q, tile);
+  if (nt64 > (1 << 20)) return QRS_ERR_UNSUPPORTED;
+  const int nt = int(nt64);
+  if (!ws || ws_bytes < qrs_predict_sparse_workspace_bytes(U, nnz, Q, tile, capacity)) return QRS_ERR_WORKSPACE;
+  if (U == 0) return QRS_OK;
+  if (nnz > 0 && (!colidx || !val)) return QRS_ERR_INVALID_ARG;
+  cudaStream_t st = as_stream(stream);
+  const PredictWs w = carve_predict_ws(ws, U, nt, nnz, capacity);
+  const int64_t cap = int64_t(sm_count()) * 8;
+  {
+    int64_t blocks = ceil_div<int64_t>(U * (nt + 1), 256);
+    if (blocks > cap) blocks = cap;
+    tile_index_kernel<<<unsigned(blocks), 256, 0, st>>>(rowptr, colidx, U, tile, nt, w.tilepos);
+    QRS_LAUNCH_CHECK();
+  }
+  {
+    int64_t blocks = ceil_div<int64_t>(U * nt, 256);
+    if (blocks > cap) blocks = cap;
+    seg_steps_kernel<<<unsigned(blocks), 256, 0, st>>>(w.tilepos, U, nt, w.steps);
+    QRS_LAUNCH_CHECK();
+  }
+  int rc = exclusive_scan_u32_to_u64(w.steps, w.seg_off, U * nt, w.scan_ws, w.scan_bytes, st);
+  if (rc != QRS_OK) return rc;
+  {
+    int64_t blocks = ceil_div<int64_t>(U * nt, 8);
+    const int64_t cap2 = int64_t(sm_count()) * 16;
+    if (blocks > cap2) blocks = cap2;
+    pack_rows_kernel<<<unsigned(blocks), 256, 0, st>>>(colidx, val, w.tilepos, w.seg_off, U, nt, tile, w.packed);
+    QRS_LAUNCH_CHECK();
+  }
+  single_rater_tie_bits_kernel<<<ceil_div(26 * 32, 256), 256, 0, st>>>(w.single_tab);
+  QRS_LAUNCH_CHECK();
+  return QRS_OK;
+}
+
+int qrs_predict_sparse(const int64_t *rowptr, const int32_t *colidx, const uint8_t *val, int64_t U, int64_t nnz,
+                       int32_t Q, const int32_t *u_idx, const double *u_val, const int32_t *u_milli,
+                       const int32_t *u_cnt, int32_t ku, int64_t user_base, int64_t n_users, int32_t tile, void *ws,
+                       size_t ws_bytes, int32_t prepared, int64_t *row_start, int32_t *row_cnt, void *cols_any,
+                       int32_t cols_mode, uint8_t *preds, int64_t capacity, int32_t n_regions,
+                       unsigned long long *cursors, void *stream) {
   int32_t *cols = static_cast<int32_t *>(cols_any);
-  if (cols_mode < 0 || cols_mode > 2 || (cols_mode == 1 && Q > 65536) || (cols_mode == 2 && tile % 32 != 0))
-    return QRS_ERR_INVALID_ARG;
-  if (!rowptr || U < 0 || Q <= 0 || !u_idx || (!u_val && !u_milli) || !u_cnt || ku <= 0 || user_base < 0 ||
+  if (cols_mode < 0 || cols_mode > 2 || (cols_mode == 1 && Q > 65536)) return QRS_ERR_INVALID_ARG;
+  if (!rowptr || U < 0 || nnz < 0 || Q <= 0 || !u_idx || (!u_val && !u_milli) || !u_cnt || ku <= 0 || user_base < 0 ||
       n_users < 0 || user_base + n_users > U || !row_start || !row_cnt || !cursors || capacity < 0 || n_regions <= 0)
     return QRS_ERR_INVALID_ARG;
   const int64_t region_cap = capacity / n_regions;
   if (capacity > 0 && (!cols || !preds)) return QRS_ERR_INVALID_ARG;
   if (tile <= 0 || tile % 32 != 0) return QRS_ERR_INVALID_ARG;
   if (tile > qrs_predict_max_tile(u_milli != nullptr) || ku > QRS_MAX_TOPK) return QRS_ERR_UNSUPPORTED;
-  if (!ws || ws_bytes < qrs_predict_sparse_workspace_bytes(U, Q, tile, capacity)) return QRS_ERR_WORKSPACE;
+  if (!ws || ws_bytes < qrs_predict_sparse_workspace_bytes(U, nnz, Q, tile, capacity)) return QRS_ERR_WORKSPACE;
   if (n_users == 0 || U == 0) return QRS_OK;
-  if (!colidx || !val) return QRS_ERR_INVALID_ARG;
+  if (nnz > 0 && (!colidx || !val)) return QRS_ERR_INVALID_ARG;
   cudaStream_t st = as_stream(stream);
+  if (!prepared) {
+    int rc = qrs_predict_prepare(rowptr, colidx, val, U, nnz, Q, tile, capacity, ws, ws_bytes, stream);
+    if (rc != QRS_OK) return rc;
+  }
   const int nt = int(ceil_div<int64_t>(Q, tile));
-  int64_t *tilepos = static_cast<int64_t *>(ws);
-  char *wsp = static_cast<char *>(ws) + round_up<size_t>(size_t(U) * size_t(nt + 1) * 8, 256);
-  unsigned long long *tie_count = reinterpret_cast<unsigned long long *>(wsp);
-  unsigned *single_tab = reinterpret_cast<unsigned *>(wsp + 256);
-  ulonglong2 *tie_list = reinterpret_cast<ulonglong2 *>(wsp + 256 + kSingleTabBytes);
-  const int64_t tie_cap = tie_list_capacity(capacity);
-  QRS_CUDA(cudaMemsetAsync(tie_count, 0, 8, st));
+  const PredictWs w = carve_predict_ws(ws, U, nt, nnz, capacity);
+  QRS_CUDA(cudaMemsetAsync(w.tie_count, 0, 8, st));
   if (u_milli) {
-    single_rater_tie_bits_kernel<<<ceil_div(26 * 32, 256), 256, 0, st>>>(single_tab);
-    QRS_LAUNCH_CHECK();
-  }
-  {
-    const int64_t total = U * (nt + 1);
-    int64_t blocks = ceil_div<int64_t>(total, 256);
-    const int64_t cap = int64_t(sm_count()) * 8;
-    if (blocks > cap) blocks = cap;
-    tile_index_kernel<<<unsigned(blocks), 256, 0, st>>>(rowptr, colidx, U, tile, nt, tilepos);
-    QRS_LAUNCH_CHECK();
-  }
-  if (u_milli) {
-    int rc = launch_predict_sparse<true>(colidx, val, Q, u_idx, u_val, u_milli, u_cnt, ku, user_base, n_users, tile,
-                                         nt, tilepos, row_start, row_cnt, cols, preds, region_cap, n_regions, cursors,
-                                         tie_count, tie_list, tie_cap, cols_mode, single_tab, st);
+    int rc = launch_predict_sparse<true>(w.packed, w.seg_off, rowptr, colidx, val, Q, u_idx, u_val, u_milli, u_cnt, ku,
+                                         user_base, n_users, tile, nt, row_start, row_cnt, cols, preds, region_cap,
+                                         n_regions, cursors, w.tie_count, w.tie_list, w.tie_cap, cols_mode, w.single_tab,
+                                         st);
     if (rc != QRS_OK || capacity == 0) return rc;
-    predict_tie_fixup_kernel<<<sm_count() * 8, 256, 0, st>>>(rowptr, colidx, val, u_idx, u_milli, u_cnt, ku, tie_count,
-                                                             tie_list, tie_cap, preds);
+    predict_tie_fixup_kernel<<<sm_count() * 8, 256, 0, st>>>(rowptr, colidx, val, u_idx, u_milli, u_cnt, ku,
+                                                             w.tie_count, w.tie_list, w.tie_cap, preds);
     QRS_LAUNCH_CHECK();
     return QRS_OK;
   }
-  return launch_predict_sparse<false>(colidx, val, Q, u_idx, u_val, u_milli, u_cnt, ku, user_base, n_users, tile, nt,
-                                      tilepos, row_start, row_cnt, cols, preds, region_cap, n_regions, cursors,
-                                      tie_count, tie_list, tie_cap, cols_mode, single_tab, st);
+  return launch_predict_sparse<false>(w.packed, w.seg_off, rowptr, colidx, val, Q, u_idx, u_val, u_milli, u_cnt, ku,
+                                      user_base, n_users, tile, nt, row_start, row_cnt, cols, preds, region_cap,
+                                      n_regions, cursors, w.tie_count, w.tie_list, w.tie_cap, cols_mode, w.single_tab, st);
 }
 
 int qrs_predict_dense(const int64_t *rowptr, const int32_t *colidx, const uint8_t *val, int64_t U, int32_t Q,

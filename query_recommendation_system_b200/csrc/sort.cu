@@ -101,10 +101,10 @@ size_t qrs_sort_workspace_bytes(int64_t n_per_seg, int32_t segs) {
 
 int qrs_sort_u64(uint64_t *keys, uint64_t *tmp, int64_t n_per_seg, int32_t segs, int32_t bit_lo, int32_t bit_hi,
                  void *ws, size_t ws_bytes, void *stream) {
-  if (!keys || !tmp || n_per_seg < 0 || segs <= 0 || bit_lo < 0 || bit_hi > 64 || bit_lo > bit_hi)
-    return QRS_ERR_INVALID_ARG;
+  if (n_per_seg < 0 || segs <= 0 || bit_lo < 0 || bit_hi > 64 || bit_lo > bit_hi) return QRS_ERR_INVALID_ARG;
   if (segs > 65535) return QRS_ERR_UNSUPPORTED;
-  if (n_per_seg == 0 || bit_lo == bit_hi) return QRS_OK;
+  if (n_per_seg == 0 || bit_lo == bit_hi) return QRS_OK;       // nothing to sort: empty buffers may be null
+  if (!keys || !tmp) return QRS_ERR_INVALID_ARG;
   if (!ws || ws_bytes < qrs_sort_workspace_bytes(n_per_seg, segs)) return QRS_ERR_WORKSPACE;
   cudaStream_t st = as_stream(stream);
   const int64_t tiles = sort_tiles(n_per_seg);

@@ -191,7 +191,8 @@ class LshCfPipeline:
                 torch.cuda.current_stream().wait_event(val_ready)
             cval, norm2_c = st.center_rows(rowptr, val)
             # equal first ids adjacent: the scoring kernel stages row i once per run
-            st.sort_u64(pairs, n_pairs, 1, 32, 32 + max(1, (n_total - 1).bit_length()))
+            if n_pairs:
+                st.sort_u64(pairs, n_pairs, 1, 32, 32 + max(1, (n_total - 1).bit_length()))
             sims = st.pair_centered_cosine(rowptr, colidx, val, cval, norm2_c, pairs, self.m, grouped=True)
         else:
             sims = sims[:n_pairs]
@@ -232,6 +233,10 @@ class LshCfPipeline:
             bounds = [n_local * ci // chunks for ci in range(chunks + 1)]
             total = 0
             out.pred_chunks = []
+            # the rows are prepared (cut at the window bounds, packed, padded to 128-byte steps) once per step
+            known = [self._pred_capacity.get((chunks, ci, self.cols_mode), 0) * regions for ci in range(chunks)]
+            plan = st.PredictPlan(rowptr_all, colidx_all, val_all, self.m, tile, capacity_hint=max(known))
+            tm.mark("predict:prepare")
             for ci in range(chunks):
                 lo, hi = bounds[ci], bounds[ci + 1]
                 rcap = self._pred_capacity.get((chunks, ci, self.cols_mode), 0)
@@ -241,7 +246,7 @@ class LshCfPipeline:
                     rs, rc, cols, preds, cursors, nzc = st.predict_sparse(rowptr_all, colidx_all, val_all, self.m, tab,
                                                                      pred_base + lo, hi - lo, tile, rcap * regions,
                                                                      u_milli=mil, n_regions=regions,
-                                                                     cols_mode=self.cols_mode)
+                                                                     cols_mode=self.cols_mode, plan=plan)
                     demand = torch.cat([cursors, nzc]).cpu()
                     nonzero = int(demand[-1].item())
                     demand = demand[:regions]

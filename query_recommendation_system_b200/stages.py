@@ -233,44 +233,64 @@ def predict_dense(rowptr, colidx, val, Q: int, q_tab: Optional[Table], u_tab: Op
     return out
 
 
-PREDICT_SEGMENT_FILL = 690.0 / 768.0   # an average neighbour segment should fill <= ~0.9 of one CTA pass
+PREDICT_TARGET_ENTRIES = 54.0   # average entries of one (neighbour row, window) sub-segment: two 32-entry steps, mostly
+PREDICT_MIN_WARPS = 8           # windows are not widened beyond what leaves this many warps on an SM
 
 
 def choose_predict_tile(Q: int, avg_len: float = 0.0, integer_tables: bool = True) -> int:
-    """Column tile of the sparse predictor.  One CTA accumulates one (user, tile) and takes two consecutive
-    entries of a neighbour's segment per thread (qrs_predict_segment_span() per pass — 768 with the shipped
-    384-thread CTAs; longer segments take a slower tail loop): the fewest equal tiles such that a tile fits one
-    CTA's shared memory and an average row leaves <= ~0.9 of a pass (690 entries) in it."""
+    """Column window of the sparse predictor.  One WARP accumulates one (user, window) and takes 32 entries of a
+    neighbour's sub-segment per step, so the window is sized for sub-segments of about two steps (wider windows
+    fill the steps better but leave fewer independent warps per SM), rounded so the windows tile Q evenly."""
     lib = _lib.load()
-    max_tile = lib.qrs_predict_max_tile(1 if integer_tables else 0)
-    target = PREDICT_SEGMENT_FILL * lib.qrs_predict_segment_span()
-    nt = max(1, math.ceil(Q / max_tile))
-    while avg_len > 0 and avg_len / nt > target and math.ceil(Q / nt) > 256:
-        nt += 1
+    it = 1 if integer_tables else 0
+    max_tile = lib.qrs_predict_max_tile(it)
+    want = Q if avg_len <= 0 else PREDICT_TARGET_ENTRIES * Q / max(avg_len, 1e-9)
+    want = int(min(max(want, 256), max_tile, max(Q, 32)))
+    while want > 256 and lib.qrs_predict_warps_per_sm(((want + 31) // 32) * 32, it) < PREDICT_MIN_WARPS:
+        want -= 32
+    nt = max(1, math.ceil(Q / want))
     return int(min(max_tile, max(32, math.ceil(math.ceil(Q / nt) / 32.0) * 32)))
+
+
+class PredictPlan:
+    """The row preparation of one ratings CSR for one window width (qrs_predict_prepare): build once, predict any
+    number of user ranges from it."""
+
+    def __init__(self, rowptr, colidx, val, Q: int, tile: int, capacity_hint: int = 0):
+        _need_cuda(rowptr, colidx, val)
+        if colidx.numel() >= 2 ** 36:
+            raise _lib.QrsError("qrs_predict_prepare: nnz < 2^36 per GPU")
+        lib = _lib.load()
+        self.rowptr, self.colidx, self.val = rowptr, colidx, val
+        self.U, self.nnz, self.Q, self.tile = rowptr.numel() - 1, colidx.numel(), int(Q), int(tile)
+        self.capacity = int(capacity_hint)
+        self.ws = _ws(lib.qrs_predict_sparse_workspace_bytes(self.U, self.nnz, self.Q, self.tile, self.capacity), rowptr.device)
+        check(lib.qrs_predict_prepare(ptr(rowptr), ptr(colidx), ptr(val), self.U, self.nnz, self.Q, self.tile, self.capacity,
+                                      ptr(self.ws), self.ws.numel(), _stream()), "qrs_predict_prepare")
 
 
 def predict_sparse(rowptr, colidx, val, Q: int, u_tab: Table, user_base: int, n_users: int, tile: int,
                    capacity: int, out_cols: Optional[torch.Tensor] = None, out_preds: Optional[torch.Tensor] = None,
-                   u_milli: Optional[torch.Tensor] = None, n_regions: int = 1, cols_mode: int = 0):
+                   u_milli: Optional[torch.Tensor] = None, n_regions: int = 1, cols_mode: int = 0,
+                   plan: Optional[PredictPlan] = None):
     """User-branch predictions in sparse form.  Returns (row_start int64[n_users, nt],
     row_cnt int32[n_users, nt], cols, preds uint8[capacity], cursors int64[n_regions] on device = entries
     requested per region of capacity // n_regions entries, nonzero int64[1] = non-zero predictions).
     u_milli: int32 table with u_val == u_milli / 1000.0 exactly (from topk_tables(want_milli=True)) selects
-    the exact-integer accumulation kernel; results are identical."""
+    the exact-integer accumulation kernel; results are identical.  plan: a PredictPlan of the same CSR and
+    window width (prepared rows are reused; its capacity hint must cover `capacity`)."""
     _need_cuda(rowptr, colidx, val, u_milli, *u_tab)
-    if colidx.numel() >= 2 ** 31:
-        raise _lib.QrsError("qrs_predict_sparse addresses the ratings CSR with 32-bit positions (nnz < 2^31 per GPU)")
     lib = _lib.load()
     dev = rowptr.device
     U = rowptr.numel() - 1
+    nnz = colidx.numel()
     nt = (Q + tile - 1) // tile
     ui, uv, uc = u_tab
     assert u_milli is None or (u_milli.dtype == torch.int32 and u_milli.shape == ui.shape)
     assert ui.dtype == torch.int32 and uv.dtype == torch.float64 and uc.dtype == torch.int32
     row_start = torch.empty((n_users, nt), dtype=torch.int64, device=dev)
     row_cnt = torch.empty((n_users, nt), dtype=torch.int32, device=dev)
-    # cols_mode 0: int32 ids; 1: uint16 ids (int16 storage); 2: touched-column bitmap per (user, tile), zeroed here
+    # cols_mode 0: int32 ids; 1: uint16 ids (int16 storage); 2: touched-column bitmap per (user, window), zeroed here
     cols_dtype = torch.int16 if cols_mode == 1 else torch.int32
     if cols_mode == 2:
         cols = torch.zeros(n_users * nt * (tile // 32), dtype=torch.int32, device=dev)
@@ -279,12 +299,15 @@ def predict_sparse(rowptr, colidx, val, Q: int, u_tab: Table, user_base: int, n_
     assert cols.dtype == cols_dtype
     preds = out_preds if out_preds is not None else torch.empty(max(capacity, 1), dtype=torch.uint8, device=dev)
     cursor = torch.zeros(n_regions + 1, dtype=torch.int64, device=dev)   # [n_regions] = non-zero count (bitmap mode)
-    ws = _ws(lib.qrs_predict_sparse_workspace_bytes(U, Q, tile, capacity), dev)
-    check(lib.qrs_predict_sparse(ptr(rowptr), ptr(colidx), ptr(val), U, Q, ptr(ui), ptr(uv), ptr(u_milli), ptr(uc),
-                                 ui.shape[1],
-                                 user_base, n_users, tile, ptr(ws), ws.numel(), ptr(row_start), ptr(row_cnt),
-                                 ptr(cols), cols_mode, ptr(preds), capacity, n_regions, ptr(cursor),
-                                 _stream()),
+    prepared = 0
+    if plan is not None and plan.tile == tile and plan.Q == Q and plan.U == U and plan.nnz == nnz and plan.capacity >= capacity:
+        ws, prepared = plan.ws, 1      # the prepared part of the workspace does not move with the capacity
+    else:
+        ws = _ws(lib.qrs_predict_sparse_workspace_bytes(U, nnz, Q, tile, capacity), dev)
+    check(lib.qrs_predict_sparse(ptr(rowptr), ptr(colidx), ptr(val), U, nnz, Q, ptr(ui), ptr(uv), ptr(u_milli), ptr(uc),
+                                 ui.shape[1], user_base, n_users, tile, ptr(ws), ws.numel(), prepared,
+                                 ptr(row_start), ptr(row_cnt), ptr(cols), cols_mode, ptr(preds), capacity, n_regions,
+                                 ptr(cursor), _stream()),
           "qrs_predict_sparse")
     return row_start, row_cnt, cols, preds, cursor[:n_regions], cursor[n_regions:]
 

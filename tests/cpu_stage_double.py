@@ -141,6 +141,13 @@ def choose_predict_tile(Q, avg_len=0.0, integer_tables=True):
     return max(32, int(math.ceil(Q / 3 / 32.0)) * 32)
 
 
+class PredictPlan:
+    """Nothing to prepare on the CPU double."""
+
+    def __init__(self, rowptr, colidx, val, Q, tile, capacity_hint=0):
+        self.tile, self.Q, self.capacity = tile, Q, capacity_hint
+
+
 def predict_sparse(rowptr, colidx, val, Q, u_tab, user_base, n_users, tile, capacity, u_milli=None, n_regions=1, **kw):
     assert n_regions == 1
     idx, v, cnt = [x.numpy() for x in u_tab]

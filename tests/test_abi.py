@@ -47,7 +47,8 @@ def test_version_status_strings_and_workspace_queries(lib):
     assert lib.qrs_pair_slots_workspace_bytes(3_200_000) >= 4 * 3_200_000
     assert lib.qrs_topk_workspace_bytes(100_000) > 16 * 100_000
     assert lib.qrs_predict_max_tile(1) % 32 == 0 and lib.qrs_predict_max_tile(0) % 32 == 0
-    assert lib.qrs_predict_sparse_workspace_bytes(1000, 10_000, 480, 0) >= 1000 * 22 * 8
+    assert lib.qrs_predict_sparse_workspace_bytes(1000, 50_000, 10_000, 480, 0) >= 1000 * 22 * 8 + 4 * 50_000
+    assert lib.qrs_predict_warps_per_sm(1024, 1) >= 16 and lib.qrs_predict_warps_per_sm(1000, 1) == 0
     assert lib.qrs_minhash_max_elements() >= 1_000_000
 
 

@@ -26,16 +26,20 @@ def test_launch_heuristics():
     r = stages.choose_head_ranks(10_000, 500)
     assert r % 32 == 0 and 32 <= r <= 2048 and (1 - 0.05) ** r < 1e-6
     assert stages.choose_head_ranks(1_000_000, 1000) == 2048
-    for q, avg in ((10_000, 500), (100_000, 1000), (1_000, 50), (37, 3)):
-        t = stages.choose_predict_tile(q, avg)
-        assert t % 32 == 0 and t <= 10_016 and -(-q // t) * t >= q
-    # the tile choice follows the library's CTA shape (shipped: 384 threads x 2 entries, two CTAs per SM)
     from query_recommendation_system_b200 import _lib
     lib = _lib.load()
-    assert lib.qrs_predict_segment_span() == 768 and lib.qrs_predict_max_tile(1) == 10_016
-    assert stages.choose_predict_tile(10_000, 495.0) == 10_016          # C2: the whole query axis in one tile
-    assert stages.choose_predict_tile(100_000, 1000.0) == 10_016        # C3: 10 tiles of an average 100 entries
-    assert stages.choose_predict_tile(10_000, 5000.0) < 1500            # dense rows: tiles keep a segment in one pass
+    max_tile = lib.qrs_predict_max_tile(1)
+    assert max_tile % 32 == 0 and 16_000 < max_tile <= 65_536 and lib.qrs_predict_max_tile(0) < max_tile
+    for q, avg in ((10_000, 500), (100_000, 1000), (1_000, 50), (37, 3), (1_000_000, 1000)):
+        t = stages.choose_predict_tile(q, avg)
+        assert t % 32 == 0 and t <= max_tile and -(-q // t) * t >= q
+        assert lib.qrs_predict_warps_per_sm(t, 1) >= min(stages.PREDICT_MIN_WARPS, lib.qrs_predict_warps_per_sm(256, 1))
+    # one warp owns one (user, window): windows are sized for ~two 32-entry steps per neighbour sub-segment
+    t2 = stages.choose_predict_tile(10_000, 495.0)                       # C2
+    assert 45 <= 495.0 * t2 / 10_000 <= 64 and lib.qrs_predict_warps_per_sm(t2, 1) >= 16
+    t3 = stages.choose_predict_tile(100_000, 1000.0)                     # C3: capped by the warps-per-SM floor
+    assert lib.qrs_predict_warps_per_sm(t3, 1) >= stages.PREDICT_MIN_WARPS and t3 > t2
+    assert stages.choose_predict_tile(10_000, 5000.0) <= 256             # dense rows: narrow windows
 
 
 def test_synth_is_deterministic_and_shardable():
