@@ -106,6 +106,37 @@ __device__ __forceinline__ uint64_t ld_stream_u64(const uint64_t *p) {
   return v;
 }
 
+// ---------------------------------------------------------------- bulk asynchronous copies (TMA unit, 1-D form)
+// global -> shared copies issued by ONE thread and completed on an mbarrier (cp.async.bulk, SASS UBLKCP): the
+// data never passes through registers, so a warp can keep many 128-byte lines in flight without register cost.
+// Addresses are shared-window byte addresses; sizes are multiples of 16 bytes, both ends 16-byte aligned.
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned arrivals) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(arrivals) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() {      // make the initialised barriers visible to the async proxy
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {   // order generic-proxy accesses before async-proxy ones
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}"
+      ::"r"(bar), "r"(parity) : "memory");
+}
+
 // ---------------------------------------------------------------- device-wide scan
 // Exclusive prefix sum of u32 counts into u64 offsets (out[n] = total).
 // ws: scan_workspace_bytes(n).  Three launches: tile sums, one-CTA scan of the

@@ -117,16 +117,25 @@ struct AccOf<true> { using type = unsigned long long; };
 // columns, so the read-modify-writes need no atomics; neighbours are serialised by the warp's own program order
 // — no block barrier anywhere in the loop), then the window is swept by the same warp.  Warps never talk to each
 // other; a CTA is just as many warps as fit one SM's shared memory.
+//
+// Data movement: a lane takes word `lane` of every 128-byte step straight into a register (one coalesced load
+// per step), kPwBatch list entries (= up to 2 * kPwBatch steps) at a time in two ping-pong register sets.
+// Two other schemes were built and measured at C2 (profiles/r2_predict_variants.md): staging the steps through
+// a shared-memory ring filled by cp.async.bulk + mbarrier (7.3 ms against 4.6 ms: 128..256-byte copies are far
+// too small for the TMA unit — the bulk copies are used where the pieces are kilobytes, in the MinHash tile scan),
+// and reading tables / offsets / first batch of the NEXT item ahead of the sweep (no gain at equal occupancy, and
+// its 120 registers cost 4 of 20 warps).  The kernel is bound by instruction issue and shared-memory wavefronts,
+// not by global latency, so what counts is instructions per entry and warps per SM.
 constexpr int kPwListCap = 128;             // step-list entries built per round
 constexpr unsigned kPwSingle = 1u << 30;    // entry covers ONE 32-word step (else two consecutive steps of one neighbour)
 constexpr int kPwBatch = 4;                 // list entries whose loads are in flight together (x2: double-buffered)
 constexpr int kPwMaxWarps = 20;             // 640 threads: up to 96 registers per thread, no spills
 constexpr int kTieBitWords = 26 * 32;       // single-rater half-way bits: 26 ratings (5, 15, .., 255) x 1024 milli
-constexpr size_t kPwCtaBytes = round_up<size_t>(kTieBitWords * 4, 16);
+constexpr size_t kPwCtaBytes = round_up<size_t>(kTieBitWords * 4, 256);
 
 // shared memory of one warp: acc[tile] | u16 jlist[tile] | step list | (F64) similarity of each neighbour
 __host__ __device__ constexpr size_t pw_warp_bytes(int tile, bool milli) {
-  return round_up<size_t>(size_t(tile) * (milli ? 8 : 16), 16) + round_up<size_t>(size_t(tile) * 2, 16) +
+  return round_up<size_t>(size_t(tile) * (milli ? 8 : 16), 128) + round_up<size_t>(size_t(tile) * 2, 128) +
          size_t(kPwListCap) * 8 + (milli ? 0 : 64 * 8);
 }
 
@@ -190,14 +199,14 @@ predict_sparse_kernel(const uint32_t *__restrict__ packed, const uint64_t *__res
                       ulonglong2 *__restrict__ tie_list, int64_t tie_capacity, int cols_mode,
                       const unsigned *__restrict__ tie_bits_g) {
   using acc_t = typename AccOf<MILLI>::type;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int warps_cta = blockDim.x >> 5;
   unsigned *tie_bits = reinterpret_cast<unsigned *>(smem_raw);           // [26 * 32] MILLI: single-rater half-way bits
   unsigned char *mine = smem_raw + kPwCtaBytes + size_t(warp) * pw_warp_bytes(tile, MILLI);
   acc_t *acc = reinterpret_cast<acc_t *>(mine);
-  uint16_t *jlist = reinterpret_cast<uint16_t *>(mine + round_up<size_t>(size_t(tile) * (MILLI ? 8 : 16), 16));
-  uint2 *steps = reinterpret_cast<uint2 *>(reinterpret_cast<unsigned char *>(jlist) + round_up<size_t>(size_t(tile) * 2, 16));
+  uint16_t *jlist = reinterpret_cast<uint16_t *>(mine + round_up<size_t>(size_t(tile) * (MILLI ? 8 : 16), 128));
+  uint2 *steps = reinterpret_cast<uint2 *>(reinterpret_cast<unsigned char *>(jlist) + round_up<size_t>(size_t(tile) * 2, 128));
   double *m_s = reinterpret_cast<double *>(steps + kPwListCap);          // [64] F64 only: similarity of each neighbour
 
   acc_t zero;
@@ -215,50 +224,52 @@ predict_sparse_kernel(const uint32_t *__restrict__ packed, const uint64_t *__res
   unsigned long long *cursor = cursors + region;
   const int64_t region_base = int64_t(region) * region_cap;
 
-  // one rating r of a neighbour into column slot j (F64 flavour; g: neighbour slot)
-  auto add_f64 = [&](int j, int r, int g) {
-    if constexpr (!MILLI) {
-      const double s = m_s[g];
-      Acc x = acc[j];
-      x.num = __dadd_rn(x.num, __dmul_rn(double(r), s));
-      x.den = __dadd_rn(x.den, s);
-      acc[j] = x;
-    }
-  };
-
   struct Batch { unsigned p0[kPwBatch], p1[kPwBatch], tag[kPwBatch]; };
 
   const int64_t items = n_users * nt;
   const int64_t warp_global = int64_t(blockIdx.x) * warps_cta + warp;
   const int64_t nwarps = int64_t(gridDim.x) * warps_cta;
+  // (user, window) of the warp's current item, advanced without a division: item + nwarps = (ul + du, t + dt) with carry
+  const int64_t du = nwarps / nt;
+  const int dt = int(nwarps - du * nt);
+  int64_t ul = warp_global / nt;                  // local user
+  int t = int(warp_global - ul * nt);
   long long nz_total = 0;
-  for (int64_t item = warp_global; item < items; item += nwarps) {
-    const int64_t ul = item / nt;                 // local user
-    const int t = int(item - ul * nt);
-    const int64_t ug = user_base + ul;            // global user = CSR row
+  for (int64_t item = warp_global; item < items; item += nwarps, ul += du, t += dt) {
+    if (t >= nt) { t -= nt; ++ul; }
     const int q0 = t * tile;
     const int width = min(tile, Q - q0);
     const int c = min(u_cnt[ul], ku);
+    const int64_t tbase = ul * ku;
 
     // ---- the neighbours' sub-segments of this window: lane <-> table slots lane and lane + 32
     unsigned o0 = 0, n0 = 0, tag0 = 0, o1 = 0, n1 = 0, tag1 = 0;
     if (lane < c) {
-      const int v = u_idx[ul * ku + lane];
+      const int v = u_idx[tbase + lane];
       const uint64_t *so = seg_off + int64_t(v) * nt + t;
       const uint64_t a = __ldg(so);
       o0 = unsigned(a);
       n0 = unsigned(__ldg(so + 1) - a);
-      if constexpr (MILLI) tag0 = unsigned(u_milli[ul * ku + lane]) | (1u << 24);
-      else { tag0 = unsigned(lane); m_s[lane] = u_val[ul * ku + lane]; }
+      if constexpr (MILLI) tag0 = unsigned(u_milli[tbase + lane]) | (1u << 24);
+      else { tag0 = unsigned(lane); m_s[lane] = u_val[tbase + lane]; }
     }
     if (lane + 32 < c) {
-      const int v = u_idx[ul * ku + lane + 32];
+      const int v = u_idx[tbase + lane + 32];
       const uint64_t *so = seg_off + int64_t(v) * nt + t;
       const uint64_t a = __ldg(so);
       o1 = unsigned(a);
       n1 = unsigned(__ldg(so + 1) - a);
-      if constexpr (MILLI) tag1 = unsigned(u_milli[ul * ku + lane + 32]) | (1u << 24);
-      else { tag1 = unsigned(lane + 32); m_s[lane + 32] = u_val[ul * ku + lane + 32]; }
+      if constexpr (MILLI) tag1 = unsigned(u_milli[tbase + lane + 32]) | (1u << 24);
+      else { tag1 = unsigned(lane + 32); m_s[lane + 32] = u_val[tbase + lane + 32]; }
+    }
+    // the user's own row in this window (its rated cells are cleared after the accumulation): the first two steps
+    // are requested now and sit in two registers until then
+    unsigned own_o, own_n, own_p0 = 0, own_p1 = 0;
+    {
+      const uint64_t *so = seg_off + (user_base + ul) * nt + t;
+      const uint64_t a = __ldg(so);
+      own_o = unsigned(a);
+      own_n = unsigned(__ldg(so + 1) - a);
     }
     // list entries (one or two steps each) in table order: slots 0..31, then 32..63
     const unsigned d0 = (n0 + 1) >> 1, d1 = (n1 + 1) >> 1;
@@ -277,6 +288,8 @@ predict_sparse_kernel(const uint32_t *__restrict__ packed, const uint64_t *__res
       if (lane == 0) { row_start[item] = region_base; row_cnt[item] = 0; }
       continue;
     }
+    if (own_n > 0) own_p0 = ld_stream_u32(packed + (size_t(own_o) << 5) + lane);
+    if (own_n > 1) own_p1 = ld_stream_u32(packed + (size_t(own_o) << 5) + 32 + lane);
 
     for (unsigned R0 = 0; R0 < total; R0 += kPwListCap) {
       __syncwarp();          // the previous round's list has been consumed (and m_s is written)
@@ -328,9 +341,19 @@ predict_sparse_kernel(const uint32_t *__restrict__ packed, const uint64_t *__res
             sts_u64_if(a0, x0, r0);
             sts_u64_if(a1, x1, r1);
           } else {
-            const int g = int(B.tag[i] & 63u);
-            if (r0) add_f64(int(B.p0[i] >> 8), int(r0), g);
-            if (r1) add_f64(int(B.p1[i] >> 8), int(r1), g);
+            const double s = m_s[B.tag[i] & 63u];
+            if (r0) {
+              Acc x = acc[B.p0[i] >> 8];
+              x.num = __dadd_rn(x.num, __dmul_rn(double(r0), s));
+              x.den = __dadd_rn(x.den, s);
+              acc[B.p0[i] >> 8] = x;
+            }
+            if (r1) {
+              Acc x = acc[B.p1[i] >> 8];
+              x.num = __dadd_rn(x.num, __dmul_rn(double(r1), s));
+              x.den = __dadd_rn(x.den, s);
+              acc[B.p1[i] >> 8] = x;
+            }
           }
           __syncwarp();      // the next entry may be another neighbour: same columns from other lanes
         }
@@ -351,48 +374,56 @@ predict_sparse_kernel(const uint32_t *__restrict__ packed, const uint64_t *__res
     }
 
     // ---- the user's own rated cells are not predicted (recommender.py:302): drop what landed there
-    {
-      const uint64_t *so = seg_off + ug * nt + t;
-      const uint64_t a = __ldg(so), e = __ldg(so + 1);
-      for (uint64_t s = a; s < e; ++s) {
-        const unsigned p = ld_stream_u32(packed + (s << 5) + lane);
-        if (p & 0xFFu) acc[p >> 8] = zero;
-      }
+    if (own_p0 & 0xFFu) acc[own_p0 >> 8] = zero;
+    if (own_p1 & 0xFFu) acc[own_p1 >> 8] = zero;
+    for (unsigned s = 2; s < own_n; ++s) {          // rows with more than 64 entries in one window
+      const unsigned p = ld_stream_u32(packed + ((size_t(own_o) + s) << 5) + lane);
+      if (p & 0xFFu) acc[p >> 8] = zero;
     }
     __syncwarp();
 
-    // ---- pass 1: ascending list of the window's columns that get a prediction byte.  A lane looks at columns
-    //      j0 + lane and j0 + 32 + lane, so the two ballots ARE the bitmap words.
+    // ---- pass 1: ascending list of the window's columns that get a prediction byte, 64 columns per round.
     const bool bitmap = cols_mode == 2;
     unsigned *const bitmap_row = reinterpret_cast<unsigned *>(cols) + item * (tile >> 5);
     int touched = 0;
+    if constexpr (MILLI) {
+      // A lane looks at the ADJACENT columns j0 + 2 * lane and j0 + 2 * lane + 1 (one 16-byte load): listed iff
+      // D != 0 (then the prediction is >= 18); an accumulator whose similarities are all 0 is cleared right here
+      // and predicts nothing (weightSum == 0, recommender.py:44)
+      for (int j0 = 0; j0 < width; j0 += 64) {
+        const int ja = j0 + 2 * lane;
+        ulonglong2 x = make_ulonglong2(0ull, 0ull);
+        if (ja < width) x = *reinterpret_cast<const ulonglong2 *>(acc + ja);       // width is even (tile % 32 == 0 ... Q)
+        const bool hit0 = (unsigned(x.x) & 0xFFFFFFu) != 0u, hit1 = (unsigned(x.y) & 0xFFFFFFu) != 0u;
+        if (!hit0 && x.x != 0ull) acc[ja] = 0ull;
+        if (!hit1 && x.y != 0ull) acc[ja + 1] = 0ull;
+        const unsigned m0 = __ballot_sync(kFull, hit0), m1 = __ballot_sync(kFull, hit1);
+        if (bitmap) {
+          // bit 2 * (lane & 15) + {0, 1} of the word of the lane's half-warp
+          const unsigned field = (unsigned(hit0) | (unsigned(hit1) << 1)) << (2 * (lane & 15));
+          const unsigned wa = __reduce_or_sync(kFull, lane < 16 ? field : 0u);
+          const unsigned wb = __reduce_or_sync(kFull, lane < 16 ? 0u : field);
+          if (lane < 2 && j0 + 32 * lane < width) bitmap_row[(j0 >> 5) + lane] = lane == 0 ? wa : wb;
+        }
+        const int pos = touched + __popc(m0 & lt) + __popc(m1 & lt);
+        if (hit0) jlist[pos] = uint16_t(ja);
+        if (hit1) jlist[pos + int(hit0)] = uint16_t(ja + 1);
+        touched += __popc(m0) + __popc(m1);
+      }
+    } else {
 #pragma unroll 2
-    for (int j0 = 0; j0 < width; j0 += 64) {
-      const int ja = j0 + lane, jb = ja + 32;
-      bool hit0 = false, hit1 = false;
-      if constexpr (MILLI) {
-        // listed iff D != 0 (then the prediction is >= 18); an accumulator whose similarities are all 0 is
-        // cleared right here and predicts nothing (weightSum == 0, recommender.py:44)
-        if (ja < width) {
-          const unsigned long long x = acc[ja];
-          hit0 = (unsigned(x) & 0xFFFFFFu) != 0u;
-          if (!hit0 && x != 0ull) acc[ja] = 0ull;
-        }
-        if (jb < width) {
-          const unsigned long long x = acc[jb];
-          hit1 = (unsigned(x) & 0xFFFFFFu) != 0u;
-          if (!hit1 && x != 0ull) acc[jb] = 0ull;
-        }
-      } else {
+      for (int j0 = 0; j0 < width; j0 += 64) {
+        const int ja = j0 + lane, jb = ja + 32;
+        bool hit0 = false, hit1 = false;
         if (ja < width) { const Acc x = acc[ja]; hit0 = x.den != 0.0 || x.num != 0.0; }
         if (jb < width) { const Acc x = acc[jb]; hit1 = x.den != 0.0 || x.num != 0.0; }
+        const unsigned m0 = __ballot_sync(kFull, hit0), m1 = __ballot_sync(kFull, hit1);
+        if (bitmap && lane < 2 && j0 + 32 * lane < width) bitmap_row[(j0 >> 5) + lane] = lane == 0 ? m0 : m1;
+        const int c0 = __popc(m0);
+        if (hit0) jlist[touched + __popc(m0 & lt)] = uint16_t(ja);
+        if (hit1) jlist[touched + c0 + __popc(m1 & lt)] = uint16_t(jb);
+        touched += c0 + __popc(m1);
       }
-      const unsigned m0 = __ballot_sync(kFull, hit0), m1 = __ballot_sync(kFull, hit1);
-      if (bitmap && lane < 2 && j0 + 32 * lane < width) bitmap_row[(j0 >> 5) + lane] = lane == 0 ? m0 : m1;
-      const int c0 = __popc(m0);
-      if (hit0) jlist[touched + __popc(m0 & lt)] = uint16_t(ja);
-      if (hit1) jlist[touched + c0 + __popc(m1 & lt)] = uint16_t(jb);
-      touched += c0 + __popc(m1);
     }
     unsigned long long base = 0;
     if (lane == 0) {
@@ -477,7 +508,7 @@ predict_dense_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__
                      const int *__restrict__ u_idx, const double *__restrict__ u_val,
                      const int *__restrict__ u_cnt, int ku, int64_t user_base, int64_t n_users,
                      int *__restrict__ out) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   double *num = reinterpret_cast<double *>(smem_raw);
   double *den = num + Q;
   uint8_t *own = reinterpret_cast<uint8_t *>(den + Q);
