@@ -237,7 +237,14 @@ size_t qrs_predict_sparse_workspace_bytes(int64_t U, int64_t nnz, int32_t Q, int
 int qrs_predict_prepare(const int64_t *rowptr, const int32_t *colidx, const uint8_t *val,
                         int64_t U, int64_t nnz, int32_t Q, int32_t tile, int64_t capacity,
                         void *ws, size_t ws_bytes, void *stream);
-/* u_milli (optional): the same similarities as integers, u_val[t] == u_milli[t] / 1000.0 exactly
+/* Rows sharded over several GPUs (one process per GPU): rowptr/colidx/val and U describe THIS rank's rows
+ * [my_peer * U, (my_peer + 1) * U) of the matrix (every rank holds U rows), neighbour ids in u_idx are GLOBAL row
+ * ids, and peer_ws[r] is rank r's prepared workspace (same U, nnz bound, Q, tile) mapped into this process
+ * (qrs_peer_export / qrs_peer_open; peer_ws[my_peer] is ignored in favour of ws).  Neighbour rows that live on
+ * other ranks are then read in place over NVLink: every rank must have finished qrs_predict_prepare before any
+ * rank predicts, and must not prepare again while a peer still predicts (prepared must be non-zero with peers).
+ * peer_ws == NULL: all rows are local (ids in u_idx are rows of this CSR).
+ * u_milli (optional): the same similarities as integers, u_val[t] == u_milli[t] / 1000.0 exactly
  * (what np.around(., 3) produces, recommender.py:204, 270; qrs_topk_tables emits it).  When given,
  * the kernel accumulates exact integers (half the shared memory, no fp64 in the inner loop) and
  * falls back to the reference's sequential fp64 arithmetic only for cells whose value is exactly
@@ -248,6 +255,7 @@ int qrs_predict_sparse(const int64_t *rowptr, const int32_t *colidx, const uint8
                        const int32_t *u_cnt, int32_t ku,
                        int64_t user_base, int64_t n_users, int32_t tile,
                        void *ws, size_t ws_bytes, int32_t prepared,
+                       const uint64_t *peer_ws /* HOST array [n_peers] or NULL */, int32_t n_peers, int32_t my_peer,
                        int64_t *row_start, int32_t *row_cnt,
                        void *cols, int32_t cols_mode /* QRS_COLS_* */, uint8_t *preds,
                        int64_t capacity, int32_t n_regions, unsigned long long *cursors, void *stream);
@@ -340,14 +348,34 @@ int qrs_csv_format_fill(const uint8_t *ids, const int64_t *ids_off, const int64_
                         const void *pred_cols, int32_t cols_mode, const uint8_t *preds, int32_t nt, int64_t n_rows,
                         int32_t Q, int32_t zero_as_empty, const int64_t *text_off, uint8_t *text, void *stream);
 
-/* ------------------------------------------------------ multi-GPU plumbing
- * Rows of the ratings CSR are sharded across GPUs; the prediction gathers neighbour rows
- * (recommender.py:320), so rows requested by other ranks are packed for sending:
- * out[out_off[t] .. out_off[t+1]) = row rows[t] (local row ids; out_off = exclusive prefix of the
- * rows' lengths, n_rows + 1 entries). */
-int qrs_gather_rows(const int64_t *rowptr, const int32_t *colidx, const uint8_t *val,
-                    const int64_t *rows, int64_t n_rows, const int64_t *out_off,
-                    int32_t *out_col, uint8_t *out_val, void *stream);
+/* ------------------------------------------------------ multi-GPU plumbing (SURVEY.md 8e)
+ * Rows of the matrix are sharded across the GPUs of one box, one process per GPU.
+ *
+ * Peer buffers: memory other ranks map and read in place (CUDA IPC).  qrs_peer_alloc allocates, qrs_peer_export
+ * writes the 64-byte handle another process passes to qrs_peer_open to obtain its own mapping of the same memory
+ * (peer access is enabled on first use); the predictor reads neighbour rows of other ranks through such
+ * mappings (qrs_predict_sparse, peer_ws). */
+int qrs_peer_alloc(size_t bytes, void **ptr);
+int qrs_peer_free(void *ptr);
+int qrs_peer_export(void *ptr, unsigned char *handle64);
+int qrs_peer_open(const unsigned char *handle64, void **ptr);
+int qrs_peer_close(void *ptr);
+/* Fixed-capacity exchanges: both all-to-alls of a step move n_ranks equal slots of `cap` 64-bit words per rank,
+ * unused entries are all-ones (a sentinel bucket hash for records, a row id no rank owns for pairs, ignored by
+ * qrs_pair_slots / qrs_topk_tables), so no split size ever has to reach the host between the collectives.
+ * counts u64[n_ranks] = entries that wanted each slot; *overflow gets bit 0 (records) / bit 1 (pairs) set when a
+ * slot was too small (the caller re-runs the step with a larger cap).
+ *   qrs_group_pad: records sorted by their top lg bits (destination rank = bucket hash prefix, 2^lg ranks)
+ *   -> out[2^lg * cap].
+ *   qrs_route_pairs: scored pairs (first min(*n_pairs_dev, capacity_in) entries) -> one word per destination
+ *   (i << 37 | j << 11 | sim + 1000; ids < 2^26), to the owner of i and, if different, of j.
+ *   qrs_unpack_routed: received words -> pairs / sim_milli (sentinels stay all-ones pairs). */
+int qrs_group_pad(const uint64_t *sorted, int64_t n, int32_t lg, int64_t cap, uint64_t *out,
+                  unsigned long long *counts, uint32_t *overflow, void *stream);
+int qrs_route_pairs(const uint64_t *pairs, const int32_t *sims, const unsigned long long *n_pairs_dev,
+                    int64_t capacity_in, int64_t rows_per_rank, int32_t n_ranks, int64_t cap, uint64_t *out,
+                    unsigned long long *counts, uint32_t *overflow, void *stream);
+int qrs_unpack_routed(const uint64_t *words, int64_t n, uint64_t *pairs, int32_t *sims, void *stream);
 
 #ifdef __cplusplus
 }

@@ -52,7 +52,14 @@ SIGNATURES = {
     "qrs_answer_sets_count": (C.c_int, [_p, _i64, _i32, _p, _i64, _p, _p, _sz, _p]),
     "qrs_answer_sets_fill": (C.c_int, [_p, _i64, _i32, _p, _i64, _p, _p, _p]),
     "qrs_recommend_topn": (C.c_int, [_p, _p, _p, _i32, _p, _i64, _i32, _i32, _p, _p, _p, _p]),
-    "qrs_gather_rows": (C.c_int, [_p, _p, _p, _p, _i64, _p, _p, _p, _p]),
+    "qrs_peer_alloc": (C.c_int, [_sz, C.POINTER(C.c_void_p)]),
+    "qrs_peer_free": (C.c_int, [_p]),
+    "qrs_peer_export": (C.c_int, [_p, _p]),
+    "qrs_peer_open": (C.c_int, [_p, C.POINTER(C.c_void_p)]),
+    "qrs_peer_close": (C.c_int, [_p]),
+    "qrs_group_pad": (C.c_int, [_p, _i64, _i32, _i64, _p, _p, _p, _p]),
+    "qrs_route_pairs": (C.c_int, [_p, _p, _p, _i64, _i64, _i32, _i64, _p, _p, _p, _p]),
+    "qrs_unpack_routed": (C.c_int, [_p, _i64, _p, _p, _p]),
     "qrs_csv_workspace_bytes": (_sz, [_i64, _i64]),
     "qrs_csv_line_ends": (C.c_int, [_p, _i64, _p, _i64, _p, _p, _sz, _p]),
     "qrs_csv_ratings_count": (C.c_int, [_p, _i64, _p, _i64, _i64, _i32, _p, _p, _p, _p, _sz, _p]),
@@ -68,7 +75,7 @@ SIGNATURES = {
     "qrs_predict_sparse_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32, _i64]),
     "qrs_predict_prepare": (C.c_int, [_p, _p, _p, _i64, _i64, _i32, _i32, _i64, _p, _sz, _p]),
     "qrs_predict_sparse": (C.c_int, [_p, _p, _p, _i64, _i64, _i32, _p, _p, _p, _p, _i32, _i64, _i64, _i32, _p, _sz, _i32,
-                                     _p, _p, _p, _i32, _p, _i64, _i32, _p, _p]),
+                                     _p, _i32, _i32, _p, _p, _p, _i32, _p, _i64, _i32, _p, _p]),
 }
 
 _lib = None

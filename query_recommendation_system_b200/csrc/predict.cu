@@ -14,6 +14,8 @@
 //                 a few steps ahead of the accumulation; only the columns a neighbour touched
 //                 are predicted and written.  No block barrier in the loop.
 //   dense form  : one CTA per user at reference scale, adds the query branch.
+#include <string.h>
+
 #include "common.cuh"
 
 namespace qrs {
@@ -158,28 +160,62 @@ __device__ __forceinline__ int predict_from(double num, double den) {
   return den != 0.0 ? hybrid_rule(0.0, num / den) : 0;
 }
 
-// the reference's sequential fp64 evaluation of one cell, re-gathered from the neighbours' CSR rows (rare path:
+// Where the prepared rows live.  Rows are sharded over `n_peers` ranks of `rows_per_peer` rows each; every rank's
+// preparation workspace has the same layout (same U, nt), so one set of byte offsets addresses all of them and
+// base[r] is rank r's workspace as mapped into THIS process (CUDA IPC; base[my] = the local one).  Neighbour ids
+// are global row ids; a neighbour row on another rank is read in place over NVLink.
+constexpr int kMaxPeers = 16;
+struct PeerView {
+  unsigned long long base[kMaxPeers];
+  int n_peers;
+  int my;
+  long long rows_per_peer;
+  unsigned long long off_tilepos, off_seg, off_packed;   // byte offsets inside a workspace
+};
+__device__ __forceinline__ const int64_t *peer_tilepos(const PeerView &pv, int r) {
+  return reinterpret_cast<const int64_t *>(pv.base[r] + pv.off_tilepos);
+}
+__device__ __forceinline__ const uint64_t *peer_seg(const PeerView &pv, int r) {
+  return reinterpret_cast<const uint64_t *>(pv.base[r] + pv.off_seg);
+}
+__device__ __forceinline__ const uint32_t *peer_packed(const PeerView &pv, int r) {
+  return reinterpret_cast<const uint32_t *>(pv.base[r] + pv.off_packed);
+}
+
+// rating of global row v at column `col` (0 if not rated), from the prepared rows: the words of a sub-segment are
+// ascending in column, the valid ones are the first tilepos[t + 1] - tilepos[t]
+__device__ __forceinline__ int prepared_rating(const PeerView &pv, int v, int col, int tile, int nt) {
+  const int r = int(v / pv.rows_per_peer);
+  const long long row = v - r * pv.rows_per_peer;
+  const int t = col / tile;
+  const unsigned key = unsigned(col - t * tile) << 8;
+  const int64_t *tp = peer_tilepos(pv, r) + row * (nt + 1) + t;
+  const int n = int(tp[1] - tp[0]);
+  const uint32_t *w = peer_packed(pv, r) + (peer_seg(pv, r)[row * nt + t] << 5);
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (w[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  if (lo < n) {
+    const unsigned x = w[lo];
+    if ((x >> 8) == (key >> 8)) return int(x & 0xFFu);
+  }
+  return 0;
+}
+
+// the reference's sequential fp64 evaluation of one cell, re-gathered from the neighbours' rows (rare path:
 // only when the list of half-way cells is full)
-__device__ __noinline__ int resolve_tie(const int64_t *__restrict__ rowptr, const int *__restrict__ colidx,
-                                        const uint8_t *__restrict__ val, const int *__restrict__ u_idx,
-                                        const int *__restrict__ u_milli, int64_t ul, int ku, int c, int col) {
+__device__ __noinline__ int resolve_tie(const PeerView &pv, const int *__restrict__ u_idx,
+                                        const int *__restrict__ u_milli, int64_t ul, int ku, int c, int col, int tile,
+                                        int nt) {
   double num = 0.0, den = 0.0;
   for (int t = 0; t < c; ++t) {
-    const int v = u_idx[ul * ku + t];
-    const double s = double(u_milli[ul * ku + t]) / 1000.0;
-    const int64_t a = rowptr[v];
-    const int n = int(rowptr[v + 1] - a);
-    int lo = 0, hi = n;
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (__ldg(colidx + a + mid) < col) lo = mid + 1; else hi = mid;
-    }
-    if (lo < n && __ldg(colidx + a + lo) == col) {
-      const int r = val[a + lo];
-      if (r != 0) {
-        num = __dadd_rn(num, __dmul_rn(double(r), s));
-        den = __dadd_rn(den, s);
-      }
+    const int r = prepared_rating(pv, u_idx[ul * ku + t], col, tile, nt);
+    if (r != 0) {
+      const double s = double(u_milli[ul * ku + t]) / 1000.0;
+      num = __dadd_rn(num, __dmul_rn(double(r), s));
+      den = __dadd_rn(den, s);
     }
   }
   return predict_from(num, den);
@@ -187,9 +223,7 @@ __device__ __noinline__ int resolve_tie(const int64_t *__restrict__ rowptr, cons
 
 template <bool MILLI>
 __global__ void __launch_bounds__(kPwMaxWarps * 32, 1)
-predict_sparse_kernel(const uint32_t *__restrict__ packed, const uint64_t *__restrict__ seg_off,
-                      const int64_t *__restrict__ rowptr, const int *__restrict__ colidx,
-                      const uint8_t *__restrict__ val, int Q,
+predict_sparse_kernel(const __grid_constant__ PeerView pv, int Q,
                       const int *__restrict__ u_idx, const double *__restrict__ u_val,
                       const int *__restrict__ u_milli, const int *__restrict__ u_cnt, int ku, int64_t user_base,
                       int64_t n_users, int tile, int nt,
@@ -242,31 +276,37 @@ predict_sparse_kernel(const uint32_t *__restrict__ packed, const uint64_t *__res
     const int c = min(u_cnt[ul], ku);
     const int64_t tbase = ul * ku;
 
-    // ---- the neighbours' sub-segments of this window: lane <-> table slots lane and lane + 32
+    // ---- the neighbours' sub-segments of this window: lane <-> table slots lane and lane + 32; a neighbour is a
+    //      GLOBAL row id: rank = id / rows_per_peer (bits 26..29 of the tag), row on that rank = the remainder
     unsigned o0 = 0, n0 = 0, tag0 = 0, o1 = 0, n1 = 0, tag1 = 0;
     if (lane < c) {
       const int v = u_idx[tbase + lane];
-      const uint64_t *so = seg_off + int64_t(v) * nt + t;
-      const uint64_t a = __ldg(so);
+      const int pr = int(v / pv.rows_per_peer);
+      const uint64_t *so = peer_seg(pv, pr) + (v - pr * pv.rows_per_peer) * nt + t;
+      const uint64_t a = so[0];
       o0 = unsigned(a);
-      n0 = unsigned(__ldg(so + 1) - a);
+      n0 = unsigned(so[1] - a);
       if constexpr (MILLI) tag0 = unsigned(u_milli[tbase + lane]) | (1u << 24);
       else { tag0 = unsigned(lane); m_s[lane] = u_val[tbase + lane]; }
+      tag0 |= unsigned(pr) << 26;
     }
     if (lane + 32 < c) {
       const int v = u_idx[tbase + lane + 32];
-      const uint64_t *so = seg_off + int64_t(v) * nt + t;
-      const uint64_t a = __ldg(so);
+      const int pr = int(v / pv.rows_per_peer);
+      const uint64_t *so = peer_seg(pv, pr) + (v - pr * pv.rows_per_peer) * nt + t;
+      const uint64_t a = so[0];
       o1 = unsigned(a);
-      n1 = unsigned(__ldg(so + 1) - a);
+      n1 = unsigned(so[1] - a);
       if constexpr (MILLI) tag1 = unsigned(u_milli[tbase + lane + 32]) | (1u << 24);
       else { tag1 = unsigned(lane + 32); m_s[lane + 32] = u_val[tbase + lane + 32]; }
+      tag1 |= unsigned(pr) << 26;
     }
     // the user's own row in this window (its rated cells are cleared after the accumulation): the first two steps
     // are requested now and sit in two registers until then
     unsigned own_o, own_n, own_p0 = 0, own_p1 = 0;
+    const uint32_t *const my_packed = peer_packed(pv, pv.my);
     {
-      const uint64_t *so = seg_off + (user_base + ul) * nt + t;
+      const uint64_t *so = peer_seg(pv, pv.my) + (user_base + ul) * nt + t;
       const uint64_t a = __ldg(so);
       own_o = unsigned(a);
       own_n = unsigned(__ldg(so + 1) - a);
@@ -288,8 +328,8 @@ predict_sparse_kernel(const uint32_t *__restrict__ packed, const uint64_t *__res
       if (lane == 0) { row_start[item] = region_base; row_cnt[item] = 0; }
       continue;
     }
-    if (own_n > 0) own_p0 = ld_stream_u32(packed + (size_t(own_o) << 5) + lane);
-    if (own_n > 1) own_p1 = ld_stream_u32(packed + (size_t(own_o) << 5) + 32 + lane);
+    if (own_n > 0) own_p0 = ld_stream_u32(my_packed + (size_t(own_o) << 5) + lane);
+    if (own_n > 1) own_p1 = ld_stream_u32(my_packed + (size_t(own_o) << 5) + 32 + lane);
 
     for (unsigned R0 = 0; R0 < total; R0 += kPwListCap) {
       __syncwarp();          // the previous round's list has been consumed (and m_s is written)
@@ -316,7 +356,7 @@ predict_sparse_kernel(const uint32_t *__restrict__ packed, const uint64_t *__res
           if (f0 + i < cnt) {                       // warp-uniform
             const uint2 e = steps[f0 + i];
             tg = e.y;
-            const uint32_t *src = packed + (size_t(e.x) << 5) + lane;
+            const uint32_t *src = peer_packed(pv, int((tg >> 26) & 15u)) + (size_t(e.x) << 5) + lane;
             a = ld_stream_u32(src);
             if (!(tg & kPwSingle)) b2 = ld_stream_u32(src + 32);
           }
@@ -331,7 +371,7 @@ predict_sparse_kernel(const uint32_t *__restrict__ packed, const uint64_t *__res
             // both read-modify-writes of the lane at once, predicated instead of branched (the two entries belong
             // to one neighbour: different columns).  inc = milli | 1 << 24 is the low word's increment (D and the
             // rater count) AND the high word's multiplier: r * inc = r << 24 | r * milli, as r * milli < 2^24
-            const unsigned inc = B.tag[i] & 0x1FFFFFFu;
+            const unsigned inc = B.tag[i] & 0x1FFFFFFu;       // bits 26.. are the rank and the single-step flag
             const unsigned a0 = acc_s + ((B.p0[i] >> 5) & ~7u), a1 = acc_s + ((B.p1[i] >> 5) & ~7u);
             unsigned long long x0 = 0, x1 = 0;
             lds_u64_if(x0, a0, r0);
@@ -377,7 +417,7 @@ predict_sparse_kernel(const uint32_t *__restrict__ packed, const uint64_t *__res
     if (own_p0 & 0xFFu) acc[own_p0 >> 8] = zero;
     if (own_p1 & 0xFFu) acc[own_p1 >> 8] = zero;
     for (unsigned s = 2; s < own_n; ++s) {          // rows with more than 64 entries in one window
-      const unsigned p = ld_stream_u32(packed + ((size_t(own_o) + s) << 5) + lane);
+      const unsigned p = ld_stream_u32(my_packed + ((size_t(own_o) + s) << 5) + lane);
       if (p & 0xFFu) acc[p >> 8] = zero;
     }
     __syncwarp();
@@ -482,7 +522,7 @@ predict_sparse_kernel(const uint32_t *__restrict__ packed, const uint64_t *__res
                 tie_list[slot] = make_ulonglong2((unsigned long long)(w_preds + x - preds),   // position in preds
                                                  ((unsigned long long)(unsigned)ul << 32) | unsigned(q0 + j));
               else
-                p = resolve_tie(rowptr, colidx, val, u_idx, u_milli, ul, ku, c, q0 + j);   // list full: settle here
+                p = resolve_tie(pv, u_idx, u_milli, ul, ku, c, q0 + j, tile, nt);   // list full: settle here
             }
             if (cols_mode == 1) reinterpret_cast<uint16_t *>(w_cols)[x] = uint16_t(q0 + j);
             else if (cols_mode == 0) reinterpret_cast<int *>(w_cols)[x] = q0 + j;
@@ -586,11 +626,10 @@ __global__ void __launch_bounds__(256) single_rater_tie_bits_kernel(unsigned *__
 }
 
 // Exact half-way cells with several raters (MILLI flavour): one warp per cell re-gathers the
-// neighbours' ratings of that column (lane <-> neighbour, binary search in the neighbour's row) and
-// replays the reference's sequential fp64 sums in table order.
+// neighbours' ratings of that column (lane <-> neighbour, binary search in the neighbour's prepared
+// sub-segment, wherever it lives) and replays the reference's sequential fp64 sums in table order.
 __global__ void __launch_bounds__(256)
-predict_tie_fixup_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ colidx,
-                         const uint8_t *__restrict__ val, const int *__restrict__ u_idx,
+predict_tie_fixup_kernel(const __grid_constant__ PeerView pv, int tile, int nt, const int *__restrict__ u_idx,
                          const int *__restrict__ u_milli, const int *__restrict__ u_cnt, int ku,
                          const unsigned long long *__restrict__ tie_count, const ulonglong2 *__restrict__ tie_list,
                          int64_t tie_capacity, uint8_t *__restrict__ preds) {
@@ -609,16 +648,8 @@ predict_tie_fixup_kernel(const int64_t *__restrict__ rowptr, const int *__restri
       int r = 0;
       double s = 0.0;
       if (t0 + lane < c) {
-        const int v = u_idx[ul * ku + t0 + lane];
         s = double(u_milli[ul * ku + t0 + lane]) / 1000.0;
-        const int64_t a = rowptr[v];
-        const int len = int(rowptr[v + 1] - a);
-        int lo = 0, hi = len;
-        while (lo < hi) {
-          const int mid = (lo + hi) >> 1;
-          if (__ldg(colidx + a + mid) < col) lo = mid + 1; else hi = mid;
-        }
-        if (lo < len && __ldg(colidx + a + lo) == col) r = val[a + lo];
+        r = prepared_rating(pv, u_idx[ul * ku + t0 + lane], col, tile, nt);
       }
       const int nn = min(32, c - t0);
       for (int t = 0; t < nn; ++t) {
@@ -643,8 +674,7 @@ static int predict_warps_per_cta(int tile, bool milli) {
 }
 
 template <bool MILLI>
-static int launch_predict_sparse(const uint32_t *packed, const uint64_t *seg_off, const int64_t *rowptr,
-                                 const int *colidx, const uint8_t *val, int Q, const int *u_idx, const double *u_val,
+static int launch_predict_sparse(const PeerView &pv, int Q, const int *u_idx, const double *u_val,
                                  const int *u_milli, const int *u_cnt, int ku, int64_t user_base, int64_t n_users,
                                  int tile, int nt, int64_t *row_start, int *row_cnt, int *cols,
                                  uint8_t *preds, int64_t region_cap, int n_regions, unsigned long long *cursors,
@@ -658,10 +688,9 @@ static int launch_predict_sparse(const uint32_t *packed, const uint64_t *seg_off
   int64_t grid = sm_count();                     // one CTA per SM: as many independent warps as its shared memory holds
   const int64_t need = ceil_div<int64_t>(n_users * nt, warps);
   if (grid > need) grid = need;
-  kern<<<unsigned(grid), warps * 32, smem, st>>>(packed, seg_off, rowptr, colidx, val, Q, u_idx, u_val, u_milli, u_cnt,
-                                                  ku, user_base, n_users, tile, nt, row_start, row_cnt, cols, preds,
-                                                  region_cap, n_regions, cursors, tie_count, tie_list, tie_capacity,
-                                                  cols_mode, single_tab);
+  kern<<<unsigned(grid), warps * 32, smem, st>>>(pv, Q, u_idx, u_val, u_milli, u_cnt, ku, user_base, n_users, tile, nt,
+                                                  row_start, row_cnt, cols, preds, region_cap, n_regions, cursors,
+                                                  tie_count, tie_list, tie_capacity, cols_mode, single_tab);
   QRS_LAUNCH_CHECK();
   return QRS_OK;
 }
@@ -784,43 +813,60 @@ int qrs_predict_prepare(const int64_t *rowptr, const int32_t *colidx, const uint
 int qrs_predict_sparse(const int64_t *rowptr, const int32_t *colidx, const uint8_t *val, int64_t U, int64_t nnz,
                        int32_t Q, const int32_t *u_idx, const double *u_val, const int32_t *u_milli,
                        const int32_t *u_cnt, int32_t ku, int64_t user_base, int64_t n_users, int32_t tile, void *ws,
-                       size_t ws_bytes, int32_t prepared, int64_t *row_start, int32_t *row_cnt, void *cols_any,
-                       int32_t cols_mode, uint8_t *preds, int64_t capacity, int32_t n_regions,
-                       unsigned long long *cursors, void *stream) {
+                       size_t ws_bytes, int32_t prepared, const uint64_t *peer_ws, int32_t n_peers, int32_t my_peer,
+                       int64_t *row_start, int32_t *row_cnt, void *cols_any, int32_t cols_mode, uint8_t *preds,
+                       int64_t capacity, int32_t n_regions, unsigned long long *cursors, void *stream) {
   int32_t *cols = static_cast<int32_t *>(cols_any);
   if (cols_mode < 0 || cols_mode > 2 || (cols_mode == 1 && Q > 65536)) return QRS_ERR_INVALID_ARG;
-  if (!rowptr || U < 0 || nnz < 0 || Q <= 0 || !u_idx || (!u_val && !u_milli) || !u_cnt || ku <= 0 || user_base < 0 ||
+  if (U < 0 || nnz < 0 || Q <= 0 || !u_idx || (!u_val && !u_milli) || !u_cnt || ku <= 0 || user_base < 0 ||
       n_users < 0 || user_base + n_users > U || !row_start || !row_cnt || !cursors || capacity < 0 || n_regions <= 0)
     return QRS_ERR_INVALID_ARG;
+  if (!prepared && !rowptr) return QRS_ERR_INVALID_ARG;
+  if (peer_ws ? (n_peers < 1 || n_peers > kMaxPeers || my_peer < 0 || my_peer >= n_peers || !prepared)
+              : (n_peers > 1))
+    return QRS_ERR_INVALID_ARG;      // remote rows can only be read from workspaces every rank has prepared already
   const int64_t region_cap = capacity / n_regions;
   if (capacity > 0 && (!cols || !preds)) return QRS_ERR_INVALID_ARG;
   if (tile <= 0 || tile % 32 != 0) return QRS_ERR_INVALID_ARG;
   if (tile > qrs_predict_max_tile(u_milli != nullptr) || ku > QRS_MAX_TOPK) return QRS_ERR_UNSUPPORTED;
-  if (!ws || ws_bytes < qrs_predict_sparse_workspace_bytes(U, nnz, Q, tile, capacity)) return QRS_ERR_WORKSPACE;
+  if (!ws || (reinterpret_cast<uintptr_t>(ws) & 255) != 0 ||
+      ws_bytes < qrs_predict_sparse_workspace_bytes(U, nnz, Q, tile, capacity))
+    return QRS_ERR_WORKSPACE;
   if (n_users == 0 || U == 0) return QRS_OK;
-  if (nnz > 0 && (!colidx || !val)) return QRS_ERR_INVALID_ARG;
   cudaStream_t st = as_stream(stream);
   if (!prepared) {
+    if (nnz > 0 && (!colidx || !val)) return QRS_ERR_INVALID_ARG;
     int rc = qrs_predict_prepare(rowptr, colidx, val, U, nnz, Q, tile, capacity, ws, ws_bytes, stream);
     if (rc != QRS_OK) return rc;
   }
   const int nt = int(ceil_div<int64_t>(Q, tile));
   const PredictWs w = carve_predict_ws(ws, U, nt, nnz, capacity);
+  PeerView pv;
+  memset(&pv, 0, sizeof(pv));
+  pv.n_peers = peer_ws ? n_peers : 1;
+  pv.my = peer_ws ? my_peer : 0;
+  pv.rows_per_peer = U > 0 ? U : 1;
+  for (int r = 0; r < pv.n_peers; ++r) pv.base[r] = peer_ws ? peer_ws[r] : 0ull;
+  pv.base[pv.my] = static_cast<unsigned long long>(reinterpret_cast<uintptr_t>(ws));
+  pv.off_tilepos = static_cast<unsigned long long>(reinterpret_cast<char *>(w.tilepos) - static_cast<char *>(ws));
+  pv.off_seg = static_cast<unsigned long long>(reinterpret_cast<char *>(w.seg_off) - static_cast<char *>(ws));
+  pv.off_packed = static_cast<unsigned long long>(reinterpret_cast<char *>(w.packed) - static_cast<char *>(ws));
+  for (int r = 0; r < pv.n_peers; ++r)
+    if (pv.base[r] == 0ull) return QRS_ERR_INVALID_ARG;
   QRS_CUDA(cudaMemsetAsync(w.tie_count, 0, 8, st));
   if (u_milli) {
-    int rc = launch_predict_sparse<true>(w.packed, w.seg_off, rowptr, colidx, val, Q, u_idx, u_val, u_milli, u_cnt, ku,
-                                         user_base, n_users, tile, nt, row_start, row_cnt, cols, preds, region_cap,
-                                         n_regions, cursors, w.tie_count, w.tie_list, w.tie_cap, cols_mode, w.single_tab,
-                                         st);
+    int rc = launch_predict_sparse<true>(pv, Q, u_idx, u_val, u_milli, u_cnt, ku, user_base, n_users, tile, nt,
+                                         row_start, row_cnt, cols, preds, region_cap, n_regions, cursors, w.tie_count,
+                                         w.tie_list, w.tie_cap, cols_mode, w.single_tab, st);
     if (rc != QRS_OK || capacity == 0) return rc;
-    predict_tie_fixup_kernel<<<sm_count() * 8, 256, 0, st>>>(rowptr, colidx, val, u_idx, u_milli, u_cnt, ku,
-                                                             w.tie_count, w.tie_list, w.tie_cap, preds);
+    predict_tie_fixup_kernel<<<sm_count() * 8, 256, 0, st>>>(pv, tile, nt, u_idx, u_milli, u_cnt, ku, w.tie_count,
+                                                             w.tie_list, w.tie_cap, preds);
     QRS_LAUNCH_CHECK();
     return QRS_OK;
   }
-  return launch_predict_sparse<false>(w.packed, w.seg_off, rowptr, colidx, val, Q, u_idx, u_val, u_milli, u_cnt, ku,
-                                      user_base, n_users, tile, nt, row_start, row_cnt, cols, preds, region_cap,
-                                      n_regions, cursors, w.tie_count, w.tie_list, w.tie_cap, cols_mode, w.single_tab, st);
+  return launch_predict_sparse<false>(pv, Q, u_idx, u_val, u_milli, u_cnt, ku, user_base, n_users, tile, nt, row_start,
+                                      row_cnt, cols, preds, region_cap, n_regions, cursors, w.tie_count, w.tie_list,
+                                      w.tie_cap, cols_mode, w.single_tab, st);
 }
 
 int qrs_predict_dense(const int64_t *rowptr, const int32_t *colidx, const uint8_t *val, int64_t U, int32_t Q,

@@ -41,6 +41,7 @@ class PipelineOutput:
     n_predictions: int = 0
     covered_cells: int = 0                 # zero cells of R decided (predicted or proven "missed")
     stage_ms: Dict[str, float] = field(default_factory=dict)
+    exchange_bytes: Dict[str, int] = field(default_factory=dict)   # several GPUs: bytes this rank sent per exchange
 
 
 class _Timer:
@@ -102,6 +103,8 @@ class LshCfPipeline:
         self.order_head = None
         self._head_for = None
         self._pred_capacity = {}
+        self._cap = {}                      # learnt buffer capacities: candidate pairs, exchange slots
+        self.peer_margin = 1.25             # several GPUs: the peer buffer is sized for this x the first shard's entries
         self.predict_chunks = 1             # > 1: predictions are produced (and can be shipped) chunk by chunk
         self.cols_mode = 0                  # prediction columns as int32 ids (0), uint16 ids (1) or a bitmap (2)
         # how a candidate pair is scored: "signature" = rounded cosine of the MinHash signatures
@@ -134,7 +137,18 @@ class LshCfPipeline:
     def run(self, rowptr: torch.Tensor, colidx: torch.Tensor, val: Optional[torch.Tensor],
             predict: bool = True, chunk_sink=None, val_ready=None) -> PipelineOutput:
         """rowptr/colidx/val: this rank's shard (rows [rank*n_local, (rank+1)*n_local)) of the users×queries
-        CSR, on `self.device`.  Every rank must hold the same number of rows."""
+        CSR, on `self.device`.  Every rank must hold the same number of rows.
+
+        Buffer capacities that depend on the data (candidate pairs, exchange slots, prediction slices) are learnt:
+        a step runs with the capacities the previous one suggested and reads ONE batch of counters back at its end;
+        if any was too small the step is repeated with the corrected value (first call of a new shape only)."""
+        for _ in range(5):
+            out, ok = self._run_once(rowptr, colidx, val, predict, chunk_sink, val_ready)
+            if ok:
+                return out
+        raise _lib.QrsError("buffer capacities did not settle after 5 attempts")
+
+    def _run_once(self, rowptr, colidx, val, predict, chunk_sink, val_ready):
         st, G, rank = self.st, self.world, self.rank
         out = PipelineOutput()
         tm = _Timer(self.profile, self.device.type == "cuda")
@@ -142,14 +156,12 @@ class LshCfPipeline:
         row_base = rank * n_local
         n_total = n_local * G
         nnz = colidx.numel()
+        dev = rowptr.device
+        if G > 1:
+            self._check_equal_shards(n_local)
         self._ensure_head(nnz / max(n_local, 1))
+        xbytes = {}
         tm.mark("start")
-
-        lens_join = None
-        if G > 1 and predict:
-            # row lengths of every shard (4 bytes per row): lets the remote-row exchange size its buffers locally
-            lens_join = self._background(
-                lambda: (self._all_gather_rows((rowptr[1:] - rowptr[:-1]).contiguous(), self._bg_group()),), (rowptr,))
 
         # a1 + a2/a3: signatures, squared norms and bucket records in one kernel
         sig, norm2, records = st.minhash(rowptr, colidx, self.m, self.perm_tab, self.order_head, b=self.b,
@@ -157,6 +169,9 @@ class LshCfPipeline:
         out.sig, out.norm2 = sig, norm2
         tm.mark("signatures+banding")
 
+        # global flags / maxima, all-reduced (MAX) once per step: [records overflow, pairs overflow, route overflow,
+        # largest record slot, largest route slot]
+        flags = torch.zeros(5, dtype=torch.int64, device=dev)
         if G == 1:
             flat = records.reshape(-1)
             st.sort_u64(flat, n_local, self.b, 40, 64)
@@ -167,26 +182,34 @@ class LshCfPipeline:
             # communicator while the bucket records are exchanged and sorted
             sig_join = self._background(lambda: (self._all_gather_rows(sig, self._bg_group()),
                                                  self._all_gather_rows(norm2, self._bg_group())), (sig, norm2))
-            flat, lg = self._exchange_records(records.reshape(-1))
+            xbytes["signatures"] = (sig.numel() * 4 + norm2.numel() * 8) * (G - 1)
+            flat, lg, rec_counts, rec_over, xbytes["records"] = self._exchange_records(records.reshape(-1))
+            flags[0] = rec_over[0]
+            flags[3] = rec_counts.max()
             tm.mark("exchange:records")
             st.sort_u64(flat, flat.numel(), 1, 32, 64 - lg)
             tm.mark("grouping")
             sig_all, norm2_all = sig_join()
             tm.mark("exchange:signatures")
 
-        # a5 + a8: slots → verified, de-duplicated, scored pairs
+        # a5 + a8: slots → verified, de-duplicated, scored pairs.  The pair buffer is sized from the previous step
+        # (entries beyond the pairs found are sentinels the table builder skips), so no counter is read back here.
         slot_off = st.pair_slots(flat)
-        n_slots = int(slot_off[-1].item())
         by_ratings = self.similarity == "ratings"
         if by_ratings and G > 1:
             raise _lib.QrsError("similarity='ratings' needs both rows of a pair on one rank: single-rank only")
         if self.similarity not in ("signature", "ratings"):
             raise ValueError("similarity must be 'signature' or 'ratings'")
-        pairs, sims, counter = st.pairs_score(flat, slot_off, sig_all, norm2_all, self.b, n_slots, 0, not by_ratings)
-        n_pairs = int(counter.item())
-        pairs = pairs[:n_pairs]
+        cap_pairs = self._cap.get("pairs", 0)
+        if by_ratings or cap_pairs == 0:
+            cap_pairs = max(int(slot_off[-1].item()), 1)            # exact upper bound (one readback, first step only)
+        pairs, sims, counter = st.pairs_score(flat, slot_off, sig_all, norm2_all, self.b, cap_pairs, 0, not by_ratings,
+                                              fill_sentinel=True)
+        flags[1] = (counter[0] > cap_pairs).to(torch.int64)
         if by_ratings:
             assert val is not None, "similarity='ratings' scores pairs on the ratings themselves"
+            n_pairs = int(counter.item())
+            pairs = pairs[:n_pairs]
             if val_ready is not None:
                 torch.cuda.current_stream().wait_event(val_ready)
             cval, norm2_c = st.center_rows(rowptr, val)
@@ -194,35 +217,27 @@ class LshCfPipeline:
             if n_pairs:
                 st.sort_u64(pairs, n_pairs, 1, 32, 32 + max(1, (n_total - 1).bit_length()))
             sims = st.pair_centered_cosine(rowptr, colidx, val, cval, norm2_c, pairs, self.m, grouped=True)
-        else:
-            sims = sims[:n_pairs]
-        out.pairs, out.sims, out.n_slots = pairs, sims, n_slots
         tm.mark("pairs+cosine")
 
         if G > 1:
-            pairs, sims = self._route_pairs(pairs, sims, n_local)
-            n_pairs = pairs.numel()
+            pairs_t, sims_t, route_counts, route_over, xbytes["pairs"] = self._route_pairs(pairs, sims, counter, n_local)
+            flags[2] = route_over[0]
+            flags[4] = route_counts.max()
             tm.mark("exchange:pairs")
+        else:
+            pairs_t, sims_t = pairs, sims
 
         # a7 + a9
-        idx, v, cnt, milli = st.topk_tables(pairs, sims, n_pairs, row_base, n_local, self.k, want_milli=True)
+        idx, v, cnt, milli = st.topk_tables(pairs_t, sims_t, pairs_t.numel(), row_base, n_local, self.k, want_milli=True)
         out.nbr_idx, out.nbr_val, out.nbr_cnt = idx, v, cnt
         tm.mark("topk")
 
+        tail = [slot_off[-1:].to(torch.int64), counter.reshape(1).to(torch.int64)]
+        launched = []
         if predict:
             assert val is not None
             if val_ready is not None:          # the ratings were still being uploaded while the LSH stages ran
                 torch.cuda.current_stream().wait_event(val_ready)
-            pred_base = row_base
-            if G > 1:
-                # only the neighbour rows that live on other ranks are fetched (deduplicated), appended to the local
-                # CSR, and the neighbour ids are re-pointed at the extended row numbering
-                rowptr_all, colidx_all, val_all, idx = self._fetch_remote_rows(rowptr, colidx, val, idx, cnt,
-                                                                               n_local, row_base, lens_join()[0])
-                pred_base = 0
-                tm.mark("exchange:ratings")
-            else:
-                rowptr_all, colidx_all, val_all = rowptr, colidx, val
             tile = self.tile or st.choose_predict_tile(self.m, nnz / max(n_local, 1), self.integer_predict)
             # Users are predicted in `predict_chunks` consecutive chunks so that a caller-supplied sink can
             # ship chunk i to the host while chunk i+1 is computed.  Inside a chunk the output slices are
@@ -231,44 +246,97 @@ class LshCfPipeline:
             regions = self.pred_regions
             chunks = max(1, min(self.predict_chunks, n_local))
             bounds = [n_local * ci // chunks for ci in range(chunks + 1)]
+            known = [self._pred_capacity.get((chunks, ci, self.cols_mode), 0) * regions for ci in range(chunks)]
+            peers = None
+            if G > 1:
+                # neighbour rows of other ranks are read in place from their prepared buffers: nobody may rewrite
+                # its buffer while a peer still predicts from it (barrier 1), nobody may predict before every
+                # buffer is written (barrier 2, which also carries the step's overflow flags)
+                peers = self._peer_workspace(n_local, nnz, tile)
+                self._stream_barrier(dev)
+            # the rows are prepared (cut at the window bounds, packed, padded to 128-byte steps) once per step
+            plan = st.PredictPlan(rowptr, colidx, val, self.m, tile, capacity_hint=max(known), peers=peers)
+            tm.mark("predict:prepare")
+            if G > 1:
+                self._all_reduce_max(flags)
+                tm.mark("exchange:barrier")
+                remote = (idx >= 0) & ((idx < row_base) | (idx >= row_base + n_local))
+                tail.append(remote.sum().reshape(1).to(torch.int64))
+            for ci in range(chunks):
+                launched.append(self._launch_chunk(st, plan, rowptr, colidx, val, idx, v, cnt, milli, ci, bounds, chunks,
+                                                   regions, tile, chunk_sink))
+            tail.append((val != 0).sum().reshape(1).to(torch.int64))
+        elif G > 1:
+            self._all_reduce_max(flags)
+
+        # ---- the step's only readback: every counter at once
+        host = torch.cat([flags] + tail + [torch.cat([c["cursors"], c["nz"]]) for c in launched]).cpu().tolist()
+        f_rec, f_pairs, f_route, max_rec, max_route = host[:5]
+        n_slots, n_found = int(host[5]), int(host[6])
+        pos = 5 + len(tail)           # the chunks' counters follow the tail
+        ok = True
+        if G > 1:
+            self._cap["records"] = int(max_rec * 1.1) + 1024
+            self._cap["route"] = int(max_route * 1.15) + 4096
+            if f_rec or f_route:
+                ok = False
+        self._cap["pairs"] = int(n_found * 1.15) + 4096
+        if f_pairs or n_found > cap_pairs:
+            ok = False            # (single rank: the flag is local; several ranks: it was all-reduced)
+        if not ok:
+            return out, False
+        n_pairs = n_found if not by_ratings else pairs.numel()
+        out.pairs, out.sims, out.n_slots = pairs[:n_pairs], (sims[:n_pairs] if sims is not None else None), n_slots
+        out.exchange_bytes = xbytes
+        if predict:
+            if G > 1:
+                xbytes["ratings(peer reads)"] = int(int(host[7]) * (nnz / max(n_local, 1)) * 4)
             total = 0
             out.pred_chunks = []
-            # the rows are prepared (cut at the window bounds, packed, padded to 128-byte steps) once per step
-            known = [self._pred_capacity.get((chunks, ci, self.cols_mode), 0) * regions for ci in range(chunks)]
-            plan = st.PredictPlan(rowptr_all, colidx_all, val_all, self.m, tile, capacity_hint=max(known))
-            tm.mark("predict:prepare")
-            for ci in range(chunks):
-                lo, hi = bounds[ci], bounds[ci + 1]
-                rcap = self._pred_capacity.get((chunks, ci, self.cols_mode), 0)
-                tab = (idx[lo:hi], v[lo:hi], cnt[lo:hi])
-                mil = milli[lo:hi] if self.integer_predict else None
+            regions = self.pred_regions
+            for c in launched:
                 while True:
-                    rs, rc, cols, preds, cursors, nzc = st.predict_sparse(rowptr_all, colidx_all, val_all, self.m, tab,
-                                                                     pred_base + lo, hi - lo, tile, rcap * regions,
-                                                                     u_milli=mil, n_regions=regions,
-                                                                     cols_mode=self.cols_mode, plan=plan)
-                    demand = torch.cat([cursors, nzc]).cpu()
-                    nonzero = int(demand[-1].item())
-                    demand = demand[:regions]
-                    need = int(demand.max().item())
-                    if need <= rcap:
+                    demand = host[pos:pos + regions] if c.get("fresh", True) else None
+                    if demand is None:          # the chunk was re-run: read its counters alone
+                        again = torch.cat([c["cursors"], c["nz"]]).cpu().tolist()
+                        demand, nonzero = again[:regions], int(again[regions])
+                    else:
+                        nonzero = int(host[pos + regions])
+                    need = int(max(demand))
+                    if need <= c["rcap"]:
                         break
-                    rcap = self._pred_capacity[(chunks, ci, self.cols_mode)] = int(need * 1.03) + 256
+                    key = (c["chunks"], c["ci"], self.cols_mode)
+                    self._pred_capacity[key] = int(need * 1.03) + 256
+                    c.update(self._launch_chunk(st, plan, rowptr, colidx, val, idx, v, cnt, milli, c["ci"], c["bounds"],
+                                                c["chunks"], regions, c["tile"], chunk_sink))
+                    c["fresh"] = False
+                pos += regions + 1
                 total += nonzero
-                chunk = {"user_lo": lo, "n_users": hi - lo, "row_start": rs, "row_cnt": rc, "cols": cols, "preds": preds,
-                         "cols_mode": self.cols_mode, "tile": tile}
-                out.pred_chunks.append(chunk)
-                if chunk_sink is not None:
-                    chunk_sink(ci, chunk)
-            if chunks == 1:
-                out.pred_row_start, out.pred_row_cnt = rs, rc
-                out.pred_cols, out.pred_vals = cols, preds
+                out.pred_chunks.append(c["chunk"])
+            if len(launched) == 1:
+                ch = launched[0]["chunk"]
+                out.pred_row_start, out.pred_row_cnt = ch["row_start"], ch["row_cnt"]
+                out.pred_cols, out.pred_vals = ch["cols"], ch["preds"]
             out.n_predictions = total
-            rated = int((val != 0).sum().item()) if val.numel() else 0
-            out.covered_cells = n_local * self.m - rated
+            out.covered_cells = n_local * self.m - int(host[5 + len(tail) - 1])
             tm.mark("predict")
         out.stage_ms = tm.result()
-        return out
+        return out, True
+
+    def _launch_chunk(self, st, plan, rowptr, colidx, val, idx, v, cnt, milli, ci, bounds, chunks, regions, tile, chunk_sink):
+        lo, hi = bounds[ci], bounds[ci + 1]
+        rcap = self._pred_capacity.get((chunks, ci, self.cols_mode), 0)
+        tab = (idx[lo:hi], v[lo:hi], cnt[lo:hi])
+        mil = milli[lo:hi] if self.integer_predict else None
+        rs, rc, cols, preds, cursors, nzc = st.predict_sparse(rowptr, colidx, val, self.m, tab, lo, hi - lo, tile,
+                                                             rcap * regions, u_milli=mil, n_regions=regions,
+                                                             cols_mode=self.cols_mode, plan=plan)
+        chunk = {"user_lo": lo, "n_users": hi - lo, "row_start": rs, "row_cnt": rc, "cols": cols, "preds": preds,
+                 "cols_mode": self.cols_mode, "tile": tile}
+        if chunk_sink is not None and rcap > 0:
+            chunk_sink(ci, chunk)
+        return {"chunk": chunk, "cursors": cursors, "nz": nzc, "rcap": rcap, "ci": ci, "bounds": bounds, "chunks": chunks,
+                "tile": tile}
 
     def recommend_top_n(self, out: PipelineOutput, N: int = 10):
         """What Recommender.top_k_queries serves (recommender.py:345-374), for every user of this rank at once:
@@ -314,107 +382,79 @@ class LshCfPipeline:
         dist.all_gather_into_tensor(outt, t.contiguous(), group=group if group is not None else self.group)
         return outt
 
-    def _all_to_all_var(self, send: torch.Tensor, send_counts, return_counts: bool = False, recv_counts=None):
-        """send is grouped by destination rank; send_counts: G host ints.  The receive split is exchanged first
-        unless the caller already knows it (recv_counts)."""
+    def _check_equal_shards(self, n_local: int):
+        """row_base = rank * n_local: every rank must hold the same number of rows (checked once per shard size)."""
         import torch.distributed as dist
-        send_l = [int(x) for x in (send_counts.tolist() if hasattr(send_counts, "tolist") else send_counts)]
-        if recv_counts is None:
-            sc = torch.tensor(send_l, dtype=torch.int64, device=send.device)
-            rcv = torch.empty_like(sc)
-            dist.all_to_all_single(rcv, sc, group=self.group)
-            rcv_l = rcv.cpu().tolist()
-        else:
-            rcv_l = [int(x) for x in recv_counts]
-        recv = torch.empty((int(sum(rcv_l)),) + tuple(send.shape[1:]), dtype=send.dtype, device=send.device)
-        dist.all_to_all_single(recv, send, output_split_sizes=rcv_l, input_split_sizes=send_l, group=self.group)
-        return (recv, rcv_l) if return_counts else recv
+        if getattr(self, "_shards_ok", None) == n_local:
+            return
+        sizes = [None] * self.world
+        dist.all_gather_object(sizes, int(n_local), group=self.group)
+        if any(x != n_local for x in sizes):
+            raise _lib.QrsError("every rank must hold the same number of rows, got %s" % sizes)
+        self._shards_ok = n_local
+
+    def _stream_barrier(self, dev):
+        """Stream-ordered barrier over the ranks: a one-element all-reduce completes on this rank's stream only after
+        every rank's stream has reached it (no host synchronisation)."""
+        self._all_reduce_max(torch.zeros(1, dtype=torch.int64, device=dev))
+
+    def _all_reduce_max(self, t: torch.Tensor):
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+
+    def _peer_workspace(self, n_local: int, nnz: int, tile: int):
+        """This rank's peer buffer for the prepared rows (collective, created on first use and kept): sized for
+        peer_margin x this shard's entries and for up to min(n_local * m, 64 * nnz) predictions per call."""
+        key = (n_local, tile)
+        pw = getattr(self, "_peers", None)
+        if pw is not None and self._peers_key == key:
+            return pw
+        if pw is not None:
+            pw.close()
+        nnz_bound = int(nnz * self.peer_margin) + 4096
+        cap_bound = int(min(n_local * self.m, 64 * max(nnz, 1)))
+        nbytes = self.st.predict_workspace_bytes(n_local, nnz_bound, self.m, tile, cap_bound)
+        self._peers = self.st.PeerWorkspace(nbytes, self.group)
+        self._peers_key = key
+        return self._peers
 
     def _exchange_records(self, flat: torch.Tensor):
-        """Bucket records go to rank = top log2(G) bits of hash24: one radix pass groups them by
-        destination, the split points come from a searchsorted on those bits."""
+        """Bucket records go to rank = top log2(G) bits of hash24: one radix pass groups them by destination, the
+        groups are padded into G equal slots (sentinel records sort last and pair with nothing) and ONE equal-split
+        all-to-all moves them — no split size reaches the host."""
+        import torch.distributed as dist
         G = self.world
         lg = G.bit_length() - 1
         if (1 << lg) != G:
             raise _lib.QrsError("the bucket exchange needs a power-of-two world size, got %d" % G)
-        self.st.sort_u64(flat, flat.numel(), 1, 64 - lg, 64)
-        dest = (flat >> (64 - lg)) & (G - 1)
-        bounds = torch.searchsorted(dest, torch.arange(G + 1, device=flat.device, dtype=dest.dtype))
-        counts = (bounds[1:] - bounds[:-1]).cpu()
-        return self._all_to_all_var(flat, counts), lg
+        n = flat.numel()
+        self.st.sort_u64(flat, n, 1, 64 - lg, 64)
+        cap = self._cap.get("records") or (int(n / G * 1.5) + 1024)
+        slots, counts, over = self.st.group_pad(flat, lg, cap)
+        recv = torch.empty_like(slots)
+        dist.all_to_all_single(recv, slots, group=self.group)
+        return recv, lg, counts, over, slots.numel() * 8 * (G - 1) // G
 
-    def _route_pairs(self, pairs: torch.Tensor, sims: torch.Tensor, n_local: int):
-        """Each scored pair goes to the owner of i and (if different) the owner of j.  Pair and similarity
-        travel as ONE int64 (i << 37 | j << 11 | sim + 1000; ids < 2^26) so a single all-to-all moves both."""
+    def _route_pairs(self, pairs: torch.Tensor, sims: torch.Tensor, counter: torch.Tensor, n_local: int):
+        """Each scored pair goes to the owner of i and (if different) the owner of j, as ONE int64
+        (i << 37 | j << 11 | sim + 1000; ids < 2^26) appended by a kernel to the destination's fixed-size slot;
+        one equal-split all-to-all moves the slots."""
+        import torch.distributed as dist
         G = self.world
         if n_local * G >= (1 << 26):
             raise _lib.QrsError("pair routing packs ids into 26 bits; %d sets do not fit" % (n_local * G))
-        i, j = pairs >> 32, pairs & 0xFFFFFFFF
-        oi = torch.div(i, n_local, rounding_mode="floor")
-        oj = torch.div(j, n_local, rounding_mode="floor")
-        rec = (i << 37) | (j << 11) | (sims.to(torch.int64) + 1000)
-        cross = oj != oi
-        rec = torch.cat([rec, rec[cross]])
-        dest, order = torch.sort(torch.cat([oi, oj[cross]]), stable=True)
-        counts = torch.bincount(dest, minlength=G).cpu()
-        got = self._all_to_all_var(rec[order], counts)
-        return ((got >> 37) << 32) | ((got >> 11) & 0x3FFFFFF), ((got & 0x7FF) - 1000).to(torch.int32)
-
-    def _fetch_remote_rows(self, rowptr, colidx, val, idx, cnt, n_local: int, row_base: int, lens_all=None):
-        """Request/response exchange of the ratings rows this rank's neighbour tables point at on other ranks.
-        Returns the extended CSR (local rows first, fetched rows after, in ascending global id) and the
-        neighbour table re-indexed into it.  lens_all: row lengths of ALL ranks' rows (gathered in the
-        background at the start of the step), so the requester sizes its receive buffers without a round trip."""
-        import torch.distributed as dist
-        G = self.world
-        dev = idx.device
-        k = idx.shape[1]
-        live = torch.arange(k, device=dev)[None, :] < cnt[:, None]
-        ids = idx.to(torch.int64)
-        is_remote = live & ((ids < row_base) | (ids >= row_base + n_local))
-        need = torch.unique(ids[is_remote])                                # sorted ⇒ grouped by owner
-        owner = torch.div(need, n_local, rounding_mode="floor")
-        # one all-gather of the G x G request-count matrix tells every rank who asks whom for how many rows
-        mine = torch.bincount(owner, minlength=G)
-        counts = torch.empty(G * G, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(counts, mine, group=self.group)
-        counts = counts.view(G, G).cpu()
-        if int(counts.sum().item()) == 0:                                  # every neighbour of every rank is local
-            new_idx = torch.where(live, ids - row_base, torch.full_like(ids, -1)).to(torch.int32)
-            return rowptr, colidx, val, new_idx.contiguous()
-        need_counts = counts[self.rank].tolist()                           # rows I ask of each owner
-        req_counts = counts[:, self.rank].tolist()                         # rows each rank asks of me
-        req = self._all_to_all_var(need, need_counts, recv_counts=req_counts)
-        # serve the requests: the rows packed by a gather kernel; both sides know every row length
-        r = req - row_base
-        lens = rowptr[r + 1] - rowptr[r]
-        csum = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(lens, 0)])
-        lens_got = lens_all[need] if lens_all is not None else \
-            self._all_to_all_var(lens.contiguous(), req_counts, recv_counts=need_counts)
-        gsum = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(lens_got, 0)])
-        rends = torch.cumsum(torch.tensor(req_counts, dtype=torch.int64, device=dev), 0)
-        nends = torch.cumsum(torch.tensor(need_counts, dtype=torch.int64, device=dev), 0)
-        splits = torch.cat([csum[rends], gsum[nends]]).cpu()               # ONE readback for both split tables
-        ent_send = torch.diff(splits[:G], prepend=torch.zeros(1, dtype=torch.int64)).tolist()
-        ent_recv = torch.diff(splits[G:], prepend=torch.zeros(1, dtype=torch.int64)).tolist()
-        tot = int(sum(ent_send))
-        col_send, val_send = self.st.gather_rows(rowptr, colidx, val, r.contiguous(), csum, tot)
-        if self.m <= 65536:      # column ids fit 16 bits: ship them as such (3 instead of 5 bytes per entry)
-            got = self._all_to_all_var(col_send.to(torch.int16).contiguous().view(torch.uint8),
-                                       [2 * x for x in ent_send], recv_counts=[2 * x for x in ent_recv])
-            col_got = got.view(torch.int16).to(torch.int32) & 0xFFFF
-        else:
-            col_got = self._all_to_all_var(col_send.contiguous(), ent_send, recv_counts=ent_recv)
-        val_got = self._all_to_all_var(val_send.contiguous(), ent_send, recv_counts=ent_recv)
-        # extended CSR and re-indexed table
-        rp = torch.cat([rowptr, rowptr[-1] + torch.cumsum(lens_got, 0)])
-        col_all = torch.cat([colidx, col_got])
-        val_all = torch.cat([val, val_got])
-        local_ix = ids - row_base
-        remote_ix = n_local + torch.searchsorted(need, ids.clamp(min=0))
-        new_idx = torch.where(is_remote, remote_ix, local_ix)
-        new_idx = torch.where(live, new_idx, torch.full_like(new_idx, -1)).to(torch.int32)
-        return rp, col_all, val_all, new_idx.contiguous()
+        cap = self._cap.get("route")
+        if not cap:
+            # first step of a shape: no slot size learnt yet.  A pair sends at most one word to a destination, so the
+            # largest pair buffer of any rank bounds every slot; the size must be the same on all ranks (equal splits)
+            t = torch.tensor([pairs.numel()], dtype=torch.int64, device=pairs.device)
+            self._all_reduce_max(t)
+            cap = int(t.item())
+        words, counts, over = self.st.route_pairs(pairs, sims, counter, n_local, G, cap)
+        recv = torch.empty_like(words)
+        dist.all_to_all_single(recv, words, group=self.group)
+        p, s = self.st.unpack_routed(recv)
+        return p, s, counts, over, words.numel() * 8 * (G - 1) // G
 
 
 class HostRunner:
@@ -480,6 +520,7 @@ class HostRunner:
         self.h2d_bytes += val_h.numel() * val_h.element_size()
         dev_in.append(d_val)
         res = {"chunks": []}
+        shipped = {}
 
         def sink(ci, chunk):
             ready = torch.cuda.Event()
@@ -490,7 +531,7 @@ class HostRunner:
                 self.copy_stream.wait_event(ready)
                 for key in ("row_start", "row_cnt", "cols", "preds"):
                     self._ship("c%d_%s" % (ci, key), chunk[key], host_chunk, key)
-            res["chunks"].append(host_chunk)
+            shipped[ci] = host_chunk          # a chunk that had to be re-run replaces its first shipment
 
         out = self.pipe.run(*dev_in, predict=True, chunk_sink=sink, val_ready=val_ready)
         ready = torch.cuda.Event()
@@ -501,6 +542,7 @@ class HostRunner:
                 self._ship(name, getattr(out, name), res)
         self.copy_stream.synchronize()
         compute.synchronize()
+        res["chunks"] = [shipped[ci] for ci in sorted(shipped)]
         res["n_predictions"] = out.n_predictions
         res["covered_cells"] = out.covered_cells
         if self.cols_format == "auto" and self.pipe.cols_mode != 2:

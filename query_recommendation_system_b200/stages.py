@@ -137,13 +137,18 @@ def pair_slots(records: torch.Tensor) -> torch.Tensor:
 
 
 def pairs_score(records: torch.Tensor, slot_off: torch.Tensor, sig: torch.Tensor, norm2: Optional[torch.Tensor],
-                b: int, capacity: int, sig_id_base: int = 0, want_sims: bool = True):
+                b: int, capacity: int, sig_id_base: int = 0, want_sims: bool = True, fill_sentinel: bool = False):
     """LSH.get_candidates (lsh.py:40-54) + rounded cosine (recommender.py:203-204).
-    Returns (pairs int64[capacity], sim_milli int32[capacity] | None, counter int64[1] on device)."""
+    Returns (pairs int64[capacity], sim_milli int32[capacity] | None, counter int64[1] on device).
+    fill_sentinel: entries beyond the pairs found are all-ones (a pair no table owns: topk_tables skips them), so
+    the whole buffer can be handed on without reading the counter back."""
     _need_cuda(records, slot_off, sig, norm2)
     dev = records.device
     K = sig.shape[1]
-    pairs = torch.empty(max(capacity, 1), dtype=torch.int64, device=dev)
+    if fill_sentinel:
+        pairs = torch.full((max(capacity, 1),), -1, dtype=torch.int64, device=dev)
+    else:
+        pairs = torch.empty(max(capacity, 1), dtype=torch.int64, device=dev)
     sims = torch.empty(max(capacity, 1), dtype=torch.int32, device=dev) if want_sims else None
     counter = torch.zeros(1, dtype=torch.int64, device=dev)
     check(_lib.load().qrs_pairs_score(ptr(records), records.numel(), ptr(slot_off), ptr(sig), ptr(norm2), sig_id_base,
@@ -252,11 +257,55 @@ def choose_predict_tile(Q: int, avg_len: float = 0.0, integer_tables: bool = Tru
     return int(min(max_tile, max(32, math.ceil(math.ceil(Q / nt) / 32.0) * 32)))
 
 
+class PeerWorkspace:
+    """A device buffer every rank of the process group maps (CUDA IPC): this rank's prepared rating rows live in
+    it and the predictors of the other ranks read neighbour rows from it in place over NVLink.  Collective:
+    every rank constructs it at the same point.  ptrs[r] = rank r's buffer as mapped here."""
+
+    def __init__(self, nbytes: int, group=None):
+        import ctypes
+        import torch.distributed as dist
+        lib = _lib.load()
+        self.nbytes = int(nbytes)
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        p = ctypes.c_void_p()
+        check(lib.qrs_peer_alloc(self.nbytes, ctypes.byref(p)), "qrs_peer_alloc")
+        self.local = int(p.value)
+        handle = (ctypes.c_ubyte * 64)()
+        check(lib.qrs_peer_export(self.local, handle), "qrs_peer_export")
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        self.ptrs = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                self.ptrs.append(self.local)
+                continue
+            q = ctypes.c_void_p()
+            buf = (ctypes.c_ubyte * 64).from_buffer_copy(h)
+            check(lib.qrs_peer_open(buf, ctypes.byref(q)), "qrs_peer_open")
+            self.ptrs.append(int(q.value))
+        self.table = (ctypes.c_uint64 * self.world)(*self.ptrs)       # host array handed to qrs_predict_sparse
+
+    def close(self):
+        lib = _lib.load()
+        for r, q in enumerate(self.ptrs):
+            if r != self.rank and q:
+                lib.qrs_peer_close(q)
+        if self.local:
+            lib.qrs_peer_free(self.local)
+        self.ptrs, self.local = [], 0
+
+
+def predict_workspace_bytes(U: int, nnz: int, Q: int, tile: int, capacity: int) -> int:
+    return int(_lib.load().qrs_predict_sparse_workspace_bytes(U, nnz, Q, tile, capacity))
+
+
 class PredictPlan:
     """The row preparation of one ratings CSR for one window width (qrs_predict_prepare): build once, predict any
-    number of user ranges from it."""
+    number of user ranges from it.  peers: a PeerWorkspace — the preparation is written into this rank's peer
+    buffer and predictions may name neighbour rows of any rank by their GLOBAL id (rank * U + row)."""
 
-    def __init__(self, rowptr, colidx, val, Q: int, tile: int, capacity_hint: int = 0):
+    def __init__(self, rowptr, colidx, val, Q: int, tile: int, capacity_hint: int = 0, peers: Optional[PeerWorkspace] = None):
         _need_cuda(rowptr, colidx, val)
         if colidx.numel() >= 2 ** 36:
             raise _lib.QrsError("qrs_predict_prepare: nnz < 2^36 per GPU")
@@ -264,9 +313,18 @@ class PredictPlan:
         self.rowptr, self.colidx, self.val = rowptr, colidx, val
         self.U, self.nnz, self.Q, self.tile = rowptr.numel() - 1, colidx.numel(), int(Q), int(tile)
         self.capacity = int(capacity_hint)
-        self.ws = _ws(lib.qrs_predict_sparse_workspace_bytes(self.U, self.nnz, self.Q, self.tile, self.capacity), rowptr.device)
+        self.peers = peers
+        need = predict_workspace_bytes(self.U, self.nnz, self.Q, self.tile, self.capacity)
+        if peers is not None:
+            if need > peers.nbytes:
+                raise _lib.QrsError("the peer buffer (%d bytes) is too small for this shard's preparation (%d bytes): "
+                                    "build the pipeline with a larger peer_margin" % (peers.nbytes, need))
+            self.ws, self.ws_ptr, self.ws_bytes = None, peers.local, peers.nbytes
+        else:
+            self.ws = _ws(need, rowptr.device)
+            self.ws_ptr, self.ws_bytes = self.ws.data_ptr(), self.ws.numel()
         check(lib.qrs_predict_prepare(ptr(rowptr), ptr(colidx), ptr(val), self.U, self.nnz, self.Q, self.tile, self.capacity,
-                                      ptr(self.ws), self.ws.numel(), _stream()), "qrs_predict_prepare")
+                                      self.ws_ptr, self.ws_bytes, _stream()), "qrs_predict_prepare")
 
 
 def predict_sparse(rowptr, colidx, val, Q: int, u_tab: Table, user_base: int, n_users: int, tile: int,
@@ -299,13 +357,21 @@ def predict_sparse(rowptr, colidx, val, Q: int, u_tab: Table, user_base: int, n_
     assert cols.dtype == cols_dtype
     preds = out_preds if out_preds is not None else torch.empty(max(capacity, 1), dtype=torch.uint8, device=dev)
     cursor = torch.zeros(n_regions + 1, dtype=torch.int64, device=dev)   # [n_regions] = non-zero count (bitmap mode)
-    prepared = 0
-    if plan is not None and plan.tile == tile and plan.Q == Q and plan.U == U and plan.nnz == nnz and plan.capacity >= capacity:
-        ws, prepared = plan.ws, 1      # the prepared part of the workspace does not move with the capacity
+    prepared, peer_tab, n_peers, my_peer = 0, None, 1, 0
+    if plan is not None and plan.tile == tile and plan.Q == Q and plan.U == U and plan.nnz == nnz and \
+            (plan.capacity >= capacity or plan.peers is not None):
+        # the prepared part of the workspace does not move with the capacity
+        ws_keep, ws_ptr, ws_bytes, prepared = plan.ws, plan.ws_ptr, plan.ws_bytes, 1
+        if plan.peers is not None:
+            peer_tab, n_peers, my_peer = plan.peers.table, plan.peers.world, plan.peers.rank
+            if predict_workspace_bytes(U, nnz, Q, tile, capacity) > ws_bytes:
+                raise _lib.QrsError("the peer buffer is too small for %d predictions per call" % capacity)
     else:
-        ws = _ws(lib.qrs_predict_sparse_workspace_bytes(U, nnz, Q, tile, capacity), dev)
+        ws_keep = _ws(lib.qrs_predict_sparse_workspace_bytes(U, nnz, Q, tile, capacity), dev)
+        ws_ptr, ws_bytes = ws_keep.data_ptr(), ws_keep.numel()
     check(lib.qrs_predict_sparse(ptr(rowptr), ptr(colidx), ptr(val), U, nnz, Q, ptr(ui), ptr(uv), ptr(u_milli), ptr(uc),
-                                 ui.shape[1], user_base, n_users, tile, ptr(ws), ws.numel(), prepared,
+                                 ui.shape[1], user_base, n_users, tile, ws_ptr, ws_bytes, prepared,
+                                 peer_tab, n_peers, my_peer,
                                  ptr(row_start), ptr(row_cnt), ptr(cols), cols_mode, ptr(preds), capacity, n_regions,
                                  ptr(cursor), _stream()),
           "qrs_predict_sparse")
@@ -351,14 +417,42 @@ def recommend_topn(row_start, row_cnt, cols, preds, N: int):
 
 
 # ---------------------------------------------------------------------- multi-GPU plumbing
-def gather_rows(rowptr, colidx, val, rows: torch.Tensor, out_off: torch.Tensor, total: int):
-    """Pack CSR rows `rows` (local ids) into contiguous (col int32[total], val uint8[total]) send buffers."""
-    _need_cuda(rowptr, colidx, val, rows, out_off)
-    col = torch.empty(max(total, 1), dtype=torch.int32, device=rowptr.device)
-    v = torch.empty(max(total, 1), dtype=torch.uint8, device=rowptr.device)
-    check(_lib.load().qrs_gather_rows(ptr(rowptr), ptr(colidx), ptr(val), ptr(rows), rows.numel(), ptr(out_off),
-                                      ptr(col), ptr(v), _stream()), "qrs_gather_rows")
-    return col[:total], v[:total]
+def group_pad(sorted_records: torch.Tensor, lg: int, cap: int):
+    """Bucket records sorted by their top lg bits (= destination rank) -> (slots int64[2^lg * cap] padded with
+    all-ones sentinels, counts int64[2^lg], overflow int32[1]): equal-size slots for an all-to-all without host-side
+    split sizes."""
+    _need_cuda(sorted_records)
+    dev = sorted_records.device
+    G = 1 << lg
+    out = torch.empty(G * cap, dtype=torch.int64, device=dev)
+    counts = torch.zeros(G, dtype=torch.int64, device=dev)
+    overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+    check(_lib.load().qrs_group_pad(ptr(sorted_records), sorted_records.numel(), lg, cap, ptr(out), ptr(counts),
+                                    ptr(overflow), _stream()), "qrs_group_pad")
+    return out, counts, overflow
+
+
+def route_pairs(pairs: torch.Tensor, sims: torch.Tensor, counter: torch.Tensor, rows_per_rank: int, n_ranks: int, cap: int):
+    """Scored pairs (the first `counter` entries of pairs / sims) -> (slots int64[n_ranks * cap] of packed words padded
+    with sentinels, counts int64[n_ranks], overflow int32[1]); a pair goes to the owner of each of its ends."""
+    _need_cuda(pairs, sims, counter)
+    dev = pairs.device
+    out = torch.empty(n_ranks * cap, dtype=torch.int64, device=dev)
+    counts = torch.empty(n_ranks, dtype=torch.int64, device=dev)
+    overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+    check(_lib.load().qrs_route_pairs(ptr(pairs), ptr(sims), ptr(counter), pairs.numel(), rows_per_rank, n_ranks, cap,
+                                      ptr(out), ptr(counts), ptr(overflow), _stream()), "qrs_route_pairs")
+    return out, counts, overflow
+
+
+def unpack_routed(words: torch.Tensor):
+    """Received words -> (pairs int64[n], sim_milli int32[n]); sentinel words become all-ones pairs."""
+    _need_cuda(words)
+    n = words.numel()
+    pairs = torch.empty(n, dtype=torch.int64, device=words.device)
+    sims = torch.empty(n, dtype=torch.int32, device=words.device)
+    check(_lib.load().qrs_unpack_routed(ptr(words), n, ptr(pairs), ptr(sims), _stream()), "qrs_unpack_routed")
+    return pairs, sims
 
 
 # ---------------------------------------------------------------------- f-4: CSV ingest

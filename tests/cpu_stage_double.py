@@ -83,7 +83,7 @@ def pair_slots(records):
     return torch.from_numpy(off)
 
 
-def pairs_score(records, slot_off, sig, norm2, b, capacity, sig_id_base=0, want_sims=True):
+def pairs_score(records, slot_off, sig, norm2, b, capacity, sig_id_base=0, want_sims=True, fill_sentinel=False):
     rec = records.numpy().view(np.uint64)
     sg = sig.numpy().astype(np.int64)
     K = sg.shape[1]
@@ -102,10 +102,11 @@ def pairs_score(records, slot_off, sig, norm2, b, capacity, sig_id_base=0, want_
     pairs = np.array(out, np.int64).reshape(-1, 2)
     packed = (pairs[:, 0].astype(np.uint64) << np.uint64(32)) | pairs[:, 1].astype(np.uint64)
     sims = spec.cosine_milli(sg, pairs - sig_id_base) if (want_sims and pairs.size) else np.zeros(pairs.shape[0], np.int32)
-    pt = torch.zeros(max(capacity, 1), dtype=torch.int64)
+    pt = torch.full((max(capacity, 1),), -1 if fill_sentinel else 0, dtype=torch.int64)
     stt = torch.zeros(max(capacity, 1), dtype=torch.int32)
-    pt[:packed.size] = torch.from_numpy(packed.view(np.int64))
-    stt[:packed.size] = torch.from_numpy(sims.astype(np.int32))
+    w = min(packed.size, capacity)                   # like the kernel: writes beyond the capacity are dropped
+    pt[:w] = torch.from_numpy(packed.view(np.int64))[:w]
+    stt[:w] = torch.from_numpy(sims.astype(np.int32))[:w]
     return pt, stt, torch.tensor([packed.size], dtype=torch.int64)
 
 
@@ -124,6 +125,10 @@ def pair_centered_cosine(rowptr, colidx, val, cval, norm2, pairs, m, grouped=Fal
 
 def topk_tables(pairs, sims, n_pairs, row_base, n_rows, k, want_milli=False):
     p = pairs.numpy().view(np.uint64)[:n_pairs]
+    keep = p != np.uint64(2 ** 64 - 1)               # sentinel entries (empty exchange / buffer slots) are skipped
+    sims = sims[:n_pairs][torch.from_numpy(keep)]
+    p = p[keep]
+    n_pairs = p.size
     pr = np.stack([(p >> np.uint64(32)).astype(np.int64), (p & np.uint64(0xFFFFFFFF)).astype(np.int64)], 1)
     # the same pair can arrive once per owned end; the kernel counts each (row, neighbour) edge once per copy,
     # so the router must not duplicate — assert it here
@@ -141,15 +146,49 @@ def choose_predict_tile(Q, avg_len=0.0, integer_tables=True):
     return max(32, int(math.ceil(Q / 3 / 32.0)) * 32)
 
 
+def predict_workspace_bytes(U, nnz, Q, tile, capacity):
+    return 0
+
+
+class PeerWorkspace:
+    """CPU stand-in: nothing is mapped; the plan below gathers the shards with gloo instead."""
+
+    def __init__(self, nbytes, group=None):
+        import torch.distributed as dist
+        self.nbytes, self.group = nbytes, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+
+    def close(self):
+        pass
+
+
 class PredictPlan:
-    """Nothing to prepare on the CPU double."""
+    """Nothing to prepare on the CPU double.  With peers the whole matrix is gathered (test infrastructure: the
+    product reads remote rows in place through CUDA IPC mappings), so neighbour ids are GLOBAL row ids."""
 
-    def __init__(self, rowptr, colidx, val, Q, tile, capacity_hint=0):
-        self.tile, self.Q, self.capacity = tile, Q, capacity_hint
+    def __init__(self, rowptr, colidx, val, Q, tile, capacity_hint=0, peers=None):
+        self.tile, self.Q, self.capacity, self.peers = tile, Q, capacity_hint, peers
+        self.row_base = 0
+        self.csr = (rowptr, colidx, val)
+        if peers is not None:
+            import torch.distributed as dist
+            parts = [None] * peers.world
+            dist.all_gather_object(parts, (rowptr.numpy(), colidx.numpy(), val.numpy()), group=peers.group)
+            n_local = rowptr.numel() - 1
+            lens = np.concatenate([np.diff(p[0]) for p in parts])
+            rp = np.zeros(lens.size + 1, np.int64)
+            np.cumsum(lens, out=rp[1:])
+            self.csr = (torch.from_numpy(rp), torch.from_numpy(np.concatenate([p[1] for p in parts])),
+                        torch.from_numpy(np.concatenate([p[2] for p in parts])))
+            self.row_base = peers.rank * n_local
 
 
-def predict_sparse(rowptr, colidx, val, Q, u_tab, user_base, n_users, tile, capacity, u_milli=None, n_regions=1, **kw):
+def predict_sparse(rowptr, colidx, val, Q, u_tab, user_base, n_users, tile, capacity, u_milli=None, n_regions=1,
+                   plan=None, **kw):
     assert n_regions == 1
+    if plan is not None and plan.peers is not None:
+        rowptr, colidx, val = plan.csr
+        user_base = user_base + plan.row_base
     idx, v, cnt = [x.numpy() for x in u_tab]
     full_idx = np.full((user_base + n_users, idx.shape[1]), -1, np.int32)
     full_val = np.zeros((user_base + n_users, idx.shape[1]))
@@ -181,11 +220,46 @@ def predict_sparse(rowptr, colidx, val, Q, u_tab, user_base, n_users, tile, capa
             torch.tensor([pos], dtype=torch.int64))
 
 
-def gather_rows(rowptr, colidx, val, rows, out_off, total):
-    rp, ci, va = rowptr.numpy(), colidx.numpy(), val.numpy()
-    cols = [ci[rp[r]:rp[r + 1]] for r in rows.numpy()]
-    vals = [va[rp[r]:rp[r + 1]] for r in rows.numpy()]
-    c = np.concatenate(cols) if cols else np.zeros(0, np.int32)
-    v = np.concatenate(vals) if vals else np.zeros(0, np.uint8)
-    assert c.size == total
-    return torch.from_numpy(c.astype(np.int32)), torch.from_numpy(v.astype(np.uint8))
+def group_pad(sorted_records, lg, cap):
+    rec = sorted_records.numpy().view(np.uint64)
+    G = 1 << lg
+    dest = (rec >> np.uint64(64 - lg)).astype(np.int64)
+    assert (np.diff(dest) >= 0).all(), "records are not grouped by destination"
+    out = np.full(G * cap, 2 ** 64 - 1, np.uint64)
+    counts = np.bincount(dest, minlength=G).astype(np.int64)
+    start = np.concatenate([[0], np.cumsum(counts)])
+    for d in range(G):
+        w = min(cap, int(counts[d]))
+        out[d * cap:d * cap + w] = rec[start[d]:start[d] + w]
+    over = np.array([1 if (counts > cap).any() else 0], np.int32)
+    return torch.from_numpy(out.view(np.int64)), torch.from_numpy(counts), torch.from_numpy(over)
+
+
+def route_pairs(pairs, sims, counter, rows_per_rank, n_ranks, cap):
+    n = min(int(counter.item()), pairs.numel())
+    p = pairs.numpy().view(np.uint64)[:n]
+    i, j = (p >> np.uint64(32)).astype(np.int64), (p & np.uint64(0xFFFFFFFF)).astype(np.int64)
+    word = (i.astype(np.uint64) << np.uint64(37)) | (j.astype(np.uint64) << np.uint64(11)) | \
+        (sims.numpy()[:n].astype(np.int64) + 1000).astype(np.uint64)
+    oi, oj = i // rows_per_rank, j // rows_per_rank
+    out = np.full(n_ranks * cap, 2 ** 64 - 1, np.uint64)
+    counts = np.zeros(n_ranks, np.int64)
+    over = 0
+    for d in range(n_ranks):
+        sel = (oi == d) | (oj == d)
+        w = word[sel]
+        counts[d] = w.size
+        if w.size > cap:
+            over = 2
+        out[d * cap:d * cap + min(cap, w.size)] = w[:cap]
+    return torch.from_numpy(out.view(np.int64)), torch.from_numpy(counts), torch.tensor([over], dtype=torch.int32)
+
+
+def unpack_routed(words):
+    w = words.numpy().view(np.uint64)
+    sent = w == np.uint64(2 ** 64 - 1)
+    pairs = ((w >> np.uint64(37)) << np.uint64(32)) | ((w >> np.uint64(11)) & np.uint64(0x3FFFFFF))
+    pairs[sent] = np.uint64(2 ** 64 - 1)
+    sims = (w & np.uint64(0x7FF)).astype(np.int64) - 1000
+    sims[sent] = 0
+    return torch.from_numpy(pairs.view(np.int64)), torch.from_numpy(sims.astype(np.int32))

@@ -556,26 +556,6 @@ def test_pair_cosine_explicit_list(golden_synth):
     assert np.array_equal(got.cpu().numpy() / 1000.0, g["b%d_pair_sims" % b])
 
 
-def test_gather_rows_packs_requested_rows():
-    """qrs_gather_rows (multi-GPU plumbing): arbitrary local rows, incl. empty ones and repeats, into one buffer."""
-    from query_recommendation_system_b200 import stages, synth
-    rowptr, colidx, val = synth.planted_csr(700, 900, 0.04, seed=3)
-    rowptr[5 + 1:] -= (rowptr[6] - rowptr[5])                       # make row 5 empty (drop its entries logically)
-    keep = torch.ones(colidx.numel(), dtype=torch.bool)
-    rp0, _, _ = synth.planted_csr(700, 900, 0.04, seed=3)
-    keep[rp0[5]:rp0[6]] = False
-    colidx, val = colidx[keep], val[keep]
-    rows = torch.tensor([699, 5, 0, 17, 17, 350], dtype=torch.int64)
-    lens = rowptr[rows + 1] - rowptr[rows]
-    off = torch.zeros(rows.numel() + 1, dtype=torch.int64)
-    off[1:] = torch.cumsum(lens, 0)
-    col, v = stages.gather_rows(cu(rowptr.numpy()), cu(colidx.numpy()), cu(val.numpy()), cu(rows.numpy()), cu(off.numpy()),
-                                int(off[-1]))
-    ref_c = torch.cat([colidx[rowptr[r]:rowptr[r + 1]] for r in rows.tolist()])
-    ref_v = torch.cat([val[rowptr[r]:rowptr[r + 1]] for r in rows.tolist()])
-    assert torch.equal(col.cpu(), ref_c) and torch.equal(v.cpu(), ref_v)
-
-
 @pytest.mark.parametrize("integer", [False, True])
 def test_predict_sparse_wide_tables_k50(integer):
     """Neighbour tables wider than one warp (k = 50, the 10M-user config's top-k): two metadata rounds."""

@@ -32,7 +32,17 @@ def _run_pipeline(rank, world, rowptr, colidx, val, tab):
     import cpu_stage_double as double
     from query_recommendation_system_b200.pipeline import LshCfPipeline
     pipe = LshCfPipeline(m=M, K=K, b=B, k=TOPK, perm_tab=tab, device="cpu", stages=double)
-    return pipe.run(rowptr, colidx, val)
+    first = pipe.run(rowptr, colidx, val)
+    learnt = dict(pipe._cap)
+    again = pipe.run(rowptr, colidx, val)                  # second step: the capacities the first one learnt
+    pipe._cap = {key: 8 for key in learnt}                 # far too small: every buffer overflows, the step is repeated
+    forced = pipe.run(rowptr, colidx, val)
+    for other in (again, forced):
+        assert torch.equal(torch.sort(first.pairs).values, torch.sort(other.pairs).values)
+        assert torch.equal(first.nbr_idx, other.nbr_idx) and torch.equal(first.nbr_val, other.nbr_val)
+        assert first.n_predictions == other.n_predictions
+    assert pipe._cap == learnt, "the repeated step must end with the same learnt capacities"
+    return first
 
 
 def _worker(rank, world, port, out_dir):
