@@ -74,9 +74,14 @@ unsigned long long qrs_launch_count(void);
  * supplied by the host as the element-major table perm_tab[e*K + i].
  */
 
-/* Setup: order_head[i*R + r] = the element e with perm_tab[e*K + i] == r, for
- * r < R <= m — the first R entries of the reference's argsort (recommender.py:121),
- * hash-major so that 32 consecutive ranks of one hash are one 128-byte line. */
+/* Setup: the first R entries of the reference's argsort (recommender.py:121) for
+ * every hash, R a multiple of 8, R <= m.  The element e with perm_tab[e*K + i] == r
+ * (r < R) is stored chunk-major, eight ranks of one hash in one 32-byte sector:
+ *     order_head[((r / 8) * Kp + i) * 8 + r % 8],   Kp = K rounded up to 32
+ * (a lane that owns hash i reads its next 8 ranks with two 16-byte loads, a warp reads
+ * one contiguous kilobyte).  order_head holds qrs_perm_head_elems(K, R) = R * Kp
+ * int32, 16-byte aligned; the padding hashes are zero. */
+int64_t qrs_perm_head_elems(int32_t K, int32_t R);
 int qrs_perm_head_invert(const int32_t *perm_tab, int32_t m, int32_t K, int32_t R,
                          int32_t *order_head, void *stream);
 

@@ -17,7 +17,7 @@ rowptr, colidx, val = synth.planted_csr(n, m, density, seed=20260102, device=dev
 np.random.seed(7)
 tab = torch.from_numpy(np.stack([np.random.permutation(m) for _ in range(K)], axis=1).astype(np.int32)).to(dev)
 head = stages.perm_head(tab, stages.choose_head_ranks(m, colidx.numel() / n))
-res = {"config": [n, m, density, K, b], "R": int(head.shape[1]), "ms": {}}
+res = {"config": [n, m, density, K, b], "R": int(head.shape[0]) * 8, "ms": {}}
 outs = {}
 for mode, name in ((_lib.MINHASH_FIRST_TOUCH, "first_touch"), (_lib.MINHASH_TILE, "tile"), (_lib.MINHASH_AUTO, "auto")):
     try:

@@ -35,6 +35,7 @@ SIGNATURES = {
     "qrs_last_cuda_error": (C.c_char_p, []),
     "qrs_device_sm_count": (C.c_int, [C.c_int]),
     "qrs_launch_count": (C.c_ulonglong, []),
+    "qrs_perm_head_elems": (_i64, [_i32, _i32]),
     "qrs_perm_head_invert": (C.c_int, [_p, _i32, _i32, _i32, _p, _p]),
     "qrs_minhash_max_elements": (_i64, []),
     "qrs_minhash_perm": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _i32, _i32, _i32, _i64, _p, _p, _p, _i64, _i32, _p]),

@@ -7,6 +7,8 @@
 // at once; the expected number of rounds is m / (32 * |set|) + 1, i.e. ~|set|^2 / m times
 // fewer table reads than the per-nonzero gather-min ("direct") formulation, which remains
 // for short sets and as the fallback when a hash is not resolved within the R-rank head.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace qrs {
@@ -15,15 +17,25 @@ constexpr int kByteMapMaxElems = 16384;           // one byte per element up to 
 constexpr int kMaxMapBytes = 200 * 1024;          // shared-memory budget for the membership map
 constexpr int64_t kMaxElemsFirstTouch = int64_t(kMaxMapBytes) * 8;
 
+// order_head layout (chunk-major): the element of rank r of hash i sits at
+//   ((r / 8) * Kp + i) * 8 + (r % 8),   Kp = round_up(K, 32)   (hashes K..Kp-1 are zero padding)
+// so that a lane that owns hash i takes its next 8 ranks with two 16-byte loads and a warp's 32 lanes read one
+// contiguous kilobyte; 32 consecutive ranks of one hash (the per-set scan) are four 32-byte sectors.
+__host__ __device__ constexpr int head_pitch(int K) { return round_up(K, 32); }
+__device__ __forceinline__ int64_t head_at(int Kp, int i, int r) {
+  return ((int64_t(r >> 3) * Kp + i) << 3) + (r & 7);
+}
+
 __global__ void perm_head_invert_kernel(const int *__restrict__ perm_tab, int m, int K, int R,
                                         int *__restrict__ order_head) {
   const int64_t total = int64_t(m) * K;
+  const int Kp = head_pitch(K);
   for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
        t += int64_t(gridDim.x) * blockDim.x) {
     int r = perm_tab[t];
     if (r < R) {
       int e = int(t / K), i = int(t - int64_t(e) * K);
-      order_head[int64_t(i) * R + r] = e;
+      order_head[head_at(Kp, i, r)] = e << 2;
     }
   }
 }
@@ -62,6 +74,7 @@ minhash_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ colid
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = THREADS / 32;
   const int r_band = b > 0 ? K / b : 0;
+  const int Kp_head = head_pitch(K);
 
   if (map_bytes > 0) {
     for (int t = tid * 16; t < map_bytes; t += THREADS * 16)
@@ -93,7 +106,7 @@ minhash_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ colid
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             int i = min(i0 + jj + u, K - 1);
-            e[u] = __ldg(order_head + int64_t(i) * R + lane);
+            e[u] = __ldg(order_head + head_at(Kp_head, i, lane)) >> 2;
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u) bal[u] = __ballot_sync(kFull, map_test<BYTEMAP>(map, e[u]));
@@ -107,7 +120,7 @@ minhash_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ colid
             } else {
               r = -1;
               for (int r0 = 32; r0 < R; r0 += 32) {
-                int ee = __ldg(order_head + int64_t(i) * R + r0 + lane);
+                int ee = __ldg(order_head + head_at(Kp_head, i, r0 + lane)) >> 2;
                 unsigned bb = __ballot_sync(kFull, map_test<BYTEMAP>(map, ee));
                 if (bb) { r = r0 + __ffs(bb) - 1; break; }
               }
@@ -183,66 +196,80 @@ minhash_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ colid
 //
 // Shared memory holds one 32-bit word per element: bit j of word e says "element e belongs
 // to set s0 + j".  A lane owns one hash and walks its permutation in rank order; each rank
-// costs ONE word load that answers the membership question for all 32 sets, and the sets
-// that meet their first element at this rank get the rank as their signature value.  The walk
-// ends when every (set, hash) of the warp is resolved: about ln(1024) * m / |set| ranks.  Measured
-// at 100k x 10k, 5 %, K = 128: ~10 warp instructions per (set, hash) instead of ~43 (0.25 ms
-// against 0.68 ms for the per-set scan above).
+// costs ONE word load that answers the membership question for all 32 sets.  The walk
+// ends when every (set, hash) of the warp is resolved: about ln(1024) * m / |set| ranks.
 //   * the word map is built without atomics: warp w owns the sets 8w .. 8w+7, i.e. byte w of
 //     every word, and adds its sets one after the other with byte read-modify-writes;
-//   * order_head is hash-major (32 ranks of one hash = one 128-byte line), the walk wants
-//     lane = hash: every warp stages 16 ranks x 32 hashes through a padded shared tile;
-//   * a hit is recorded per bit (the set's signature value = the rank), except that a lane which
-//     meets many of its sets in one step hands them to the warp: lane j writes its own bit's rank;
+//   * order_head is chunk-major (head_at): a lane takes the next 8 ranks of its hash with two
+//     16-byte loads, three chunks ahead of their use — nothing is staged or transposed;
+//   * hits are NOT recorded one by one.  The rank at which set j is first met is kept BIT-SLICED:
+//     plane p of a lane is a 32-bit word whose bit j is bit p of that rank.  A set is met exactly
+//     once (the word is masked with `found`), so a rank is recorded by OR-ing the new bits into the
+//     planes selected by the rank's binary digits — the three low planes by position inside the
+//     unrolled 8-rank chunk (one LOP3 each: plane |= word & ~found), the high planes once per chunk
+//     with a warp-uniform mask of the chunk index.  No branch, no divergence, ~5 instructions per
+//     rank for 32 x 32 (set, hash) pairs; the planes are un-sliced once per pass, two sets per
+//     operation (bits j and j + 16 land in the two halves of one register).
 //   * short sets (len*len < m, AUTO only) are left out of the map and take the direct
 //     gather-min; a (set, hash) still open after R ranks takes direct_min_one_hash.
-//   * everything staged in shared memory is 16 bits wide (m <= 32768 bounds element ids, ranks and
-//     signature values), which is what lets four CTAs share an SM at the bench shape.
-//   dynamic smem: long long rp[40] | unsigned bm[m] | short sigt[32][Kp] | u16 xpose[NW][32][24]
+//   * the signature tile is staged 16 bits wide (m <= 32768 bounds ranks and signature values);
+//     four CTAs share an SM at the bench shape.
+//   dynamic smem: long long rp[40] | unsigned bm[m] | short sigt[32][Kp] | long long wsum[NW][32]
 constexpr int kTileSets = 32;
 constexpr int kTileThreads = 128;
 constexpr int kTileMaxElems = 32768;           // one 32-bit word per element: 128 KB at most; ids fit 15 bits
 constexpr int kTileMaxSmemBytes = 227 * 1024;
 constexpr bool kAutoUsesTile = true;   // AUTO takes the tile scan whenever the word map fits
-constexpr int kTileCoopBits = 6;       // new sets of one lane in one 8-rank step from which the warp records them
-                                       // (measured 3 / 6 / 12: 0.262 / 0.246 / 0.247 ms)
-constexpr int kTileChunk = 16;         // ranks staged per round
-constexpr int kTilePitch = 24;         // u16 per staged hash row: 48-byte rows keep the 16-byte reads conflict-free
 
-__device__ __forceinline__ unsigned bfind(unsigned x) {   // index of the most significant set bit
-  unsigned r;
-  asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
-  return r;
-}
-__device__ __forceinline__ void st_shared_s16(unsigned addr, int v) {
-  asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(short(v)) : "memory");
+__device__ __forceinline__ void st_shared_b16(unsigned addr, unsigned v) {
+  asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"((unsigned short)(v)) : "memory");
 }
 __device__ __forceinline__ void prefetch_l2(const void *p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+__device__ __forceinline__ unsigned ld_map(unsigned addr) {
+  unsigned v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+// plane | (word & ~found) in one LOP3
+__device__ __forceinline__ unsigned or_andn(unsigned plane, unsigned word, unsigned found) {
+  unsigned d;
+  asm("lop3.b32 %0, %1, %2, %3, 0xF4;" : "=r"(d) : "r"(plane), "r"(word), "r"(found));
+  return d;
 }
 
 // signature-tile pitch in shorts: (pitch / 2) odd, so the 32 rows start in 32 different banks
 __host__ __device__ constexpr int tile_sig_stride(int K) { return round_up(K, 32) + 2; }
 
-__global__ void __launch_bounds__(kTileThreads)
+// NH = number of high planes: ranks < 8 << NH
+template <int NH>
+__global__ void __launch_bounds__(kTileThreads, 4)
 minhash_tile_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ colidx, int64_t n, int m,
                     const int *__restrict__ perm_tab, const int *__restrict__ order_head, int R, int K, int b,
                     int64_t id_base, int *__restrict__ sig, long long *__restrict__ norm2,
                     uint64_t *__restrict__ records, int64_t rec_stride, int mode, int map_words) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NW = kTileThreads / 32;
+  constexpr int NP = 3 + NH;
   static_assert(NW * 8 == kTileSets, "warp w owns byte w of every map word");
+  static_assert(NP <= 16, "two un-sliced ranks share one register");
+  static_assert(NH >= 3, "the three lowest chunk digits are static");
   const int Kp = tile_sig_stride(K);
   long long *rp = reinterpret_cast<long long *>(smem_raw);
   unsigned *bm = reinterpret_cast<unsigned *>(rp + 40);   // 16-byte aligned: map_words % 4 == 0
   short *sigt = reinterpret_cast<short *>(bm + map_words);
-  unsigned short *xpose = reinterpret_cast<unsigned short *>(sigt + kTileSets * Kp);   // Kp % 8 == 2: see tile_smem_bytes
+  long long *wsum = reinterpret_cast<long long *>(sigt + kTileSets * Kp);   // 64 * Kp bytes: 8-byte aligned
   unsigned char *bmb = reinterpret_cast<unsigned char *>(bm);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int r_band = b > 0 ? K / b : 0;
   const int64_t tiles = ceil_div<int64_t>(n, kTileSets);
-  unsigned short *xp = xpose + warp * (32 * kTilePitch);
+  const int nchunks = R >> 3;
+  const size_t chunk_stride = size_t(head_pitch(K)) << 1;          // int4 units per 8-rank chunk
+  const unsigned sigt_s = unsigned(__cvta_generic_to_shared(sigt));
+  const unsigned bm_s = unsigned(__cvta_generic_to_shared(bm));
+  const unsigned Kp2 = unsigned(Kp) * 2u;
 
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int64_t s0 = tile * kTileSets;
@@ -323,78 +350,86 @@ minhash_tile_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ 
       for (int64_t off = int64_t(tid) * 128; off < (e - a) * 4; off += kTileThreads * 128) prefetch_l2(base + off);
     }
 
-    // ---- walk: lane = hash, 16 ranks staged per round
+    // ---- walk: lane = hash
     for (int i0 = warp * 32; i0 < K; i0 += NW * 32) {
-      const int i = i0 + lane;
+      const int i = i0 + lane;             // i < head_pitch(K): the padding hashes read element 0 and write nothing
       unsigned found = (i < K) ? ~scanmask : kFull;
-      // column i of the signature tile as a shared-window byte address (only lanes with i < K write)
-      const unsigned srow_s = unsigned(__cvta_generic_to_shared(sigt + i));
-      const unsigned Kp2 = unsigned(Kp) * 2u;
-      for (int r0 = 0; r0 < R; r0 += kTileChunk) {
-        if (__all_sync(kFull, found == kFull)) break;
-        // 16-byte loads: 4 lanes cover the 16 ranks of one hash, a warp load covers 8 hashes; ids packed to u16
+      unsigned P[NP];
 #pragma unroll
-        for (int s8 = 0; s8 < 32; s8 += 8) {
-          const int hh = s8 + (lane >> 2), rq4 = (lane & 3) * 4;
-          const int ih = min(i0 + hh, K - 1);
-          const int4 v = __ldg(reinterpret_cast<const int4 *>(order_head + int64_t(ih) * R + r0 + rq4));
-          *reinterpret_cast<uint2 *>(xp + hh * kTilePitch + rq4) =
-              make_uint2(unsigned(v.x) | (unsigned(v.y) << 16), unsigned(v.z) | (unsigned(v.w) << 16));
+      for (int p = 0; p < NP; ++p) P[p] = 0u;
+      const int4 *hp = reinterpret_cast<const int4 *>(order_head) + (size_t(i) << 1);
+      // four chunks in flight (R >= 32: they exist); buffer c % 4 is re-loaded with chunk c + 4 as soon as its
+      // eight word loads have been issued
+      int4 a0 = __ldg(hp), b0 = __ldg(hp + 1);
+      int4 a1 = __ldg(hp + chunk_stride), b1 = __ldg(hp + chunk_stride + 1);
+      int4 a2 = __ldg(hp + 2 * chunk_stride), b2 = __ldg(hp + 2 * chunk_stride + 1);
+      int4 a3 = __ldg(hp + 3 * chunk_stride), b3 = __ldg(hp + 3 * chunk_stride + 1);
+      // one 8-rank chunk, CC = its position inside a 64-rank group (compile time: the rank's six low digits are
+      // static); true = stop (every pair of the warp resolved, or the head is exhausted).  Table entries are
+      // byte offsets into the word map (4 * element).
+      auto chunk = [&](auto cc_tag, int c, int4 &qa, int4 &qb) -> bool {
+        constexpr int CC = decltype(cc_tag)::value;
+        if (c >= nchunks || __all_sync(kFull, found == kFull)) return true;
+        const unsigned w0 = ld_map(bm_s + unsigned(qa.x)), w1 = ld_map(bm_s + unsigned(qa.y));
+        const unsigned w2 = ld_map(bm_s + unsigned(qa.z)), w3 = ld_map(bm_s + unsigned(qa.w));
+        const unsigned w4 = ld_map(bm_s + unsigned(qb.x)), w5 = ld_map(bm_s + unsigned(qb.y));
+        const unsigned w6 = ld_map(bm_s + unsigned(qb.z)), w7 = ld_map(bm_s + unsigned(qb.w));
+        if (c + 4 < nchunks) {             // warp-uniform
+          const int4 *nx = hp + size_t(c + 4) * chunk_stride;
+          qa = __ldg(nx);
+          qb = __ldg(nx + 1);
         }
-        __syncwarp();
-        // 8 ranks per step; the second step's words are loaded before the first step's hits are recorded
-        unsigned w[8], wn[8];
-        {
-          const uint4 q = *reinterpret_cast<const uint4 *>(xp + lane * kTilePitch);
-          w[0] = bm[q.x & 0xFFFFu]; w[1] = bm[q.x >> 16]; w[2] = bm[q.y & 0xFFFFu]; w[3] = bm[q.y >> 16];
-          w[4] = bm[q.z & 0xFFFFu]; w[5] = bm[q.z >> 16]; w[6] = bm[q.w & 0xFFFFu]; w[7] = bm[q.w >> 16];
-        }
+        const unsigned before = found;
+        found |= w0;
+        P[0] = or_andn(P[0], w1, found); found |= w1;
+        P[1] = or_andn(P[1], w2, found); found |= w2;
+        P[0] = or_andn(P[0], w3, found); P[1] = or_andn(P[1], w3, found); found |= w3;
+        P[2] = or_andn(P[2], w4, found); found |= w4;
+        P[0] = or_andn(P[0], w5, found); P[2] = or_andn(P[2], w5, found); found |= w5;
+        P[1] = or_andn(P[1], w6, found); P[2] = or_andn(P[2], w6, found); found |= w6;
+        P[0] = or_andn(P[0], w7, found); P[1] = or_andn(P[1], w7, found); P[2] = or_andn(P[2], w7, found);
+        found |= w7;
+        if (CC & 1) P[3] = or_andn(P[3], found, before);
+        if (CC & 2) P[4] = or_andn(P[4], found, before);
+        if (CC & 4) P[5] = or_andn(P[5], found, before);
+        return false;
+      };
+      for (int c8 = 0;; c8 += 8) {
+        const unsigned before8 = found;
+        const bool stop = chunk(std::integral_constant<int, 0>{}, c8, a0, b0) ||
+                          chunk(std::integral_constant<int, 1>{}, c8 + 1, a1, b1) ||
+                          chunk(std::integral_constant<int, 2>{}, c8 + 2, a2, b2) ||
+                          chunk(std::integral_constant<int, 3>{}, c8 + 3, a3, b3) ||
+                          chunk(std::integral_constant<int, 4>{}, c8 + 4, a0, b0) ||
+                          chunk(std::integral_constant<int, 5>{}, c8 + 5, a1, b1) ||
+                          chunk(std::integral_constant<int, 6>{}, c8 + 6, a2, b2) ||
+                          chunk(std::integral_constant<int, 7>{}, c8 + 7, a3, b3);
+        // digits 6.. of the ranks met in this 64-rank group: one warp-uniform mask per plane
+        const unsigned new8 = found & ~before8;
 #pragma unroll
-        for (int rq = 0; rq < kTileChunk; rq += 8) {
-          if (rq == 0) {
-            const uint4 q = *reinterpret_cast<const uint4 *>(xp + lane * kTilePitch + 8);
-            wn[0] = bm[q.x & 0xFFFFu]; wn[1] = bm[q.x >> 16]; wn[2] = bm[q.y & 0xFFFFu]; wn[3] = bm[q.y >> 16];
-            wn[4] = bm[q.z & 0xFFFFu]; wn[5] = bm[q.z >> 16]; wn[6] = bm[q.w & 0xFFFFu]; wn[7] = bm[q.w >> 16];
-          }
-          unsigned nw[8], all_new = 0;
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            nw[u] = w[u] & ~found;
-            found |= w[u];
-            all_new |= nw[u];
-          }
-          // a lane that meets many of its sets in this step (a shared element of a taste group) hands the
-          // recording to the warp: lane j looks for its own bit and writes one value, no per-bit loop
-          unsigned big = __ballot_sync(kFull, __popc(all_new) >= kTileCoopBits);
-          if (big) {
-            if ((big >> lane) & 1u) all_new = 0;
-            do {
-              const int src = __ffs(big) - 1;
-              big &= big - 1;
-              int rk = -1;
-#pragma unroll
-              for (int u = 0; u < 8; ++u)
-                if ((__shfl_sync(kFull, nw[u], src) >> lane) & 1u) rk = u;
-              if (rk >= 0) sigt[lane * Kp + i0 + src] = short(r0 + rq + rk);
-            } while (big);
-          }
-          if (__any_sync(kFull, all_new != 0)) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              unsigned x = nw[u] & all_new;
-              while (x) {
-                const unsigned j = bfind(x);
-                x ^= 1u << j;
-                st_shared_s16(srow_s + j * Kp2, r0 + rq + u);
-              }
-            }
-          }
-          if (__all_sync(kFull, found == kFull)) break;
-#pragma unroll
-          for (int u = 0; u < 8; ++u) w[u] = wn[u];
-        }
-        __syncwarp();   // xp is rewritten by the next round
+        for (int h = 3; h < NH; ++h) P[3 + h] |= new8 & (0u - ((unsigned(c8) >> h) & 1u));
+        if (stop) break;
       }
+
+      // ---- un-slice: sets j and j + 16 together (their bits of plane p go to bits p and p + 16)
+      if (i < K) {
+        const unsigned col_s = sigt_s + unsigned(i) * 2u;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const bool lo_on = (scanmask >> j) & 1u, hi_on = (scanmask >> (j + 16)) & 1u;     // warp-uniform
+          if (lo_on || hi_on) {
+            unsigned v2 = 0;
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+              const unsigned t = p >= j ? (P[p] << (p - j)) : (P[p] >> (j - p));
+              v2 |= t & (0x00010001u << p);
+            }
+            if (lo_on) st_shared_b16(col_s + unsigned(j) * Kp2, v2);
+            if (hi_on) st_shared_b16(col_s + unsigned(j + 16) * Kp2, v2 >> 16);
+          }
+        }
+      }
+      __syncwarp();
       // still open after the head: gather-min per (set, hash), the whole warp on each
       unsigned miss = ~found;
       unsigned lanes_open = __ballot_sync(kFull, miss != 0);
@@ -435,55 +470,101 @@ minhash_tile_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ 
     }
     __syncthreads();
 
-    // ---- epilogue: rows to global (+ norm2), bucket records with lane = set
-    for (int j = warp; j < nsets; j += NW) {
+    // ---- epilogue 1: the tile's rows to global — consecutive sets are one contiguous block of 32 * K ints
+    if ((K & 1) == 0) {
+      const int halfK = K >> 1;
+      for (int j = warp; j < nsets; j += NW) {
+        int2 *dst = reinterpret_cast<int2 *>(sig + (s0 + j) * K);
+        const unsigned *src = reinterpret_cast<const unsigned *>(sigt + j * Kp);     // Kp even: 4-byte aligned rows
+        for (int q = lane; q < halfK; q += 32) {
+          const unsigned x = src[q];
+          dst[q] = make_int2(int(short(x & 0xFFFFu)), int(x) >> 16);
+        }
+      }
+    } else {
+      for (int j = warp; j < nsets; j += NW)
+        for (int i = lane; i < K; i += 32) sig[(s0 + j) * K + i] = sigt[j * Kp + i];
+    }
+    // ---- epilogue 2: lane = set.  Bucket records of the warp's bands and, from the same values, its share of
+    //      the squared norm; the rows' pitch (odd number of words) keeps the 32 lanes in 32 banks
+    if (records != nullptr || norm2 != nullptr) {
       long long acc = 0;
-      for (int i = lane; i < K; i += 32) {
-        const int x = sigt[j * Kp + i];
-        sig[(s0 + j) * K + i] = x;
-        acc += (long long)x * x;
+      const short *row = sigt + lane * Kp;
+      if (lane < nsets) {
+        if (records != nullptr) {
+          for (int band = warp; band < b; band += NW) {
+            uint32_t h = band_hash_init(uint32_t(band));
+            bool all_neg = true;
+            for (int c = 0; c < r_band; ++c) {
+              const int x = row[band * r_band + c];
+              acc += (long long)x * x;
+              const uint32_t l16 = uint32_t(x) & 0xFFFFu;
+              all_neg = all_neg && (l16 == 0xFFFFu);
+              h = band_hash_step(h, l16);
+            }
+            records[int64_t(band) * rec_stride + s0 + lane] =
+                make_record(band_hash_finish(h, all_neg), uint32_t(band), uint32_t(id_base + s0 + lane));
+          }
+        } else {
+          for (int i = warp; i < K; i += NW) {
+            const int x = row[i];
+            acc += (long long)x * x;
+          }
+        }
       }
       if (norm2 != nullptr) {
-        acc = warp_sum_ll(acc);
-        if (lane == 0) norm2[s0 + j] = acc;
+        wsum[warp * 32 + lane] = acc;
+        __syncthreads();
+        if (warp == 0 && lane < nsets) {
+          long long tot = 0;
+#pragma unroll
+          for (int w = 0; w < NW; ++w) tot += wsum[w * 32 + lane];
+          norm2[s0 + lane] = tot;
+        }
       }
     }
-    if (records != nullptr) {
-      for (int idx = tid; idx < b * kTileSets; idx += kTileThreads) {
-        const int band = idx >> 5, j = idx & 31;
-        if (j < nsets)
-          records[int64_t(band) * rec_stride + s0 + j] =
-              band_record(sigt + j * Kp + band * r_band, r_band, uint32_t(band), uint32_t(id_base + s0 + j));
-      }
-    }
-    __syncthreads();   // rp / sigt / bm are rewritten by the next tile
+    __syncthreads();   // rp / sigt / bm / wsum are rewritten by the next tile
   }
 }
 
 static size_t tile_smem_bytes(int K, int map_words) {
-  // sigt: 32 * Kp shorts with Kp % 8 == 2 -> 64 * Kp bytes, a multiple of 16: xpose stays 16-byte aligned
   return 40 * 8 + size_t(map_words) * 4 + size_t(kTileSets) * tile_sig_stride(K) * 2 +
-         size_t(kTileThreads / 32) * 32 * kTilePitch * 2;
+         size_t(kTileThreads / 32) * 32 * 8;
+}
+
+template <int NH>
+static int launch_minhash_tile_nh(const int64_t *rowptr, const int *colidx, int64_t n, int m, const int *perm_tab,
+                                  const int *order_head, int R, int K, int b, int64_t id_base, int *sig,
+                                  long long *norm2, uint64_t *records, int64_t rec_stride, int mode,
+                                  cudaStream_t stream) {
+  auto kern = minhash_tile_kernel<NH>;
+  const int map_words = round_up(m, 4);
+  const size_t smem = tile_smem_bytes(K, map_words);
+  QRS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  int per_sm = 0;
+  QRS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTileThreads, smem));
+  if (per_sm < 1) return QRS_ERR_UNSUPPORTED;
+  int64_t grid = int64_t(sm_count()) * per_sm;
+  const int64_t tiles = ceil_div<int64_t>(n, kTileSets);
+  if (grid > tiles) grid = tiles;
+  kern<<<unsigned(grid), kTileThreads, smem, stream>>>(rowptr, colidx, n, m, perm_tab, order_head, R, K, b, id_base,
+                                                       sig, norm2, records, rec_stride, mode, map_words);
+  QRS_LAUNCH_CHECK();
+  return QRS_OK;
 }
 
 static int launch_minhash_tile(const int64_t *rowptr, const int *colidx, int64_t n, int m, const int *perm_tab,
                                const int *order_head, int R, int K, int b, int64_t id_base, int *sig,
                                long long *norm2, uint64_t *records, int64_t rec_stride, int mode,
                                cudaStream_t stream) {
-  const int map_words = round_up(m, 4);
-  const size_t smem = tile_smem_bytes(K, map_words);
-  QRS_CUDA(cudaFuncSetAttribute(minhash_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  int per_sm = 0;
-  QRS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, minhash_tile_kernel, kTileThreads, smem));
-  if (per_sm < 1) return QRS_ERR_UNSUPPORTED;
-  int64_t grid = int64_t(sm_count()) * per_sm;
-  const int64_t tiles = ceil_div<int64_t>(n, kTileSets);
-  if (grid > tiles) grid = tiles;
-  minhash_tile_kernel<<<unsigned(grid), kTileThreads, smem, stream>>>(rowptr, colidx, n, m, perm_tab, order_head, R,
-                                                                      K, b, id_base, sig, norm2, records, rec_stride,
-                                                                      mode, map_words);
-  QRS_LAUNCH_CHECK();
-  return QRS_OK;
+  if (R <= (8 << 6))
+    return launch_minhash_tile_nh<6>(rowptr, colidx, n, m, perm_tab, order_head, R, K, b, id_base, sig, norm2,
+                                     records, rec_stride, mode, stream);
+  if (R <= (8 << 9))
+    return launch_minhash_tile_nh<9>(rowptr, colidx, n, m, perm_tab, order_head, R, K, b, id_base, sig, norm2,
+                                     records, rec_stride, mode, stream);
+  return launch_minhash_tile_nh<12>(rowptr, colidx, n, m, perm_tab, order_head, R, K, b, id_base, sig, norm2,
+                                    records, rec_stride, mode, stream);
 }
 
 template <bool BYTEMAP, int THREADS>
@@ -513,13 +594,21 @@ extern "C" {
 
 int64_t qrs_minhash_max_elements(void) { return kMaxElemsFirstTouch; }
 
+int64_t qrs_perm_head_elems(int32_t K, int32_t R) {
+  if (K <= 0 || R <= 0) return 0;
+  return int64_t(head_pitch(K)) * R;
+}
+
 int qrs_perm_head_invert(const int32_t *perm_tab, int32_t m, int32_t K, int32_t R, int32_t *order_head,
                          void *stream) {
   if (!perm_tab || !order_head || m <= 0 || K <= 0 || R <= 0 || R > m) return QRS_ERR_INVALID_ARG;
+  if (R % 8 != 0) return QRS_ERR_INVALID_ARG;
   const int64_t total = int64_t(m) * K;
   int64_t blocks = ceil_div<int64_t>(total, 256);
   const int64_t cap = int64_t(sm_count()) * 16;
   if (blocks > cap) blocks = cap;
+  // the padding hashes K .. round_up(K, 32) - 1 read as element 0
+  QRS_CUDA(cudaMemsetAsync(order_head, 0, size_t(qrs_perm_head_elems(K, R)) * 4, as_stream(stream)));
   perm_head_invert_kernel<<<unsigned(blocks), 256, 0, as_stream(stream)>>>(perm_tab, m, K, R, order_head);
   QRS_LAUNCH_CHECK();
   return QRS_OK;

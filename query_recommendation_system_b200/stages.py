@@ -43,13 +43,16 @@ def choose_head_ranks(m: int, avg_len: float) -> int:
 
 
 def perm_head(perm_tab: torch.Tensor, R: int) -> Optional[torch.Tensor]:
-    """order_head[K, R] (recommender.py:121's argsort, first R ranks of each permutation)."""
+    """First R ranks of each permutation (recommender.py:121's argsort) in the library's chunk-major layout:
+    int32[R / 8, Kp, 8] with Kp = K rounded up to 32 (include/qrs_b200.h, qrs_perm_head_invert)."""
     _need_cuda(perm_tab)
     m, K = perm_tab.shape
     if R <= 0:
         return None
-    assert perm_tab.dtype == torch.int32
-    out = torch.empty((K, R), dtype=torch.int32, device=perm_tab.device)
+    assert perm_tab.dtype == torch.int32 and R % 8 == 0
+    lib = _lib.load()
+    Kp = lib.qrs_perm_head_elems(K, R) // R
+    out = torch.empty((R // 8, Kp, 8), dtype=torch.int32, device=perm_tab.device)
     check(_lib.load().qrs_perm_head_invert(ptr(perm_tab), m, K, R, ptr(out), _stream()), "qrs_perm_head_invert")
     return out
 
@@ -74,7 +77,7 @@ def minhash(rowptr: torch.Tensor, colidx: torch.Tensor, m: int, perm_tab: torch.
     records = None
     if b > 0:
         records = out_records if out_records is not None else torch.empty((b, n), dtype=torch.int64, device=dev)
-    R = 0 if order_head is None else order_head.shape[1]
+    R = 0 if order_head is None else order_head.shape[0] * 8
     check(_lib.load().qrs_minhash_perm(ptr(rowptr), ptr(colidx), n, m, ptr(perm_tab), ptr(order_head), R, K, b,
                                        id_base, ptr(sig), ptr(norm2), ptr(records), n, mode, _stream()),
           "qrs_minhash_perm")

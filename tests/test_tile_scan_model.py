@@ -28,10 +28,12 @@ def test_tile_scan_model_reproduces_reference_signatures_synth(name):
 
 
 @pytest.mark.parametrize("n,m,K,R,force_tile,maxlen", [(70, 300, 40, 32, True, 290), (45, 500, 64, 64, False, 80),
-                                                       (33, 200, 32, 96, True, 30), (64, 1000, 96, 32, False, 10)])
+                                                       (33, 200, 32, 96, True, 30), (64, 1000, 96, 32, False, 10),
+                                                       (40, 1200, 32, 576, True, 6)])
 def test_tile_scan_model_ragged_against_oracle(n, m, K, R, force_tile, maxlen):
     """partial tiles, K not a multiple of 32, sets longer than one 256-entry build step, a 32-rank head that most
-    hashes of the short sets exhaust (gather-min fallback), AUTO's short sets beside scanned ones"""
+    hashes of the short sets exhaust (gather-min fallback), AUTO's short sets beside scanned ones, a 576-rank head
+    walked almost to its end (chunk digits above the static ones, nine high planes)"""
     rng = np.random.default_rng(n + K)
     rows = [np.sort(rng.choice(m, size=rng.integers(0, maxlen), replace=False)).astype(np.int32) for _ in range(n)]
     rowptr = np.zeros(n + 1, np.int64)

@@ -1,24 +1,36 @@
 """Lane-level NumPy/Python model of minhash_tile_kernel (query_recommendation_system_b200/csrc/minhash.cu): the same
 shared-memory layouts, index arithmetic and step order, one Python loop iteration per lane.  Test infrastructure
-only — it exists so that the ALGORITHM of the tile scan (byte-wise word map, 16-rank staging through the padded
-16-bit tile, first-touch recording, head-exhaustion and short-set fallbacks) is pinned to the reference's golden
-signatures on the CPU, where the CUDA kernel cannot run."""
+only — it exists so that the ALGORITHM of the tile scan (byte-wise word map, chunk-major head table of byte offsets,
+bit-sliced first-touch ranks with static low digits and masked high digits, pairwise un-slicing, head-exhaustion and
+short-set fallbacks) is pinned to the reference's golden signatures on the CPU, where the CUDA kernel cannot run."""
 import numpy as np
 
-NW, TILE_SETS, CHUNK, PITCH = 4, 32, 16, 24
+NW, TILE_SETS = 4, 32
+M32 = 0xFFFFFFFF
 
 
 def _ffs(x):
     return (x & -x).bit_length()
 
 
+def head_pitch(K):
+    return (K + 31) // 32 * 32
+
+
 def order_head(tab, R):
-    """qrs_perm_head_invert: order_head[i*R + r] = the element with perm_tab[e, i] == r (r < R)."""
+    """qrs_perm_head_invert: entry ((r / 8) * Kp + i) * 8 + r % 8 = 4 * (the element with perm_tab[e, i] == r),
+    r < R; the padding hashes K..Kp-1 stay zero."""
     m, K = tab.shape
-    head = np.zeros(K * R, np.int64)
+    Kp = head_pitch(K)
+    head = np.zeros(R * Kp, np.int64)
     e_idx, i_idx = np.nonzero(tab < R)
-    head[i_idx * R + tab[e_idx, i_idx]] = e_idx
+    r = tab[e_idx, i_idx]
+    head[((r >> 3) * Kp + i_idx) * 8 + (r & 7)] = e_idx * 4
     return head
+
+
+def nh_for(R):
+    return 6 if R <= (8 << 6) else 9 if R <= (8 << 9) else 12
 
 
 def tile_scan(rowptr, colidx, m, tab, R, force_tile):
@@ -61,32 +73,56 @@ def tile_scan(rowptr, colidx, m, tab, R, force_tile):
                     jj = _ffs(todo) - 1 if todo else -1
                     t0 = 0
         bm = bmb.view(np.uint32)
+        Kh, nchunks, NH = head_pitch(K), R >> 3, nh_for(R)
+        NP = 3 + NH
         for warp in range(NW):                                      # walk: lane = hash
             for i0 in range(warp * 32, K, NW * 32):
-                found = [((~scanmask) & 0xFFFFFFFF) if i0 + l < K else 0xFFFFFFFF for l in range(32)]
-                xp = np.zeros(32 * PITCH, np.int64)
-                r0 = 0
-                while r0 < R and not all(f == 0xFFFFFFFF for f in found):
-                    for s8 in range(0, 32, 8):                      # staging: 4 lanes per hash row
-                        for lane in range(32):
-                            hh, rq4 = s8 + (lane >> 2), (lane & 3) * 4
-                            ih = min(i0 + hh, K - 1)
-                            xp[hh * PITCH + rq4:hh * PITCH + rq4 + 4] = head[ih * R + r0 + rq4:ih * R + r0 + rq4 + 4]
-                    for rq in range(0, CHUNK, 8):
-                        for lane in range(32):
-                            for u in range(8):
-                                w = int(bm[int(xp[lane * PITCH + rq + u])])
-                                nw = w & ~found[lane] & 0xFFFFFFFF
-                                found[lane] |= w
-                                while nw:
-                                    j = _ffs(nw) - 1
-                                    nw &= nw - 1
-                                    sigt[j * Kp + i0 + lane] = r0 + rq + u
-                        if all(f == 0xFFFFFFFF for f in found):
+                found = [((~scanmask) & M32) if i0 + l < K else M32 for l in range(32)]
+                P = [[0] * NP for _ in range(32)]                   # bit-sliced ranks: P[lane][plane]
+                c8, stop = 0, False
+                while not stop:
+                    before8 = list(found)
+                    for cc in range(8):
+                        c = c8 + cc
+                        if c >= nchunks or all(f == M32 for f in found):
+                            stop = True
                             break
-                    r0 += CHUNK
+                        for lane in range(32):
+                            i = i0 + lane
+                            q = head[(c * Kh + i) * 8:(c * Kh + i) * 8 + 8]      # two 16-byte loads
+                            before = found[lane]
+                            for u in range(8):
+                                w = int(bm[int(q[u]) >> 2])                          # byte offset into the word map
+                                for p in range(3):
+                                    if (u >> p) & 1:
+                                        P[lane][p] |= w & ~found[lane] & M32
+                                found[lane] |= w
+                            for p in range(3):                                        # static digits of the chunk
+                                if (cc >> p) & 1:
+                                    P[lane][3 + p] |= found[lane] & ~before & M32
+                    for lane in range(32):                                            # masked high digits
+                        new8 = found[lane] & ~before8[lane] & M32
+                        for h in range(3, NH):
+                            if (c8 >> h) & 1:
+                                P[lane][3 + h] |= new8
+                    c8 += 8
+                for lane in range(32):                              # un-slice: sets j and j + 16 together
+                    if i0 + lane >= K:
+                        continue
+                    for j in range(16):
+                        lo_on, hi_on = (scanmask >> j) & 1, (scanmask >> (j + 16)) & 1
+                        if not (lo_on or hi_on):
+                            continue
+                        v2 = 0
+                        for p in range(NP):
+                            t = (P[lane][p] << (p - j)) & M32 if p >= j else P[lane][p] >> (j - p)
+                            v2 |= t & ((0x00010001 << p) & M32)
+                        if lo_on:
+                            sigt[j * Kp + i0 + lane] = v2 & 0xFFFF
+                        if hi_on:
+                            sigt[(j + 16) * Kp + i0 + lane] = v2 >> 16
                 for src in range(32):                               # still open after the head: gather-min
-                    mm = (~found[src]) & 0xFFFFFFFF
+                    mm = (~found[src]) & M32
                     while mm:
                         j = _ffs(mm) - 1
                         mm &= mm - 1
