@@ -85,15 +85,18 @@ int64_t qrs_perm_head_elems(int32_t K, int32_t R);
 int qrs_perm_head_invert(const int32_t *perm_tab, int32_t m, int32_t K, int32_t R,
                          int32_t *order_head, void *stream);
 
-#define QRS_MINHASH_AUTO 0         /* tile scan when the word map fits shared memory (m <= 32768);
+#define QRS_MINHASH_AUTO 0         /* tile scan when a word map fits shared memory (see TILE);
                                       otherwise per set: first-touch when len*len >= m, else
                                       direct.  Sets with len*len < m always take direct.     */
 #define QRS_MINHASH_DIRECT 1       /* per-nonzero gather-min from perm_tab                */
 #define QRS_MINHASH_FIRST_TOUCH 2  /* membership-map scan in permuted order (the reference's
                                       own first-touch walk, recommender.py:125-129), one set
                                       per CTA                                             */
-#define QRS_MINHASH_TILE 3         /* the same walk for 32 consecutive sets at once: one
-                                      32-bit membership word per element, lane = hash     */
+#define QRS_MINHASH_TILE 3         /* the same walk for 32 / 16 / 8 consecutive sets at once:
+                                      one 32- / 16- / 8-bit membership word per element in
+                                      shared memory (32 sets up to m = 32768, 16 sets up to
+                                      m ~ 100k, 8 sets up to m ~ 200k), lane = hash, ranks kept
+                                      bit-sliced                                          */
 
 /* Signatures + fused epilogue.  Optional outputs (pass NULL to skip):
  *   norm2[s]   = sum_i sig[s][i]^2                       (for a8)
@@ -101,8 +104,9 @@ int qrs_perm_head_invert(const int32_t *perm_tab, int32_t m, int32_t K, int32_t 
  *                requires 0 < b <= QRS_MAX_BANDS and K % b == 0.
  * order_head/R may be NULL/0, which forces the DIRECT kernel; R must be a
  * multiple of 32.  First-touch needs m <= qrs_minhash_max_elements(), the tile
- * scan m <= 32768 and K small enough for a 32 x K signature tile in shared memory
- * (QRS_ERR_UNSUPPORTED when a forced mode does not fit). */
+ * scan a word map plus a (sets x K) signature tile in shared memory and R <= 32768
+ * (QRS_ERR_UNSUPPORTED when a forced mode does not fit).  colidx needs 4-byte
+ * alignment only and is never read beyond rowptr[n] entries. */
 int64_t qrs_minhash_max_elements(void);
 int qrs_minhash_perm(const int64_t *rowptr, const int32_t *colidx, int64_t n, int32_t m,
                      const int32_t *perm_tab, const int32_t *order_head, int32_t R,

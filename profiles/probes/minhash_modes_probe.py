@@ -12,6 +12,7 @@ sys.path.insert(0, ROOT)
 from query_recommendation_system_b200 import _lib, stages, synth  # noqa: E402
 
 n, m, density, K, b, k = synth.config_shape(os.environ.get("QRS_CONFIG", "C2"))
+n = int(os.environ.get("QRS_PROBE_N", n))
 dev = torch.device("cuda:0")
 rowptr, colidx, val = synth.planted_csr(n, m, density, seed=20260102, device=dev)
 np.random.seed(7)

@@ -43,21 +43,22 @@ int sm_count();
 
 // ---------------------------------------------------------------- bucket records
 // hash24 of one band: the r int16 lanes (low 16 bits of the signature values,
-// lsh.py:28) folded together.  Grouping is by (hash24, band); qrs_pairs_score
-// re-verifies every pair on the exact lanes, so collisions cost work, never
-// correctness.
-__host__ __device__ __forceinline__ uint32_t mix32(uint32_t h) {
-  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
-  return h;
-}
+// lsh.py:28) taken two at a time as 32-bit words (lane 2k in the low half; a trailing
+// odd lane alone) and folded with multiply / xor-shift rounds.  Grouping is by
+// (hash24, band); qrs_pairs_score re-verifies every pair on the exact lanes, so
+// collisions cost work, never correctness (measured on geometric lanes: the number of
+// distinct hashes equals the birthday bound of an ideal 24-bit hash).
 __host__ __device__ __forceinline__ uint32_t band_hash_init(uint32_t band) {
   return 0x9E3779B9u * (band + 1u);
 }
-__host__ __device__ __forceinline__ uint32_t band_hash_step(uint32_t h, uint32_t lane16) {
-  return mix32(h ^ lane16) * 0x9E3779B1u + 0x7F4A7C15u;
+__host__ __device__ __forceinline__ uint32_t band_hash_word(uint32_t h, uint32_t word) {
+  h = (h ^ word) * 0x9E3779B1u;
+  return h ^ (h >> 15);
 }
 __host__ __device__ __forceinline__ uint32_t band_hash_finish(uint32_t h, bool all_neg) {
-  h = mix32(h) >> (32 - QRS_HASH_BITS);
+  h *= 0x85EBCA6Bu;
+  h ^= h >> 16;
+  h >>= (32 - QRS_HASH_BITS);
   if (h == QRS_SENTINEL_HASH) h = QRS_SENTINEL_HASH - 1u;
   return all_neg ? QRS_SENTINEL_HASH : h;
 }
@@ -74,10 +75,15 @@ template <typename T>
 __device__ __forceinline__ uint64_t band_record(const T *lanes, int r, uint32_t band, uint32_t id) {
   uint32_t h = band_hash_init(band);
   bool all_neg = true;
-  for (int c = 0; c < r; ++c) {
-    uint32_t l16 = uint32_t(lanes[c]) & 0xFFFFu;
-    all_neg = all_neg && (l16 == 0xFFFFu);
-    h = band_hash_step(h, l16);
+  for (int c = 0; c < r; c += 2) {
+    uint32_t w = uint32_t(lanes[c]) & 0xFFFFu;
+    all_neg = all_neg && (w == 0xFFFFu);
+    if (c + 1 < r) {
+      const uint32_t hi = uint32_t(lanes[c + 1]) & 0xFFFFu;
+      all_neg = all_neg && (hi == 0xFFFFu);
+      w |= hi << 16;
+    }
+    h = band_hash_word(h, w);
   }
   return make_record(band_hash_finish(h, all_neg), band, id);
 }
@@ -87,6 +93,13 @@ __device__ __forceinline__ long long warp_sum_ll(long long v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
   return v;
+}
+// sum over the warp of values below 2^48: three REDUX.SUM on 16-bit pieces instead of ten 32-bit shuffles
+__device__ __forceinline__ unsigned long long warp_sum_u48(unsigned long long v) {
+  const unsigned a = __reduce_add_sync(kFull, unsigned(v) & 0xFFFFu);
+  const unsigned b = __reduce_add_sync(kFull, unsigned(v >> 16) & 0xFFFFu);
+  const unsigned c = __reduce_add_sync(kFull, unsigned(v >> 32) & 0xFFFFu);
+  return (unsigned long long)a + ((unsigned long long)b << 16) + ((unsigned long long)c << 32);
 }
 __device__ __forceinline__ unsigned lanemask_lt() {
   unsigned m;

@@ -7,6 +7,8 @@
 // at once; the expected number of rounds is m / (32 * |set|) + 1, i.e. ~|set|^2 / m times
 // fewer table reads than the per-nonzero gather-min ("direct") formulation, which remains
 // for short sets and as the fallback when a hash is not resolved within the R-rank head.
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "common.cuh"
@@ -192,45 +194,60 @@ minhash_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ colid
 }
 
 // ---------------------------------------------------------------------------------------------
-// Tile scan (QRS_MINHASH_TILE): the same first-touch walk for 32 consecutive sets at once.
+// Tile scan (QRS_MINHASH_TILE): the same first-touch walk for SETS consecutive sets at once.
 //
-// Shared memory holds one 32-bit word per element: bit j of word e says "element e belongs
+// Shared memory holds one SETS-bit word per element: bit j of word e says "element e belongs
 // to set s0 + j".  A lane owns one hash and walks its permutation in rank order; each rank
-// costs ONE word load that answers the membership question for all 32 sets.  The walk
-// ends when every (set, hash) of the warp is resolved: about ln(1024) * m / |set| ranks.
-//   * the word map is built without atomics: warp w owns the sets 8w .. 8w+7, i.e. byte w of
-//     every word, and adds its sets one after the other with byte read-modify-writes;
+// costs ONE word load that answers the membership question for all SETS sets.  The walk
+// ends when every (set, hash) of the warp is resolved: about ln(32 * SETS) * m / |set| ranks.
+//   * SETS = 32 (32-bit words, m <= 32768, 4 warps, 4 CTAs per SM at the bench shape), 16 (16-bit words,
+//     8 warps, one CTA per SM up to m ~ 100k) or 8 (bytes, 8 warps, up to m ~ 200k);
+//   * the word map is built without atomics: a byte of every word — 8 sets — belongs to a group of
+//     G warps (G = 1 / 4 / 8), which add those sets one after the other with byte read-modify-writes,
+//     the G warps taking alternate 256-entry steps of the row and meeting at a named barrier between sets;
 //   * order_head is chunk-major (head_at): a lane takes the next 8 ranks of its hash with two
-//     16-byte loads, three chunks ahead of their use — nothing is staged or transposed;
+//     16-byte loads, four chunks ahead of their use — nothing is staged or transposed;
 //   * hits are NOT recorded one by one.  The rank at which set j is first met is kept BIT-SLICED:
-//     plane p of a lane is a 32-bit word whose bit j is bit p of that rank.  A set is met exactly
+//     plane p of a lane is a word whose bit j is bit p of that rank.  A set is met exactly
 //     once (the word is masked with `found`), so a rank is recorded by OR-ing the new bits into the
-//     planes selected by the rank's binary digits — the three low planes by position inside the
-//     unrolled 8-rank chunk (one LOP3 each: plane |= word & ~found), the high planes once per chunk
-//     with a warp-uniform mask of the chunk index.  No branch, no divergence, ~5 instructions per
-//     rank for 32 x 32 (set, hash) pairs; the planes are un-sliced once per pass, two sets per
-//     operation (bits j and j + 16 land in the two halves of one register).
+//     planes selected by the rank's binary digits — the six low planes by position inside the
+//     unrolled 64-rank group (one LOP3 each: plane |= word & ~found), the high planes once per group
+//     with a warp-uniform mask of the group index.  No branch, no divergence, ~6 instructions per
+//     rank for 32 x SETS (set, hash) pairs; the planes are un-sliced once per pass (SETS = 32: two sets
+//     per operation, bits j and j + 16 land in the two halves of one register);
 //   * short sets (len*len < m, AUTO only) are left out of the map and take the direct
-//     gather-min; a (set, hash) still open after R ranks takes direct_min_one_hash.
-//   * the signature tile is staged 16 bits wide (m <= 32768 bounds ranks and signature values);
-//     four CTAs share an SM at the bench shape.
-//   dynamic smem: long long rp[40] | unsigned bm[m] | short sigt[32][Kp] | long long wsum[NW][32]
-constexpr int kTileSets = 32;
-constexpr int kTileThreads = 128;
-constexpr int kTileMaxElems = 32768;           // one 32-bit word per element: 128 KB at most; ids fit 15 bits
-constexpr int kTileMaxSmemBytes = 227 * 1024;
-constexpr bool kAutoUsesTile = true;   // AUTO takes the tile scan whenever the word map fits
+//     gather-min; a (set, hash) still open after R ranks takes direct_min_one_hash;
+//   * the signature tile is staged 16 bits wide when m <= 32768 (ranks and values fit), else as ints.
+//   dynamic smem: long long rp[40] | map (m words of SETS bits + a spare 16 bytes) | sig_t sigt[SETS][Kp]
+constexpr int kTileMaxElems16 = 32768;         // 16-bit signature tile (and the 32-set form) up to here
+constexpr int kTileMaxSmemBytes = 226 * 1024;
+constexpr bool kAutoUsesTile = true;   // AUTO takes the tile scan whenever a word map fits
 
 __device__ __forceinline__ void st_shared_b16(unsigned addr, unsigned v) {
   asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"((unsigned short)(v)) : "memory");
 }
+__device__ __forceinline__ void st_shared_b32(unsigned addr, unsigned v) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 __device__ __forceinline__ void prefetch_l2(const void *p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
-__device__ __forceinline__ unsigned ld_map(unsigned addr) {
+// membership word of the element whose head-table entry (4 * element) is `entry`
+template <int SETS>
+__device__ __forceinline__ unsigned ld_map(unsigned bm_s, int entry) {
   unsigned v;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  if (SETS == 32) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(bm_s + unsigned(entry)));
+  else if (SETS == 16) asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(bm_s + (unsigned(entry) >> 1)));
+  else asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(bm_s + (unsigned(entry) >> 2)));
   return v;
+}
+__device__ __forceinline__ unsigned ld_map_u8(unsigned addr) {
+  unsigned v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_map_u8(unsigned addr, unsigned v) {
+  asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 // plane | (word & ~found) in one LOP3
 __device__ __forceinline__ unsigned or_andn(unsigned plane, unsigned word, unsigned found) {
@@ -239,46 +256,56 @@ __device__ __forceinline__ unsigned or_andn(unsigned plane, unsigned word, unsig
   return d;
 }
 
-// signature-tile pitch in shorts: (pitch / 2) odd, so the 32 rows start in 32 different banks
-__host__ __device__ constexpr int tile_sig_stride(int K) { return round_up(K, 32) + 2; }
+template <int SETS>
+struct TileShape {
+  static constexpr int kWarps = SETS == 32 ? 4 : 8;
+  static constexpr int kThreads = kWarps * 32;
+  static constexpr int kGroup = kWarps / (SETS / 8);      // warps that share one byte of the map words
+  static constexpr int kWordBytes = SETS / 8;
+  static constexpr int kMinCtas = SETS == 32 ? 4 : (SETS == 16 ? 1 : 2);
+  static constexpr int kSetsPerWarp = SETS / kWarps;
+};
 
-// NH = number of high planes: ranks < 8 << NH
-template <int NH>
-__global__ void __launch_bounds__(kTileThreads, 4)
+// signature-tile pitch in elements: an odd number of 32-bit words per row, so the rows start in different banks
+__host__ __device__ constexpr int tile_sig_stride(int K, bool wide) { return round_up(K, 32) + (wide ? 1 : 2); }
+
+// NH = number of high planes: ranks < 8 << NH.  WIDE: signature values need more than 15 bits (int tile).
+template <int SETS, int NH, bool WIDE>
+__global__ void __launch_bounds__(TileShape<SETS>::kThreads, TileShape<SETS>::kMinCtas)
 minhash_tile_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ colidx, int64_t n, int m,
                     const int *__restrict__ perm_tab, const int *__restrict__ order_head, int R, int K, int b,
                     int64_t id_base, int *__restrict__ sig, long long *__restrict__ norm2,
-                    uint64_t *__restrict__ records, int64_t rec_stride, int mode, int map_words) {
+                    uint64_t *__restrict__ records, int64_t rec_stride, int mode, int map_bytes) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int NW = kTileThreads / 32;
+  using Shape = TileShape<SETS>;
+  using sig_t = typename std::conditional<WIDE, int, short>::type;
+  constexpr int NW = Shape::kWarps, G = Shape::kGroup, WB = Shape::kWordBytes, SPW = Shape::kSetsPerWarp;
   constexpr int NP = 3 + NH;
-  static_assert(NW * 8 == kTileSets, "warp w owns byte w of every map word");
   static_assert(NP <= 16, "two un-sliced ranks share one register");
   static_assert(NH >= 3, "the three lowest chunk digits are static");
-  const int Kp = tile_sig_stride(K);
+  static_assert(SETS == 32 || WIDE, "the narrower maps exist for element counts beyond the 16-bit tile");
+  const int Kp = tile_sig_stride(K, WIDE);
   long long *rp = reinterpret_cast<long long *>(smem_raw);
-  unsigned *bm = reinterpret_cast<unsigned *>(rp + 40);   // 16-byte aligned: map_words % 4 == 0
-  short *sigt = reinterpret_cast<short *>(bm + map_words);
-  long long *wsum = reinterpret_cast<long long *>(sigt + kTileSets * Kp);   // 64 * Kp bytes: 8-byte aligned
-  unsigned char *bmb = reinterpret_cast<unsigned char *>(bm);
+  unsigned char *bmb = reinterpret_cast<unsigned char *>(rp + 40);        // 16-byte aligned
+  sig_t *sigt = reinterpret_cast<sig_t *>(bmb + map_bytes + 16);          // map_bytes % 16 == 0; the spare word
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int r_band = b > 0 ? K / b : 0;
-  const int64_t tiles = ceil_div<int64_t>(n, kTileSets);
+  const int64_t tiles = ceil_div<int64_t>(n, SETS);
   const int nchunks = R >> 3;
   const size_t chunk_stride = size_t(head_pitch(K)) << 1;          // int4 units per 8-rank chunk
   const unsigned sigt_s = unsigned(__cvta_generic_to_shared(sigt));
-  const unsigned bm_s = unsigned(__cvta_generic_to_shared(bm));
-  const unsigned Kp2 = unsigned(Kp) * 2u;
+  const unsigned bm_s = unsigned(__cvta_generic_to_shared(bmb));
+  const unsigned row_bytes = unsigned(Kp) * unsigned(sizeof(sig_t));
 
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const int64_t s0 = tile * kTileSets;
-    const int nsets = int(min(int64_t(kTileSets), n - s0));
+    const int64_t s0 = tile * SETS;
+    const int nsets = int(min(int64_t(SETS), n - s0));
 
     // ---- stage the row bounds, clear the map
-    if (tid <= kTileSets) rp[tid] = rowptr[s0 + min(tid, nsets)];
-    for (int t = tid * 4; t < map_words; t += kTileThreads * 4)
-      *reinterpret_cast<uint4 *>(bm + t) = make_uint4(0, 0, 0, 0);
+    if (tid <= SETS) rp[tid] = rowptr[s0 + min(tid, nsets)];
+    for (int t = tid * 16; t < map_bytes; t += Shape::kThreads * 16)
+      *reinterpret_cast<uint4 *>(bmb + t) = make_uint4(0, 0, 0, 0);
     __syncthreads();
 
     // scanmask: sets that take part in the walk; the others are empty (-1 row), absent, or short
@@ -293,61 +320,78 @@ minhash_tile_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ 
     }
 
     // ---- empty sets: a row of -1
-    for (int jj = 0; jj < 8; ++jj) {
-      const int j = warp * 8 + jj;
+    for (int jj = 0; jj < SPW; ++jj) {
+      const int j = warp * SPW + jj;
       if (j < nsets && rp[j + 1] == rp[j])
-        for (int i = lane; i < K; i += 32) sigt[j * Kp + i] = -1;
+        for (int i = lane; i < K; i += 32) sigt[j * Kp + i] = sig_t(-1);
     }
 
-    // ---- build: warp w adds its (up to) 8 sets to byte w of the words, one set after the other, 256 entries
-    //      per step; the NEXT step's column indices are loaded before this step's bytes are updated
+    // ---- build: byte `bidx` of the words (sets 8 * bidx ..) belongs to G warps, which add those sets one after
+    //      the other, warp g of the group taking the 256-entry steps g, g + G, ... of a row; the NEXT step's
+    //      column indices are loaded before this step's bytes are updated.  Entries past the end of a row point
+    //      at a spare word behind the map, so the read-modify-writes carry no predicate, and a step that lies
+    //      inside its row loads without bounds checks.  Every warp of a group takes at least one (possibly empty)
+    //      step per set and the group meets at a barrier before the next set.
     {
-      unsigned todo = (scanmask >> (warp * 8)) & 0xFFu;
+      const int bidx = warp / G, g = warp % G;
+      unsigned todo = (scanmask >> (bidx * 8)) & 0xFFu;
       int jj = todo ? __ffs(todo) - 1 : -1;
-      int t0 = 0;
+      int t0 = g * 256;
       int e[8];
+      const int spare = map_bytes / WB;
       auto load8 = [&](int (&dst)[8], int set, int first) {
-        const int64_t lo = rp[warp * 8 + set];
-        const int len = int(rp[warp * 8 + set + 1] - lo);
+        const int64_t lo = rp[bidx * 8 + set];
+        const int len = int(rp[bidx * 8 + set + 1] - lo);
+        const int *src = colidx + lo + first + lane;
+        if (first + 256 <= len) {          // warp-uniform
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int t = first + lane + 32 * u;
-          dst[u] = t < len ? ld_stream_s32(colidx + lo + t) : -1;
+          for (int u = 0; u < 8; ++u) dst[u] = ld_stream_s32(src + 32 * u);
+        } else {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) dst[u] = first + lane + 32 * u < len ? ld_stream_s32(src + 32 * u) : spare;
         }
       };
-      if (jj >= 0) load8(e, jj, 0);
-      while (jj >= 0) {
-        const int len = int(rp[warp * 8 + jj + 1] - rp[warp * 8 + jj]);
-        int njj = jj, nt0 = t0 + 256;
+      // one step: the entries in `cur` (set jj, from t0) go into the map while the next step's are loaded into
+      // `nxt`; the two register sets swap roles from step to step (no copies); false when the warp is done
+      const unsigned bmw_s = bm_s + unsigned(bidx);
+      auto step = [&](int (&cur)[8], int (&nxt)[8]) -> bool {
+        const int len = int(rp[bidx * 8 + jj + 1] - rp[bidx * 8 + jj]);
+        int njj = jj, nt0 = t0 + G * 256;
         if (nt0 >= len) {
           todo &= todo - 1;
           njj = todo ? __ffs(todo) - 1 : -1;
-          nt0 = 0;
+          nt0 = g * 256;
         }
-        int en[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
-        if (njj >= 0) load8(en, njj, nt0);
-        const unsigned char bit = (unsigned char)(1u << jj);
+        if (njj >= 0) load8(nxt, njj, nt0);
+        const unsigned bit = 1u << jj;
+        unsigned old[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
-          if (e[u] >= 0) {                 // distinct elements of one row: no two lanes share a byte
-            unsigned char *p = bmb + e[u] * 4 + warp;
-            *p = *p | bit;
-          }
-        if (njj != jj) __syncwarp();       // the next set may touch the bytes other lanes just wrote
-#pragma unroll
-        for (int u = 0; u < 8; ++u) e[u] = en[u];
+        for (int u = 0; u < 8; ++u) old[u] = ld_map_u8(bmw_s + unsigned(WB) * unsigned(cur[u]));   // distinct elements
+#pragma unroll                                                       // of one row: no two lanes share a byte (but the spare)
+        for (int u = 0; u < 8; ++u) st_map_u8(bmw_s + unsigned(WB) * unsigned(cur[u]), old[u] | bit);
+        if (njj != jj) {                   // the next set may touch the bytes other lanes / warps just wrote
+          if (G == 1) __syncwarp();
+          else asm volatile("bar.sync %0, %1;" ::"r"(1 + bidx), "n"(G * 32) : "memory");
+        }
         jj = njj;
         t0 = nt0;
+        return jj >= 0;
+      };
+      if (jj >= 0) {
+        int en[8];
+        load8(e, jj, t0);
+        while (step(e, en) && step(en, e)) {
+        }
       }
     }
     __syncthreads();
 
     // the next tile's column indices (one contiguous CSR span, read once) on their way into L2
     if (tile + gridDim.x < tiles) {
-      const int64_t sn = (tile + gridDim.x) * kTileSets;
-      const int64_t a = rowptr[sn], e = rowptr[min(sn + kTileSets, n)];
+      const int64_t sn = (tile + gridDim.x) * SETS;
+      const int64_t a = rowptr[sn], e = rowptr[min(sn + SETS, n)];
       const char *base = reinterpret_cast<const char *>(colidx + a);
-      for (int64_t off = int64_t(tid) * 128; off < (e - a) * 4; off += kTileThreads * 128) prefetch_l2(base + off);
+      for (int64_t off = int64_t(tid) * 128; off < (e - a) * 4; off += Shape::kThreads * 128) prefetch_l2(base + off);
     }
 
     // ---- walk: lane = hash
@@ -364,21 +408,22 @@ minhash_tile_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ 
       int4 a1 = __ldg(hp + chunk_stride), b1 = __ldg(hp + chunk_stride + 1);
       int4 a2 = __ldg(hp + 2 * chunk_stride), b2 = __ldg(hp + 2 * chunk_stride + 1);
       int4 a3 = __ldg(hp + 3 * chunk_stride), b3 = __ldg(hp + 3 * chunk_stride + 1);
+      const int4 *nx = hp + 4 * chunk_stride;                    // the chunk the next re-load takes
       // one 8-rank chunk, CC = its position inside a 64-rank group (compile time: the rank's six low digits are
       // static); true = stop (every pair of the warp resolved, or the head is exhausted).  Table entries are
-      // byte offsets into the word map (4 * element).
+      // byte offsets into a 32-bit word map (4 * element).
       auto chunk = [&](auto cc_tag, int c, int4 &qa, int4 &qb) -> bool {
         constexpr int CC = decltype(cc_tag)::value;
         if (c >= nchunks || __all_sync(kFull, found == kFull)) return true;
-        const unsigned w0 = ld_map(bm_s + unsigned(qa.x)), w1 = ld_map(bm_s + unsigned(qa.y));
-        const unsigned w2 = ld_map(bm_s + unsigned(qa.z)), w3 = ld_map(bm_s + unsigned(qa.w));
-        const unsigned w4 = ld_map(bm_s + unsigned(qb.x)), w5 = ld_map(bm_s + unsigned(qb.y));
-        const unsigned w6 = ld_map(bm_s + unsigned(qb.z)), w7 = ld_map(bm_s + unsigned(qb.w));
+        const unsigned w0 = ld_map<SETS>(bm_s, qa.x), w1 = ld_map<SETS>(bm_s, qa.y);
+        const unsigned w2 = ld_map<SETS>(bm_s, qa.z), w3 = ld_map<SETS>(bm_s, qa.w);
+        const unsigned w4 = ld_map<SETS>(bm_s, qb.x), w5 = ld_map<SETS>(bm_s, qb.y);
+        const unsigned w6 = ld_map<SETS>(bm_s, qb.z), w7 = ld_map<SETS>(bm_s, qb.w);
         if (c + 4 < nchunks) {             // warp-uniform
-          const int4 *nx = hp + size_t(c + 4) * chunk_stride;
           qa = __ldg(nx);
           qb = __ldg(nx + 1);
         }
+        nx += chunk_stride;
         const unsigned before = found;
         found |= w0;
         P[0] = or_andn(P[0], w1, found); found |= w1;
@@ -411,21 +456,38 @@ minhash_tile_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ 
         if (stop) break;
       }
 
-      // ---- un-slice: sets j and j + 16 together (their bits of plane p go to bits p and p + 16)
+      // ---- un-slice
       if (i < K) {
-        const unsigned col_s = sigt_s + unsigned(i) * 2u;
+        const unsigned col_s = sigt_s + unsigned(i) * unsigned(sizeof(sig_t));
+        if (SETS == 32 && !WIDE) {
+          // sets j and j + 16 together: their bits of plane p go to bits p and p + 16
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const bool lo_on = (scanmask >> j) & 1u, hi_on = (scanmask >> (j + 16)) & 1u;     // warp-uniform
-          if (lo_on || hi_on) {
-            unsigned v2 = 0;
+          for (int j = 0; j < 16; ++j) {
+            const bool lo_on = (scanmask >> j) & 1u, hi_on = (scanmask >> (j + 16)) & 1u;     // warp-uniform
+            if (lo_on || hi_on) {
+              unsigned v2 = 0;
 #pragma unroll
-            for (int p = 0; p < NP; ++p) {
-              const unsigned t = p >= j ? (P[p] << (p - j)) : (P[p] >> (j - p));
-              v2 |= t & (0x00010001u << p);
+              for (int p = 0; p < NP; ++p) {
+                const unsigned t = p >= j ? (P[p] << (p - j)) : (P[p] >> (j - p));
+                v2 |= t & (0x00010001u << p);
+              }
+              if (lo_on) st_shared_b16(col_s + unsigned(j) * row_bytes, v2);
+              if (hi_on) st_shared_b16(col_s + unsigned(j + 16) * row_bytes, v2 >> 16);
             }
-            if (lo_on) st_shared_b16(col_s + unsigned(j) * Kp2, v2);
-            if (hi_on) st_shared_b16(col_s + unsigned(j + 16) * Kp2, v2 >> 16);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < SETS; ++j) {
+            if ((scanmask >> j) & 1u) {                                                        // warp-uniform
+              unsigned v = 0;
+#pragma unroll
+              for (int p = 0; p < NP; ++p) {
+                const unsigned t = p >= j ? (P[p] << (p - j)) : (P[p] >> (j - p));
+                v |= t & (1u << p);
+              }
+              if (WIDE) st_shared_b32(col_s + unsigned(j) * row_bytes, v);
+              else st_shared_b16(col_s + unsigned(j) * row_bytes, v);
+            }
           }
         }
       }
@@ -442,14 +504,14 @@ minhash_tile_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ 
           mm &= mm - 1;
           const int64_t lo = rp[j];
           const int v = direct_min_one_hash(colidx, lo, int(rp[j + 1] - lo), perm_tab, K, i0 + src, lane);
-          if (lane == 0) sigt[j * Kp + i0 + src] = short(v);
+          if (lane == 0) sigt[j * Kp + i0 + src] = sig_t(v);
         }
       }
     }
 
     // ---- short sets (AUTO): direct gather-min, lane owns a hash, elements broadcast 32 at a time
-    for (int jj = 0; jj < 8; ++jj) {
-      const int j = warp * 8 + jj;
+    for (int jj = 0; jj < SPW; ++jj) {
+      const int j = warp * SPW + jj;
       if (j >= nsets) break;
       const int64_t lo = rp[j];
       const int len = int(rp[j + 1] - lo);
@@ -465,106 +527,134 @@ minhash_tile_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ 
             v = min(v, __ldg(perm_tab + int64_t(e0) * K + i));
           }
         }
-        if (i0 + lane < K) sigt[j * Kp + i0 + lane] = short(v);
+        if (i0 + lane < K) sigt[j * Kp + i0 + lane] = sig_t(v);
       }
     }
     __syncthreads();
 
-    // ---- epilogue 1: the tile's rows to global — consecutive sets are one contiguous block of 32 * K ints
-    if ((K & 1) == 0) {
-      const int halfK = K >> 1;
-      for (int j = warp; j < nsets; j += NW) {
+    // ---- epilogue 1: the tile's rows to global (consecutive sets are one contiguous block of SETS * K ints) and
+    //      their squared norms
+    for (int j = warp; j < nsets; j += NW) {
+      unsigned long long acc = 0;
+      if (!WIDE && (K & 1) == 0) {
         int2 *dst = reinterpret_cast<int2 *>(sig + (s0 + j) * K);
         const unsigned *src = reinterpret_cast<const unsigned *>(sigt + j * Kp);     // Kp even: 4-byte aligned rows
-        for (int q = lane; q < halfK; q += 32) {
+        for (int q = lane; q < (K >> 1); q += 32) {
           const unsigned x = src[q];
-          dst[q] = make_int2(int(short(x & 0xFFFFu)), int(x) >> 16);
+          const int v0 = int(short(x & 0xFFFFu)), v1 = int(x) >> 16;
+          dst[q] = make_int2(v0, v1);
+          acc += unsigned(v0 * v0) + (unsigned long long)unsigned(v1 * v1);          // |v| <= 32768
         }
-      }
-    } else {
-      for (int j = warp; j < nsets; j += NW)
-        for (int i = lane; i < K; i += 32) sig[(s0 + j) * K + i] = sigt[j * Kp + i];
-    }
-    // ---- epilogue 2: lane = set.  Bucket records of the warp's bands and, from the same values, its share of
-    //      the squared norm; the rows' pitch (odd number of words) keeps the 32 lanes in 32 banks
-    if (records != nullptr || norm2 != nullptr) {
-      long long acc = 0;
-      const short *row = sigt + lane * Kp;
-      if (lane < nsets) {
-        if (records != nullptr) {
-          for (int band = warp; band < b; band += NW) {
-            uint32_t h = band_hash_init(uint32_t(band));
-            bool all_neg = true;
-            for (int c = 0; c < r_band; ++c) {
-              const int x = row[band * r_band + c];
-              acc += (long long)x * x;
-              const uint32_t l16 = uint32_t(x) & 0xFFFFu;
-              all_neg = all_neg && (l16 == 0xFFFFu);
-              h = band_hash_step(h, l16);
-            }
-            records[int64_t(band) * rec_stride + s0 + lane] =
-                make_record(band_hash_finish(h, all_neg), uint32_t(band), uint32_t(id_base + s0 + lane));
-          }
-        } else {
-          for (int i = warp; i < K; i += NW) {
-            const int x = row[i];
-            acc += (long long)x * x;
-          }
+      } else {
+        for (int i = lane; i < K; i += 32) {
+          const long long v = sigt[j * Kp + i];
+          sig[(s0 + j) * K + i] = int(v);
+          acc += (unsigned long long)(v * v);
         }
       }
       if (norm2 != nullptr) {
-        wsum[warp * 32 + lane] = acc;
-        __syncthreads();
-        if (warp == 0 && lane < nsets) {
-          long long tot = 0;
-#pragma unroll
-          for (int w = 0; w < NW; ++w) tot += wsum[w * 32 + lane];
-          norm2[s0 + lane] = tot;
-        }
+        if (WIDE) acc = (unsigned long long)warp_sum_ll((long long)acc);
+        else acc = warp_sum_u48(acc);      // K <= 8192 values below 2^30 per row
+        if (lane == 0) norm2[s0 + j] = (long long)acc;
       }
     }
-    __syncthreads();   // rp / sigt / bm / wsum are rewritten by the next tile
+    // ---- epilogue 2: bucket records, lane = set (the rows' pitch, an odd number of words, keeps the lanes in
+    //      different banks); a 16-bit tile with an even r reads the band's lanes two at a time, as the words the
+    //      hash folds
+    if (records != nullptr && lane < nsets) {
+      const sig_t *row = sigt + lane * Kp;
+      const uint32_t id = uint32_t(id_base + s0 + lane);
+      if (!WIDE && (r_band & 1) == 0) {
+        const unsigned *roww = reinterpret_cast<const unsigned *>(row);
+        const int wpb = r_band >> 1;
+        for (int band = warp; band < b; band += NW) {
+          uint32_t h = band_hash_init(uint32_t(band));
+          uint32_t all = 0xFFFFFFFFu;
+          for (int c = 0; c < wpb; ++c) {
+            const uint32_t w = roww[band * wpb + c];
+            all &= w;
+            h = band_hash_word(h, w);
+          }
+          records[int64_t(band) * rec_stride + s0 + lane] =
+              make_record(band_hash_finish(h, all == 0xFFFFFFFFu), uint32_t(band), id);
+        }
+      } else {
+        for (int band = warp; band < b; band += NW)
+          records[int64_t(band) * rec_stride + s0 + lane] = band_record(row + band * r_band, r_band, uint32_t(band), id);
+      }
+    }
+    __syncthreads();   // rp / sigt / the map are rewritten by the next tile
   }
 }
 
-static size_t tile_smem_bytes(int K, int map_words) {
-  return 40 * 8 + size_t(map_words) * 4 + size_t(kTileSets) * tile_sig_stride(K) * 2 +
-         size_t(kTileThreads / 32) * 32 * 8;
+// word-map bytes for m elements (a multiple of 16) and the whole dynamic shared memory of one CTA
+static int tile_map_bytes(int m, int sets) { return round_up(m * (sets / 8), 16); }
+static size_t tile_smem_bytes(int K, int m, int sets, bool wide) {
+  return 40 * 8 + size_t(tile_map_bytes(m, sets)) + 16 + size_t(sets) * tile_sig_stride(K, wide) * (wide ? 4 : 2);
 }
 
-template <int NH>
-static int launch_minhash_tile_nh(const int64_t *rowptr, const int *colidx, int64_t n, int m, const int *perm_tab,
-                                  const int *order_head, int R, int K, int b, int64_t id_base, int *sig,
-                                  long long *norm2, uint64_t *records, int64_t rec_stride, int mode,
-                                  cudaStream_t stream) {
-  auto kern = minhash_tile_kernel<NH>;
-  const int map_words = round_up(m, 4);
-  const size_t smem = tile_smem_bytes(K, map_words);
+// sets per tile for this shape: 32 while a 16-bit tile can hold the values, then the widest map that fits; 0 = none
+static int tile_sets_for(int m, int K) {
+  if (m <= kTileMaxElems16 && tile_smem_bytes(K, m, 32, false) <= size_t(kTileMaxSmemBytes)) return 32;
+  if (m <= kTileMaxElems16) return 0;
+  if (tile_smem_bytes(K, m, 16, true) <= size_t(kTileMaxSmemBytes)) return 16;
+  if (tile_smem_bytes(K, m, 8, true) <= size_t(kTileMaxSmemBytes)) return 8;
+  return 0;
+}
+
+template <int SETS, int NH, bool WIDE>
+static int launch_minhash_tile_t(const int64_t *rowptr, const int *colidx, int64_t n, int m, const int *perm_tab,
+                                 const int *order_head, int R, int K, int b, int64_t id_base, int *sig,
+                                 long long *norm2, uint64_t *records, int64_t rec_stride, int mode,
+                                 cudaStream_t stream) {
+  auto kern = minhash_tile_kernel<SETS, NH, WIDE>;
+  const int map_bytes = tile_map_bytes(m, SETS);
+  const size_t smem = tile_smem_bytes(K, m, SETS, WIDE);
   QRS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   int per_sm = 0;
-  QRS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTileThreads, smem));
+  QRS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TileShape<SETS>::kThreads, smem));
   if (per_sm < 1) return QRS_ERR_UNSUPPORTED;
   int64_t grid = int64_t(sm_count()) * per_sm;
-  const int64_t tiles = ceil_div<int64_t>(n, kTileSets);
+  const int64_t tiles = ceil_div<int64_t>(n, SETS);
   if (grid > tiles) grid = tiles;
-  kern<<<unsigned(grid), kTileThreads, smem, stream>>>(rowptr, colidx, n, m, perm_tab, order_head, R, K, b, id_base,
-                                                       sig, norm2, records, rec_stride, mode, map_words);
+  kern<<<unsigned(grid), TileShape<SETS>::kThreads, smem, stream>>>(rowptr, colidx, n, m, perm_tab, order_head, R, K,
+                                                                    b, id_base, sig, norm2, records, rec_stride, mode,
+                                                                    map_bytes);
   QRS_LAUNCH_CHECK();
   return QRS_OK;
 }
 
-static int launch_minhash_tile(const int64_t *rowptr, const int *colidx, int64_t n, int m, const int *perm_tab,
-                               const int *order_head, int R, int K, int b, int64_t id_base, int *sig,
-                               long long *norm2, uint64_t *records, int64_t rec_stride, int mode,
-                               cudaStream_t stream) {
+template <int SETS, bool WIDE>
+static int launch_minhash_tile_s(const int64_t *rowptr, const int *colidx, int64_t n, int m, const int *perm_tab,
+                                 const int *order_head, int R, int K, int b, int64_t id_base, int *sig,
+                                 long long *norm2, uint64_t *records, int64_t rec_stride, int mode,
+                                 cudaStream_t stream) {
   if (R <= (8 << 6))
-    return launch_minhash_tile_nh<6>(rowptr, colidx, n, m, perm_tab, order_head, R, K, b, id_base, sig, norm2,
-                                     records, rec_stride, mode, stream);
+    return launch_minhash_tile_t<SETS, 6, WIDE>(rowptr, colidx, n, m, perm_tab, order_head, R, K, b, id_base, sig,
+                                                norm2, records, rec_stride, mode, stream);
   if (R <= (8 << 9))
-    return launch_minhash_tile_nh<9>(rowptr, colidx, n, m, perm_tab, order_head, R, K, b, id_base, sig, norm2,
-                                     records, rec_stride, mode, stream);
-  return launch_minhash_tile_nh<12>(rowptr, colidx, n, m, perm_tab, order_head, R, K, b, id_base, sig, norm2,
-                                    records, rec_stride, mode, stream);
+    return launch_minhash_tile_t<SETS, 9, WIDE>(rowptr, colidx, n, m, perm_tab, order_head, R, K, b, id_base, sig,
+                                                norm2, records, rec_stride, mode, stream);
+  if (R <= (8 << 12))
+    return launch_minhash_tile_t<SETS, 12, WIDE>(rowptr, colidx, n, m, perm_tab, order_head, R, K, b, id_base, sig,
+                                                 norm2, records, rec_stride, mode, stream);
+  return QRS_ERR_UNSUPPORTED;
+}
+
+static int launch_minhash_tile(int sets, const int64_t *rowptr, const int *colidx, int64_t n, int m,
+                               const int *perm_tab, const int *order_head, int R, int K, int b, int64_t id_base,
+                               int *sig, long long *norm2, uint64_t *records, int64_t rec_stride, int mode,
+                               cudaStream_t stream) {
+  if (sets == 32)
+    return launch_minhash_tile_s<32, false>(rowptr, colidx, n, m, perm_tab, order_head, R, K, b, id_base, sig, norm2,
+                                            records, rec_stride, mode, stream);
+  if (sets == 16)
+    return launch_minhash_tile_s<16, true>(rowptr, colidx, n, m, perm_tab, order_head, R, K, b, id_base, sig, norm2,
+                                           records, rec_stride, mode, stream);
+  if (sets == 8)
+    return launch_minhash_tile_s<8, true>(rowptr, colidx, n, m, perm_tab, order_head, R, K, b, id_base, sig, norm2,
+                                          records, rec_stride, mode, stream);
+  return QRS_ERR_UNSUPPORTED;
 }
 
 template <bool BYTEMAP, int THREADS>
@@ -633,15 +723,18 @@ int qrs_minhash_perm(const int64_t *rowptr, const int32_t *colidx, int64_t n, in
   if (R % 32 != 0 || R > m) return QRS_ERR_INVALID_ARG;
   bool ft_possible = R >= 32 && mode != QRS_MINHASH_DIRECT && m <= kMaxElemsFirstTouch;
   if (mode == QRS_MINHASH_FIRST_TOUCH && !ft_possible) return QRS_ERR_UNSUPPORTED;
-  const bool tile_possible = R >= 32 && m <= kTileMaxElems &&
-                             (reinterpret_cast<uintptr_t>(order_head) & 15) == 0 &&
-                             tile_smem_bytes(K, round_up(m, 4)) <= size_t(kTileMaxSmemBytes);
-  if (mode == QRS_MINHASH_TILE && !tile_possible) return QRS_ERR_UNSUPPORTED;
+  // sets per tile: the widest word map that fits shared memory (QRS_MINHASH_TILE_SETS=8|16 narrows it, for measurements)
+  int tile_sets = (R >= 32 && R <= (8 << 12) && (reinterpret_cast<uintptr_t>(order_head) & 15) == 0) ? tile_sets_for(m, K) : 0;
+  if (tile_sets == 16) {
+    static const int forced = [] { const char *s = getenv("QRS_MINHASH_TILE_SETS"); return s ? atoi(s) : 0; }();
+    if (forced == 8 && tile_smem_bytes(K, m, 8, true) <= size_t(kTileMaxSmemBytes)) tile_sets = 8;
+  }
+  if (mode == QRS_MINHASH_TILE && tile_sets == 0) return QRS_ERR_UNSUPPORTED;
   cudaStream_t st = as_stream(stream);
   long long *n2 = reinterpret_cast<long long *>(norm2);
-  if (tile_possible && (mode == QRS_MINHASH_TILE || (mode == QRS_MINHASH_AUTO && kAutoUsesTile)))
-    return launch_minhash_tile(rowptr, colidx, n, m, perm_tab, order_head, R, K, b, id_base, sig, n2, records,
-                               rec_stride, mode, st);
+  if (tile_sets != 0 && (mode == QRS_MINHASH_TILE || (mode == QRS_MINHASH_AUTO && kAutoUsesTile)))
+    return launch_minhash_tile(tile_sets, rowptr, colidx, n, m, perm_tab, order_head, R, K, b, id_base, sig, n2,
+                               records, rec_stride, mode, st);
   if (!ft_possible)
     return launch_minhash<true, 128>(rowptr, colidx, n, m, perm_tab, order_head, 0, K, b, id_base, sig, n2,
                                      records, rec_stride, QRS_MINHASH_DIRECT, 0, st);

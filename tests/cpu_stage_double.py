@@ -18,16 +18,6 @@ from oracle import spec
 U32 = np.uint32
 
 
-def _mix32(h):
-    h = h.astype(U32)
-    h ^= h >> U32(16)
-    h = (h * U32(0x85EBCA6B)).astype(U32)
-    h ^= h >> U32(13)
-    h = (h * U32(0xC2B2AE35)).astype(U32)
-    h ^= h >> U32(16)
-    return h
-
-
 def band_records_np(sig, b, id_base):
     """common.cuh band_record(): hash24 << 40 | band << 32 | id, sentinel 0xFFFFFF for all-(-1) bands."""
     n, K = sig.shape
@@ -35,9 +25,15 @@ def band_records_np(sig, b, id_base):
     lanes = (sig.astype(np.int64) & 0xFFFF).astype(U32).reshape(n, b, r)
     with np.errstate(over="ignore"):
         h = (U32(0x9E3779B9) * (np.arange(b, dtype=U32) + U32(1)))[None, :].repeat(n, 0)
-        for c in range(r):
-            h = (_mix32(h ^ lanes[:, :, c]) * U32(0x9E3779B1) + U32(0x7F4A7C15)).astype(U32)
-        h = _mix32(h) >> U32(8)
+        for c in range(0, r, 2):
+            w = lanes[:, :, c].copy()
+            if c + 1 < r:
+                w |= lanes[:, :, c + 1] << U32(16)
+            h = ((h ^ w) * U32(0x9E3779B1)).astype(U32)
+            h ^= h >> U32(15)
+        h = (h * U32(0x85EBCA6B)).astype(U32)
+        h ^= h >> U32(16)
+        h = h >> U32(8)
     h[h == 0xFFFFFF] = 0xFFFFFE
     h[(lanes == 0xFFFF).all(axis=2)] = 0xFFFFFF
     ids = (np.arange(n, dtype=np.uint64) + np.uint64(id_base))[:, None]

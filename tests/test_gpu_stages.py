@@ -38,7 +38,7 @@ def gpu_signatures(g_rowptr, g_colidx, tab, b=0, mode=0, R=None):
 
 
 # ------------------------------------------------------------------------------ a1
-TILE_MAX_ELEMENTS = 32768   # QRS_MINHASH_TILE: one 32-bit word per element, 128 KB of shared memory
+TILE_MAX_ELEMENTS = 220000   # QRS_MINHASH_TILE: 32-bit words up to 32768 elements, then 16-bit words, then bytes
 
 
 @pytest.mark.parametrize("mode", [0, 1, 2, 3])
@@ -88,15 +88,19 @@ def _ragged_rows(rng, n, m, lens):
 
 @pytest.mark.parametrize("mode", [0, 3])
 @pytest.mark.parametrize("n,m,K,b", [(1, 64, 32, 8), (31, 900, 96, 24), (33, 900, 100, 25), (517, 3000, 180, 60),
-                                       (1000, 10000, 128, 32), (200, 32768, 64, 16)])
+                                       (1000, 10000, 128, 32), (200, 32768, 64, 16),
+                                       (150, 32769, 64, 16), (90, 70000, 100, 20), (45, 104000, 256, 64),
+                                       (70, 120000, 96, 32), (37, 200000, 40, 8)])
 def test_minhash_tile_ragged_tiles(mode, n, m, K, b):
-    """Tile scan (32 sets per CTA step): partial last tile, K not a multiple of 32, empty / one-element /
-    short / long sets side by side in one tile (AUTO sends the short ones to the direct path), and the
-    fused norm2 + bucket records."""
+    """Tile scan (32 sets per CTA step up to 32768 elements, 16 sets with 16-bit words while they fit shared memory —
+    values beyond 16 bits at m = 70000 / 104000 —, 8 sets with bytes beyond: m = 120000 / 200000): partial last tile,
+    K not a multiple of 32, empty / one-element / short / long sets side by side in one tile (AUTO sends the short
+    ones to the direct path), rows longer than one 256-entry build step per warp of a group, and the fused norm2 +
+    bucket records."""
     from query_recommendation_system_b200 import stages
     rng = np.random.default_rng(n * 7 + K)
     kinds = rng.integers(0, 5, size=n)
-    hi = max(2, min(m // 8, 600))
+    hi = max(2, min(m // 8, 600 if m <= 32768 else 2600))
     lens = np.where(kinds == 0, 0, np.where(kinds == 1, 1, np.where(kinds == 2, rng.integers(2, 12, size=n),
                                                                    rng.integers(hi // 2, hi, size=n))))
     if lens.sum() == 0:
@@ -128,7 +132,7 @@ def test_minhash_tile_equals_first_touch_at_bench_density():
 def test_minhash_tile_refuses_large_m():
     from query_recommendation_system_b200 import _lib
     rng = np.random.default_rng(2)
-    n, m, K = 40, TILE_MAX_ELEMENTS + 1, 32
+    n, m, K = 40, 300000, 32        # not even one byte per element fits shared memory
     rowptr, colidx = _ragged_rows(rng, n, m, rng.integers(50, 400, size=n))
     tab = spec.permutation_table(m, K, seed=1)
     with pytest.raises(_lib.QrsError):
