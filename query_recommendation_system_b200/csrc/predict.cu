@@ -16,6 +16,8 @@
 //   dense form  : one CTA per user at reference scale, adds the query branch.
 #include <string.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace qrs {
@@ -39,10 +41,17 @@ __device__ __forceinline__ int hybrid_rule(double q, double u) {
 // window.  qrs_predict_prepare lays the rows out for exactly that access: row v is cut at the window bounds
 // (binary searches, rows are ascending) and every (row, window) sub-segment is written as 32-bit words
 //   (column - t * tile) << 8 | rating
-// padded with zero words to a multiple of 32, so that one warp step is ONE aligned 128-byte line, needs no bounds
+// padded to a multiple of 32 with words of rating 0 whose column is the spare accumulator slot (pw_spare_col), so
+// that one warp step is ONE aligned 128-byte line, needs no bounds
 // or alignment handling, and costs one load per entry instead of a column and a rating load.  seg_off[v * nt + t]
 // is the sub-segment's first step (units of 32 words); sub-segments are consecutive in (v, t) order, so the next
 // entry is its end.  The caller's colidx / val need no alignment or padding.
+
+// Accumulator slots of one warp: the window's columns rounded up to the 64-column sweep step, then one spare slot
+// (padded to 128 bytes) that the padding words of the prepared rows point at — a padding lane read-modify-writes
+// the spare slot like any other, so the integer flavour's accumulation carries no predicate.
+__host__ __device__ constexpr int pw_spare_col(int tile) { return round_up(tile, 64); }
+__host__ __device__ constexpr int pw_acc_slots(int tile) { return round_up(tile, 64) + 16; }
 
 // tilepos[v*(nt+1) + t] = rowptr[v] + number of entries of row v with col < t*tile (t = 0..nt)
 __global__ void __launch_bounds__(256)
@@ -77,7 +86,8 @@ seg_steps_kernel(const int64_t *__restrict__ tilepos, int64_t U, int nt, uint32_
 // one warp per (row, window) sub-segment
 __global__ void __launch_bounds__(256)
 pack_rows_kernel(const int *__restrict__ colidx, const uint8_t *__restrict__ val, const int64_t *__restrict__ tilepos,
-                 const uint64_t *__restrict__ seg_off, int64_t U, int nt, int tile, uint32_t *__restrict__ packed) {
+                 const uint64_t *__restrict__ seg_off, int64_t U, int nt, int tile, uint32_t *__restrict__ packed,
+                 unsigned *__restrict__ zero_flag) {
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
@@ -88,10 +98,15 @@ pack_rows_kernel(const int *__restrict__ colidx, const uint8_t *__restrict__ val
     const int64_t a = tilepos[v * (nt + 1) + t], e = tilepos[v * (nt + 1) + t + 1];
     const uint64_t o = seg_off[x], n = seg_off[x + 1] - o;
     const int q0 = t * tile;
+    const uint32_t pad = uint32_t(pw_spare_col(tile)) << 8;      // rating 0, column = the spare accumulator slot
     for (uint64_t s = 0; s < n; ++s) {
       const int64_t i = a + int64_t(s) * 32 + lane;
-      uint32_t w = 0;
-      if (i < e) w = (uint32_t(ld_stream_s32(colidx + i) - q0) << 8) | uint32_t(val[i]);
+      uint32_t w = pad;
+      if (i < e) {
+        const uint32_t r = val[i];
+        w = (uint32_t(ld_stream_s32(colidx + i) - q0) << 8) | r;
+        if (r == 0) *zero_flag = 1u;       // an explicit rating 0 (= not rated, recommender.py:41): the predictor
+      }                                    // takes its guarded accumulation path
       packed[((o + s) << 5) + lane] = w;
     }
   }
@@ -135,20 +150,18 @@ constexpr int kPwMaxWarps = 20;             // 640 threads: up to 96 registers p
 constexpr int kTieBitWords = 26 * 32;       // single-rater half-way bits: 26 ratings (5, 15, .., 255) x 1024 milli
 constexpr size_t kPwCtaBytes = round_up<size_t>(kTieBitWords * 4, 256);
 
-// shared memory of one warp: acc[tile] | u16 jlist[tile] | step list | (F64) similarity of each neighbour
+// shared memory of one warp: acc[slots] | u16 jlist[tile] | step list | (F64) similarity of each neighbour
 __host__ __device__ constexpr size_t pw_warp_bytes(int tile, bool milli) {
-  return round_up<size_t>(size_t(tile) * (milli ? 8 : 16), 128) + round_up<size_t>(size_t(tile) * 2, 128) +
+  return size_t(pw_acc_slots(tile)) * (milli ? 8 : 16) + round_up<size_t>(size_t(tile) * 2, 128) +
          size_t(kPwListCap) * 8 + (milli ? 0 : 64 * 8);
 }
 
-// predicated 8-byte shared-memory load / store (cond != 0), by shared-window byte address
-__device__ __forceinline__ void lds_u64_if(unsigned long long &x, unsigned addr, unsigned cond) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.shared.u64 %0, [%1];\n\t}"
-               : "+l"(x) : "r"(addr), "r"(cond) : "memory");
+// 8-byte shared-memory load / store as two 32-bit halves, by shared-window byte address
+__device__ __forceinline__ void lds_v2(unsigned &lo, unsigned &hi, unsigned addr) {
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(addr) : "memory");
 }
-__device__ __forceinline__ void sts_u64_if(unsigned addr, unsigned long long x, unsigned cond) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.u64 [%0], %1;\n\t}"
-               :: "r"(addr), "l"(x), "r"(cond) : "memory");
+__device__ __forceinline__ void sts_v2(unsigned addr, unsigned lo, unsigned hi) {
+  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(lo), "r"(hi) : "memory");
 }
 __device__ __forceinline__ unsigned ld_stream_u32(const uint32_t *p) {
   unsigned v;
@@ -170,7 +183,7 @@ struct PeerView {
   int n_peers;
   int my;
   long long rows_per_peer;
-  unsigned long long off_tilepos, off_seg, off_packed;   // byte offsets inside a workspace
+  unsigned long long off_tilepos, off_seg, off_packed, off_flag;   // byte offsets inside a workspace
 };
 __device__ __forceinline__ const int64_t *peer_tilepos(const PeerView &pv, int r) {
   return reinterpret_cast<const int64_t *>(pv.base[r] + pv.off_tilepos);
@@ -239,13 +252,13 @@ predict_sparse_kernel(const __grid_constant__ PeerView pv, int Q,
   unsigned *tie_bits = reinterpret_cast<unsigned *>(smem_raw);           // [26 * 32] MILLI: single-rater half-way bits
   unsigned char *mine = smem_raw + kPwCtaBytes + size_t(warp) * pw_warp_bytes(tile, MILLI);
   acc_t *acc = reinterpret_cast<acc_t *>(mine);
-  uint16_t *jlist = reinterpret_cast<uint16_t *>(mine + round_up<size_t>(size_t(tile) * (MILLI ? 8 : 16), 128));
+  uint16_t *jlist = reinterpret_cast<uint16_t *>(mine + size_t(pw_acc_slots(tile)) * (MILLI ? 8 : 16));
   uint2 *steps = reinterpret_cast<uint2 *>(reinterpret_cast<unsigned char *>(jlist) + round_up<size_t>(size_t(tile) * 2, 128));
   double *m_s = reinterpret_cast<double *>(steps + kPwListCap);          // [64] F64 only: similarity of each neighbour
 
   acc_t zero;
   if constexpr (MILLI) zero = 0ull; else zero = Acc{0.0, 0.0};
-  for (int j = lane; j < tile; j += 32) acc[j] = zero;
+  for (int j = lane; j < pw_acc_slots(tile); j += 32) acc[j] = zero;
   if constexpr (MILLI)
     for (int w = tid; w < kTieBitWords; w += blockDim.x) tie_bits[w] = tie_bits_g[w];
   __syncthreads();          // the only block barrier: the table every warp reads
@@ -259,6 +272,12 @@ predict_sparse_kernel(const __grid_constant__ PeerView pv, int Q,
   const int64_t region_base = int64_t(region) * region_cap;
 
   struct Batch { unsigned p0[kPwBatch], p1[kPwBatch], tag[kPwBatch]; };
+  const unsigned pad = unsigned(pw_spare_col(tile)) << 8;      // the padding word of the prepared rows
+  // explicit zero ratings anywhere in the rows this launch can read?  (warp-uniform, rare: guarded accumulation)
+  bool has_zeros = false;
+  for (int r = 0; r < pv.n_peers; ++r)
+    has_zeros |= *reinterpret_cast<const unsigned *>(pv.base[r] + pv.off_flag) != 0u;
+  const bool one_peer = pv.n_peers == 1;
 
   const int64_t items = n_users * nt;
   const int64_t warp_global = int64_t(blockIdx.x) * warps_cta + warp;
@@ -286,7 +305,10 @@ predict_sparse_kernel(const __grid_constant__ PeerView pv, int Q,
       const uint64_t a = so[0];
       o0 = unsigned(a);
       n0 = unsigned(so[1] - a);
-      if constexpr (MILLI) tag0 = unsigned(u_milli[tbase + lane]) | (1u << 24);
+      if constexpr (MILLI) {
+        tag0 = unsigned(u_milli[tbase + lane]) | (1u << 24);
+        if (tag0 == (1u << 24)) n0 = 0;      // similarity 0.000: adds nothing to N or D (recommender.py:36-47)
+      }
       else { tag0 = unsigned(lane); m_s[lane] = u_val[tbase + lane]; }
       tag0 |= unsigned(pr) << 26;
     }
@@ -297,7 +319,10 @@ predict_sparse_kernel(const __grid_constant__ PeerView pv, int Q,
       const uint64_t a = so[0];
       o1 = unsigned(a);
       n1 = unsigned(so[1] - a);
-      if constexpr (MILLI) tag1 = unsigned(u_milli[tbase + lane + 32]) | (1u << 24);
+      if constexpr (MILLI) {
+        tag1 = unsigned(u_milli[tbase + lane + 32]) | (1u << 24);
+        if (tag1 == (1u << 24)) n1 = 0;
+      }
       else { tag1 = unsigned(lane + 32); m_s[lane + 32] = u_val[tbase + lane + 32]; }
       tag1 |= unsigned(pr) << 26;
     }
@@ -352,34 +377,39 @@ predict_sparse_kernel(const __grid_constant__ PeerView pv, int Q,
       auto load_batch = [&](Batch &B, int f0) {
 #pragma unroll
         for (int i = 0; i < kPwBatch; ++i) {
-          unsigned a = 0, b2 = 0, tg = 0;
+          unsigned a = pad, b2 = pad, tg = 0;
           if (f0 + i < cnt) {                       // warp-uniform
             const uint2 e = steps[f0 + i];
             tg = e.y;
-            const uint32_t *src = peer_packed(pv, int((tg >> 26) & 15u)) + (size_t(e.x) << 5) + lane;
+            const uint32_t *src = (one_peer ? my_packed : peer_packed(pv, int((tg >> 26) & 15u))) + (size_t(e.x) << 5) + lane;
             a = ld_stream_u32(src);
             if (!(tg & kPwSingle)) b2 = ld_stream_u32(src + 32);
           }
           B.p0[i] = a; B.p1[i] = b2; B.tag[i] = tg;
         }
       };
-      auto process_batch = [&](const Batch &B) {
+      // ZEROS (compile-time tag): the rows may hold explicit ratings of 0, which must not count as raters
+      auto process_batch = [&](const Batch &B, auto zeros_tag) {
+        constexpr bool ZEROS = decltype(zeros_tag)::value;
 #pragma unroll
         for (int i = 0; i < kPwBatch; ++i) {
           const unsigned r0 = B.p0[i] & 0xFFu, r1 = B.p1[i] & 0xFFu;
           if constexpr (MILLI) {
-            // both read-modify-writes of the lane at once, predicated instead of branched (the two entries belong
-            // to one neighbour: different columns).  inc = milli | 1 << 24 is the low word's increment (D and the
-            // rater count) AND the high word's multiplier: r * inc = r << 24 | r * milli, as r * milli < 2^24
+            // both read-modify-writes of the lane at once, no predicate: a padding word (rating 0) points at the
+            // spare slot, and the two entries belong to one neighbour, i.e. different columns.  inc = milli | 1 << 24
+            // is the low word's increment (D and the rater count, no carry out of 32 bits: at most 64 raters of
+            // 1000) AND the high word's multiplier: r * inc = r << 24 | r * milli, as r * milli < 2^24
             const unsigned inc = B.tag[i] & 0x1FFFFFFu;       // bits 26.. are the rank and the single-step flag
-            const unsigned a0 = acc_s + ((B.p0[i] >> 5) & ~7u), a1 = acc_s + ((B.p1[i] >> 5) & ~7u);
-            unsigned long long x0 = 0, x1 = 0;
-            lds_u64_if(x0, a0, r0);
-            lds_u64_if(x1, a1, r1);
-            x0 += (static_cast<unsigned long long>(r0 * inc) << 32) | inc;
-            x1 += (static_cast<unsigned long long>(r1 * inc) << 32) | inc;
-            sts_u64_if(a0, x0, r0);
-            sts_u64_if(a1, x1, r1);
+            const unsigned a0 = acc_s + ((B.p0[i] >> 5) & 0x7FFFFF8u), a1 = acc_s + ((B.p1[i] >> 5) & 0x7FFFFF8u);
+            unsigned lo0, hi0, lo1, hi1;
+            lds_v2(lo0, hi0, a0);
+            lds_v2(lo1, hi1, a1);
+            lo0 += ZEROS ? (r0 ? inc : 0u) : inc;
+            lo1 += ZEROS ? (r1 ? inc : 0u) : inc;
+            hi0 += r0 * inc;
+            hi1 += r1 * inc;
+            sts_v2(a0, lo0, hi0);
+            sts_v2(a1, lo1, hi1);
           } else {
             const double s = m_s[B.tag[i] & 63u];
             if (r0) {
@@ -398,16 +428,20 @@ predict_sparse_kernel(const __grid_constant__ PeerView pv, int Q,
           __syncwarp();      // the next entry may be another neighbour: same columns from other lanes
         }
       };
+      auto process = [&](const Batch &B) {
+        if (has_zeros) process_batch(B, std::true_type{});
+        else process_batch(B, std::false_type{});
+      };
       {
         Batch A, B;
         load_batch(A, 0);
         for (int f0 = 0; f0 < cnt; f0 += 2 * kPwBatch) {
           const bool more = f0 + kPwBatch < cnt;
           if (more) load_batch(B, f0 + kPwBatch);
-          process_batch(A);
+          process(A);
           if (more) {
             if (f0 + 2 * kPwBatch < cnt) load_batch(A, f0 + 2 * kPwBatch);
-            process_batch(B);
+            process(B);
           }
         }
       }
@@ -427,28 +461,19 @@ predict_sparse_kernel(const __grid_constant__ PeerView pv, int Q,
     unsigned *const bitmap_row = reinterpret_cast<unsigned *>(cols) + item * (tile >> 5);
     int touched = 0;
     if constexpr (MILLI) {
-      // A lane looks at the ADJACENT columns j0 + 2 * lane and j0 + 2 * lane + 1 (one 16-byte load): listed iff
-      // D != 0 (then the prediction is >= 18); an accumulator whose similarities are all 0 is cleared right here
-      // and predicts nothing (weightSum == 0, recommender.py:44)
+      // A lane looks at columns j0 + lane and j0 + 32 + lane: the two ballots ARE the bitmap words of the 64 columns.
+      // Listed iff D != 0 (then the prediction is >= 18).  Neighbours of similarity 0 never enter the step list, so
+      // an accumulator is either untouched (all zero) or has D != 0; columns beyond the window's width stay zero.
+#pragma unroll 1
       for (int j0 = 0; j0 < width; j0 += 64) {
-        const int ja = j0 + 2 * lane;
-        ulonglong2 x = make_ulonglong2(0ull, 0ull);
-        if (ja < width) x = *reinterpret_cast<const ulonglong2 *>(acc + ja);       // width is even (tile % 32 == 0 ... Q)
-        const bool hit0 = (unsigned(x.x) & 0xFFFFFFu) != 0u, hit1 = (unsigned(x.y) & 0xFFFFFFu) != 0u;
-        if (!hit0 && x.x != 0ull) acc[ja] = 0ull;
-        if (!hit1 && x.y != 0ull) acc[ja + 1] = 0ull;
+        const unsigned long long x0 = acc[j0 + lane], x1 = acc[j0 + 32 + lane];     // acc holds round_up(tile, 64) words
+        const bool hit0 = (unsigned(x0) & 0xFFFFFFu) != 0u, hit1 = (unsigned(x1) & 0xFFFFFFu) != 0u;
         const unsigned m0 = __ballot_sync(kFull, hit0), m1 = __ballot_sync(kFull, hit1);
-        if (bitmap) {
-          // bit 2 * (lane & 15) + {0, 1} of the word of the lane's half-warp
-          const unsigned field = (unsigned(hit0) | (unsigned(hit1) << 1)) << (2 * (lane & 15));
-          const unsigned wa = __reduce_or_sync(kFull, lane < 16 ? field : 0u);
-          const unsigned wb = __reduce_or_sync(kFull, lane < 16 ? 0u : field);
-          if (lane < 2 && j0 + 32 * lane < width) bitmap_row[(j0 >> 5) + lane] = lane == 0 ? wa : wb;
-        }
-        const int pos = touched + __popc(m0 & lt) + __popc(m1 & lt);
-        if (hit0) jlist[pos] = uint16_t(ja);
-        if (hit1) jlist[pos + int(hit0)] = uint16_t(ja + 1);
-        touched += __popc(m0) + __popc(m1);
+        if (bitmap && lane < 2 && j0 + 32 * lane < width) bitmap_row[(j0 >> 5) + lane] = lane == 0 ? m0 : m1;
+        const int c0 = __popc(m0);
+        if (hit0) jlist[touched + __popc(m0 & lt)] = uint16_t(j0 + lane);
+        if (hit1) jlist[touched + c0 + __popc(m1 & lt)] = uint16_t(j0 + 32 + lane);
+        touched += c0 + __popc(m1);
       }
     } else {
 #pragma unroll 2
@@ -783,6 +808,7 @@ int qrs_predict_prepare(const int64_t *rowptr, const int32_t *colidx, const uint
   if (nnz > 0 && (!colidx || !val)) return QRS_ERR_INVALID_ARG;
   cudaStream_t st = as_stream(stream);
   const PredictWs w = carve_predict_ws(ws, U, nt, nnz, capacity);
+  QRS_CUDA(cudaMemsetAsync(w.tie_count, 0, 256, st));      // tie counter | "explicit zero ratings present" flag
   const int64_t cap = int64_t(sm_count()) * 8;
   {
     int64_t blocks = ceil_div<int64_t>(U * (nt + 1), 256);
@@ -802,7 +828,8 @@ int qrs_predict_prepare(const int64_t *rowptr, const int32_t *colidx, const uint
     int64_t blocks = ceil_div<int64_t>(U * nt, 8);
     const int64_t cap2 = int64_t(sm_count()) * 16;
     if (blocks > cap2) blocks = cap2;
-    pack_rows_kernel<<<unsigned(blocks), 256, 0, st>>>(colidx, val, w.tilepos, w.seg_off, U, nt, tile, w.packed);
+    pack_rows_kernel<<<unsigned(blocks), 256, 0, st>>>(colidx, val, w.tilepos, w.seg_off, U, nt, tile, w.packed,
+                                                       reinterpret_cast<unsigned *>(w.tie_count + 1));
     QRS_LAUNCH_CHECK();
   }
   single_rater_tie_bits_kernel<<<ceil_div(26 * 32, 256), 256, 0, st>>>(w.single_tab);
@@ -851,6 +878,7 @@ int qrs_predict_sparse(const int64_t *rowptr, const int32_t *colidx, const uint8
   pv.off_tilepos = static_cast<unsigned long long>(reinterpret_cast<char *>(w.tilepos) - static_cast<char *>(ws));
   pv.off_seg = static_cast<unsigned long long>(reinterpret_cast<char *>(w.seg_off) - static_cast<char *>(ws));
   pv.off_packed = static_cast<unsigned long long>(reinterpret_cast<char *>(w.packed) - static_cast<char *>(ws));
+  pv.off_flag = static_cast<unsigned long long>(reinterpret_cast<char *>(w.tie_count + 1) - static_cast<char *>(ws));
   for (int r = 0; r < pv.n_peers; ++r)
     if (pv.base[r] == 0ull) return QRS_ERR_INVALID_ARG;
   QRS_CUDA(cudaMemsetAsync(w.tie_count, 0, 8, st));

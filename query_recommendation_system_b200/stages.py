@@ -241,23 +241,22 @@ def predict_dense(rowptr, colidx, val, Q: int, q_tab: Optional[Table], u_tab: Op
     return out
 
 
-PREDICT_TARGET_ENTRIES = 54.0   # average entries of one (neighbour row, window) sub-segment: two 32-entry steps, mostly
-PREDICT_MIN_WARPS = 8           # windows are not widened beyond what leaves this many warps on an SM
-
-
 def choose_predict_tile(Q: int, avg_len: float = 0.0, integer_tables: bool = True) -> int:
-    """Column window of the sparse predictor.  One WARP accumulates one (user, window) and takes 32 entries of a
-    neighbour's sub-segment per step, so the window is sized for sub-segments of about two steps (wider windows
-    fill the steps better but leave fewer independent warps per SM), rounded so the windows tile Q evenly."""
+    """Column window of the sparse predictor.  One WARP accumulates one (user, window) in its slice of shared
+    memory, and what the kernel needs most is independent warps: measured at C2 (5 % of 10 000 columns) and C3
+    (1 % of 100 000) the time falls with the window width up to the widest window that still leaves the full 20
+    warps on an SM (1 024 columns for the integer accumulators) and rises beyond it whatever the row length
+    (profiles/r2_predict_variants.md), so that window is taken, rounded so the windows tile Q evenly.  `avg_len`
+    is kept for callers that pass it; the choice does not depend on it."""
     lib = _lib.load()
     it = 1 if integer_tables else 0
-    max_tile = lib.qrs_predict_max_tile(it)
-    want = Q if avg_len <= 0 else PREDICT_TARGET_ENTRIES * Q / max(avg_len, 1e-9)
-    want = int(min(max(want, 256), max_tile, max(Q, 32)))
-    while want > 256 and lib.qrs_predict_warps_per_sm(((want + 31) // 32) * 32, it) < PREDICT_MIN_WARPS:
-        want -= 32
-    nt = max(1, math.ceil(Q / want))
-    return int(min(max_tile, max(32, math.ceil(math.ceil(Q / nt) / 32.0) * 32)))
+    top = lib.qrs_predict_warps_per_sm(32, it)
+    tile = 32
+    while tile + 32 <= 65536 and lib.qrs_predict_warps_per_sm(tile + 32, it) >= top:
+        tile += 32
+    tile = min(tile, max(32, math.ceil(Q / 32.0) * 32))
+    nt = max(1, math.ceil(Q / tile))
+    return int(max(32, math.ceil(math.ceil(Q / nt) / 32.0) * 32))
 
 
 class PeerWorkspace:

@@ -30,16 +30,17 @@ def test_launch_heuristics():
     lib = _lib.load()
     max_tile = lib.qrs_predict_max_tile(1)
     assert max_tile % 32 == 0 and 16_000 < max_tile <= 65_536 and lib.qrs_predict_max_tile(0) < max_tile
+    top = lib.qrs_predict_warps_per_sm(32, 1)
     for q, avg in ((10_000, 500), (100_000, 1000), (1_000, 50), (37, 3), (1_000_000, 1000)):
         t = stages.choose_predict_tile(q, avg)
         assert t % 32 == 0 and t <= max_tile and -(-q // t) * t >= q
-        assert lib.qrs_predict_warps_per_sm(t, 1) >= min(stages.PREDICT_MIN_WARPS, lib.qrs_predict_warps_per_sm(256, 1))
-    # one warp owns one (user, window): windows are sized for ~two 32-entry steps per neighbour sub-segment
-    t2 = stages.choose_predict_tile(10_000, 495.0)                       # C2
-    assert 45 <= 495.0 * t2 / 10_000 <= 64 and lib.qrs_predict_warps_per_sm(t2, 1) >= 16
-    t3 = stages.choose_predict_tile(100_000, 1000.0)                     # C3: capped by the warps-per-SM floor
-    assert lib.qrs_predict_warps_per_sm(t3, 1) >= stages.PREDICT_MIN_WARPS and t3 > t2
-    assert stages.choose_predict_tile(10_000, 5000.0) <= 256             # dense rows: narrow windows
+        assert lib.qrs_predict_warps_per_sm(t, 1) == top           # the window never costs a warp
+    # the widest window that keeps every warp: 1 024 columns for the integer accumulators, whatever the rows
+    assert stages.choose_predict_tile(10_000, 495.0) == 1024                     # C2: ten windows
+    assert stages.choose_predict_tile(100_000, 1000.0) in (1024, 992)            # C3: 98 .. 101 windows
+    assert lib.qrs_predict_warps_per_sm(1024 + 64, 1) < top
+    tf = stages.choose_predict_tile(10_000, 495.0, integer_tables=False)
+    assert tf < 1024 and lib.qrs_predict_warps_per_sm(tf, 0) == lib.qrs_predict_warps_per_sm(32, 0)
 
 
 def test_synth_is_deterministic_and_shardable():
