@@ -246,6 +246,7 @@ predict_sparse_kernel(const __grid_constant__ PeerView pv, int Q,
                       ulonglong2 *__restrict__ tie_list, int64_t tie_capacity, int cols_mode,
                       const unsigned *__restrict__ tie_bits_g) {
   using acc_t = typename AccOf<MILLI>::type;
+  unsigned long long *const user_counter = tie_count + 1;      // zeroed with the tie counter before every launch
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int warps_cta = blockDim.x >> 5;
@@ -265,11 +266,9 @@ predict_sparse_kernel(const __grid_constant__ PeerView pv, int Q,
 
   const unsigned lt = lanemask_lt();
   const unsigned acc_s = unsigned(__cvta_generic_to_shared(acc));   // shared-window byte address of acc[0]
-  // output slices are reserved from one of n_regions cursors (a single cursor would serialise
-  // millions of same-address atomics in L2); region r owns [r * region_cap, (r + 1) * region_cap)
-  const int region = int(blockIdx.x % n_regions);
-  unsigned long long *cursor = cursors + region;
-  const int64_t region_base = int64_t(region) * region_cap;
+  // output slices are reserved from one of n_regions cursors (a single cursor would serialise millions of
+  // same-address atomics in L2); region r owns [r * region_cap, (r + 1) * region_cap) and takes the users
+  // ul = r (mod n_regions), so a region's demand does not depend on which warp happened to take which user
 
   struct Batch { unsigned p0[kPwBatch], p1[kPwBatch], tag[kPwBatch]; };
   const unsigned pad = unsigned(pw_spare_col(tile)) << 8;      // the padding word of the prepared rows
@@ -279,63 +278,70 @@ predict_sparse_kernel(const __grid_constant__ PeerView pv, int Q,
     has_zeros |= *reinterpret_cast<const unsigned *>(pv.base[r] + pv.off_flag) != 0u;
   const bool one_peer = pv.n_peers == 1;
 
-  const int64_t items = n_users * nt;
-  const int64_t warp_global = int64_t(blockIdx.x) * warps_cta + warp;
-  const int64_t nwarps = int64_t(gridDim.x) * warps_cta;
-  // (user, window) of the warp's current item, advanced without a division: item + nwarps = (ul + du, t + dt) with carry
-  const int64_t du = nwarps / nt;
-  const int dt = int(nwarps - du * nt);
-  int64_t ul = warp_global / nt;                  // local user
-  int t = int(warp_global - ul * nt);
+  // A warp takes one USER at a time (dynamic: a device counter) and walks its windows in order, so what depends
+  // on the user only — neighbour ids, ranks, similarities, the rows' offset tables — is set up once, and since the
+  // sub-segments of a row are consecutive in (row, window) order the end of one window is the start of the next:
+  // one 4-byte load per neighbour and window.
   long long nz_total = 0;
-  for (int64_t item = warp_global; item < items; item += nwarps, ul += du, t += dt) {
-    if (t >= nt) { t -= nt; ++ul; }
-    const int q0 = t * tile;
-    const int width = min(tile, Q - q0);
+  const uint32_t *const my_packed = peer_packed(pv, pv.my);
+  for (;;) {
+    long long ul = 0;
+    if (lane == 0) ul = (long long)atomicAdd(user_counter, 1ull);
+    ul = __shfl_sync(kFull, ul, 0);
+    if (ul >= n_users) break;
     const int c = min(u_cnt[ul], ku);
     const int64_t tbase = ul * ku;
 
-    // ---- the neighbours' sub-segments of this window: lane <-> table slots lane and lane + 32; a neighbour is a
-    //      GLOBAL row id: rank = id / rows_per_peer (bits 26..29 of the tag), row on that rank = the remainder
-    unsigned o0 = 0, n0 = 0, tag0 = 0, o1 = 0, n1 = 0, tag1 = 0;
+    // ---- lane <-> table slots lane and lane + 32; a neighbour is a GLOBAL row id: rank = id / rows_per_peer
+    //      (bits 26..29 of the tag), row on that rank = the remainder.  so0 / so1 = the low words of the row's
+    //      offset table (step counts stay below 2^32), null when the slot is empty or its similarity is 0.000
+    //      (such a neighbour adds nothing to N or D, recommender.py:36-47)
+    const unsigned *so0 = nullptr, *so1 = nullptr;
+    unsigned tag0 = 0, tag1 = 0;
+    __syncwarp();            // F64: the previous user's m_s has been consumed
     if (lane < c) {
       const int v = u_idx[tbase + lane];
-      const int pr = int(v / pv.rows_per_peer);
-      const uint64_t *so = peer_seg(pv, pr) + (v - pr * pv.rows_per_peer) * nt + t;
-      const uint64_t a = so[0];
-      o0 = unsigned(a);
-      n0 = unsigned(so[1] - a);
+      const int pr = one_peer ? 0 : int(unsigned(v) / unsigned(pv.rows_per_peer));
+      const long long row = one_peer ? v : v - pr * pv.rows_per_peer;
+      so0 = reinterpret_cast<const unsigned *>(peer_seg(pv, pr) + row * nt);
       if constexpr (MILLI) {
         tag0 = unsigned(u_milli[tbase + lane]) | (1u << 24);
-        if (tag0 == (1u << 24)) n0 = 0;      // similarity 0.000: adds nothing to N or D (recommender.py:36-47)
+        if (tag0 == (1u << 24)) so0 = nullptr;
+      } else {
+        tag0 = unsigned(lane);
+        m_s[lane] = u_val[tbase + lane];
       }
-      else { tag0 = unsigned(lane); m_s[lane] = u_val[tbase + lane]; }
       tag0 |= unsigned(pr) << 26;
     }
     if (lane + 32 < c) {
       const int v = u_idx[tbase + lane + 32];
-      const int pr = int(v / pv.rows_per_peer);
-      const uint64_t *so = peer_seg(pv, pr) + (v - pr * pv.rows_per_peer) * nt + t;
-      const uint64_t a = so[0];
-      o1 = unsigned(a);
-      n1 = unsigned(so[1] - a);
+      const int pr = one_peer ? 0 : int(unsigned(v) / unsigned(pv.rows_per_peer));
+      const long long row = one_peer ? v : v - pr * pv.rows_per_peer;
+      so1 = reinterpret_cast<const unsigned *>(peer_seg(pv, pr) + row * nt);
       if constexpr (MILLI) {
         tag1 = unsigned(u_milli[tbase + lane + 32]) | (1u << 24);
-        if (tag1 == (1u << 24)) n1 = 0;
+        if (tag1 == (1u << 24)) so1 = nullptr;
+      } else {
+        tag1 = unsigned(lane + 32);
+        m_s[lane + 32] = u_val[tbase + lane + 32];
       }
-      else { tag1 = unsigned(lane + 32); m_s[lane + 32] = u_val[tbase + lane + 32]; }
       tag1 |= unsigned(pr) << 26;
     }
+    const unsigned *const own_so = reinterpret_cast<const unsigned *>(peer_seg(pv, pv.my) + (user_base + ul) * nt);
+    unsigned s0 = so0 ? so0[0] : 0u, s1 = so1 ? so1[0] : 0u, sown = __ldg(own_so);     // starts of window 0
+   for (int t = 0; t < nt; ++t) {
+    const int64_t item = ul * nt + t;
+    const int q0 = t * tile;
+    const int width = min(tile, Q - q0);
+    // this window's sub-segments: [start, end) in 128-byte steps; the end is the next window's start
+    const unsigned o0 = s0, o1 = s1, own_o = sown;
+    s0 = so0 ? so0[2 * (t + 1)] : 0u;
+    s1 = so1 ? so1[2 * (t + 1)] : 0u;
+    sown = __ldg(own_so + 2 * (t + 1));
+    const unsigned n0 = s0 - o0, n1 = s1 - o1, own_n = sown - own_o;
     // the user's own row in this window (its rated cells are cleared after the accumulation): the first two steps
-    // are requested now and sit in two registers until then
-    unsigned own_o, own_n, own_p0 = 0, own_p1 = 0;
-    const uint32_t *const my_packed = peer_packed(pv, pv.my);
-    {
-      const uint64_t *so = peer_seg(pv, pv.my) + (user_base + ul) * nt + t;
-      const uint64_t a = __ldg(so);
-      own_o = unsigned(a);
-      own_n = unsigned(__ldg(so + 1) - a);
-    }
+    // are requested below and sit in two registers until then
+    unsigned own_p0 = 0, own_p1 = 0;
     // list entries (one or two steps each) in table order: slots 0..31, then 32..63
     const unsigned d0 = (n0 + 1) >> 1, d1 = (n1 + 1) >> 1;
     unsigned ex0 = d0, ex1 = d1;
@@ -350,7 +356,7 @@ predict_sparse_kernel(const __grid_constant__ PeerView pv, int Q,
     ex1 = ex1 - d1 + tot0;
 
     if (total == 0) {       // nothing gathered: no prediction in this window (the bitmap rows are zeroed by the caller)
-      if (lane == 0) { row_start[item] = region_base; row_cnt[item] = 0; }
+      if (lane == 0) { row_start[item] = int64_t(unsigned(ul) % unsigned(n_regions)) * region_cap; row_cnt[item] = 0; }
       continue;
     }
     if (own_n > 0) own_p0 = ld_stream_u32(my_packed + (size_t(own_o) << 5) + lane);
@@ -491,8 +497,10 @@ predict_sparse_kernel(const __grid_constant__ PeerView pv, int Q,
       }
     }
     unsigned long long base = 0;
+    const int region = int(unsigned(ul) % unsigned(n_regions));     // (a launch has fewer than 2^32 users)
+    const int64_t region_base = int64_t(region) * region_cap;
     if (lane == 0) {
-      if (touched > 0) base = atomicAdd(cursor, (unsigned long long)touched);
+      if (touched > 0) base = atomicAdd(cursors + region, (unsigned long long)touched);
       row_start[item] = region_base + int64_t(base);
       row_cnt[item] = touched;
     }
@@ -559,6 +567,7 @@ predict_sparse_kernel(const __grid_constant__ PeerView pv, int Q,
       nz_total += nz;
     }
     __syncwarp();
+   }
   }
   // non-zero predictions of this launch (statistics): one atomic per warp
   if (lane == 0 && nz_total > 0) atomicAdd(cursors + n_regions, (unsigned long long)nz_total);
@@ -808,7 +817,7 @@ int qrs_predict_prepare(const int64_t *rowptr, const int32_t *colidx, const uint
   if (nnz > 0 && (!colidx || !val)) return QRS_ERR_INVALID_ARG;
   cudaStream_t st = as_stream(stream);
   const PredictWs w = carve_predict_ws(ws, U, nt, nnz, capacity);
-  QRS_CUDA(cudaMemsetAsync(w.tie_count, 0, 256, st));      // tie counter | "explicit zero ratings present" flag
+  QRS_CUDA(cudaMemsetAsync(w.tie_count, 0, 256, st));      // tie counter | next-user counter | "explicit zero ratings" flag
   const int64_t cap = int64_t(sm_count()) * 8;
   {
     int64_t blocks = ceil_div<int64_t>(U * (nt + 1), 256);
@@ -829,7 +838,7 @@ int qrs_predict_prepare(const int64_t *rowptr, const int32_t *colidx, const uint
     const int64_t cap2 = int64_t(sm_count()) * 16;
     if (blocks > cap2) blocks = cap2;
     pack_rows_kernel<<<unsigned(blocks), 256, 0, st>>>(colidx, val, w.tilepos, w.seg_off, U, nt, tile, w.packed,
-                                                       reinterpret_cast<unsigned *>(w.tie_count + 1));
+                                                       reinterpret_cast<unsigned *>(w.tie_count + 2));
     QRS_LAUNCH_CHECK();
   }
   single_rater_tie_bits_kernel<<<ceil_div(26 * 32, 256), 256, 0, st>>>(w.single_tab);
@@ -878,10 +887,10 @@ int qrs_predict_sparse(const int64_t *rowptr, const int32_t *colidx, const uint8
   pv.off_tilepos = static_cast<unsigned long long>(reinterpret_cast<char *>(w.tilepos) - static_cast<char *>(ws));
   pv.off_seg = static_cast<unsigned long long>(reinterpret_cast<char *>(w.seg_off) - static_cast<char *>(ws));
   pv.off_packed = static_cast<unsigned long long>(reinterpret_cast<char *>(w.packed) - static_cast<char *>(ws));
-  pv.off_flag = static_cast<unsigned long long>(reinterpret_cast<char *>(w.tie_count + 1) - static_cast<char *>(ws));
+  pv.off_flag = static_cast<unsigned long long>(reinterpret_cast<char *>(w.tie_count + 2) - static_cast<char *>(ws));
   for (int r = 0; r < pv.n_peers; ++r)
     if (pv.base[r] == 0ull) return QRS_ERR_INVALID_ARG;
-  QRS_CUDA(cudaMemsetAsync(w.tie_count, 0, 8, st));
+  QRS_CUDA(cudaMemsetAsync(w.tie_count, 0, 16, st));      // tie counter | next-user counter
   if (u_milli) {
     int rc = launch_predict_sparse<true>(pv, Q, u_idx, u_val, u_milli, u_cnt, ku, user_base, n_users, tile, nt,
                                          row_start, row_cnt, cols, preds, region_cap, n_regions, cursors, w.tie_count,
