@@ -357,6 +357,10 @@ int qrs_csv_format_fill(const uint8_t *ids, const int64_t *ids_off, const int64_
                         const void *pred_cols, int32_t cols_mode, const uint8_t *preds, int32_t nt, int64_t n_rows,
                         int32_t Q, int32_t zero_as_empty, const int64_t *text_off, uint8_t *text, void *stream);
 
+/* Compact CSR wire format of a utility matrix with at most 65536 queries: 16-bit column ids, widened on the
+ * device to the int32 colidx every stage takes (half the host -> device bytes of the largest input). */
+int qrs_cols_widen_u16(const uint16_t *cols16, int64_t n, int32_t *colidx, void *stream);
+
 /* ------------------------------------------------------ multi-GPU plumbing
  * Rows of the matrix are sharded across the GPUs of one box, one process per GPU.
  *

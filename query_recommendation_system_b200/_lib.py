@@ -67,6 +67,7 @@ SIGNATURES = {
     "qrs_csv_ratings_fill": (C.c_int, [_p, _i64, _p, _i64, _i64, _i32, _p, _p, _p, _p]),
     "qrs_csv_format_workspace_bytes": (_sz, [_i64]),
     "qrs_csv_format_count": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _i64, _i32, _i32, _p, _p, _sz, _p]),
+    "qrs_cols_widen_u16": (C.c_int, [_p, _i64, _p, _p]),
     "qrs_csv_format_fill": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _i32, _i64, _i32, _i32, _p, _p, _p]),
     "qrs_center_rows": (C.c_int, [_p, _p, _i64, _p, _p, _p]),
     "qrs_pair_centered_cosine": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _p, _p]),

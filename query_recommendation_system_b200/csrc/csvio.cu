@@ -259,7 +259,39 @@ csv_ratings_kernel(const uint8_t *__restrict__ text, int64_t n_bytes, const int6
 
 using namespace qrs;
 
+namespace {
+// compact CSR wire format: 16-bit column ids (m <= 65536) widened on the device, 16 bytes in / 32 bytes out per thread
+__global__ void __launch_bounds__(256) widen_u16_kernel(const uint16_t *__restrict__ in, int64_t n, int *__restrict__ out) {
+  const int64_t n8 = n >> 3;
+  const bool vec = ((reinterpret_cast<uintptr_t>(in) & 15) | (reinterpret_cast<uintptr_t>(out) & 15)) == 0;
+  const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x, nth = int64_t(gridDim.x) * blockDim.x;
+  if (vec) {
+    for (int64_t i = tid; i < n8; i += nth) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4 *>(in) + i);
+      int4 *o = reinterpret_cast<int4 *>(out) + 2 * i;
+      o[0] = make_int4(int(v.x & 0xFFFFu), int(v.x >> 16), int(v.y & 0xFFFFu), int(v.y >> 16));
+      o[1] = make_int4(int(v.z & 0xFFFFu), int(v.z >> 16), int(v.w & 0xFFFFu), int(v.w >> 16));
+    }
+    for (int64_t i = (n8 << 3) + tid; i < n; i += nth) out[i] = in[i];
+  } else {
+    for (int64_t i = tid; i < n; i += nth) out[i] = in[i];
+  }
+}
+}  // namespace
+
 extern "C" {
+
+int qrs_cols_widen_u16(const uint16_t *cols16, int64_t n, int32_t *colidx, void *stream) {
+  if (n < 0 || (n > 0 && (!cols16 || !colidx))) return QRS_ERR_INVALID_ARG;
+  if (n == 0) return QRS_OK;
+  int64_t blocks = ceil_div<int64_t>(ceil_div<int64_t>(n, 8), 256);
+  const int64_t cap = int64_t(sm_count()) * 8;
+  if (blocks > cap) blocks = cap;
+  widen_u16_kernel<<<unsigned(blocks), 256, 0, as_stream(stream)>>>(cols16, n, colidx);
+  QRS_LAUNCH_CHECK();
+  return QRS_OK;
+}
+
 
 size_t qrs_csv_workspace_bytes(int64_t n_bytes, int64_t n_rows) {
   if (n_bytes < 0 || n_rows < 0) return 0;

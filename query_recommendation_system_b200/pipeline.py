@@ -32,6 +32,7 @@ class PipelineOutput:
     n_slots: int = 0                       # pre-dedup (pair, band) coincidences examined on this rank
     nbr_idx: torch.Tensor = None           # int32[n_local, k]
     nbr_val: torch.Tensor = None           # float64[n_local, k]
+    nbr_milli: torch.Tensor = None         # int32[n_local, k]: 1000 * nbr_val, exact (similarities have 3 decimals)
     nbr_cnt: torch.Tensor = None           # int32[n_local]
     pred_row_start: torch.Tensor = None    # int64[n_local, nt]
     pred_row_cnt: torch.Tensor = None      # int32[n_local, nt]
@@ -135,7 +136,7 @@ class LshCfPipeline:
 
     # ------------------------------------------------------------------ the path
     def run(self, rowptr: torch.Tensor, colidx: torch.Tensor, val: Optional[torch.Tensor],
-            predict: bool = True, chunk_sink=None, val_ready=None) -> PipelineOutput:
+            predict: bool = True, chunk_sink=None, val_ready=None, tables_sink=None) -> PipelineOutput:
         """rowptr/colidx/val: this rank's shard (rows [rank*n_local, (rank+1)*n_local)) of the users×queries
         CSR, on `self.device`.  Every rank must hold the same number of rows.
 
@@ -143,12 +144,12 @@ class LshCfPipeline:
         a step runs with the capacities the previous one suggested and reads ONE batch of counters back at its end;
         if any was too small the step is repeated with the corrected value (first call of a new shape only)."""
         for _ in range(5):
-            out, ok = self._run_once(rowptr, colidx, val, predict, chunk_sink, val_ready)
+            out, ok = self._run_once(rowptr, colidx, val, predict, chunk_sink, val_ready, tables_sink)
             if ok:
                 return out
         raise _lib.QrsError("buffer capacities did not settle after 5 attempts")
 
-    def _run_once(self, rowptr, colidx, val, predict, chunk_sink, val_ready):
+    def _run_once(self, rowptr, colidx, val, predict, chunk_sink, val_ready, tables_sink=None):
         st, G, rank = self.st, self.world, self.rank
         out = PipelineOutput()
         tm = _Timer(self.profile, self.device.type == "cuda")
@@ -229,7 +230,9 @@ class LshCfPipeline:
 
         # a7 + a9
         idx, v, cnt, milli = st.topk_tables(pairs_t, sims_t, pairs_t.numel(), row_base, n_local, self.k, want_milli=True)
-        out.nbr_idx, out.nbr_val, out.nbr_cnt = idx, v, cnt
+        out.nbr_idx, out.nbr_val, out.nbr_cnt, out.nbr_milli = idx, v, cnt, milli
+        if tables_sink is not None:
+            tables_sink(out)          # the neighbour tables are final here: a caller may ship them while the predictor runs
         tm.mark("topk")
 
         tail = [slot_off[-1:].to(torch.int64), counter.reshape(1).to(torch.int64)]
@@ -460,11 +463,15 @@ class LshCfPipeline:
 class HostRunner:
     """The call a user of the drop-in makes with HOST data: pinned utility-matrix CSR in; sparse
     predictions + neighbour tables out, in pinned host memory.  Host↔device copies are part of the
-    call: the CSR goes up on the compute stream, predictions come back chunk by chunk on a second
-    stream while the next chunk of users is being predicted (column ids as uint16 when they fit).
+    call: the CSR goes up on the compute stream (column ids may be passed as uint16 when the matrix has at most
+    65536 queries: half the bytes of the largest input, widened on the device), the neighbour tables come back
+    as soon as the top-k stage has written them, predictions come back chunk by chunk on a second stream while
+    the next chunk of users is being predicted (touched-column bitmap or uint16 column ids when they fit).
+    The similarities travel as the exact integers `nbr_milli` = 1000 * similarity (3 decimals by construction,
+    recommender.py:204): `HostRunner.similarities(res)` is the float64 table.
     Buffers are allocated once and reused across calls."""
 
-    def __init__(self, pipe: LshCfPipeline, chunks: int = 4, cols_format: str = "auto"):
+    def __init__(self, pipe: LshCfPipeline, chunks: int = 8, cols_format: str = "auto"):
         """cols_format: "i32" | "u16" | "bitmap" | "auto" (u16 when the column ids fit, switching to the
         touched-column bitmap once a call has shown that more than 1/16 of the cells get a prediction —
         the point where m/8 bitmap bytes per user beat 2 bytes per prediction)."""
@@ -478,6 +485,11 @@ class HostRunner:
         self.copy_stream = torch.cuda.Stream(device=pipe.device)
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+
+    @staticmethod
+    def similarities(res) -> torch.Tensor:
+        """float64 similarity table of a result (the same doubles the device holds: milli / 1000.0)."""
+        return res["nbr_milli"].to(torch.float64) / 1000.0
 
     def _dev_like(self, name, t):
         buf = self._dev.get(name)
@@ -508,6 +520,13 @@ class HostRunner:
             d = self._dev_like(name, t)
             d.copy_(t, non_blocking=True)
             self.h2d_bytes += t.numel() * t.element_size()
+            if name == "colidx" and t.dtype in (torch.uint16, torch.int16):      # compact wire format
+                if self.pipe.m > 65536:
+                    raise _lib.QrsError("16-bit column ids need a matrix of at most 65536 queries")
+                wide = self._dev.get("colidx32")
+                if wide is None or wide.numel() < t.numel():
+                    wide = self._dev["colidx32"] = torch.empty(t.numel(), dtype=torch.int32, device=self.pipe.device)
+                d = self.pipe.st.widen_cols_u16(d, wide)
             dev_in.append(d)
         # the rating values are needed only by the prediction stage: upload them on the copy stream while the
         # signature / LSH stages run
@@ -533,13 +552,15 @@ class HostRunner:
                     self._ship("c%d_%s" % (ci, key), chunk[key], host_chunk, key)
             shipped[ci] = host_chunk          # a chunk that had to be re-run replaces its first shipment
 
-        out = self.pipe.run(*dev_in, predict=True, chunk_sink=sink, val_ready=val_ready)
-        ready = torch.cuda.Event()
-        ready.record(compute)
-        with torch.cuda.stream(self.copy_stream):
-            self.copy_stream.wait_event(ready)
-            for name in ("nbr_idx", "nbr_val", "nbr_cnt"):
-                self._ship(name, getattr(out, name), res)
+        def tables(out):
+            ready = torch.cuda.Event()
+            ready.record(compute)
+            with torch.cuda.stream(self.copy_stream):
+                self.copy_stream.wait_event(ready)
+                for name in ("nbr_idx", "nbr_milli", "nbr_cnt"):
+                    self._ship(name, getattr(out, name), res)
+
+        out = self.pipe.run(*dev_in, predict=True, chunk_sink=sink, val_ready=val_ready, tables_sink=tables)
         self.copy_stream.synchronize()
         compute.synchronize()
         res["chunks"] = [shipped[ci] for ci in sorted(shipped)]

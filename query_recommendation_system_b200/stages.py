@@ -84,6 +84,18 @@ def minhash(rowptr: torch.Tensor, colidx: torch.Tensor, m: int, perm_tab: torch.
     return sig, norm2, records
 
 
+def widen_cols_u16(cols16: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """16-bit column ids (the compact wire format of a matrix with at most 65536 queries) → the int32 colidx."""
+    _need_cuda(cols16, out)
+    assert cols16.dtype in (torch.uint16, torch.int16)
+    n = cols16.numel()
+    if out is None:
+        out = torch.empty(n, dtype=torch.int32, device=cols16.device)
+    assert out.dtype == torch.int32 and out.numel() >= n
+    check(_lib.load().qrs_cols_widen_u16(ptr(cols16), n, ptr(out), _stream()), "qrs_cols_widen_u16")
+    return out[:n]
+
+
 # ------------------------------------------------------------------------ a2/a3
 def band_keys(sig: torch.Tensor, b: int):
     """Exact bucket ids (lsh.py:17-38): keys int64[n, b] (+ keys_hi for r > 4), skipped uint8[n, b]."""

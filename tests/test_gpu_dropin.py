@@ -160,10 +160,20 @@ def test_host_runner_chunked_matches_device_run(fmt):
     assert res["n_predictions"] == ref.n_predictions and len(res["chunks"]) == 4
     assert runner.d2h_bytes > 0 and runner.h2d_bytes == rowptr.numel() * 8 + colidx.numel() * 4 + val.numel()
     assert torch.equal(res["nbr_idx"].reshape(n, k), ref.nbr_idx.cpu())
+    assert torch.equal(HostRunner.similarities(res).reshape(n, k), ref.nbr_val.cpu())       # the same doubles
+    # the compact wire format (16-bit column ids, widened on the device) gives the same result with half the bytes
+    cols16 = torch.from_numpy(colidx.numpy().astype(np.uint16)).pin_memory()
+    res = {"n_predictions": res["n_predictions"], "nbr_idx": res["nbr_idx"].clone(),      # the pinned buffers are reused
+           "chunks": [{key: (v.clone() if torch.is_tensor(v) else v) for key, v in ch.items()} for ch in res["chunks"]]}
+    res16 = runner(rowptr.pin_memory(), cols16, val.pin_memory())
+    assert runner.h2d_bytes == rowptr.numel() * 8 + colidx.numel() * 2 + val.numel()
+    assert res16["n_predictions"] == res["n_predictions"] and torch.equal(res16["nbr_idx"], res["nbr_idx"])
+    for a, b2 in zip(res16["chunks"], res["chunks"]):
+        assert torch.equal(a["row_cnt"], b2["row_cnt"])       # (the slices' places inside a region depend on timing)
     if fmt in ("bitmap", "auto"):
         assert all(ch["cols_mode"] == 2 for ch in res["chunks"])
     seen = 0
-    for ch in res["chunks"]:
+    for ch in res["chunks"] + res16["chunks"]:
         for t in range(0, ch["n_users"], 37):
             u = ch["user_lo"] + t
             mine_c, mine_p = _decode_chunk_user(ch, t, nt)
@@ -171,7 +181,7 @@ def test_host_runner_chunked_matches_device_run(fmt):
             ref_p = np.concatenate([preds[rs[u, x]:rs[u, x] + rc[u, x]] for x in range(nt)])
             assert np.array_equal(mine_c, ref_c) and np.array_equal(mine_p, ref_p)
         seen += ch["n_users"]
-    assert seen == n
+    assert seen == 2 * n
 
 
 def test_user_branch_lsh_tables_and_hybrid_scores(golden_c1):
