@@ -341,6 +341,9 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: 'weak' = one shard of the config's size per GPU (default), 'strong' = the config's n split over the GPUs")
     ap.add_argument("--sweep", action="store_true", help="band/row sweep of the LSH stages (extra, not the bench line)")
+    ap.add_argument("--lsh-only", action="store_true",
+                    help="stop after the neighbour tables (signatures .. top-k): for shapes whose predictions cannot be "
+                         "materialised (C4: ~5e11 predictions); no e2e leg")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
@@ -385,8 +388,9 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     warm = max(args.warmup, 3)
+    do_predict = not args.lsh_only
     for _ in range(warm):
-        out = pipe.run(rowptr, colidx, val)
+        out = pipe.run(rowptr, colidx, val, predict=do_predict)
         if pipe.cols_mode == 1 and out.n_predictions * 16 > n * m:
             pipe.cols_mode = 2          # touched-column bitmap beats 2 bytes per prediction (HostRunner's "auto" rule)
     barrier()
@@ -399,7 +403,7 @@ def main():
     ev0.record()
     outs = []
     for _ in range(args.steps):
-        out = pipe.run(rowptr, colidx, val)
+        out = pipe.run(rowptr, colidx, val, predict=do_predict)
         outs.append(out.stage_ms)
     ev1.record()
     barrier()
@@ -455,9 +459,11 @@ def main():
                     "bytes_per_launch": pred_bytes, "ms": ms_pred,
                     "note": "stage = row preparation + predict kernel + tie fix-up + one cursor readback"},
     }
+    if not do_predict:
+        del rl["predict"]
     for v in rl.values():
         v["frac"] = v["achieved"] / peak
-    dominant = max(("signatures+banding", "predict"), key=lambda s: stage_ms.get(s, 0.0))
+    dominant = max(rl, key=lambda s: stage_ms.get(s, 0.0))
     roofline = dict(rl[dominant])
     kernel_name = "predict_sparse_kernel" if dominant == "predict" else "minhash_tile_kernel"
     traffic = None
@@ -487,7 +493,7 @@ def main():
                 parity = {"config": args.config, "skipped": "full-size oracle pass too large for the bench run"}
         else:
             from query_recommendation_system_b200 import selfcheck
-            n_red = min(n, 16384)
+            n_red = min(n, 16384 if m <= 200_000 else 4096)
             parity = selfcheck.multi_rank_invariance(n_red, m, density, K, b, k, tab, dev, seed=DATA_SEED)
             if rank == 0:
                 parity = dict(parity, config="%s at %d sets per rank" % (args.config, n_red),
@@ -501,30 +507,33 @@ def main():
     if world > 1:
         exchanges = exchange_report(outs, out, stage_ms, dev, world)
 
-    runner = HostRunner(pipe)
-    # host inputs: the CSR of this rank's shard in pinned memory; column ids in the compact 16-bit wire format when the
-    # matrix has at most 65536 queries (HostRunner widens them on the device, inside the timed call)
-    h_rowptr, h_val = rowptr.cpu().pin_memory(), val.cpu().pin_memory()
-    h_colidx = colidx.cpu()
-    if m <= 65536:
-        h_colidx = torch.from_numpy(h_colidx.numpy().astype(np.uint16))
-    h_colidx = h_colidx.pin_memory()
-    for _ in range(2):
-        res = runner(h_rowptr, h_colidx, h_val)
-    barrier()
-    t0 = time.perf_counter()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(e2e_steps):
-        res = runner(h_rowptr, h_colidx, h_val)
-    e1.record()
-    barrier()
-    e2e_wall_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
-    te = torch.tensor([e0.elapsed_time(e1) / e2e_steps], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_ms = float(te.item())
+    e2e_ms = e2e_wall_ms = None
+    runner = None
+    if do_predict:
+        runner = HostRunner(pipe)
+        # host inputs: the CSR of this rank's shard in pinned memory; column ids in the compact 16-bit wire format when the
+        # matrix has at most 65536 queries (HostRunner widens them on the device, inside the timed call)
+        h_rowptr, h_val = rowptr.cpu().pin_memory(), val.cpu().pin_memory()
+        h_colidx = colidx.cpu()
+        if m <= 65536:
+            h_colidx = torch.from_numpy(h_colidx.numpy().astype(np.uint16))
+        h_colidx = h_colidx.pin_memory()
+        for _ in range(2):
+            res = runner(h_rowptr, h_colidx, h_val)
+        barrier()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        e2e_steps = max(3, min(args.steps, 10))
+        for _ in range(e2e_steps):
+            res = runner(h_rowptr, h_colidx, h_val)
+        e1.record()
+        barrier()
+        e2e_wall_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+        te = torch.tensor([e0.elapsed_time(e1) / e2e_steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_ms = float(te.item())
 
     rc = 0
     if rank == 0:
@@ -551,10 +560,16 @@ def main():
                 "gpu_same_sample": gpu_on_cpu_sample(args.config, n_cpu, tab, dev, cres)}
         line["rooflines"] = rl
         line["roofline"] = roofline
-        line["e2e"] = {"value": n_total / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "wall_ms_per_step": e2e_wall_ms,
-                       "h2d_bytes_per_step": runner.h2d_bytes, "d2h_bytes_per_step": runner.d2h_bytes, "steps": e2e_steps,
-                       "call": "pipeline.HostRunner(pipe)(rowptr, colidx, val) with pinned host tensors (column ids uint16 when "
-                               "m <= 65536); returns pinned sparse predictions + neighbour tables (ids, 1000 x similarity, counts)"}
+        if e2e_ms is None:
+            line["e2e"] = None
+            line["notes"]["lsh_only"] = ("--lsh-only: the step ends with the neighbour tables; the predictions of this shape cannot be "
+                                         "materialised, so there is no prediction stage and no e2e leg")
+        else:
+            line["e2e"] = {
+                "value": n_total / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "wall_ms_per_step": e2e_wall_ms,
+                "h2d_bytes_per_step": runner.h2d_bytes, "d2h_bytes_per_step": runner.d2h_bytes, "steps": e2e_steps,
+                "call": "pipeline.HostRunner(pipe)(rowptr, colidx, val) with pinned host tensors (column ids uint16 when "
+                        "m <= 65536); returns pinned sparse predictions + neighbour tables (ids, 1000 x similarity, counts)"}
         if exchanges is not None:
             line["exchanges"] = exchanges
         line["parity_check"] = parity
@@ -563,8 +578,8 @@ def main():
             "sigs_per_s": n_total / (ms_sig * 1e-3),
             "candidate_pairs_per_s": n_pairs / (sum(stage_ms.get(s, 0.0) for s in ("grouping", "pairs+cosine")) * 1e-3),
             "pair_slots_per_s": n_slots / (sum(stage_ms.get(s, 0.0) for s in ("grouping", "pairs+cosine")) * 1e-3),
-            "predicted_ratings_per_s": covered / (ms_pred * 1e-3),
-            "nonzero_predictions_per_s": n_pred / (ms_pred * 1e-3),
+            "predicted_ratings_per_s": covered / (ms_pred * 1e-3) if do_predict else None,
+            "nonzero_predictions_per_s": n_pred / (ms_pred * 1e-3) if do_predict else None,
             "counts": {"sets": n_total, "nnz_per_gpu": nnz, "candidate_pairs": n_pairs, "pair_slots": n_slots,
                        "nonzero_predictions": n_pred, "covered_cells": covered},
             "ms": {kx: round(v, 4) for kx, v in stage_ms.items()},
@@ -637,7 +652,15 @@ def exchange_report(outs, out, stage_ms, dev, world):
         ms = stage_ms.get("exchange:" + name)
         rep[name] = {"bytes_sent_per_rank_max": int(bts), "ms": ms,
                      "nvlink_frac_of_770GBps": (bts / (ms * 1e-3) / 770e9) if ms else None}
+        if name == "signatures":
+            # all-gather on a second stream and communicator, behind the record exchange and the grouping: `ms` is its own
+            # duration, `exposed_ms` what the main stream waited for it
+            bg = stage_ms.get("background:signatures")
+            rep[name].update({"ms": bg, "exposed_ms": ms, "nvlink_frac_of_770GBps": (bts / (bg * 1e-3) / 770e9) if bg else None})
+        if name.startswith("ratings"):
+            rep[name]["note"] = "neighbour rows of other ranks, read in place by the prediction kernel (no separate exchange stage)"
     rep["total_ms"] = sum(v for kx, v in stage_ms.items() if kx.startswith("exchange:"))
+    rep["total_note"] = "time on the main stream: record all-to-all, pair all-to-all, exposed wait for the signature all-gather, barrier"
     return rep
 
 

@@ -83,33 +83,52 @@ seg_steps_kernel(const int64_t *__restrict__ tilepos, int64_t U, int nt, uint32_
   }
 }
 
-// one warp per (row, window) sub-segment
-__global__ void __launch_bounds__(256)
+// One warp per ROW; one warp iteration = one 128-byte output step.  The row's window bounds (tilepos) and step
+// offsets (seg_off) are held one per lane, 31 windows at a time, so the window of output step q is a ballot + popc
+// and its bounds are three shuffles: no dependent global load per sub-segment, every iteration independent of the
+// others (the loads of several steps are in flight together), loads and stores coalesced.
+__global__ void __launch_bounds__(256, 5)
 pack_rows_kernel(const int *__restrict__ colidx, const uint8_t *__restrict__ val, const int64_t *__restrict__ tilepos,
                  const uint64_t *__restrict__ seg_off, int64_t U, int nt, int tile, uint32_t *__restrict__ packed,
                  unsigned *__restrict__ zero_flag) {
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
-  const int64_t total = U * nt;
-  for (int64_t x = warp_global; x < total; x += nwarps) {
-    const int64_t v = x / nt;
-    const int t = int(x - v * nt);
-    const int64_t a = tilepos[v * (nt + 1) + t], e = tilepos[v * (nt + 1) + t + 1];
-    const uint64_t o = seg_off[x], n = seg_off[x + 1] - o;
-    const int q0 = t * tile;
-    const uint32_t pad = uint32_t(pw_spare_col(tile)) << 8;      // rating 0, column = the spare accumulator slot
-    for (uint64_t s = 0; s < n; ++s) {
-      const int64_t i = a + int64_t(s) * 32 + lane;
-      uint32_t w = pad;
-      if (i < e) {
-        const uint32_t r = val[i];
-        w = (uint32_t(ld_stream_s32(colidx + i) - q0) << 8) | r;
-        if (r == 0) *zero_flag = 1u;       // an explicit rating 0 (= not rated, recommender.py:41): the predictor
-      }                                    // takes its guarded accumulation path
-      packed[((o + s) << 5) + lane] = w;
+  const uint32_t pad = uint32_t(pw_spare_col(tile)) << 8;      // rating 0, column = the spare accumulator slot
+  bool saw_zero = false;
+  for (int64_t v = warp_global; v < U; v += nwarps) {
+    const int64_t *tp = tilepos + v * (nt + 1);
+    const uint64_t *so = seg_off + v * nt;
+    const int64_t row_lo = tp[0];                   // = rowptr[v]: positions inside the row fit 32 bits
+    const int *const row_col = colidx + row_lo;
+    const uint8_t *const row_val = val + row_lo;
+    for (int tb = 0; tb < nt; tb += 31) {
+      // lane l: bounds of window tb + l (lanes beyond the row's last bound repeat it: empty windows)
+      const int tl = min(tb + lane, nt);
+      const unsigned my_tp = unsigned(tp[tl] - row_lo);
+      const uint64_t my_so = so[tl];              // so[nt] = the next row's first step (seg_off has U * nt + 1 entries)
+      const int nwin = min(31, nt - tb);
+      const uint64_t q_first = __shfl_sync(kFull, my_so, 0);
+      const unsigned rel = unsigned(my_so - q_first);
+      const unsigned q_count = __shfl_sync(kFull, rel, nwin);
+      uint32_t *const out = packed + (q_first << 5) + lane;
+#pragma unroll 8
+      for (unsigned q = 0; q < q_count; ++q) {
+        // window of step q: the last one (of this chunk) whose first step is <= q
+        const int w = __popc(__ballot_sync(kFull, rel <= q && lane <= nwin)) - 1;
+        const unsigned a = __shfl_sync(kFull, my_tp, w), e = __shfl_sync(kFull, my_tp, w + 1);
+        const unsigned i = a + (q - __shfl_sync(kFull, rel, w)) * 32u + unsigned(lane);
+        uint32_t word = pad;
+        if (i < e) {
+          const uint32_t r = row_val[i];
+          word = (uint32_t(ld_stream_s32(row_col + i) - (tb + w) * tile) << 8) | r;
+          saw_zero |= r == 0;              // an explicit rating 0 (= not rated, recommender.py:41): the predictor
+        }                                  // takes its guarded accumulation path
+        out[size_t(q) << 5] = word;
+      }
     }
   }
+  if (saw_zero) *zero_flag = 1u;
 }
 
 // ------------------------------------------------------------------ sparse form
@@ -282,15 +301,15 @@ predict_sparse_kernel(const __grid_constant__ PeerView pv, int Q,
   // on the user only — neighbour ids, ranks, similarities, the rows' offset tables — is set up once, and since the
   // sub-segments of a row are consecutive in (row, window) order the end of one window is the start of the next:
   // one 4-byte load per neighbour and window.
-  long long nz_total = 0;
+  unsigned nz_total = 0;      // non-zero predictions written by this warp (far below 2^32)
   const uint32_t *const my_packed = peer_packed(pv, pv.my);
   for (;;) {
-    long long ul = 0;
-    if (lane == 0) ul = (long long)atomicAdd(user_counter, 1ull);
+    unsigned ul = 0;           // a launch has fewer than 2^32 users (the tie list packs the user in 32 bits as well)
+    if (lane == 0) ul = unsigned(min(atomicAdd(user_counter, 1ull), 0xFFFFFFFFull));
     ul = __shfl_sync(kFull, ul, 0);
-    if (ul >= n_users) break;
+    if (int64_t(ul) >= n_users) break;
     const int c = min(u_cnt[ul], ku);
-    const int64_t tbase = ul * ku;
+    const int64_t tbase = int64_t(ul) * ku;
 
     // ---- lane <-> table slots lane and lane + 32; a neighbour is a GLOBAL row id: rank = id / rows_per_peer
     //      (bits 26..29 of the tag), row on that rank = the remainder.  so0 / so1 = the low words of the row's
@@ -327,17 +346,19 @@ predict_sparse_kernel(const __grid_constant__ PeerView pv, int Q,
       }
       tag1 |= unsigned(pr) << 26;
     }
-    const unsigned *const own_so = reinterpret_cast<const unsigned *>(peer_seg(pv, pv.my) + (user_base + ul) * nt);
-    unsigned s0 = so0 ? so0[0] : 0u, s1 = so1 ? so1[0] : 0u, sown = __ldg(own_so);     // starts of window 0
+    // the user's own offset table: an index (a launch has fewer than 2^32 sub-segments) off a uniform base
+    const uint64_t *const seg_my = peer_seg(pv, pv.my);
+    const unsigned own_x = unsigned((user_base + int64_t(ul)) * nt);
+    unsigned s0 = so0 ? so0[0] : 0u, s1 = so1 ? so1[0] : 0u, sown = unsigned(__ldg(seg_my + own_x));     // starts of window 0
    for (int t = 0; t < nt; ++t) {
-    const int64_t item = ul * nt + t;
+    const int64_t item = int64_t(ul) * nt + t;
     const int q0 = t * tile;
     const int width = min(tile, Q - q0);
     // this window's sub-segments: [start, end) in 128-byte steps; the end is the next window's start
     const unsigned o0 = s0, o1 = s1, own_o = sown;
     s0 = so0 ? so0[2 * (t + 1)] : 0u;
     s1 = so1 ? so1[2 * (t + 1)] : 0u;
-    sown = __ldg(own_so + 2 * (t + 1));
+    sown = unsigned(__ldg(seg_my + own_x + unsigned(t + 1)));
     const unsigned n0 = s0 - o0, n1 = s1 - o1, own_n = sown - own_o;
     // the user's own row in this window (its rated cells are cleared after the accumulation): the first two steps
     // are requested below and sit in two registers until then
@@ -356,7 +377,7 @@ predict_sparse_kernel(const __grid_constant__ PeerView pv, int Q,
     ex1 = ex1 - d1 + tot0;
 
     if (total == 0) {       // nothing gathered: no prediction in this window (the bitmap rows are zeroed by the caller)
-      if (lane == 0) { row_start[item] = int64_t(unsigned(ul) % unsigned(n_regions)) * region_cap; row_cnt[item] = 0; }
+      if (lane == 0) { row_start[item] = int64_t(ul % unsigned(n_regions)) * region_cap; row_cnt[item] = 0; }
       continue;
     }
     if (own_n > 0) own_p0 = ld_stream_u32(my_packed + (size_t(own_o) << 5) + lane);
@@ -467,19 +488,33 @@ predict_sparse_kernel(const __grid_constant__ PeerView pv, int Q,
     unsigned *const bitmap_row = reinterpret_cast<unsigned *>(cols) + item * (tile >> 5);
     int touched = 0;
     if constexpr (MILLI) {
-      // A lane looks at columns j0 + lane and j0 + 32 + lane: the two ballots ARE the bitmap words of the 64 columns.
+      // A lane looks at columns j0 + lane and j0 + 32 + lane: the two ballots ARE the bitmap words of the 64 columns
+      // (lane w keeps word w of the current 1024-column group; one coalesced store per group).
       // Listed iff D != 0 (then the prediction is >= 18).  Neighbours of similarity 0 never enter the step list, so
       // an accumulator is either untouched (all zero) or has D != 0; columns beyond the window's width stay zero.
+      // Only the low words are read (32-bit loads, explicit so that the compiler does not widen the test).
+      unsigned my_word = 0u;
+      const unsigned jl_s = unsigned(__cvta_generic_to_shared(jlist));
+      unsigned a_s = acc_s + 8u * unsigned(lane);
+      const unsigned ltm = (1u << lane) - 1u;      // = %lanemask_lt, as ALU work (the special-register read is slow)
 #pragma unroll 1
       for (int j0 = 0; j0 < width; j0 += 64) {
-        const unsigned long long x0 = acc[j0 + lane], x1 = acc[j0 + 32 + lane];     // acc holds round_up(tile, 64) words
-        const bool hit0 = (unsigned(x0) & 0xFFFFFFu) != 0u, hit1 = (unsigned(x1) & 0xFFFFFFu) != 0u;
+        unsigned x0, x1;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x0) : "r"(a_s));            // acc holds round_up(tile, 64) words
+        asm volatile("ld.shared.u32 %0, [%1+256];" : "=r"(x1) : "r"(a_s));
+        a_s += 512u;
+        const bool hit0 = (x0 & 0xFFFFFFu) != 0u, hit1 = (x1 & 0xFFFFFFu) != 0u;
         const unsigned m0 = __ballot_sync(kFull, hit0), m1 = __ballot_sync(kFull, hit1);
-        if (bitmap && lane < 2 && j0 + 32 * lane < width) bitmap_row[(j0 >> 5) + lane] = lane == 0 ? m0 : m1;
+        const int w0 = (j0 >> 5) & 31;
+        my_word = lane == w0 ? m0 : (lane == w0 + 1 ? m1 : my_word);
         const int c0 = __popc(m0);
-        if (hit0) jlist[touched + __popc(m0 & lt)] = uint16_t(j0 + lane);
-        if (hit1) jlist[touched + c0 + __popc(m1 & lt)] = uint16_t(j0 + 32 + lane);
+        if (hit0) asm volatile("st.shared.u16 [%0], %1;" ::"r"(jl_s + 2u * unsigned(touched + __popc(m0 & ltm))), "h"((unsigned short)(j0 + lane)) : "memory");
+        if (hit1) asm volatile("st.shared.u16 [%0], %1;" ::"r"(jl_s + 2u * unsigned(touched + c0 + __popc(m1 & ltm))), "h"((unsigned short)(j0 + 32 + lane)) : "memory");
         touched += c0 + __popc(m1);
+        if (w0 == 30 || j0 + 64 >= width) {          // warp-uniform: the group of 32 words is complete (or the window ends)
+          if (bitmap && (j0 & ~1023) + 32 * lane < width) bitmap_row[((j0 >> 10) << 5) + lane] = my_word;
+          my_word = 0u;
+        }
       }
     } else {
 #pragma unroll 2
@@ -497,7 +532,7 @@ predict_sparse_kernel(const __grid_constant__ PeerView pv, int Q,
       }
     }
     unsigned long long base = 0;
-    const int region = int(unsigned(ul) % unsigned(n_regions));     // (a launch has fewer than 2^32 users)
+    const int region = int(ul % unsigned(n_regions));
     const int64_t region_base = int64_t(region) * region_cap;
     if (lane == 0) {
       if (touched > 0) base = atomicAdd(cursors + region, (unsigned long long)touched);
@@ -553,9 +588,9 @@ predict_sparse_kernel(const __grid_constant__ PeerView pv, int Q,
               const unsigned long long slot = atomicAdd(tie_count, 1ull);
               if (int64_t(slot) < tie_capacity)
                 tie_list[slot] = make_ulonglong2((unsigned long long)(w_preds + x - preds),   // position in preds
-                                                 ((unsigned long long)(unsigned)ul << 32) | unsigned(q0 + j));
+                                                 ((unsigned long long)ul << 32) | unsigned(q0 + j));
               else
-                p = resolve_tie(pv, u_idx, u_milli, ul, ku, c, q0 + j, tile, nt);   // list full: settle here
+                p = resolve_tie(pv, u_idx, u_milli, int64_t(ul), ku, c, q0 + j, tile, nt);   // list full: settle here
             }
             if (cols_mode == 1) reinterpret_cast<uint16_t *>(w_cols)[x] = uint16_t(q0 + j);
             else if (cols_mode == 0) reinterpret_cast<int *>(w_cols)[x] = q0 + j;
@@ -564,7 +599,7 @@ predict_sparse_kernel(const __grid_constant__ PeerView pv, int Q,
         }
         nz += __popc(__ballot_sync(kFull, p != 0));
       }
-      nz_total += nz;
+      nz_total += unsigned(nz);
     }
     __syncwarp();
    }
@@ -810,7 +845,7 @@ int qrs_predict_prepare(const int64_t *rowptr, const int32_t *colidx, const uint
   if (tile <= 0 || tile % 32 != 0) return QRS_ERR_INVALID_ARG;
   if (nnz >= (int64_t(1) << 36)) return QRS_ERR_UNSUPPORTED;
   const int64_t nt64 = ceil_div<int64_t>(Q, tile);
-  if (nt64 > (1 << 20)) return QRS_ERR_UNSUPPORTED;
+  if (nt64 > (1 << 20) || U * nt64 >= (int64_t(1) << 32)) return QRS_ERR_UNSUPPORTED;
   const int nt = int(nt64);
   if (!ws || ws_bytes < qrs_predict_sparse_workspace_bytes(U, nnz, Q, tile, capacity)) return QRS_ERR_WORKSPACE;
   if (U == 0) return QRS_OK;
@@ -834,7 +869,7 @@ int qrs_predict_prepare(const int64_t *rowptr, const int32_t *colidx, const uint
   int rc = exclusive_scan_u32_to_u64(w.steps, w.seg_off, U * nt, w.scan_ws, w.scan_bytes, st);
   if (rc != QRS_OK) return rc;
   {
-    int64_t blocks = ceil_div<int64_t>(U * nt, 8);
+    int64_t blocks = ceil_div<int64_t>(U, 8);
     const int64_t cap2 = int64_t(sm_count()) * 16;
     if (blocks > cap2) blocks = cap2;
     pack_rows_kernel<<<unsigned(blocks), 256, 0, st>>>(colidx, val, w.tilepos, w.seg_off, U, nt, tile, w.packed,
@@ -865,6 +900,7 @@ int qrs_predict_sparse(const int64_t *rowptr, const int32_t *colidx, const uint8
   if (capacity > 0 && (!cols || !preds)) return QRS_ERR_INVALID_ARG;
   if (tile <= 0 || tile % 32 != 0) return QRS_ERR_INVALID_ARG;
   if (tile > qrs_predict_max_tile(u_milli != nullptr) || ku > QRS_MAX_TOPK) return QRS_ERR_UNSUPPORTED;
+  if (n_users >= (int64_t(1) << 32)) return QRS_ERR_UNSUPPORTED;      // the kernel counts users in 32 bits
   if (!ws || (reinterpret_cast<uintptr_t>(ws) & 255) != 0 ||
       ws_bytes < qrs_predict_sparse_workspace_bytes(U, nnz, Q, tile, capacity))
     return QRS_ERR_WORKSPACE;

@@ -324,6 +324,9 @@ class LshCfPipeline:
             out.covered_cells = n_local * self.m - int(host[5 + len(tail) - 1])
             tm.mark("predict")
         out.stage_ms = tm.result()
+        if self.profile and getattr(self, "_bg_events", None) is not None:
+            out.stage_ms["background:signatures"] = self._bg_events[0].elapsed_time(self._bg_events[1])
+            self._bg_events = None
         return out, True
 
     def _launch_chunk(self, st, plan, rowptr, colidx, val, idx, v, cnt, milli, ci, bounds, chunks, regions, tile, chunk_sink):
@@ -367,7 +370,13 @@ class LshCfPipeline:
         main = torch.cuda.current_stream()
         self._side.wait_stream(main)
         with torch.cuda.stream(self._side):
+            if self.profile:          # the background work's own duration (it overlaps the main stream)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
             res = fn()
+            if self.profile:
+                e1.record()
+                self._bg_events = (e0, e1)
         for t in inputs:
             t.record_stream(self._side)
 

@@ -470,6 +470,26 @@ def test_cpu_double_record_hash_matches_cuda():
         assert np.array_equal(rec.cpu().numpy().view(np.uint64), double.band_records_np(sig, b, 1000))
 
 
+@pytest.mark.parametrize("n,K,b", [(1, 128, 32), (63, 128, 32), (64, 128, 32), (65, 128, 32), (1000, 256, 64), (777, 128, 64),
+                                   (300, 96, 32), (130, 128, 16), (200, 64, 64), (90, 126, 42), (5000, 128, 32)])
+def test_band_records_tile_form(n, K, b):
+    """qrs_band_records in its tile form (signature tiles staged by bulk asynchronous copies, records transposed in
+    shared memory): partial tiles, r = 1 / 2 / 3 / 4 / 8, -1 rows (sentinel hash), int16 wrap; K = 126 takes the
+    per-row kernel (a tile is not a 16-byte multiple).  Against the NumPy record layout, norm2 against int64 sums."""
+    import cpu_stage_double as double
+    from query_recommendation_system_b200 import stages
+    rng = np.random.default_rng(n * 131 + K + b)
+    sig = rng.integers(0, 70000, size=(n, K)).astype(np.int64)
+    sig[rng.random(n) < 0.1] = -1                      # empty sets
+    if n > 2:
+        sig[2, : K // b] = -1                          # one all-(-1) band inside a regular row
+    rec, norm2 = stages.band_records(cu(sig, torch.int32), b, 12345)
+    assert np.array_equal(rec.cpu().numpy().view(np.uint64), double.band_records_np(sig, b, 12345))
+    assert np.array_equal(norm2.cpu().numpy(), (sig * sig).sum(axis=1))
+    rec_only, none = stages.band_records(cu(sig, torch.int32), b, 0, want_norm2=False)
+    assert none is None and np.array_equal(rec_only.cpu().numpy().view(np.uint64), double.band_records_np(sig, b, 0))
+
+
 def test_predict_sparse_regions_and_overflow():
     """Slices reserved from several cursors: same per-user content; a too-small region drops writes but
     still reports the demand, so the caller can size the buffer and run again."""
