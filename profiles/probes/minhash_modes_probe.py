@@ -17,20 +17,23 @@ dev = torch.device("cuda:0")
 rowptr, colidx, val = synth.planted_csr(n, m, density, seed=20260102, device=dev)
 np.random.seed(7)
 tab = torch.from_numpy(np.stack([np.random.permutation(m) for _ in range(K)], axis=1).astype(np.int32)).to(dev)
-head = stages.perm_head(tab, stages.choose_head_ranks(m, colidx.numel() / n))
+R_probe = int(os.environ.get("QRS_PROBE_R", 0)) or stages.choose_head_ranks(m, colidx.numel() / n)
+head = stages.perm_head(tab, R_probe)
+REPS = int(os.environ.get("QRS_PROBE_REPS", 10))
 res = {"config": [n, m, density, K, b], "R": int(head.shape[0]) * 8, "ms": {}}
 outs = {}
-for mode, name in ((_lib.MINHASH_FIRST_TOUCH, "first_touch"), (_lib.MINHASH_TILE, "tile"), (_lib.MINHASH_AUTO, "auto")):
+for mode, name in ((_lib.MINHASH_FIRST_TOUCH, "first_touch"), (_lib.MINHASH_TILE, "tile"), (_lib.MINHASH_AUTO, "auto"),
+                   (_lib.MINHASH_DIRECT, "direct")):
     try:
-        for _ in range(3):
+        for _ in range(2):
             o = stages.minhash(rowptr, colidx, m, tab, head, b=b, mode=mode)
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record()
-        for _ in range(10):
+        for _ in range(REPS):
             o = stages.minhash(rowptr, colidx, m, tab, head, b=b, mode=mode)
         t1.record()
         torch.cuda.synchronize()
-        res["ms"][name] = t0.elapsed_time(t1) / 10
+        res["ms"][name] = t0.elapsed_time(t1) / REPS
         outs[name] = o
     except _lib.QrsError as e:
         res["ms"][name] = str(e)
@@ -40,4 +43,5 @@ for name, o in outs.items():
         res["equal_" + name] = bool(torch.equal(o[0], ref[0]) and torch.equal(o[1], ref[1]) and torch.equal(o[2], ref[2]))
 print(json.dumps(res))
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-json.dump(res, open(os.path.join(ROOT, "gpurun_out", "minhash_modes_%s.json" % os.environ.get("QRS_CONFIG", "C2")), "w"))
+with open(os.path.join(ROOT, "gpurun_out", "minhash_modes_%s.jsonl" % os.environ.get("QRS_CONFIG", "C2")), "a") as f:
+    f.write(json.dumps(res) + "\n")

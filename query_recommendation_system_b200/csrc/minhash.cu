@@ -139,6 +139,15 @@ minhash_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ colid
           int mine = (t0 + lane < len) ? __ldg(colidx + lo + t0 + lane) : -1;
           const int cnt = min(32, len - t0);
           int t = 0;
+          for (; t + 8 <= cnt; t += 8) {          // eight table rows in flight per lane (the table is far larger than L2
+            int ev[8], vv[8];                     // at the shapes that take this path)
+#pragma unroll
+            for (int u = 0; u < 8; ++u) ev[u] = __shfl_sync(kFull, mine, t + u);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) vv[u] = __ldg(perm_tab + int64_t(ev[u]) * K + i);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v = min(v, vv[u]);
+          }
           for (; t + 4 <= cnt; t += 4) {
             int e0 = __shfl_sync(kFull, mine, t), e1 = __shfl_sync(kFull, mine, t + 1);
             int e2 = __shfl_sync(kFull, mine, t + 2), e3 = __shfl_sync(kFull, mine, t + 3);
@@ -228,6 +237,12 @@ __device__ __forceinline__ void st_shared_b16(unsigned addr, unsigned v) {
 }
 __device__ __forceinline__ void st_shared_b32(unsigned addr, unsigned v) {
   asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ int4 ld_stream_v4(const int *p) {      // 16-byte streaming (read-once) load
+  int4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
 }
 __device__ __forceinline__ void prefetch_l2(const void *p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
@@ -339,9 +354,40 @@ minhash_tile_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ 
       int t0 = g * 256;
       int e[8];
       const int spare = map_bytes / WB;
+      const bool vec = (reinterpret_cast<uintptr_t>(colidx) & 15) == 0;
+      const int64_t nnz_all = rowptr[n];
+      // 128-bit form (colidx 16-byte aligned): a row is walked from its start rounded DOWN to 16 bytes, a lane takes
+      // entries 4 * lane .. + 3 and 128 + 4 * lane .. + 3 of a step with two 16-byte loads; what lies before the row
+      // (up to 3 entries of the previous one), behind it, or behind the end of the array points at the spare word.
+      auto row_head = [&](int set) -> int { return vec ? int(rp[bidx * 8 + set] & 3) : 0; };
       auto load8 = [&](int (&dst)[8], int set, int first) {
         const int64_t lo = rp[bidx * 8 + set];
         const int len = int(rp[bidx * 8 + set + 1] - lo);
+        if (vec) {
+          const int head = int(lo & 3), vlen = len + head;
+          const int64_t vbase = lo - head;
+          const bool interior = first >= head && first + 256 <= vlen;          // warp-uniform: every entry is the row's
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int vp = first + 128 * u + 4 * lane;
+            int4 v = make_int4(spare, spare, spare, spare);
+            if (interior || (vp < vlen && vbase + vp + 4 <= nnz_all)) {
+              v = ld_stream_v4(colidx + vbase + vp);
+            } else if (vp < vlen) {                                            // the last 16 bytes of the array
+              if (vbase + vp < nnz_all) v.x = ld_stream_s32(colidx + vbase + vp);
+              if (vbase + vp + 1 < nnz_all) v.y = ld_stream_s32(colidx + vbase + vp + 1);
+              if (vbase + vp + 2 < nnz_all) v.z = ld_stream_s32(colidx + vbase + vp + 2);
+            }
+            if (!interior) {
+              if (vp < head || vp >= vlen) v.x = spare;
+              if (vp + 1 < head || vp + 1 >= vlen) v.y = spare;
+              if (vp + 2 < head || vp + 2 >= vlen) v.z = spare;
+              if (vp + 3 < head || vp + 3 >= vlen) v.w = spare;
+            }
+            dst[4 * u] = v.x; dst[4 * u + 1] = v.y; dst[4 * u + 2] = v.z; dst[4 * u + 3] = v.w;
+          }
+          return;
+        }
         const int *src = colidx + lo + first + lane;
         if (first + 256 <= len) {          // warp-uniform
 #pragma unroll
@@ -355,7 +401,7 @@ minhash_tile_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ 
       // `nxt`; the two register sets swap roles from step to step (no copies); false when the warp is done
       const unsigned bmw_s = bm_s + unsigned(bidx);
       auto step = [&](int (&cur)[8], int (&nxt)[8]) -> bool {
-        const int len = int(rp[bidx * 8 + jj + 1] - rp[bidx * 8 + jj]);
+        const int len = int(rp[bidx * 8 + jj + 1] - rp[bidx * 8 + jj]) + row_head(jj);      // steps count from the aligned start
         int njj = jj, nt0 = t0 + G * 256;
         if (nt0 >= len) {
           todo &= todo - 1;

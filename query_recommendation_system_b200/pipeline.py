@@ -107,6 +107,8 @@ class LshCfPipeline:
         self._cap = {}                      # learnt buffer capacities: candidate pairs, exchange slots
         self.peer_margin = 1.25             # several GPUs: the peer buffer is sized for this x the first shard's entries
         self.predict_chunks = 1             # > 1: predictions are produced (and can be shipped) chunk by chunk
+        self.chunk_schedule = "equal"       # "ramp": geometric chunk sizes (see _chunk_bounds)
+        self.chunk_growth = 1.7
         self.cols_mode = 0                  # prediction columns as int32 ids (0), uint16 ids (1) or a bitmap (2)
         # how a candidate pair is scored: "signature" = rounded cosine of the MinHash signatures
         # (recommender.py:203-204, the query branch); "ratings" = rounded, clamped cosine of the mean-centred
@@ -248,7 +250,7 @@ class LshCfPipeline:
             # kept for later steps, re-run only if a region would overflow.
             regions = self.pred_regions
             chunks = max(1, min(self.predict_chunks, n_local))
-            bounds = [n_local * ci // chunks for ci in range(chunks + 1)]
+            bounds = self._chunk_bounds(n_local, chunks)
             known = [self._pred_capacity.get((chunks, ci, self.cols_mode), 0) * regions for ci in range(chunks)]
             peers = None
             if G > 1:
@@ -328,6 +330,22 @@ class LshCfPipeline:
             out.stage_ms["background:signatures"] = self._bg_events[0].elapsed_time(self._bg_events[1])
             self._bg_events = None
         return out, True
+
+    def _chunk_bounds(self, n_local: int, chunks: int):
+        """User ranges of the prediction chunks.  "equal": equal parts.  "ramp": each chunk `chunk_growth` times the
+        previous one — a caller that ships chunk i while chunk i + 1 is computed (HostRunner) gets its first bytes
+        after a small fraction of the prediction time, and since the download is slower than the computation, a
+        growth below (download time / prediction time) keeps the copy stream busy from then on."""
+        if self.chunk_schedule == "ramp" and chunks > 1:
+            w = [self.chunk_growth ** i for i in range(chunks)]
+            tot, acc, bounds = sum(w), 0.0, [0]
+            for x in w[:-1]:
+                acc += x
+                bounds.append(int(round(n_local * acc / tot)))
+            bounds.append(n_local)
+            if all(b2 > b1 for b1, b2 in zip(bounds[:-1], bounds[1:])):
+                return bounds
+        return [n_local * ci // chunks for ci in range(chunks + 1)]
 
     def _launch_chunk(self, st, plan, rowptr, colidx, val, idx, v, cnt, milli, ci, bounds, chunks, regions, tile, chunk_sink):
         lo, hi = bounds[ci], bounds[ci + 1]
@@ -480,12 +498,13 @@ class HostRunner:
     recommender.py:204): `HostRunner.similarities(res)` is the float64 table.
     Buffers are allocated once and reused across calls."""
 
-    def __init__(self, pipe: LshCfPipeline, chunks: int = 8, cols_format: str = "auto"):
+    def __init__(self, pipe: LshCfPipeline, chunks: int = 8, cols_format: str = "auto", schedule: str = "ramp"):
         """cols_format: "i32" | "u16" | "bitmap" | "auto" (u16 when the column ids fit, switching to the
         touched-column bitmap once a call has shown that more than 1/16 of the cells get a prediction —
         the point where m/8 bitmap bytes per user beat 2 bytes per prediction)."""
         self.pipe = pipe
         pipe.predict_chunks = chunks
+        pipe.chunk_schedule = schedule
         self.cols_format = cols_format
         fits16 = pipe.m <= 65536
         pipe.cols_mode = {"i32": 0, "u16": 1, "bitmap": 2, "auto": 1 if fits16 else 0}[cols_format]

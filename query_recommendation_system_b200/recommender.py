@@ -233,6 +233,8 @@ class Recommender:
         if band is None:
             raise QrsError("no band count satisfies the reference rule for PERM=%d (recommender.py:156-165); "
                            "pass bands= explicitly" % K)
+        if kmax > 64:
+            self._log("MAX_CANDIDATES %d clamped to 64 (the top-k kernel keeps 64 keys per row)" % kmax)
         kmax = max(1, min(kmax, 64))
         lsh = LSH(band, device=sig.device)
         lsh.compute_buckets_batch(sig)                                                    # recommender.py:171-174
@@ -334,6 +336,13 @@ class Recommender:
         """recommender.py:292-343 → (scores_to_predict int[P, 2], predictions DataFrame[int], missed int[M, 2])."""
         if (QUERY_WEIGHT, USER_WEIGHT, DEFAULT_MEAN) != (0.6, 0.4, 60):
             raise QrsError("the prediction kernel is built with the reference's weights (0.6, 0.4, 60)")
+        # limits of the dense drop-in kernel, checked before any work is done (INTEGRATION.md "Limits")
+        n_q = len(self.queriesIDs)
+        if n_q * 17 > 200 * 1024:
+            raise QrsError("compute_scores() keeps one user's whole query axis in shared memory: at most %d queries, "
+                           "got %d — use pipeline.LshCfPipeline (sparse predictor) at this scale" % (200 * 1024 // 17, n_q))
+        if self.ratings.min() < 0 or self.ratings.max() > 255:
+            raise QrsError("ratings must be in 0..255 (generator.py uses 1..100)")
         self._log("\n========== QUERY SIMILARITY ==========")
         self.compute_querySimilarities()
         self._log("\n========== USER SIMILARITY ==========")

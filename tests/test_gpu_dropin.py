@@ -73,6 +73,7 @@ def test_compute_scores_end_to_end(golden_c1):
     # neighbour ORDER inside ties is unspecified in the reference (set iteration + unstable argsort), which can
     # move an fp64 sum by an ulp; integer predictions may then differ only on exact .5 ties — expect none or a handful
     diff = np.argwhere(got != ref)
+    print("compute_scores(): %d of %d cells differ from the reference's predictions" % (diff.shape[0], got.size))
     assert diff.shape[0] <= 3 and (np.abs(got - ref)[got != ref] <= 1).all(), diff
     if diff.shape[0] == 0:
         assert np.array_equal(missed, g["missed"])

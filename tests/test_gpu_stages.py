@@ -115,6 +115,29 @@ def test_minhash_tile_ragged_tiles(mode, n, m, K, b):
     assert torch.equal(rec, rec2) and torch.equal(norm2, norm2b)
 
 
+@pytest.mark.parametrize("shift", [0, 1, 2, 3])
+@pytest.mark.parametrize("m,K", [(3000, 64), (70000, 64)])
+def test_minhash_tile_colidx_alignment(shift, m, K):
+    """The tile scan reads the column indices with 16-byte loads from each row's start rounded down to 16 bytes:
+    every row misalignment (rows of all lengths mod 4), the array's last 16 bytes (exactly-sized tail), and a colidx
+    pointer that is itself only 4-byte aligned (shift != 0: the scalar form) give the oracle's signatures."""
+    from query_recommendation_system_b200 import stages
+    rng = np.random.default_rng(1000 + shift + m)
+    n = 133
+    lens = rng.integers(250, 700, size=n)
+    lens[:8] = [256, 257, 258, 259, 511, 512, 513, 1]
+    rowptr, colidx = _ragged_rows(rng, n, m, lens)
+    tab = spec.permutation_table(m, K, seed=5)
+    ref = spec.signatures(rowptr, colidx, tab)
+    tab_d = cu(tab, torch.int32)
+    head = stages.perm_head(tab_d, stages.choose_head_ranks(m, colidx.size / n))
+    buf = torch.empty(colidx.size + shift, dtype=torch.int32, device=DEV)
+    buf[shift:] = torch.from_numpy(colidx).to(DEV)
+    sig, norm2, _ = stages.minhash(cu(rowptr, torch.int64), buf[shift:], m, tab_d, head, b=0, mode=3)
+    assert np.array_equal(sig.cpu().numpy().astype(np.int64), ref)
+    assert np.array_equal(norm2.cpu().numpy(), (ref * ref).sum(axis=1))
+
+
 def test_minhash_tile_equals_first_touch_at_bench_density():
     """C2-like rows (5 % of 10 000 elements, planted groups): the three scans agree, records included."""
     from query_recommendation_system_b200 import synth
