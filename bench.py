@@ -457,7 +457,8 @@ def main():
                                "bytes_per_launch": sig_bytes, "ms": ms_sig, "launches_per_step": 1},
         "predict": {"bound": "hbm", "achieved": pred_bytes / (ms_pred * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                     "bytes_per_launch": pred_bytes, "ms": ms_pred,
-                    "note": "stage = row preparation + predict kernel + tie fix-up + one cursor readback"},
+                    "note": "stage = predict kernel + tie fix-up + the step's one counter readback (the once-per-step row preparation is the "
+                            "separate stage predict:prepare)"},
     }
     if not do_predict:
         del rl["predict"]

@@ -305,6 +305,8 @@ minhash_tile_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ 
   sig_t *sigt = reinterpret_cast<sig_t *>(bmb + map_bytes + 16);          // map_bytes % 16 == 0; the spare word
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool force_scalar = (mode & 0x100) != 0;
+  mode &= 0xFF;
   const int r_band = b > 0 ? K / b : 0;
   const int64_t tiles = ceil_div<int64_t>(n, SETS);
   const int nchunks = R >> 3;
@@ -354,7 +356,7 @@ minhash_tile_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ 
       int t0 = g * 256;
       int e[8];
       const int spare = map_bytes / WB;
-      const bool vec = (reinterpret_cast<uintptr_t>(colidx) & 15) == 0;
+      const bool vec = (reinterpret_cast<uintptr_t>(colidx) & 15) == 0 && !force_scalar;
       const int64_t nnz_all = rowptr[n];
       // 128-bit form (colidx 16-byte aligned): a row is walked from its start rounded DOWN to 16 bytes, a lane takes
       // entries 4 * lane .. + 3 and 128 + 4 * lane .. + 3 of a step with two 16-byte loads; what lies before the row
@@ -779,8 +781,17 @@ int qrs_minhash_perm(const int64_t *rowptr, const int32_t *colidx, int64_t n, in
   cudaStream_t st = as_stream(stream);
   long long *n2 = reinterpret_cast<long long *>(norm2);
   if (tile_sets != 0 && (mode == QRS_MINHASH_TILE || (mode == QRS_MINHASH_AUTO && kAutoUsesTile)))
+  {
+    // The map build reads the column indices one 128-byte line per warp load (32 lanes x 4 bytes).  The 16-byte
+    // form (a lane takes 4 consecutive entries, rows walked from their 16-byte aligned start) is kept behind
+    // QRS_MINHASH_V4_CSR=1: measured SLOWER on B200 — 0.180 against 0.141 ms at C2, 2.57 against 2.25 ms per 200 k sets
+    // at C3 (profiles/r2_minhash_csr_load_width.jsonl): the loads were never the limiter (the walk and the byte
+    // read-modify-writes are), and masking the row ends per component costs more than the six saved load
+    // instructions per step.  Bit 8 of the kernel's mode word = scalar form.
+    static const bool scalar_csr = [] { const char *e = getenv("QRS_MINHASH_V4_CSR"); return !(e && atoi(e) != 0); }();
     return launch_minhash_tile(tile_sets, rowptr, colidx, n, m, perm_tab, order_head, R, K, b, id_base, sig, n2,
-                               records, rec_stride, mode, st);
+                               records, rec_stride, mode | (scalar_csr ? 0x100 : 0), st);
+  }
   if (!ft_possible)
     return launch_minhash<true, 128>(rowptr, colidx, n, m, perm_tab, order_head, 0, K, b, id_base, sig, n2,
                                      records, rec_stride, QRS_MINHASH_DIRECT, 0, st);

@@ -108,7 +108,7 @@ class LshCfPipeline:
         self.peer_margin = 1.25             # several GPUs: the peer buffer is sized for this x the first shard's entries
         self.predict_chunks = 1             # > 1: predictions are produced (and can be shipped) chunk by chunk
         self.chunk_schedule = "equal"       # "ramp": geometric chunk sizes (see _chunk_bounds)
-        self.chunk_growth = 1.7
+        self.chunk_growth = 1.5
         self.cols_mode = 0                  # prediction columns as int32 ids (0), uint16 ids (1) or a bitmap (2)
         # how a candidate pair is scored: "signature" = rounded cosine of the MinHash signatures
         # (recommender.py:203-204, the query branch); "ratings" = rounded, clamped cosine of the mean-centred

@@ -45,9 +45,11 @@ def choose_head_ranks(m: int, avg_len: float) -> int:
 def minhash_prefers_direct(m: int, avg_len: float) -> bool:
     """AUTO's choice of kernel family.  The first-touch scans test ~m / |S| ranks per (set, hash) against a
     membership map in shared memory; the direct form gathers |S| table rows of K values per set with no shared
-    memory at all (64 warps per SM, eight rows in flight per lane).  Where the sets are short against the element
-    count (C4: 1 000 of 1 000 000) the map of ONE set fills an SM's shared memory and the scan runs at one CTA per
-    SM, so the gather wins: measured crossover |S|^2 ~ 4 m (profiles/r2_minhash_modes_c4.jsonl)."""
+    memory at all (64 warps per SM, eight rows in flight per lane).  Beyond the tile scan's reach (m > ~200 000) the
+    map of ONE set fills an SM's shared memory, the scan runs at one CTA per SM, and short sets (|S|^2 < 4 m) are
+    far cheaper to gather: 10.4 against 264 ms for 131 072 sets of ~1 000 of 1 000 000 elements, K = 128 (C4's
+    shard shape, profiles/r2_minhash_modes_c4.jsonl).  Where a tile scan exists it wins by 13x to 24x (C3 / C2:
+    2.25 against 28.5 ms, 0.14 against 3.3 ms), so the rule only applies above it."""
     return avg_len * avg_len < 4.0 * m and m > 200_000
 
 

@@ -118,9 +118,10 @@ def test_minhash_tile_ragged_tiles(mode, n, m, K, b):
 @pytest.mark.parametrize("shift", [0, 1, 2, 3])
 @pytest.mark.parametrize("m,K", [(3000, 64), (70000, 64)])
 def test_minhash_tile_colidx_alignment(shift, m, K):
-    """The tile scan reads the column indices with 16-byte loads from each row's start rounded down to 16 bytes:
-    every row misalignment (rows of all lengths mod 4), the array's last 16 bytes (exactly-sized tail), and a colidx
-    pointer that is itself only 4-byte aligned (shift != 0: the scalar form) give the oracle's signatures."""
+    """The tile scan's map build for every row misalignment (rows of all lengths mod 4), the array's last 16 bytes
+    (exactly-sized tail) and a colidx pointer that is itself only 4-byte aligned gives the oracle's signatures —
+    in the shipped 4-byte form and (test_minhash_tile_v4_csr_form re-runs this test with QRS_MINHASH_V4_CSR=1) in
+    the 16-byte form, which walks each row from its start rounded down to 16 bytes."""
     from query_recommendation_system_b200 import stages
     rng = np.random.default_rng(1000 + shift + m)
     n = 133
@@ -136,6 +137,21 @@ def test_minhash_tile_colidx_alignment(shift, m, K):
     sig, norm2, _ = stages.minhash(cu(rowptr, torch.int64), buf[shift:], m, tab_d, head, b=0, mode=3)
     assert np.array_equal(sig.cpu().numpy().astype(np.int64), ref)
     assert np.array_equal(norm2.cpu().numpy(), (ref * ref).sum(axis=1))
+
+
+def test_minhash_tile_v4_csr_form():
+    """The kept 16-byte CSR-load form of the map build (QRS_MINHASH_V4_CSR=1, read once per process) is bit-exact too."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("QRS_MINHASH_V4_CSR") == "1":
+        pytest.skip("already inside the re-run")
+    env = dict(os.environ, QRS_MINHASH_V4_CSR="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", os.path.abspath(__file__), "-k",
+                        "test_minhash_tile_colidx_alignment or test_minhash_tile_ragged_tiles"],
+                       env=env, cwd=root, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
 
 
 def test_minhash_tile_equals_first_touch_at_bench_density():
