@@ -233,6 +233,126 @@ pairs_score_r4_kernel(const uint64_t *__restrict__ records, int64_t n_records, c
   }
 }
 
+// The same for K = 128 * CH with CH known at compile time (CH = 1, 2: the headline configs), restructured around
+// what bound the kernel above — one slot at a time per warp, every slot waiting a full L2 round trip for two
+// 4K-byte rows:
+//   * the slots of record p (p against every earlier record of its run) are consecutive, so p's row is loaded
+//     once and kept in registers while it repeats (runs of taste-group size make this most of the slots);
+//   * the other row of slot sl + 1 is requested before slot sl is evaluated;
+//   * the 64-bit dot is formed only for slots that emit a pair (own band, no earlier band), and summed with three
+//     REDUX on 16-bit pieces when the lane partials stay below 2^48 (five 64-bit shuffle steps otherwise).
+template <int CH>
+__global__ void __launch_bounds__(kPairThreads)
+pairs_score_r4c_kernel(const uint64_t *__restrict__ records, int64_t n_records, const uint64_t *__restrict__ slot_off,
+                       const int *__restrict__ sig, const long long *__restrict__ norm2, int64_t sig_id_base,
+                       uint64_t *__restrict__ pairs, int *__restrict__ sim_milli, int64_t capacity,
+                       unsigned long long *__restrict__ n_pairs) {
+  __shared__ uint64_t s_pair[kPairWarps][32];
+  __shared__ long long s_dot[kPairWarps][32];
+  constexpr int K = 128 * CH;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t total = slot_off[n_records];
+  const uint64_t chunks = (total + 31) / 32;
+  const uint64_t warp_global = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = (uint64_t(gridDim.x) * blockDim.x) >> 5;
+  auto row_of = [&](uint64_t rec) {
+    return reinterpret_cast<const int4 *>(sig + (int64_t(rec_id(rec)) - sig_id_base) * K) + lane;
+  };
+
+  for (uint64_t c = warp_global; c < chunks; c += nwarps) {
+    const uint64_t q = c * 32 + lane;
+    uint64_t recB = 0, recA = 0;
+    const bool have = q < total;
+    if (have) {
+      int64_t lo = 0, hi = n_records;   // invariant: slot_off[lo] <= q < slot_off[hi]
+      while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (slot_off[mid] <= q) lo = mid; else hi = mid;
+      }
+      const uint64_t tq = q - slot_off[lo];
+      const uint64_t tp = slot_off[lo + 1] - slot_off[lo];
+      recB = records[lo];
+      recA = records[lo - int64_t(tp) + int64_t(tq)];
+    }
+    const int nslots = __popc(__ballot_sync(kFull, have));
+    int nout = 0;
+    int4 an[CH], bq[CH];
+    uint64_t cached = ~0ull;            // the record whose row sits in bq
+    if (nslots > 0) {
+      const int4 *r0 = row_of(__shfl_sync(kFull, recA, 0));
+#pragma unroll
+      for (int ch = 0; ch < CH; ++ch) an[ch] = __ldg(r0 + ch * 32);
+    }
+    for (int sl = 0; sl < nslots; ++sl) {
+      const uint64_t ra = __shfl_sync(kFull, recA, sl), rb = __shfl_sync(kFull, recB, sl);
+      int4 a[CH];
+#pragma unroll
+      for (int ch = 0; ch < CH; ++ch) a[ch] = an[ch];
+      if (rb != cached) {               // warp-uniform
+        const int4 *rowb = row_of(rb);
+#pragma unroll
+        for (int ch = 0; ch < CH; ++ch) bq[ch] = __ldg(rowb + ch * 32);
+        cached = rb;
+      }
+      if (sl + 1 < nslots) {            // warp-uniform: the next slot's other row, before this slot is evaluated
+        const int4 *r1 = row_of(__shfl_sync(kFull, recA, sl + 1));
+#pragma unroll
+        for (int ch = 0; ch < CH; ++ch) an[ch] = __ldg(r1 + ch * 32);
+      }
+      const int band = int(rec_band(rb));
+      bool own = false, earlier = false;
+#pragma unroll
+      for (int ch = 0; ch < CH; ++ch) {
+        const int4 x = a[ch], y = bq[ch];
+        const unsigned dx = unsigned(x.x ^ y.x) | unsigned(x.y ^ y.y) | unsigned(x.z ^ y.z) | unsigned(x.w ^ y.w);
+        const unsigned an4 = unsigned(x.x & x.y & x.z & x.w);
+        const bool match = (dx & 0xFFFFu) == 0u && (an4 & 0xFFFFu) != 0xFFFFu;   // equal int16 lanes, not all -1
+        const unsigned mm = __ballot_sync(kFull, match);
+        const int rel = band - ch * 32;                                          // band's lane in this chunk
+        if (rel >= 32) earlier = earlier || mm != 0u;
+        else if (rel >= 0) {
+          own = (mm >> rel) & 1u;
+          earlier = earlier || (mm & ((1u << rel) - 1u)) != 0u;
+        }
+      }
+      if (own && !earlier) {            // warp-uniform
+        long long dot = 0;
+        if (sim_milli != nullptr) {
+#pragma unroll
+          for (int ch = 0; ch < CH; ++ch) {
+            const int4 x = a[ch], y = bq[ch];
+            dot += (long long)x.x * y.x + (long long)x.y * y.y + (long long)x.z * y.z + (long long)x.w * y.w;
+          }
+          // rows that reach a pair hold no -1 (an empty set has sentinel records only), so the partials are >= 0
+          if (__any_sync(kFull, (unsigned long long)dot >> 48)) dot = warp_sum_ll(dot);
+          else dot = (long long)warp_sum_u48((unsigned long long)dot);
+        }
+        if (lane == 0) {
+          const uint32_t ia = rec_id(ra), ib = rec_id(rb);
+          s_pair[warp][nout] = (uint64_t(min(ia, ib)) << 32) | uint64_t(max(ia, ib));
+          s_dot[warp][nout] = dot;
+        }
+        ++nout;
+      }
+    }
+    __syncwarp();
+    if (nout > 0) {
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(n_pairs, (unsigned long long)nout);
+      base = __shfl_sync(kFull, base, 0);
+      if (lane < nout && int64_t(base + lane) < capacity) {
+        const uint64_t pr = s_pair[warp][lane];
+        pairs[base + lane] = pr;
+        if (sim_milli != nullptr) {
+          const int64_t a0 = int64_t(pr >> 32) - sig_id_base, b0 = int64_t(pr & 0xFFFFFFFFu) - sig_id_base;
+          sim_milli[base + lane] = to_milli(cosine_of(s_dot[warp][lane], norm2[a0], norm2[b0]));
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
 __global__ void __launch_bounds__(256)
 pair_cosine_kernel(const int *__restrict__ sig, const long long *__restrict__ norm2, int K,
                    const uint64_t *__restrict__ pairs, int64_t n_pairs, int *__restrict__ sim_milli) {
@@ -290,6 +410,17 @@ int qrs_pairs_score(const uint64_t *records, int64_t n_records, const uint64_t *
   const int grid = sm_count() * 8;
   // the r = 4 kernel reads signature rows with 16-byte loads: only for a 16-byte aligned matrix (rows are K * 4 bytes,
   // K % 128 == 0); anything else takes the generic kernel's 4-byte loads
+  if (K / b == 4 && (K == 128 || K == 256) && (reinterpret_cast<uintptr_t>(sig) & 15) == 0) {
+    const long long *n2 = reinterpret_cast<const long long *>(norm2);
+    if (K == 128)
+      pairs_score_r4c_kernel<1><<<grid, kPairThreads, 0, as_stream(stream)>>>(records, n_records, slot_off, sig, n2,
+                                                                              sig_id_base, pairs, sim_milli, capacity, n_pairs);
+    else
+      pairs_score_r4c_kernel<2><<<grid, kPairThreads, 0, as_stream(stream)>>>(records, n_records, slot_off, sig, n2,
+                                                                              sig_id_base, pairs, sim_milli, capacity, n_pairs);
+    QRS_LAUNCH_CHECK();
+    return QRS_OK;
+  }
   if (K / b == 4 && K % 128 == 0 && (reinterpret_cast<uintptr_t>(sig) & 15) == 0) {
     pairs_score_r4_kernel<<<grid, kPairThreads, 0, as_stream(stream)>>>(
         records, n_records, slot_off, sig, reinterpret_cast<const long long *>(norm2), sig_id_base, K, pairs, sim_milli,
