@@ -238,7 +238,7 @@ pairs_score_r4_kernel(const uint64_t *__restrict__ records, int64_t n_records, c
 // 4K-byte rows:
 //   * the slots of record p (p against every earlier record of its run) are consecutive, so p's row is loaded
 //     once and kept in registers while it repeats (runs of taste-group size make this most of the slots);
-//   * the other row of slot sl + 1 is requested before slot sl is evaluated;
+//   * the other rows of the next three slots are in flight while a slot is evaluated;
 //   * the 64-bit dot is formed only for slots that emit a pair (own band, no earlier band), and summed with three
 //     REDUX on 16-bit pieces when the lane partials stay below 2^48 (five 64-bit shuffle steps otherwise).
 template <int CH>
@@ -264,7 +264,8 @@ pairs_score_r4c_kernel(const uint64_t *__restrict__ records, int64_t n_records, 
     uint64_t recB = 0, recA = 0;
     const bool have = q < total;
     if (have) {
-      int64_t lo = 0, hi = n_records;   // invariant: slot_off[lo] <= q < slot_off[hi]
+      int64_t lo = 0, hi = n_records;   // invariant: slot_off[lo] <= q < slot_off[hi]  (a warp-cooperative 32-ary
+                                        // search for the chunk's ends was measured: no gain, the top levels stay cached)
       while (hi - lo > 1) {
         const int64_t mid = (lo + hi) >> 1;
         if (slot_off[mid] <= q) lo = mid; else hi = mid;
@@ -276,28 +277,36 @@ pairs_score_r4c_kernel(const uint64_t *__restrict__ records, int64_t n_records, 
     }
     const int nslots = __popc(__ballot_sync(kFull, have));
     int nout = 0;
-    int4 an[CH], bq[CH];
+    constexpr int AHEAD = 3;            // rows of later slots in flight while a slot is evaluated
+    int4 an[AHEAD][CH], bq[CH];
     uint64_t cached = ~0ull;            // the record whose row sits in bq
-    if (nslots > 0) {
-      const int4 *r0 = row_of(__shfl_sync(kFull, recA, 0));
 #pragma unroll
-      for (int ch = 0; ch < CH; ++ch) an[ch] = __ldg(r0 + ch * 32);
+    for (int d = 0; d < AHEAD; ++d) {
+      if (d < nslots) {                 // warp-uniform
+        const int4 *r0 = row_of(__shfl_sync(kFull, recA, d));
+#pragma unroll
+        for (int ch = 0; ch < CH; ++ch) an[d][ch] = __ldg(r0 + ch * 32);
+      }
     }
     for (int sl = 0; sl < nslots; ++sl) {
       const uint64_t ra = __shfl_sync(kFull, recA, sl), rb = __shfl_sync(kFull, recB, sl);
       int4 a[CH];
 #pragma unroll
-      for (int ch = 0; ch < CH; ++ch) a[ch] = an[ch];
+      for (int ch = 0; ch < CH; ++ch) a[ch] = an[0][ch];
+#pragma unroll
+      for (int d = 0; d + 1 < AHEAD; ++d)
+#pragma unroll
+        for (int ch = 0; ch < CH; ++ch) an[d][ch] = an[d + 1][ch];
       if (rb != cached) {               // warp-uniform
         const int4 *rowb = row_of(rb);
 #pragma unroll
         for (int ch = 0; ch < CH; ++ch) bq[ch] = __ldg(rowb + ch * 32);
         cached = rb;
       }
-      if (sl + 1 < nslots) {            // warp-uniform: the next slot's other row, before this slot is evaluated
-        const int4 *r1 = row_of(__shfl_sync(kFull, recA, sl + 1));
+      if (sl + AHEAD < nslots) {        // warp-uniform: a later slot's other row, before this slot is evaluated
+        const int4 *r1 = row_of(__shfl_sync(kFull, recA, sl + AHEAD));
 #pragma unroll
-        for (int ch = 0; ch < CH; ++ch) an[ch] = __ldg(r1 + ch * 32);
+        for (int ch = 0; ch < CH; ++ch) an[AHEAD - 1][ch] = __ldg(r1 + ch * 32);
       }
       const int band = int(rec_band(rb));
       bool own = false, earlier = false;
