@@ -238,7 +238,7 @@ pairs_score_r4_kernel(const uint64_t *__restrict__ records, int64_t n_records, c
 // 4K-byte rows:
 //   * the slots of record p (p against every earlier record of its run) are consecutive, so p's row is loaded
 //     once and kept in registers while it repeats (runs of taste-group size make this most of the slots);
-//   * the other rows of the next three slots are in flight while a slot is evaluated;
+//   * the other row of slot sl + 1 is requested before slot sl is evaluated;
 //   * the 64-bit dot is formed only for slots that emit a pair (own band, no earlier band), and summed with three
 //     REDUX on 16-bit pieces when the lane partials stay below 2^48 (five 64-bit shuffle steps otherwise).
 template <int CH>
@@ -277,7 +277,8 @@ pairs_score_r4c_kernel(const uint64_t *__restrict__ records, int64_t n_records, 
     }
     const int nslots = __popc(__ballot_sync(kFull, have));
     int nout = 0;
-    constexpr int AHEAD = 3;            // rows of later slots in flight while a slot is evaluated
+    constexpr int AHEAD = 1;            // rows of later slots in flight while a slot is evaluated (the kernel is
+                                        // issue-bound, 72 % of the slots: deeper read-ahead measured no gain)
     int4 an[AHEAD][CH], bq[CH];
     uint64_t cached = ~0ull;            // the record whose row sits in bq
 #pragma unroll
@@ -288,6 +289,7 @@ pairs_score_r4c_kernel(const uint64_t *__restrict__ records, int64_t n_records, 
         for (int ch = 0; ch < CH; ++ch) an[d][ch] = __ldg(r0 + ch * 32);
       }
     }
+#pragma unroll 2
     for (int sl = 0; sl < nslots; ++sl) {
       const uint64_t ra = __shfl_sync(kFull, recA, sl), rb = __shfl_sync(kFull, recB, sl);
       int4 a[CH];
