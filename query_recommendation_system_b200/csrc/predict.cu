@@ -493,7 +493,6 @@ predict_sparse_kernel(const __grid_constant__ PeerView pv, int Q,
     int touched = 0;
     if constexpr (MILLI) {
       // A lane looks at columns j0 + lane and j0 + 32 + lane: the two ballots ARE the bitmap words of the 64 columns
-      // (lane w keeps word w of the current 1024-column group; one coalesced store per group).
       // Listed iff D != 0 (then the prediction is >= 18).  Neighbours of similarity 0 never enter the step list, so
       // an accumulator is either untouched (all zero) or has D != 0; columns beyond the window's width stay zero.
       // Only the low words are read (32-bit loads, explicit so that the compiler does not widen the test).
@@ -501,24 +500,36 @@ predict_sparse_kernel(const __grid_constant__ PeerView pv, int Q,
       const unsigned jl_s = unsigned(__cvta_generic_to_shared(jlist));
       unsigned a_s = acc_s + 8u * unsigned(lane);
       const unsigned ltm = (1u << lane) - 1u;      // = %lanemask_lt, as ALU work (the special-register read is slow)
-#pragma unroll 1
-      for (int j0 = 0; j0 < width; j0 += 64) {
+      // one 64-column round; BITMAP (compile-time tag): the ballots are also kept as the window's bitmap words
+      auto list_round = [&](int j0, auto bitmap_tag) {
+        constexpr bool BITMAP = decltype(bitmap_tag)::value;
         unsigned x0, x1;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x0) : "r"(a_s));            // acc holds round_up(tile, 64) words
         asm volatile("ld.shared.u32 %0, [%1+256];" : "=r"(x1) : "r"(a_s));
         a_s += 512u;
         const bool hit0 = (x0 & 0xFFFFFFu) != 0u, hit1 = (x1 & 0xFFFFFFu) != 0u;
         const unsigned m0 = __ballot_sync(kFull, hit0), m1 = __ballot_sync(kFull, hit1);
-        const int w0 = (j0 >> 5) & 31;
-        my_word = lane == w0 ? m0 : (lane == w0 + 1 ? m1 : my_word);
         const int c0 = __popc(m0);
         if (hit0) asm volatile("st.shared.u16 [%0], %1;" ::"r"(jl_s + 2u * unsigned(touched + __popc(m0 & ltm))), "h"((unsigned short)(j0 + lane)) : "memory");
         if (hit1) asm volatile("st.shared.u16 [%0], %1;" ::"r"(jl_s + 2u * unsigned(touched + c0 + __popc(m1 & ltm))), "h"((unsigned short)(j0 + 32 + lane)) : "memory");
         touched += c0 + __popc(m1);
-        if (w0 == 30 || j0 + 64 >= width) {          // warp-uniform: the group of 32 words is complete (or the window ends)
-          if (bitmap && (j0 & ~1023) + 32 * lane < width) bitmap_row[((j0 >> 10) << 5) + lane] = my_word;
-          my_word = 0u;
+        if constexpr (BITMAP) {
+          // lane w keeps word w of the current 1024-column group; one coalesced store per group.  (Parking the words in
+          // shared memory through lane 0 instead: fewer instructions, measured 2 % slower.)
+          const int w0 = (j0 >> 5) & 31;
+          my_word = lane == w0 ? m0 : (lane == w0 + 1 ? m1 : my_word);
+          if (w0 == 30 || j0 + 64 >= width) {        // warp-uniform: the group of 32 words is complete (or the window ends)
+            if ((j0 & ~1023) + 32 * lane < width) bitmap_row[((j0 >> 10) << 5) + lane] = my_word;
+            my_word = 0u;
+          }
         }
+      };
+      if (bitmap) {
+#pragma unroll 1
+        for (int j0 = 0; j0 < width; j0 += 64) list_round(j0, std::true_type{});
+      } else {        // explicit column ids (sparse windows, C3 / C4): the listing pass is a quarter of the kernel there
+#pragma unroll 1
+        for (int j0 = 0; j0 < width; j0 += 64) list_round(j0, std::false_type{});
       }
     } else {
 #pragma unroll 2
