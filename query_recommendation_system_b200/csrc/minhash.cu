@@ -16,6 +16,11 @@
 namespace qrs {
 
 constexpr int kByteMapMaxElems = 16384;           // one byte per element up to here, one bit beyond
+// Beyond the tile scan's reach the membership map of ONE set fills most of an SM's shared memory and the per-set scan
+// runs at one CTA per SM; sets with |S|^2 < kDirectFactor * m then go to a separate, map-less launch of the direct
+// gather (64 warps per SM, eight table rows in flight per lane): 10.4 against 264 ms for 131 072 sets of ~1 000 of
+// 1 000 000 elements at K = 128 (profiles/r2_minhash_modes_c4.jsonl); the gather grows with |S|, the scan with m / |S|.
+constexpr int64_t kDirectFactor = 16;
 constexpr int kMaxMapBytes = 200 * 1024;          // shared-memory budget for the membership map
 constexpr int64_t kMaxElemsFirstTouch = int64_t(kMaxMapBytes) * 8;
 
@@ -84,9 +89,17 @@ minhash_kernel(const int64_t *__restrict__ rowptr, const int *__restrict__ colid
   }
   __syncthreads();
 
+  // bits 9..10 of the mode word: row filter of a split launch (1: rows with |S|^2 < kDirectFactor * m only — and the
+  // empty ones; 2: the others only)
+  const int filt = (mode >> 9) & 3;
+  mode &= 0xFF;
   for (int64_t s = blockIdx.x; s < n; s += gridDim.x) {
     const int64_t lo = rowptr[s];
     const int len = int(rowptr[s + 1] - lo);
+    if (filt != 0) {                      // CTA-uniform
+      const bool short_row = int64_t(len) * len < kDirectFactor * int64_t(m);
+      if ((filt == 1) != short_row) continue;
+    }
     const bool use_ft = map_bytes > 0 && R >= 32 && len > 0 &&
                         (mode == QRS_MINHASH_FIRST_TOUCH || (mode == QRS_MINHASH_AUTO && int64_t(len) * len >= m));
     if (use_ft) {
@@ -804,6 +817,15 @@ int qrs_minhash_perm(const int64_t *rowptr, const int32_t *colidx, int64_t n, in
   if (map_bytes <= 24 * 1024)
     return launch_minhash<false, 128>(rowptr, colidx, n, m, perm_tab, order_head, R, K, b, id_base, sig, n2,
                                       records, rec_stride, mode, map_bytes, st);
+  if (mode == QRS_MINHASH_AUTO) {
+    // split by row length (kDirectFactor): short and empty sets in a map-less direct launch at full occupancy, the
+    // long ones in the scan; every row is written by exactly one of the two
+    int rc = launch_minhash<true, 128>(rowptr, colidx, n, m, perm_tab, order_head, 0, K, b, id_base, sig, n2, records,
+                                       rec_stride, QRS_MINHASH_DIRECT | (1 << 9), 0, st);
+    if (rc != QRS_OK) return rc;
+    return launch_minhash<false, 512>(rowptr, colidx, n, m, perm_tab, order_head, R, K, b, id_base, sig, n2,
+                                      records, rec_stride, QRS_MINHASH_FIRST_TOUCH | (2 << 9), map_bytes, st);
+  }
   return launch_minhash<false, 512>(rowptr, colidx, n, m, perm_tab, order_head, R, K, b, id_base, sig, n2,
                                     records, rec_stride, mode, map_bytes, st);
 }

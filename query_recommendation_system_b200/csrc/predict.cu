@@ -253,7 +253,8 @@ __device__ __noinline__ int resolve_tie(const PeerView &pv, const int *__restric
   return predict_from(num, den);
 }
 
-template <bool MILLI>
+// ONE_PEER (compile time): every neighbour row is local — no rank arithmetic, no base-pointer selection per step
+template <bool MILLI, bool ONE_PEER>
 __global__ void __launch_bounds__(kPwMaxWarps * 32, 1)
 predict_sparse_kernel(const __grid_constant__ PeerView pv, int Q,
                       const int *__restrict__ u_idx, const double *__restrict__ u_val,
@@ -295,7 +296,7 @@ predict_sparse_kernel(const __grid_constant__ PeerView pv, int Q,
   bool has_zeros = false;
   for (int r = 0; r < pv.n_peers; ++r)
     has_zeros |= *reinterpret_cast<const unsigned *>(pv.base[r] + pv.off_flag) != 0u;
-  const bool one_peer = pv.n_peers == 1;
+  constexpr bool one_peer = ONE_PEER;
 
   // A warp takes one USER at a time (dynamic: a device counter) and walks its windows in order, so what depends
   // on the user only — neighbour ids, ranks, similarities, the rows' offset tables — is set up once, and since the
@@ -764,7 +765,7 @@ static int launch_predict_sparse(const PeerView &pv, int Q, const int *u_idx, co
                                  uint8_t *preds, int64_t region_cap, int n_regions, unsigned long long *cursors,
                                  unsigned long long *tie_count, ulonglong2 *tie_list, int64_t tie_capacity,
                                  int cols_mode, const unsigned *single_tab, cudaStream_t st) {
-  auto kern = predict_sparse_kernel<MILLI>;
+  auto kern = pv.n_peers == 1 ? predict_sparse_kernel<MILLI, true> : predict_sparse_kernel<MILLI, false>;
   const int warps = predict_warps_per_cta(tile, MILLI);
   if (warps < 1) return QRS_ERR_UNSUPPORTED;
   const size_t smem = kPwCtaBytes + size_t(warps) * pw_warp_bytes(tile, MILLI);

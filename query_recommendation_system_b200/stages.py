@@ -42,17 +42,6 @@ def choose_head_ranks(m: int, avg_len: float) -> int:
     return min(r, (m // 32) * 32)
 
 
-def minhash_prefers_direct(m: int, avg_len: float) -> bool:
-    """AUTO's choice of kernel family.  The first-touch scans test ~m / |S| ranks per (set, hash) against a
-    membership map in shared memory; the direct form gathers |S| table rows of K values per set with no shared
-    memory at all (64 warps per SM, eight rows in flight per lane).  Beyond the tile scan's reach (m > ~200 000) the
-    map of ONE set fills an SM's shared memory, the scan runs at one CTA per SM, and short sets (|S|^2 < 4 m) are
-    far cheaper to gather: 10.4 against 264 ms for 131 072 sets of ~1 000 of 1 000 000 elements, K = 128 (C4's
-    shard shape, profiles/r2_minhash_modes_c4.jsonl).  Where a tile scan exists it wins by 13x to 24x (C3 / C2:
-    2.25 against 28.5 ms, 0.14 against 3.3 ms), so the rule only applies above it."""
-    return avg_len * avg_len < 4.0 * m and m > 200_000
-
-
 def perm_head(perm_tab: torch.Tensor, R: int) -> Optional[torch.Tensor]:
     """First R ranks of each permutation (recommender.py:121's argsort) in the library's chunk-major layout:
     int32[R / 8, Kp, 8] with Kp = K rounded up to 32 (include/qrs_b200.h, qrs_perm_head_invert)."""
@@ -89,8 +78,6 @@ def minhash(rowptr: torch.Tensor, colidx: torch.Tensor, m: int, perm_tab: torch.
     if b > 0:
         records = out_records if out_records is not None else torch.empty((b, n), dtype=torch.int64, device=dev)
     R = 0 if order_head is None else order_head.shape[0] * 8
-    if mode == _lib.MINHASH_AUTO and minhash_prefers_direct(m, colidx.numel() / max(n, 1)):
-        mode = _lib.MINHASH_DIRECT
     check(_lib.load().qrs_minhash_perm(ptr(rowptr), ptr(colidx), n, m, ptr(perm_tab), ptr(order_head), R, K, b,
                                        id_base, ptr(sig), ptr(norm2), ptr(records), n, mode, _stream()),
           "qrs_minhash_perm")

@@ -154,6 +154,26 @@ def test_minhash_tile_v4_csr_form():
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
 
 
+def test_minhash_auto_beyond_the_tile_scan_splits_by_row_length():
+    """m = 300 000 (no tile scan; the map of one set is 37 KB): AUTO runs the short and the empty sets in a map-less
+    direct launch and the long ones (|S|^2 >= 16 m) in the per-set scan — every row written once, all bit-exact,
+    records and norm2 included; DIRECT and FIRST_TOUCH on the same input agree."""
+    from query_recommendation_system_b200 import stages
+    rng = np.random.default_rng(77)
+    m, K, b = 300_000, 32, 8
+    lens = np.array([0, 1, 50, 800, 2000, 2190, 2191, 2500, 3000, 0, 40, 2600] * 5)
+    rowptr, colidx = _ragged_rows(rng, lens.size, m, lens)
+    tab = spec.permutation_table(m, K, seed=9)
+    ref = spec.signatures(rowptr, colidx, tab)
+    outs = []
+    for mode in (0, 1, 2):
+        sig, norm2, rec = gpu_signatures(rowptr, colidx, tab, b=b, mode=mode)
+        assert np.array_equal(sig.cpu().numpy().astype(np.int64), ref), mode
+        assert np.array_equal(norm2.cpu().numpy(), (ref * ref).sum(axis=1))
+        outs.append(rec)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
 def test_minhash_tile_equals_first_touch_at_bench_density():
     """C2-like rows (5 % of 10 000 elements, planted groups): the three scans agree, records included."""
     from query_recommendation_system_b200 import synth
