@@ -217,7 +217,7 @@ __device__ __forceinline__ const uint32_t *peer_packed(const PeerView &pv, int r
 // rating of global row v at column `col` (0 if not rated), from the prepared rows: the words of a sub-segment are
 // ascending in column, the valid ones are the first tilepos[t + 1] - tilepos[t]
 __device__ __forceinline__ int prepared_rating(const PeerView &pv, int v, int col, int tile, int nt) {
-  const int r = int(v / pv.rows_per_peer);
+  const int r = pv.n_peers == 1 ? 0 : int(unsigned(v) / unsigned(pv.rows_per_peer));      // (no 64-bit division)
   const long long row = v - r * pv.rows_per_peer;
   const int t = col / tile;
   const unsigned key = unsigned(col - t * tile) << 8;
@@ -253,8 +253,10 @@ __device__ __noinline__ int resolve_tie(const PeerView &pv, const int *__restric
   return predict_from(num, den);
 }
 
-// ONE_PEER (compile time): every neighbour row is local — no rank arithmetic, no base-pointer selection per step
-template <bool MILLI, bool ONE_PEER>
+// ONE_PEER (compile time): every neighbour row is local — no rank arithmetic, no base-pointer selection per step.
+// WIDE_K (compile time): the tables hold more than 32 neighbours, i.e. a lane carries two table slots; with at most 32
+// the second slot's offsets, scans and list loop do not exist
+template <bool MILLI, bool ONE_PEER, bool WIDE_K>
 __global__ void __launch_bounds__(kPwMaxWarps * 32, 1)
 predict_sparse_kernel(const __grid_constant__ PeerView pv, int Q,
                       const int *__restrict__ u_idx, const double *__restrict__ u_val,
@@ -335,7 +337,7 @@ predict_sparse_kernel(const __grid_constant__ PeerView pv, int Q,
       }
       tag0 |= unsigned(pr) << 26;
     }
-    if (lane + 32 < c) {
+    if (WIDE_K && lane + 32 < c) {
       const int v = u_idx[tbase + lane + 32];
       const int pr = one_peer ? 0 : int(unsigned(v) / unsigned(pv.rows_per_peer));
       const long long row = one_peer ? v : v - pr * pv.rows_per_peer;
@@ -352,7 +354,7 @@ predict_sparse_kernel(const __grid_constant__ PeerView pv, int Q,
     // the user's own offset table: an index (a launch has fewer than 2^32 sub-segments) off a uniform base
     const uint64_t *const seg_my = peer_seg(pv, pv.my);
     const unsigned own_x = unsigned((user_base + int64_t(ul)) * nt);
-    unsigned s0 = so0 ? so0[0] : 0u, s1 = so1 ? so1[0] : 0u, sown = unsigned(__ldg(seg_my + own_x));     // starts of window 0
+    unsigned s0 = so0 ? so0[0] : 0u, s1 = (WIDE_K && so1) ? so1[0] : 0u, sown = unsigned(__ldg(seg_my + own_x));     // starts of window 0
    for (int t = 0; t < nt; ++t) {
     const int64_t item = int64_t(ul) * nt + t;
     const int q0 = t * tile;
@@ -360,7 +362,7 @@ predict_sparse_kernel(const __grid_constant__ PeerView pv, int Q,
     // this window's sub-segments: [start, end) in 128-byte steps; the end is the next window's start
     const unsigned o0 = s0, o1 = s1, own_o = sown;
     s0 = so0 ? so0[2 * (t + 1)] : 0u;
-    s1 = so1 ? so1[2 * (t + 1)] : 0u;
+    s1 = (WIDE_K && so1) ? so1[2 * (t + 1)] : 0u;
     sown = unsigned(__ldg(seg_my + own_x + unsigned(t + 1)));
     const unsigned n0 = s0 - o0, n1 = s1 - o1, own_n = sown - own_o;
     // the user's own row in this window (its rated cells are cleared after the accumulation): the first two steps
@@ -371,11 +373,16 @@ predict_sparse_kernel(const __grid_constant__ PeerView pv, int Q,
     unsigned ex0 = d0, ex1 = d1;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const unsigned y0 = __shfl_up_sync(kFull, ex0, o), y1 = __shfl_up_sync(kFull, ex1, o);
-      if (lane >= o) { ex0 += y0; ex1 += y1; }
+      const unsigned y0 = __shfl_up_sync(kFull, ex0, o);
+      if (lane >= o) ex0 += y0;
+      if constexpr (WIDE_K) {
+        const unsigned y1 = __shfl_up_sync(kFull, ex1, o);
+        if (lane >= o) ex1 += y1;
+      }
     }
     const unsigned tot0 = __shfl_sync(kFull, ex0, 31);
-    const unsigned total = tot0 + __shfl_sync(kFull, ex1, 31);
+    unsigned total = tot0;
+    if constexpr (WIDE_K) total += __shfl_sync(kFull, ex1, 31);
     ex0 -= d0;
     ex1 = ex1 - d1 + tot0;
 
@@ -394,9 +401,11 @@ predict_sparse_kernel(const __grid_constant__ PeerView pv, int Q,
           const unsigned j = k - ex0;
           steps[k - R0] = make_uint2(o0 + 2 * j, tag0 | ((2 * j + 1 >= n0) ? kPwSingle : 0u));
         }
-        for (unsigned k = max(ex1, R0); k < min(ex1 + d1, hi); ++k) {
-          const unsigned j = k - ex1;
-          steps[k - R0] = make_uint2(o1 + 2 * j, tag1 | ((2 * j + 1 >= n1) ? kPwSingle : 0u));
+        if constexpr (WIDE_K) {
+          for (unsigned k = max(ex1, R0); k < min(ex1 + d1, hi); ++k) {
+            const unsigned j = k - ex1;
+            steps[k - R0] = make_uint2(o1 + 2 * j, tag1 | ((2 * j + 1 >= n1) ? kPwSingle : 0u));
+          }
         }
       }
       __syncwarp();
@@ -765,7 +774,8 @@ static int launch_predict_sparse(const PeerView &pv, int Q, const int *u_idx, co
                                  uint8_t *preds, int64_t region_cap, int n_regions, unsigned long long *cursors,
                                  unsigned long long *tie_count, ulonglong2 *tie_list, int64_t tie_capacity,
                                  int cols_mode, const unsigned *single_tab, cudaStream_t st) {
-  auto kern = pv.n_peers == 1 ? predict_sparse_kernel<MILLI, true> : predict_sparse_kernel<MILLI, false>;
+  auto kern = pv.n_peers == 1 ? (ku > 32 ? predict_sparse_kernel<MILLI, true, true> : predict_sparse_kernel<MILLI, true, false>)
+                              : (ku > 32 ? predict_sparse_kernel<MILLI, false, true> : predict_sparse_kernel<MILLI, false, false>);
   const int warps = predict_warps_per_cta(tile, MILLI);
   if (warps < 1) return QRS_ERR_UNSUPPORTED;
   const size_t smem = kPwCtaBytes + size_t(warps) * pw_warp_bytes(tile, MILLI);
