@@ -240,7 +240,10 @@ size_t qrs_predict_sparse_workspace_bytes(int64_t U, int64_t nnz, int32_t Q, int
 /* Row preparation, once per ratings CSR and window width: cuts every row at the window bounds and writes the
  * (row, window) sub-segments as 32-bit words (column - window start) << 8 | rating, zero-padded to whole
  * 128-byte steps, into the workspace (at most 4 * (nnz + 32 * U * nt) bytes of it).  The predictor reads only
- * this copy in its loop, so colidx / val need no particular alignment or padding.  qrs_predict_sparse calls it
+ * this copy in its loop, so colidx / val need no particular alignment or padding.  The order of the words inside
+ * a sub-segment is the library's business (column order, or — where windows hold some 24 entries or more on
+ * average — one cell per shared-memory bank class so that the predictor's accumulator updates do not collide;
+ * the workspace records which, environment QRS_PREDICT_PACK=class|column forces one).  qrs_predict_sparse calls it
  * itself unless `prepared` != 0 says the workspace already holds the preparation of the same CSR, Q and tile
  * (several user ranges predicted from one preparation). */
 int qrs_predict_prepare(const int64_t *rowptr, const int32_t *colidx, const uint8_t *val,

@@ -14,6 +14,7 @@
 //                 a few steps ahead of the accumulation; only the columns a neighbour touched
 //                 are predicted and written.  No block barrier in the loop.
 //   dense form  : one CTA per user at reference scale, adds the query branch.
+#include <stdlib.h>
 #include <string.h>
 
 #include <type_traits>
@@ -131,6 +132,134 @@ pack_rows_kernel(const int *__restrict__ colidx, const uint8_t *__restrict__ val
   if (saw_zero) *zero_flag = 1u;
 }
 
+// ------------------------------------------------------------------ bank-class layout of a sub-segment
+// The predictor's 8-byte read-modify-writes are served half a warp at a time, and two lanes of a half-warp whose
+// columns agree mod 16 (same pair of banks, different address) cost an extra shared-memory wavefront each: with the
+// entries of a sub-segment in column order a half-warp access takes 2.6 wavefronts instead of 1 (ncu, and the
+// balls-in-bins model of 16 random columns), which is what bounds the kernel.  The order of the entries INSIDE one
+// neighbour's sub-segment is free (distinct columns), so a sub-segment of n <= kDealMax entries is laid out by bank
+// class: its steps * 32 words are H = 2 * steps half-steps of 16 lanes, and the i-th entry of
+// class c = column mod 16 sits in half-step i at lane c (i = the order the class counter handed out, not the
+// column order) — every half-step then touches 16 different bank pairs.
+// Classes with more than H entries put the rest ("extras") into cells left free by shorter classes, last half-step
+// first; an extra shares its half-step with an entry of its own class (one more wavefront there).  Padding words in
+// lane l point at spare accumulator slot l mod 16, which no entry of that half-step can share a bank with.
+// Mean wavefronts per half-step access: 2.61 -> 1.67 at C2 (50 entries), 1.71 -> 1.19 at C3 (10 entries).
+// Longer sub-segments keep the column order.
+constexpr int kDealMax = 128;
+__device__ __forceinline__ unsigned deal_cell(unsigned half_step, unsigned lane16) {
+  return (half_step >> 1) * 32u + (half_step & 1u) * 16u + lane16;
+}
+
+// One warp per ROW, its windows one after the other: the entries of a sub-segment take their rank inside their class
+// from a shared-memory counter (atomic: lanes of one class are ranked in whatever order the unit serves them — any
+// order inside a class is as good), are scattered into a staging area at their cells and leave as whole 128-byte
+// steps.  Extras park their words in a list; the free cells, last step first, pick them up.  The kernel is bound by
+// instruction issue (one window is ~50 entries), hence the counters instead of ballots and prefix counts.
+__global__ void __launch_bounds__(256, 5)
+pack_rows_dealt_kernel(const int *__restrict__ colidx, const uint8_t *__restrict__ val,
+                       const int64_t *__restrict__ tilepos, const uint64_t *__restrict__ seg_off, int64_t U, int nt,
+                       int tile, uint32_t *__restrict__ packed, unsigned *__restrict__ zero_flag) {
+  __shared__ uint32_t s_stage[8][kDealMax];
+  __shared__ uint32_t s_extra[8][kDealMax];
+  __shared__ uint32_t s_count[8][32];       // 16 class counters | extras parked | free cells handed out
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t warp_global = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  const uint32_t pad = uint32_t(pw_spare_col(tile) + (lane & 15)) << 8;      // rating 0, column = this lane's spare slot
+  uint32_t *const stage = s_stage[warp];
+  uint32_t *const extra = s_extra[warp];
+  uint32_t *const count = s_count[warp];
+  count[lane] = 0u;
+  __syncwarp();
+  uint32_t least = 255u;          // smallest rating seen: 0 = an explicit "not rated" entry (recommender.py:41)
+  for (int64_t v = warp_global; v < U; v += nwarps) {
+    const int64_t *tp = tilepos + v * (nt + 1);
+    const uint64_t *so = seg_off + v * nt;
+    const int64_t row_lo = tp[0];
+    const int *const row_col = colidx + row_lo + lane;
+    const uint8_t *const row_val = val + row_lo + lane;
+    for (int tb = 0; tb < nt; tb += 31) {
+      const int tl = min(tb + lane, nt);
+      const unsigned my_tp = unsigned(tp[tl] - row_lo);
+      const uint64_t my_so = so[tl];
+      const int nwin = min(31, nt - tb);
+      for (int w = 0; w < nwin; ++w) {
+        const unsigned a = __shfl_sync(kFull, my_tp, w);
+        const unsigned n = __shfl_sync(kFull, my_tp, w + 1) - a;
+        if (n == 0u) continue;                                   // warp-uniform
+        uint32_t *const out = packed + (__shfl_sync(kFull, my_so, w) << 5) + lane;
+        const int *const c0 = row_col + a;
+        const uint8_t *const v0 = row_val + a;
+        const unsigned steps = (n + 31u) >> 5;
+        const int q0 = (tb + w) * tile;
+        if (n > unsigned(kDealMax)) {                            // long sub-segment: column order
+          for (unsigned s2 = 0; s2 < steps; ++s2) {
+            uint32_t x = pad;
+            if (s2 * 32u + unsigned(lane) < n) {
+              const uint32_t r = v0[s2 * 32u];
+              x = (uint32_t(ld_stream_s32(c0 + s2 * 32u) - q0) << 8) | r;
+              least = min(least, r);
+            }
+            out[size_t(s2) << 5] = x;
+          }
+          continue;
+        }
+        const unsigned H = 2u * steps;
+        // ---- the sub-segment's words (all loads in flight together), the staging area pre-filled with padding
+        uint32_t word[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          word[j] = pad;
+          if (unsigned(j) < steps) {                             // warp-uniform
+            if (unsigned(j * 32 + lane) < n) {
+              const uint32_t r = v0[j * 32];
+              word[j] = (uint32_t(ld_stream_s32(c0 + j * 32) - q0) << 8) | r;
+              least = min(least, r);
+            }
+            stage[j * 32 + lane] = pad;
+          }
+        }
+        __syncwarp();
+        // ---- class cells for the first H entries of a class, the list of extras for the others
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (unsigned(j) < steps && word[j] != pad) {           // (a real entry's column is inside the window)
+            const unsigned cls = (word[j] >> 8) & 15u;
+            const unsigned rank = atomicAdd(count + cls, 1u);
+            if (rank < H) stage[deal_cell(rank, cls)] = word[j];
+            else extra[atomicAdd(count + 16, 1u)] = word[j];
+          }
+        }
+        __syncwarp();
+        const unsigned n_extra = count[16];
+        if (n_extra > 0u) {                                      // warp-uniform
+          // cell (half-step h, lane c) is free when class c has at most h entries: last step first, a free cell
+          // takes the next parked extra
+          const unsigned cnt = count[lane & 15];
+          unsigned n_free = 0u;
+          for (int s2 = int(steps) - 1; s2 >= 0 && n_free < n_extra; --s2) {
+            const bool is_free = cnt <= 2u * unsigned(s2) + unsigned(lane >> 4);
+            if (is_free) {
+              const unsigned idx = atomicAdd(count + 17, 1u);
+              if (idx < n_extra) stage[s2 * 32 + lane] = extra[idx];
+            }
+            n_free += unsigned(__popc(__ballot_sync(kFull, is_free)));
+          }
+          __syncwarp();
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (unsigned(j) < steps) out[size_t(j) << 5] = stage[j * 32 + lane];
+        if (lane < 18) count[lane] = 0u;
+        __syncwarp();
+      }
+    }
+  }
+  if (least == 0u) *zero_flag = 1u;
+  if (blockIdx.x == 0 && threadIdx.x == 0) zero_flag[1] = 1u;      // layout of this workspace: bank-class cells
+}
+
 // ------------------------------------------------------------------ sparse form
 struct __align__(16) Acc { double num, den; };
 
@@ -214,16 +343,46 @@ __device__ __forceinline__ const uint32_t *peer_packed(const PeerView &pv, int r
   return reinterpret_cast<const uint32_t *>(pv.base[r] + pv.off_packed);
 }
 
-// rating of global row v at column `col` (0 if not rated), from the prepared rows: the words of a sub-segment are
-// ascending in column, the valid ones are the first tilepos[t + 1] - tilepos[t]
+// rating of global row v at column `col` (0 if not rated), from the prepared rows.  Column order: the words of a
+// sub-segment are ascending in column, the valid ones are the first tilepos[t + 1] - tilepos[t].  Bank-class layout
+// (`dealt`, sub-segments of at most kDealMax entries): the column's class cells in half-step order, and every word
+// of the sub-segment only if the class filled all its cells (then it may be an extra).
 __device__ __forceinline__ int prepared_rating(const PeerView &pv, int v, int col, int tile, int nt) {
   const int r = pv.n_peers == 1 ? 0 : int(unsigned(v) / unsigned(pv.rows_per_peer));      // (no 64-bit division)
+  const bool dealt = reinterpret_cast<const unsigned *>(pv.base[r] + pv.off_flag)[1] != 0u;   // the owner's layout
   const long long row = v - r * pv.rows_per_peer;
   const int t = col / tile;
   const unsigned key = unsigned(col - t * tile) << 8;
   const int64_t *tp = peer_tilepos(pv, r) + row * (nt + 1) + t;
   const int n = int(tp[1] - tp[0]);
+  if (n == 0) return 0;
   const uint32_t *w = peer_packed(pv, r) + (peer_seg(pv, r)[row * nt + t] << 5);
+  if (dealt && n <= kDealMax) {
+    // the class's cells, all requested at once: a hit, or a cell that is not the class's (a padding word — its
+    // column lies beyond the window — or another class's extra) ends the search
+    const unsigned steps = unsigned(n + 31) >> 5, cls = (key >> 8) & 15u;
+    unsigned x[8];
+#pragma unroll
+    for (unsigned h = 0; h < 8; ++h) x[h] = h < 2u * steps ? w[deal_cell(h, cls)] : 0xFFFFFFFFu;
+    bool full = true;
+#pragma unroll
+    for (unsigned h = 0; h < 8; ++h) {
+      if (h < 2u * steps) {
+        if ((x[h] >> 8) == (key >> 8)) return int(x[h] & 0xFFu);
+        full = full && (x[h] >> 8) < unsigned(tile) && ((x[h] >> 8) & 15u) == cls;
+      }
+    }
+    if (!full) return 0;
+    // every cell holds another entry of the class: the column may be one of the class's extras, anywhere
+    for (unsigned i = 0; i < steps * 32u; i += 4) {
+      const uint4 q = *reinterpret_cast<const uint4 *>(w + i);
+      if ((q.x >> 8) == (key >> 8)) return int(q.x & 0xFFu);
+      if ((q.y >> 8) == (key >> 8)) return int(q.y & 0xFFu);
+      if ((q.z >> 8) == (key >> 8)) return int(q.z & 0xFFu);
+      if ((q.w >> 8) == (key >> 8)) return int(q.w & 0xFFu);
+    }
+    return 0;
+  }
   int lo = 0, hi = n;
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
@@ -293,7 +452,7 @@ predict_sparse_kernel(const __grid_constant__ PeerView pv, int Q,
   // ul = r (mod n_regions), so a region's demand does not depend on which warp happened to take which user
 
   struct Batch { unsigned p0[kPwBatch], p1[kPwBatch], tag[kPwBatch]; };
-  const unsigned pad = unsigned(pw_spare_col(tile)) << 8;      // the padding word of the prepared rows
+  const unsigned pad = unsigned(pw_spare_col(tile) + (lane & 15)) << 8;      // a padding word: this lane's spare slot
   // explicit zero ratings anywhere in the rows this launch can read?  (warp-uniform, rare: guarded accumulation)
   bool has_zeros = false;
   for (int r = 0; r < pv.n_peers; ++r)
@@ -797,6 +956,19 @@ using namespace qrs;
 namespace {
 
 int64_t tie_list_capacity(int64_t capacity) { return capacity / 32 + 65536; }
+
+// Layout of the prepared rows.  The bank-class cells pay where the predictor is bound by shared-memory wavefronts,
+// i.e. where a sub-segment fills its steps (C2: 50 entries per window, predict stage 3.86 -> 3.60 ms for 0.18 ms more
+// preparation); with ~10 entries per window (C3 / C4) the predictor is bound by instruction issue, gains nothing
+// (24.8 -> 24.4 ms per 100k rows) and the dearer preparation (+1.0 ms) is a loss: column order there.  The rule
+// looks at this workspace's rows only; the layout is recorded in the workspace (flag word 1) for whoever reads it.
+// QRS_PREDICT_PACK=class|column overrides (A/B measurements, tests).
+bool pack_dealt(int64_t U, int64_t nt, int64_t nnz) {
+  const char *e = getenv("QRS_PREDICT_PACK");
+  if (e && strcmp(e, "column") == 0) return false;
+  if (e && strcmp(e, "class") == 0) return true;
+  return nnz >= 24 * U * nt;
+}
 constexpr size_t kSingleTabBytes = round_up<size_t>(26 * 32 * 4, 256);
 
 // workspace: tile index | steps per sub-segment | seg_off | scan scratch | tie counter | single-rater table |
@@ -878,7 +1050,7 @@ int qrs_predict_prepare(const int64_t *rowptr, const int32_t *colidx, const uint
   if (nnz > 0 && (!colidx || !val)) return QRS_ERR_INVALID_ARG;
   cudaStream_t st = as_stream(stream);
   const PredictWs w = carve_predict_ws(ws, U, nt, nnz, capacity);
-  QRS_CUDA(cudaMemsetAsync(w.tie_count, 0, 256, st));      // tie counter | next-user counter | "explicit zero ratings" flag
+  QRS_CUDA(cudaMemsetAsync(w.tie_count, 0, 256, st));      // tie counter | next-user counter | "explicit zero ratings" flag, layout flag
   const int64_t cap = int64_t(sm_count()) * 8;
   {
     int64_t blocks = ceil_div<int64_t>(U * (nt + 1), 256);
@@ -898,8 +1070,12 @@ int qrs_predict_prepare(const int64_t *rowptr, const int32_t *colidx, const uint
     int64_t blocks = ceil_div<int64_t>(U, 8);
     const int64_t cap2 = int64_t(sm_count()) * 16;
     if (blocks > cap2) blocks = cap2;
-    pack_rows_kernel<<<unsigned(blocks), 256, 0, st>>>(colidx, val, w.tilepos, w.seg_off, U, nt, tile, w.packed,
-                                                       reinterpret_cast<unsigned *>(w.tie_count + 2));
+    if (pack_dealt(U, nt, nnz))
+      pack_rows_dealt_kernel<<<unsigned(blocks), 256, 0, st>>>(colidx, val, w.tilepos, w.seg_off, U, nt, tile, w.packed,
+                                                               reinterpret_cast<unsigned *>(w.tie_count + 2));
+    else
+      pack_rows_kernel<<<unsigned(blocks), 256, 0, st>>>(colidx, val, w.tilepos, w.seg_off, U, nt, tile, w.packed,
+                                                         reinterpret_cast<unsigned *>(w.tie_count + 2));
     QRS_LAUNCH_CHECK();
   }
   single_rater_tie_bits_kernel<<<ceil_div(26 * 32, 256), 256, 0, st>>>(w.single_tab);

@@ -163,3 +163,32 @@ def test_odd_nnz_exactly_sized_buffers(integer):
     cnt = np.append(cnt, cnt[0])
     idx[:n - 1, 0] = n - 1                                                 # ... plus the last row for everybody
     run_and_check(rowptr, colidx, val, m, idx, sims, cnt, 704, integer, exact_alloc=True)
+
+
+@pytest.mark.parametrize("pack", ["class", "column"])
+@pytest.mark.parametrize("integer", [False, True])
+def test_prepared_row_layouts(pack, integer, monkeypatch):
+    """Both layouts of the prepared rows (bank-class cells / column order, QRS_PREDICT_PACK) on columns that are all
+    multiples of 16 — ONE bank class, so nearly every entry of a sub-segment is an 'extra' parked in another class's
+    cell — with tie-heavy ratings, so that the half-way fix-up looks entries up in those sub-segments too; windows
+    of 0 .. ~40 entries and a few of more than 128 (which keep the column order in either layout)."""
+    monkeypatch.setenv("QRS_PREDICT_PACK", pack)
+    n, m, k = 160, 16_384, 20
+    rng = np.random.default_rng(123)
+    lens = rng.integers(0, 400, n)
+    lens[::17] = 1000                                  # a few rows with ~62 entries in every window ...
+    rowptr = np.zeros(n + 1, np.int64)
+    np.cumsum(lens, out=rowptr[1:])
+    colidx = np.empty(rowptr[-1], np.int32)
+    for i in range(n):
+        colidx[rowptr[i]:rowptr[i + 1]] = 16 * np.sort(rng.choice(m // 16, lens[i], replace=False))
+    big = np.sort(rng.choice(1024, 300, replace=False)).astype(np.int32)       # ... and one with 300 in window 0
+    colidx = np.concatenate([colidx[:rowptr[1]], big, colidx[rowptr[2]:]])
+    lens[1] = big.size
+    np.cumsum(lens, out=rowptr[1:])
+    val = rng.choice(np.array([5, 15, 25, 35], np.uint8), size=colidx.size, p=[0.55, 0.25, 0.1, 0.1])
+    idx, sims, cnt = random_tables(n, k, seed=124, tie_heavy=True)
+    idx[:, 0] = np.where(np.arange(n) == 1, 2, 1)      # the long row is everybody's first neighbour
+    cnt = np.maximum(cnt, 1)
+    sims[:, 0] = np.maximum(sims[:, 0], 0.5)
+    run_and_check(rowptr, colidx, val, m, idx, sims, cnt, 1024, integer, cols_mode=1 if integer else 0)
