@@ -151,27 +151,82 @@ __device__ __forceinline__ unsigned deal_cell(unsigned half_step, unsigned lane1
   return (half_step >> 1) * 32u + (half_step & 1u) * 16u + lane16;
 }
 
-// One warp per ROW, its windows one after the other: the entries of a sub-segment take their rank inside their class
-// from a shared-memory counter (atomic: lanes of one class are ranked in whatever order the unit serves them — any
-// order inside a class is as good), are scattered into a staging area at their cells and leave as whole 128-byte
-// steps.  Extras park their words in a list; the free cells, last step first, pick them up.  The kernel is bound by
-// instruction issue (one window is ~50 entries), hence the counters instead of ballots and prefix counts.
-__global__ void __launch_bounds__(256, 5)
+// One window by itself, whatever its class sizes (the careful path): the entries take their rank inside their class
+// from a shared-memory counter, are scattered into a staging area at their cells and leave as whole 128-byte steps;
+// extras park their words in a list and the free cells, last step first, pick them up.  scratch = 2 * kDealMax + 32
+// words of the warp.  c0 / v0 point at this lane's first entry of the window.
+__device__ __noinline__ void deal_window(const int *c0, const uint8_t *v0, unsigned n, int q0, uint32_t pad,
+                                         uint32_t *out, uint32_t *scratch) {
+  const int lane = threadIdx.x & 31;
+  uint32_t *const stage = scratch, *const extra = scratch + kDealMax, *const count = scratch + 2 * kDealMax;
+  const unsigned steps = (n + 31u) >> 5, H = 2u * steps;
+  count[lane] = 0u;       // 16 class counters | extras parked | free cells handed out
+  uint32_t word[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    word[j] = pad;
+    if (unsigned(j) < steps) {                                   // warp-uniform
+      if (unsigned(j * 32 + lane) < n) word[j] = (uint32_t(ld_stream_s32(c0 + j * 32) - q0) << 8) | v0[j * 32];
+      stage[j * 32 + lane] = pad;
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (unsigned(j) < steps && word[j] != pad) {                 // (a real entry's column is inside the window)
+      const unsigned cls = (word[j] >> 8) & 15u;
+      const unsigned rank = atomicAdd(count + cls, 1u);
+      if (rank < H) stage[deal_cell(rank, cls)] = word[j];
+      else extra[atomicAdd(count + 16, 1u)] = word[j];
+    }
+  }
+  __syncwarp();
+  const unsigned n_extra = count[16];
+  if (n_extra > 0u) {                                            // warp-uniform
+    const unsigned cnt = count[lane & 15];
+    for (int s2 = int(steps) - 1; s2 >= 0; --s2) {
+      if (cnt <= 2u * unsigned(s2) + unsigned(lane >> 4)) {      // this lane's cell of step s2 is free
+        const unsigned idx = atomicAdd(count + 17, 1u);
+        if (idx < n_extra) stage[s2 * 32 + lane] = extra[idx];
+      }
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (unsigned(j) < steps) out[size_t(j) << 5] = stage[j * 32 + lane];
+  __syncwarp();
+}
+
+// One warp per ROW, kDealGroup windows at a time.  Pass 1 runs over the group's entries, 32 per iteration and every
+// iteration independent of the others: an entry finds its window, takes its rank from the (window, class) counter
+// (shared-memory atomic: lanes of one class are ranked in whatever order the unit serves them — any order inside a
+// class is as good) and is stored straight into its cell, or parked in its window's short list of extras.  Pass 2
+// visits the cells the counters leave free: the window's parked extras first, padding words for the rest.  (Per
+// window — rank, stage, store as whole steps — the same work is a chain of dependent latencies for ~50 entries:
+// 0.33 ms for C2's rows against 0.17 ms for the plain column order; profiles/r2_predict_variants.md.)
+constexpr int kDealGroup = 16;      // windows of a row handled together
+constexpr int kDealExtras = 16;     // parked extras per window; a window with more goes the careful way
+#ifndef QRS_PACK_CTAS
+#define QRS_PACK_CTAS 5
+#endif
+__global__ void __launch_bounds__(256, QRS_PACK_CTAS)
 pack_rows_dealt_kernel(const int *__restrict__ colidx, const uint8_t *__restrict__ val,
                        const int64_t *__restrict__ tilepos, const uint64_t *__restrict__ seg_off, int64_t U, int nt,
                        int tile, uint32_t *__restrict__ packed, unsigned *__restrict__ zero_flag) {
-  __shared__ uint32_t s_stage[8][kDealMax];
-  __shared__ uint32_t s_extra[8][kDealMax];
-  __shared__ uint32_t s_count[8][32];       // 16 class counters | extras parked | free cells handed out
+  __shared__ uint32_t s_cnt[8][kDealGroup * 16];                 // entries per (window, class)
+  __shared__ uint32_t s_tab[8][4 * kDealGroup];                  // per window: H | first step | extras parked | free cells served
+  __shared__ uint32_t s_park[8][kDealGroup * kDealExtras];
+  __shared__ uint32_t s_scratch[8][2 * kDealMax + 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t warp_global = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
   const uint32_t pad = uint32_t(pw_spare_col(tile) + (lane & 15)) << 8;      // rating 0, column = this lane's spare slot
-  uint32_t *const stage = s_stage[warp];
-  uint32_t *const extra = s_extra[warp];
-  uint32_t *const count = s_count[warp];
-  count[lane] = 0u;
-  __syncwarp();
+  uint32_t *const cnt = s_cnt[warp];
+  uint32_t *const tab_h = s_tab[warp], *const tab_so = tab_h + kDealGroup, *const tab_x = tab_so + kDealGroup,
+                  *const tab_f = tab_x + kDealGroup;
+  uint32_t *const park = s_park[warp];
+  const float inv_tile = 1.0f / float(tile);
   uint32_t least = 255u;          // smallest rating seen: 0 = an explicit "not rated" entry (recommender.py:41)
   for (int64_t v = warp_global; v < U; v += nwarps) {
     const int64_t *tp = tilepos + v * (nt + 1);
@@ -179,81 +234,88 @@ pack_rows_dealt_kernel(const int *__restrict__ colidx, const uint8_t *__restrict
     const int64_t row_lo = tp[0];
     const int *const row_col = colidx + row_lo + lane;
     const uint8_t *const row_val = val + row_lo + lane;
-    for (int tb = 0; tb < nt; tb += 31) {
+    for (int tb = 0; tb < nt; tb += kDealGroup) {
+      const int nwin = min(kDealGroup, nt - tb);
       const int tl = min(tb + lane, nt);
       const unsigned my_tp = unsigned(tp[tl] - row_lo);
-      const uint64_t my_so = so[tl];
-      const int nwin = min(31, nt - tb);
+      const uint64_t my_so = so[tl];              // so[nt] = the next row's first step (seg_off has U * nt + 1 entries)
+      const unsigned g_lo = __shfl_sync(kFull, my_tp, 0), g_hi = __shfl_sync(kFull, my_tp, nwin);
+      const unsigned my_n = __shfl_down_sync(kFull, my_tp, 1) - my_tp;
+      if (g_lo == g_hi) continue;                                // warp-uniform: nothing in these windows
+      const uint64_t g_so = __shfl_sync(kFull, my_so, 0);
+      uint32_t *const g_out = packed + (g_so << 5);
+      if (lane < nwin) {
+        tab_h[lane] = (my_n == 0u || my_n > unsigned(kDealMax)) ? 0u : 2u * ((my_n + 31u) >> 5);
+        tab_so[lane] = unsigned(my_so - g_so) << 5;
+        tab_x[lane] = 0u;
+        tab_f[lane] = 0u;
+      }
+      for (int j = lane; j < nwin * 16; j += 32) cnt[j] = 0u;
+      __syncwarp();
+      // ---- pass 1 (two iterations' loads in flight together)
+      auto place = [&](uint32_t r, int c) {
+        least = min(least, r);
+        unsigned wq = unsigned(float(c) * inv_tile);             // c < 2^24: off by one at most
+        if (wq * unsigned(tile) > unsigned(c)) --wq;
+        else if ((wq + 1u) * unsigned(tile) <= unsigned(c)) ++wq;
+        const unsigned w = wq - unsigned(tb);
+        const unsigned H = tab_h[w];
+        if (H != 0u) {
+          const unsigned rel = unsigned(c) - wq * unsigned(tile), cls = rel & 15u;
+          const uint32_t word = (rel << 8) | r;
+          const unsigned rank = atomicAdd(cnt + w * 16u + cls, 1u);
+          if (rank < H) {
+            g_out[tab_so[w] + deal_cell(rank, cls)] = word;
+          } else {
+            const unsigned k = atomicAdd(tab_x + w, 1u);
+            if (k < unsigned(kDealExtras)) park[w * kDealExtras + k] = word;
+          }
+        }
+      };
+      for (unsigned i = g_lo; i < g_hi; i += 64u) {
+        const bool in0 = i + unsigned(lane) < g_hi, in1 = i + 32u + unsigned(lane) < g_hi;
+        uint32_t r0 = 0, r1 = 0;
+        int c0 = 0, c1 = 0;
+        if (in0) { r0 = row_val[i]; c0 = ld_stream_s32(row_col + i); }
+        if (in1) { r1 = row_val[i + 32u]; c1 = ld_stream_s32(row_col + i + 32u); }
+        if (in0) place(r0, c0);
+        if (in1) place(r1, c1);
+      }
+      __syncwarp();
+      // ---- pass 2
       for (int w = 0; w < nwin; ++w) {
         const unsigned a = __shfl_sync(kFull, my_tp, w);
-        const unsigned n = __shfl_sync(kFull, my_tp, w + 1) - a;
+        const unsigned n = __shfl_sync(kFull, my_n, w);
         if (n == 0u) continue;                                   // warp-uniform
-        uint32_t *const out = packed + (__shfl_sync(kFull, my_so, w) << 5) + lane;
-        const int *const c0 = row_col + a;
-        const uint8_t *const v0 = row_val + a;
+        uint32_t *const out = g_out + tab_so[w] + lane;
         const unsigned steps = (n + 31u) >> 5;
         const int q0 = (tb + w) * tile;
         if (n > unsigned(kDealMax)) {                            // long sub-segment: column order
           for (unsigned s2 = 0; s2 < steps; ++s2) {
             uint32_t x = pad;
-            if (s2 * 32u + unsigned(lane) < n) {
-              const uint32_t r = v0[s2 * 32u];
-              x = (uint32_t(ld_stream_s32(c0 + s2 * 32u) - q0) << 8) | r;
-              least = min(least, r);
-            }
+            if (s2 * 32u + unsigned(lane) < n) x = (uint32_t(ld_stream_s32(row_col + a + s2 * 32u) - q0) << 8) | row_val[a + s2 * 32u];
             out[size_t(s2) << 5] = x;
           }
           continue;
         }
-        const unsigned H = 2u * steps;
-        // ---- the sub-segment's words (all loads in flight together), the staging area pre-filled with padding
-        uint32_t word[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          word[j] = pad;
-          if (unsigned(j) < steps) {                             // warp-uniform
-            if (unsigned(j * 32 + lane) < n) {
-              const uint32_t r = v0[j * 32];
-              word[j] = (uint32_t(ld_stream_s32(c0 + j * 32) - q0) << 8) | r;
-              least = min(least, r);
+        const unsigned parked = tab_x[w];
+        if (parked > unsigned(kDealExtras)) {                    // (one class holds most of the window)
+          deal_window(row_col + a, row_val + a, n, q0, pad, out, s_scratch[warp]);
+          continue;
+        }
+        const unsigned in_class = cnt[w * 16 + (lane & 15)];
+        for (int s2 = int(steps) - 1; s2 >= 0; --s2) {
+          if (in_class <= 2u * unsigned(s2) + unsigned(lane >> 4)) {      // this lane's cell of step s2 is free
+            uint32_t x = pad;
+            if (parked != 0u) {
+              const unsigned idx = atomicAdd(tab_f + w, 1u);
+              if (idx < parked) x = park[w * kDealExtras + idx];
             }
-            stage[j * 32 + lane] = pad;
+            out[size_t(s2) << 5] = x;
           }
         }
-        __syncwarp();
-        // ---- class cells for the first H entries of a class, the list of extras for the others
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (unsigned(j) < steps && word[j] != pad) {           // (a real entry's column is inside the window)
-            const unsigned cls = (word[j] >> 8) & 15u;
-            const unsigned rank = atomicAdd(count + cls, 1u);
-            if (rank < H) stage[deal_cell(rank, cls)] = word[j];
-            else extra[atomicAdd(count + 16, 1u)] = word[j];
-          }
-        }
-        __syncwarp();
-        const unsigned n_extra = count[16];
-        if (n_extra > 0u) {                                      // warp-uniform
-          // cell (half-step h, lane c) is free when class c has at most h entries: last step first, a free cell
-          // takes the next parked extra
-          const unsigned cnt = count[lane & 15];
-          unsigned n_free = 0u;
-          for (int s2 = int(steps) - 1; s2 >= 0 && n_free < n_extra; --s2) {
-            const bool is_free = cnt <= 2u * unsigned(s2) + unsigned(lane >> 4);
-            if (is_free) {
-              const unsigned idx = atomicAdd(count + 17, 1u);
-              if (idx < n_extra) stage[s2 * 32 + lane] = extra[idx];
-            }
-            n_free += unsigned(__popc(__ballot_sync(kFull, is_free)));
-          }
-          __syncwarp();
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (unsigned(j) < steps) out[size_t(j) << 5] = stage[j * 32 + lane];
-        if (lane < 18) count[lane] = 0u;
-        __syncwarp();
       }
+      __syncwarp();
     }
   }
   if (least == 0u) *zero_flag = 1u;
@@ -963,7 +1025,8 @@ int64_t tie_list_capacity(int64_t capacity) { return capacity / 32 + 65536; }
 // (24.8 -> 24.4 ms per 100k rows) and the dearer preparation (+1.0 ms) is a loss: column order there.  The rule
 // looks at this workspace's rows only; the layout is recorded in the workspace (flag word 1) for whoever reads it.
 // QRS_PREDICT_PACK=class|column overrides (A/B measurements, tests).
-bool pack_dealt(int64_t U, int64_t nt, int64_t nnz) {
+bool pack_dealt(int64_t U, int64_t nt, int64_t nnz, int tile) {
+  if (nt * int64_t(tile) > (int64_t(1) << 24)) return false;      // (the kernel finds an entry's window in fp32)
   const char *e = getenv("QRS_PREDICT_PACK");
   if (e && strcmp(e, "column") == 0) return false;
   if (e && strcmp(e, "class") == 0) return true;
@@ -1070,7 +1133,7 @@ int qrs_predict_prepare(const int64_t *rowptr, const int32_t *colidx, const uint
     int64_t blocks = ceil_div<int64_t>(U, 8);
     const int64_t cap2 = int64_t(sm_count()) * 16;
     if (blocks > cap2) blocks = cap2;
-    if (pack_dealt(U, nt, nnz))
+    if (pack_dealt(U, nt, nnz, tile))
       pack_rows_dealt_kernel<<<unsigned(blocks), 256, 0, st>>>(colidx, val, w.tilepos, w.seg_off, U, nt, tile, w.packed,
                                                                reinterpret_cast<unsigned *>(w.tie_count + 2));
     else
