@@ -650,7 +650,7 @@ def exchange_report(outs, out, stage_ms, dev, world):
     dist.all_reduce(mx, op=dist.ReduceOp.MAX)
     rep = {}
     for name, bts in zip(names, mx.tolist()):
-        ms = stage_ms.get("exchange:" + name)
+        ms = stage_ms.get("exchange:ratings" if name.startswith("ratings") else "exchange:" + name)
         rep[name] = {"bytes_sent_per_rank_max": int(bts), "ms": ms,
                      "nvlink_frac_of_770GBps": (bts / (ms * 1e-3) / 770e9) if ms else None}
         if name == "signatures":
@@ -659,9 +659,16 @@ def exchange_report(outs, out, stage_ms, dev, world):
             bg = stage_ms.get("background:signatures")
             rep[name].update({"ms": bg, "exposed_ms": ms, "nvlink_frac_of_770GBps": (bts / (bg * 1e-3) / 770e9) if bg else None})
         if name.startswith("ratings"):
-            rep[name]["note"] = "neighbour rows of other ranks, read in place by the prediction kernel (no separate exchange stage)"
+            staged = bool(getattr(out, "peer_rows_staged", False))
+            rep[name]["staged"] = staged
+            rep[name]["note"] = ("neighbour rows of other ranks copied into a local buffer before the prediction kernel "
+                                 "(qrs_peer_rows_stage: steps per reference, scan, copy; ms = the whole stage, bytes = what came over NVLink)"
+                                 if staged else
+                                 "neighbour rows of other ranks, read in place by the prediction kernel (no separate exchange stage)")
+            if not staged:
+                rep[name]["ms"], rep[name]["nvlink_frac_of_770GBps"] = None, None
     rep["total_ms"] = sum(v for kx, v in stage_ms.items() if kx.startswith("exchange:"))
-    rep["total_note"] = "time on the main stream: record all-to-all, pair all-to-all, exposed wait for the signature all-gather, barrier"
+    rep["total_note"] = "time on the main stream: record all-to-all, pair all-to-all, exposed wait for the signature all-gather, barrier, staging of remote neighbour rows"
     return rep
 
 

@@ -261,6 +261,18 @@ int qrs_predict_prepare(const int64_t *rowptr, const int32_t *colidx, const uint
  * the kernel accumulates exact integers (half the shared memory, no fp64 in the inner loop) and
  * falls back to the reference's sequential fp64 arithmetic only for cells whose value is exactly
  * half-way between two integers — the results are identical to the u_val path bit for bit. */
+/* Staged peer rows (optional, several GPUs).  Reading a neighbour row over NVLink one 128-byte step at a time
+ * costs the predicting warp a link round trip per batch; qrs_peer_rows_stage instead copies every row that the
+ * table (u_idx / u_cnt of local users 0 .. n_users-1, global ids) names on another rank into `stage` — whole rows,
+ * thousands of lines in flight — and qrs_predict_sparse, given the same buffer as peer_stage (stage_users = that
+ * n_users), reads them locally.  cap_steps = 128-byte steps the buffer can hold; the device word stage[0] (u64)
+ * receives the steps this table needs, and when that exceeds cap_steps nothing is copied and the predictor reads
+ * the rows in place as without staging (the caller reads the word back with its other counters and sizes the
+ * next call).  Call after every rank has prepared, before predicting; results are identical either way. */
+size_t qrs_peer_rows_stage_bytes(int64_t n_users, int32_t ku, int32_t Q, int32_t tile, int64_t cap_steps);
+int qrs_peer_rows_stage(const uint64_t *peer_ws /* HOST array [n_peers] */, int32_t n_peers, int32_t my_peer,
+                        int64_t U, int32_t Q, int32_t tile, const int32_t *u_idx, const int32_t *u_cnt, int32_t ku,
+                        int64_t n_users, int64_t cap_steps, void *stage, size_t stage_bytes, void *stream);
 int qrs_predict_sparse(const int64_t *rowptr, const int32_t *colidx, const uint8_t *val,
                        int64_t U, int64_t nnz, int32_t Q,
                        const int32_t *u_idx, const double *u_val, const int32_t *u_milli,
@@ -268,6 +280,7 @@ int qrs_predict_sparse(const int64_t *rowptr, const int32_t *colidx, const uint8
                        int64_t user_base, int64_t n_users, int32_t tile,
                        void *ws, size_t ws_bytes, int32_t prepared,
                        const uint64_t *peer_ws /* HOST array [n_peers] or NULL */, int32_t n_peers, int32_t my_peer,
+                       const void *peer_stage /* or NULL */, int64_t stage_users,
                        int64_t *row_start, int32_t *row_cnt,
                        void *cols, int32_t cols_mode /* QRS_COLS_* */, uint8_t *preds,
                        int64_t capacity, int32_t n_regions, unsigned long long *cursors, void *stream);

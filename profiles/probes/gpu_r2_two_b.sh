@@ -1,18 +1,21 @@
 #!/bin/bash
-# One `gpurun --gpus 2` call: hardware multi-GPU invariance (G = 2, both row layouts), weak C2 at N = 2.
+# One `gpurun --gpus N` call: hardware multi-GPU invariance, weak C2 at N with remote neighbour rows staged / read in place.
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 N=${N:-2}
 run() { python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 "$@"; }
-t0=$SECONDS
-timeout 400 python -m pytest tests/test_gpu_multigpu.py -x -q > gpurun_out/t_multi.log 2>&1
-echo "multi-GPU test rc=$? t=$((SECONDS-t0))"; tail -5 gpurun_out/t_multi.log
-QRS_PREDICT_PACK=class timeout 400 python -m pytest tests/test_gpu_multigpu.py -x -q > gpurun_out/t_multi_class.log 2>&1
-echo "multi-GPU test (class layout forced) rc=$? t=$((SECONDS-t0))"; tail -5 gpurun_out/t_multi_class.log
-timeout 300 bash -c "$(declare -f run); N=$N run bench.py --gpus $N --no-extras --no-cpu-baseline" > gpurun_out/r2_c2_weak_g$N.json 2> gpurun_out/r2_c2_weak_g$N.err
-echo "weak C2 rc=$? t=$((SECONDS-t0))"; python - <<PY
+show() { python - <<PY
 import json
-d = json.load(open('gpurun_out/r2_c2_weak_g$N.json'))
-print(d['ms_per_step'], d['stages']['ms'], d['e2e']['ms_per_step'], d['parity_check'])
+for l in open('$1'):
+    if l.startswith('{"metric'):
+        d = json.loads(l)
+        print(d['ms_per_step'], d['stages']['ms'], d['e2e']['ms_per_step'], d['parity_check']['identical'], (d.get('exchanges') or {}).get('ratings(peer reads)'))
 PY
-tail -c 600 gpurun_out/r2_c2_weak_g$N.err
+}
+t0=$SECONDS
+timeout 600 python -m pytest tests/test_gpu_multigpu.py tests/test_gpu_predict_shapes.py -x -q -k "sharded or another_rank" > gpurun_out/t_multi.log 2>&1
+echo "multi-GPU test rc=$? t=$((SECONDS-t0))"; tail -5 gpurun_out/t_multi.log
+timeout 300 bash -c "$(declare -f run); N=$N run bench.py --gpus $N --no-extras --no-cpu-baseline" > gpurun_out/r2_c2_weak_g$N.json 2> gpurun_out/r2_c2_weak_g$N.err
+echo "weak C2 (staged) rc=$? t=$((SECONDS-t0))"; show gpurun_out/r2_c2_weak_g$N.json; tail -c 400 gpurun_out/r2_c2_weak_g$N.err
+QRS_STAGE_PEER_ROWS=0 timeout 300 bash -c "$(declare -f run); N=$N run bench.py --gpus $N --no-extras --no-cpu-baseline" > gpurun_out/r2_c2_weak_g${N}_inplace.json 2> gpurun_out/r2_c2_weak_g${N}_inplace.err
+echo "weak C2 (in place) rc=$? t=$((SECONDS-t0))"; show gpurun_out/r2_c2_weak_g${N}_inplace.json; tail -c 400 gpurun_out/r2_c2_weak_g${N}_inplace.err

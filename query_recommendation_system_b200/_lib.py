@@ -76,8 +76,10 @@ SIGNATURES = {
     "qrs_predict_warps_per_sm": (_i32, [_i32, _i32]),
     "qrs_predict_sparse_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32, _i64]),
     "qrs_predict_prepare": (C.c_int, [_p, _p, _p, _i64, _i64, _i32, _i32, _i64, _p, _sz, _p]),
+    "qrs_peer_rows_stage_bytes": (_sz, [_i64, _i32, _i32, _i32, _i64]),
+    "qrs_peer_rows_stage": (C.c_int, [_p, _i32, _i32, _i64, _i32, _i32, _p, _p, _i32, _i64, _i64, _p, _sz, _p]),
     "qrs_predict_sparse": (C.c_int, [_p, _p, _p, _i64, _i64, _i32, _p, _p, _p, _p, _i32, _i64, _i64, _i32, _p, _sz, _i32,
-                                     _p, _i32, _i32, _p, _p, _p, _i32, _p, _i64, _i32, _p, _p]),
+                                     _p, _i32, _i32, _p, _i64, _p, _p, _p, _i32, _p, _i64, _i32, _p, _p]),
 }
 
 _lib = None

@@ -373,6 +373,11 @@ __device__ __forceinline__ void lds_v2(unsigned &lo, unsigned &hi, unsigned addr
 __device__ __forceinline__ void sts_v2(unsigned addr, unsigned lo, unsigned hi) {
   asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(lo), "r"(hi) : "memory");
 }
+__device__ __forceinline__ uint4 ld_stream_v4(const uint4 *p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ unsigned ld_stream_u32(const uint32_t *p) {
   unsigned v;
   asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
@@ -387,6 +392,14 @@ __device__ __forceinline__ int predict_from(double num, double den) {
 // preparation workspace has the same layout (same U, nt), so one set of byte offsets addresses all of them and
 // base[r] is rank r's workspace as mapped into THIS process (CUDA IPC; base[my] = the local one).  Neighbour ids
 // are global row ids; a neighbour row on another rank is read in place over NVLink.
+//
+// Staged peer rows (optional, qrs_peer_rows_stage): reading a neighbour's steps over NVLink one 128-byte line at a
+// time leaves the warp waiting a link round trip per batch (C2 shards on 8 GPUs: 5 % of the gathered bytes are remote
+// and the predictor takes 80 % longer).  So the rows this rank's users name on other ranks are first copied, whole
+// and by many warps at once, into a local buffer; reference x = local user * ku + table slot owns the offset-table
+// row stage_seg[x * nt .. x * nt + nt] (consecutive sub-segments like everywhere else), and base[n_peers] is set so
+// that peer_packed(pv, n_peers) is the buffer's step area.  stage_hdr[1] != 0 says the staging of this step fitted;
+// otherwise (and in the rare tie paths, which go by global row id) rows are read in place.
 constexpr int kMaxPeers = 16;
 struct PeerView {
   unsigned long long base[kMaxPeers];
@@ -394,6 +407,8 @@ struct PeerView {
   int my;
   long long rows_per_peer;
   unsigned long long off_tilepos, off_seg, off_packed, off_flag;   // byte offsets inside a workspace
+  const unsigned long long *stage_hdr;      // null: no staged rows.  [0] steps this step needs, [1] staged and complete
+  const uint64_t *stage_seg;
 };
 __device__ __forceinline__ const int64_t *peer_tilepos(const PeerView &pv, int r) {
   return reinterpret_cast<const int64_t *>(pv.base[r] + pv.off_tilepos);
@@ -520,6 +535,7 @@ predict_sparse_kernel(const __grid_constant__ PeerView pv, int Q,
   for (int r = 0; r < pv.n_peers; ++r)
     has_zeros |= *reinterpret_cast<const unsigned *>(pv.base[r] + pv.off_flag) != 0u;
   constexpr bool one_peer = ONE_PEER;
+  const bool staged = !ONE_PEER && pv.stage_hdr != nullptr && pv.stage_hdr[1] != 0ull;      // warp-uniform
 
   // A warp takes one USER at a time (dynamic: a device counter) and walks its windows in order, so what depends
   // on the user only — neighbour ids, ranks, similarities, the rows' offset tables — is set up once, and since the
@@ -546,9 +562,13 @@ predict_sparse_kernel(const __grid_constant__ PeerView pv, int Q,
     __syncwarp();            // F64: the previous user's m_s has been consumed
     if (lane < c) {
       const int v = u_idx[tbase + lane];
-      const int pr = one_peer ? 0 : int(unsigned(v) / unsigned(pv.rows_per_peer));
+      int pr = one_peer ? 0 : int(unsigned(v) / unsigned(pv.rows_per_peer));
       const long long row = one_peer ? v : v - pr * pv.rows_per_peer;
       so0 = reinterpret_cast<const unsigned *>(peer_seg(pv, pr) + row * nt);
+      if (!one_peer && staged && pr != pv.my) {         // a remote row, copied here before the launch
+        so0 = reinterpret_cast<const unsigned *>(pv.stage_seg + ((user_base + int64_t(ul)) * ku + lane) * nt);
+        pr = pv.n_peers;
+      }
       if constexpr (MILLI) {
         tag0 = unsigned(u_milli[tbase + lane]) | (1u << 24);
         if (tag0 == (1u << 24)) so0 = nullptr;
@@ -560,9 +580,13 @@ predict_sparse_kernel(const __grid_constant__ PeerView pv, int Q,
     }
     if (WIDE_K && lane + 32 < c) {
       const int v = u_idx[tbase + lane + 32];
-      const int pr = one_peer ? 0 : int(unsigned(v) / unsigned(pv.rows_per_peer));
+      int pr = one_peer ? 0 : int(unsigned(v) / unsigned(pv.rows_per_peer));
       const long long row = one_peer ? v : v - pr * pv.rows_per_peer;
       so1 = reinterpret_cast<const unsigned *>(peer_seg(pv, pr) + row * nt);
+      if (!one_peer && staged && pr != pv.my) {
+        so1 = reinterpret_cast<const unsigned *>(pv.stage_seg + ((user_base + int64_t(ul)) * ku + lane + 32) * nt);
+        pr = pv.n_peers;
+      }
       if constexpr (MILLI) {
         tag1 = unsigned(u_milli[tbase + lane + 32]) | (1u << 24);
         if (tag1 == (1u << 24)) so1 = nullptr;
@@ -980,6 +1004,96 @@ predict_tie_fixup_kernel(const __grid_constant__ PeerView pv, int tile, int nt, 
   }
 }
 
+// ------------------------------------------------------------------ staged peer rows
+// steps of the prepared row behind reference x = (local user, table slot), 0 unless the row lives on another rank
+__global__ void __launch_bounds__(256)
+peer_ref_steps_kernel(const __grid_constant__ PeerView pv, int nt, const int *__restrict__ u_idx,
+                      const int *__restrict__ u_cnt, int ku, int64_t n_users, uint32_t *__restrict__ ref_steps,
+                      uint64_t *__restrict__ ref_src) {
+  const int64_t total = n_users * ku;
+  for (int64_t x = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; x < total; x += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t ul = x / ku;
+    const int t = int(x - ul * ku);
+    uint32_t steps = 0;
+    if (t < min(u_cnt[ul], ku)) {
+      const int v = u_idx[x];
+      const int pr = int(unsigned(v) / unsigned(pv.rows_per_peer));
+      if (pr != pv.my) {
+        const uint64_t *seg = peer_seg(pv, pr) + (v - pr * pv.rows_per_peer) * nt;
+        const uint64_t first = seg[0];
+        steps = uint32_t(seg[nt] - first);
+        ref_src[x] = first;        // (so that the copy needs no second trip over the link before it can start)
+      }
+    }
+    ref_steps[x] = steps;
+  }
+}
+
+// One warp per remote reference: the row's steps and its offset-table row, rebased to the staging buffer.  Nothing
+// is copied (and hdr[1] stays 0: rows are read in place this step) when the step needs more than `cap_steps`.
+__global__ void __launch_bounds__(256)
+peer_rows_copy_kernel(const __grid_constant__ PeerView pv, int nt, const int *__restrict__ u_idx,
+                      const int *__restrict__ u_cnt, int ku, int64_t n_refs,
+                      const uint32_t *__restrict__ ref_steps, const uint64_t *__restrict__ ref_src,
+                      const uint64_t *__restrict__ ref_first,
+                      int64_t cap_steps, unsigned long long *__restrict__ hdr, uint64_t *__restrict__ stage_seg,
+                      uint32_t *__restrict__ stage_packed) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  const uint64_t need = ref_first[n_refs];
+  const bool fits = need <= uint64_t(cap_steps);
+  if (blockIdx.x == 0 && threadIdx.x == 0) { hdr[0] = need; hdr[1] = fits ? 1ull : 0ull; }
+  if (!fits) return;
+  // 32 references looked at per warp iteration (most are local rows or empty slots), the remote ones copied one
+  // after the other by the whole warp
+  for (int64_t x0 = warp_global * 32; x0 < n_refs; x0 += nwarps * 32) {
+    const int64_t xl = x0 + lane;
+    bool remote = false;
+    int v = 0, pr = 0;
+    uint32_t my_steps = 0;
+    uint64_t my_src = 0, my_dst = 0;
+    if (xl < n_refs) {
+      const int64_t ul = xl / ku;
+      if (int(xl - ul * ku) < min(u_cnt[ul], ku)) {
+        v = u_idx[xl];
+        pr = int(unsigned(v) / unsigned(pv.rows_per_peer));
+        remote = pr != pv.my;                                    // (an empty remote row still needs its offsets)
+        if (remote) { my_steps = ref_steps[xl]; my_src = ref_src[xl]; my_dst = ref_first[xl]; }
+      }
+    }
+    for (unsigned todo = __ballot_sync(kFull, remote); todo != 0u; todo &= todo - 1u) {
+      const int from = __ffs(todo) - 1;
+      const int64_t x = x0 + from;
+      const int vx = __shfl_sync(kFull, v, from), prx = __shfl_sync(kFull, pr, from);
+      const uint32_t steps = __shfl_sync(kFull, my_steps, from);
+      const uint64_t src0 = __shfl_sync(kFull, my_src, from), dst0 = __shfl_sync(kFull, my_dst, from);
+      const uint64_t *seg = peer_seg(pv, prx) + (vx - prx * pv.rows_per_peer) * nt;
+      // the row's steps as one run of 16-byte pieces (eight per step): the offset-table row and up to 32 steps
+      // leave in ONE trip over the link, 512 bytes per warp load
+      const uint4 *src = reinterpret_cast<const uint4 *>(peer_packed(pv, prx) + (src0 << 5)) + lane;
+      uint4 *dst = reinterpret_cast<uint4 *>(stage_packed + (dst0 << 5)) + lane;
+      const uint32_t pieces = steps * 8u;
+      uint64_t off[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) off[j] = lane + 32 * j <= nt ? seg[lane + 32 * j] : 0ull;
+      for (uint32_t q = 0; q < pieces; q += 256u) {
+        uint4 w[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (q + 32u * j + unsigned(lane) < pieces) w[j] = ld_stream_v4(src + q + 32 * j);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (q + 32u * j + unsigned(lane) < pieces) dst[q + 32 * j] = w[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        if (lane + 32 * j <= nt) stage_seg[x * nt + lane + 32 * j] = dst0 + (off[j] - src0);
+      for (int t = lane + 64; t <= nt; t += 32) stage_seg[x * nt + t] = dst0 + (seg[t] - src0);
+    }
+  }
+}
+
 // warps (each with its own window) that fit one CTA = one SM: 227 KB minus the CTA's table and 1 KB the system keeps
 static int predict_warps_per_cta(int tile, bool milli) {
   const size_t budget = size_t(227) * 1024 - 1024 - kPwCtaBytes;
@@ -1146,12 +1260,106 @@ int qrs_predict_prepare(const int64_t *rowptr, const int32_t *colidx, const uint
   return QRS_OK;
 }
 
+namespace {
+struct StageBuf {
+  unsigned long long *hdr;
+  uint64_t *seg;
+  uint32_t *ref_steps;
+  uint64_t *ref_src;
+  uint64_t *ref_first;
+  void *scan_ws;
+  size_t scan_bytes;
+  uint32_t *packed;
+  size_t total;
+};
+StageBuf carve_stage(void *buf, int64_t n_users, int64_t ku, int64_t nt, int64_t cap_steps) {
+  StageBuf b;
+  char *p = static_cast<char *>(buf);
+  const size_t refs = size_t(n_users > 0 ? n_users : 1) * size_t(ku);
+  b.hdr = reinterpret_cast<unsigned long long *>(p);
+  p += 256;
+  b.seg = reinterpret_cast<uint64_t *>(p);
+  p += round_up<size_t>((refs * size_t(nt) + 1) * 8, 256);
+  b.ref_steps = reinterpret_cast<uint32_t *>(p);
+  p += round_up<size_t>(refs * 4, 256);
+  b.ref_src = reinterpret_cast<uint64_t *>(p);
+  p += round_up<size_t>(refs * 8, 256);
+  b.ref_first = reinterpret_cast<uint64_t *>(p);
+  p += round_up<size_t>((refs + 1) * 8, 256);
+  b.scan_ws = p;
+  b.scan_bytes = scan_workspace_bytes(int64_t(refs));
+  p += round_up<size_t>(b.scan_bytes, 256);
+  b.packed = reinterpret_cast<uint32_t *>(p);
+  p += round_up<size_t>(size_t(cap_steps > 0 ? cap_steps : 0) * 128, 256);
+  b.total = size_t(p - static_cast<char *>(buf));
+  return b;
+}
+
+int fill_peer_view(PeerView &pv, void *ws, const PredictWs &w, const uint64_t *peer_ws, int n_peers, int my_peer,
+                   int64_t U) {
+  memset(&pv, 0, sizeof(pv));
+  pv.n_peers = peer_ws ? n_peers : 1;
+  pv.my = peer_ws ? my_peer : 0;
+  pv.rows_per_peer = U > 0 ? U : 1;
+  for (int r = 0; r < pv.n_peers; ++r) pv.base[r] = peer_ws ? peer_ws[r] : 0ull;
+  if (ws) pv.base[pv.my] = static_cast<unsigned long long>(reinterpret_cast<uintptr_t>(ws));
+  pv.off_tilepos = static_cast<unsigned long long>(reinterpret_cast<char *>(w.tilepos) - static_cast<char *>(ws));
+  pv.off_seg = static_cast<unsigned long long>(reinterpret_cast<char *>(w.seg_off) - static_cast<char *>(ws));
+  pv.off_packed = static_cast<unsigned long long>(reinterpret_cast<char *>(w.packed) - static_cast<char *>(ws));
+  pv.off_flag = static_cast<unsigned long long>(reinterpret_cast<char *>(w.tie_count + 2) - static_cast<char *>(ws));
+  for (int r = 0; r < pv.n_peers; ++r)
+    if (pv.base[r] == 0ull) return QRS_ERR_INVALID_ARG;
+  return QRS_OK;
+}
+}  // namespace
+
+size_t qrs_peer_rows_stage_bytes(int64_t n_users, int32_t ku, int32_t Q, int32_t tile, int64_t cap_steps) {
+  if (n_users < 0 || ku <= 0 || Q <= 0 || tile <= 0 || cap_steps < 0) return 0;
+  return carve_stage(nullptr, n_users, ku, ceil_div<int64_t>(Q, tile), cap_steps).total;
+}
+
+int qrs_peer_rows_stage(const uint64_t *peer_ws, int32_t n_peers, int32_t my_peer, int64_t U, int32_t Q, int32_t tile,
+                        const int32_t *u_idx, const int32_t *u_cnt, int32_t ku, int64_t n_users, int64_t cap_steps,
+                        void *stage, size_t stage_bytes, void *stream) {
+  if (!peer_ws || n_peers < 2 || n_peers >= kMaxPeers || my_peer < 0 || my_peer >= n_peers || U <= 0 || Q <= 0 ||
+      tile <= 0 || tile % 32 != 0 || !u_idx || !u_cnt || ku <= 0 || n_users < 0 || n_users > U || cap_steps < 0)
+    return QRS_ERR_INVALID_ARG;
+  if (!stage || (reinterpret_cast<uintptr_t>(stage) & 255) != 0 ||
+      stage_bytes < qrs_peer_rows_stage_bytes(n_users, ku, Q, tile, cap_steps))
+    return QRS_ERR_WORKSPACE;
+  const int nt = int(ceil_div<int64_t>(Q, tile));
+  const StageBuf b = carve_stage(stage, n_users, ku, nt, cap_steps);
+  cudaStream_t st = as_stream(stream);
+  QRS_CUDA(cudaMemsetAsync(b.hdr, 0, 256, st));
+  if (n_users == 0) return QRS_OK;
+  // every rank's workspace has the same layout up to the packed rows (it does not depend on nnz or capacity)
+  PeerView pv;
+  void *mine = reinterpret_cast<void *>(uintptr_t(peer_ws[my_peer]));
+  int rc = fill_peer_view(pv, mine, carve_predict_ws(mine, U, nt, 0, 0), peer_ws, n_peers, my_peer, U);
+  if (rc != QRS_OK) return rc;
+  const int64_t refs = n_users * ku;
+  {
+    int64_t blocks = ceil_div<int64_t>(refs, 256);
+    const int64_t cap = int64_t(sm_count()) * 8;
+    if (blocks > cap) blocks = cap;
+    peer_ref_steps_kernel<<<unsigned(blocks), 256, 0, st>>>(pv, nt, u_idx, u_cnt, ku, n_users, b.ref_steps, b.ref_src);
+    QRS_LAUNCH_CHECK();
+  }
+  rc = exclusive_scan_u32_to_u64(b.ref_steps, b.ref_first, refs, b.scan_ws, b.scan_bytes, st);
+  if (rc != QRS_OK) return rc;
+  peer_rows_copy_kernel<<<sm_count() * 8, 256, 0, st>>>(pv, nt, u_idx, u_cnt, ku, refs, b.ref_steps, b.ref_src, b.ref_first, cap_steps,
+                                                        b.hdr, b.seg, b.packed);
+  QRS_LAUNCH_CHECK();
+  return QRS_OK;
+}
+
 int qrs_predict_sparse(const int64_t *rowptr, const int32_t *colidx, const uint8_t *val, int64_t U, int64_t nnz,
                        int32_t Q, const int32_t *u_idx, const double *u_val, const int32_t *u_milli,
                        const int32_t *u_cnt, int32_t ku, int64_t user_base, int64_t n_users, int32_t tile, void *ws,
                        size_t ws_bytes, int32_t prepared, const uint64_t *peer_ws, int32_t n_peers, int32_t my_peer,
-                       int64_t *row_start, int32_t *row_cnt, void *cols_any, int32_t cols_mode, uint8_t *preds,
-                       int64_t capacity, int32_t n_regions, unsigned long long *cursors, void *stream) {
+                       const void *peer_stage, int64_t stage_users, int64_t *row_start, int32_t *row_cnt, void *cols_any,
+                       int32_t cols_mode, uint8_t *preds, int64_t capacity, int32_t n_regions,
+                       unsigned long long *cursors, void *stream) {
   int32_t *cols = static_cast<int32_t *>(cols_any);
   if (cols_mode < 0 || cols_mode > 2 || (cols_mode == 1 && Q > 65536)) return QRS_ERR_INVALID_ARG;
   if (U < 0 || nnz < 0 || Q <= 0 || !u_idx || (!u_val && !u_milli) || !u_cnt || ku <= 0 || user_base < 0 ||
@@ -1179,18 +1387,17 @@ int qrs_predict_sparse(const int64_t *rowptr, const int32_t *colidx, const uint8
   const int nt = int(ceil_div<int64_t>(Q, tile));
   const PredictWs w = carve_predict_ws(ws, U, nt, nnz, capacity);
   PeerView pv;
-  memset(&pv, 0, sizeof(pv));
-  pv.n_peers = peer_ws ? n_peers : 1;
-  pv.my = peer_ws ? my_peer : 0;
-  pv.rows_per_peer = U > 0 ? U : 1;
-  for (int r = 0; r < pv.n_peers; ++r) pv.base[r] = peer_ws ? peer_ws[r] : 0ull;
-  pv.base[pv.my] = static_cast<unsigned long long>(reinterpret_cast<uintptr_t>(ws));
-  pv.off_tilepos = static_cast<unsigned long long>(reinterpret_cast<char *>(w.tilepos) - static_cast<char *>(ws));
-  pv.off_seg = static_cast<unsigned long long>(reinterpret_cast<char *>(w.seg_off) - static_cast<char *>(ws));
-  pv.off_packed = static_cast<unsigned long long>(reinterpret_cast<char *>(w.packed) - static_cast<char *>(ws));
-  pv.off_flag = static_cast<unsigned long long>(reinterpret_cast<char *>(w.tie_count + 2) - static_cast<char *>(ws));
-  for (int r = 0; r < pv.n_peers; ++r)
-    if (pv.base[r] == 0ull) return QRS_ERR_INVALID_ARG;
+  {
+    int rc = fill_peer_view(pv, ws, w, peer_ws, n_peers, my_peer, U);
+    if (rc != QRS_OK) return rc;
+  }
+  if (peer_stage) {      // rows of other ranks staged by qrs_peer_rows_stage for the table of `stage_users` local users
+    if (!peer_ws || n_peers >= kMaxPeers || stage_users < user_base + n_users) return QRS_ERR_INVALID_ARG;
+    const StageBuf b = carve_stage(const_cast<void *>(peer_stage), stage_users, ku, nt, 0);
+    pv.stage_hdr = b.hdr;
+    pv.stage_seg = b.seg;
+    pv.base[pv.n_peers] = static_cast<unsigned long long>(reinterpret_cast<uintptr_t>(b.packed)) - pv.off_packed;
+  }
   QRS_CUDA(cudaMemsetAsync(w.tie_count, 0, 16, st));      // tie counter | next-user counter
   if (u_milli) {
     int rc = launch_predict_sparse<true>(pv, Q, u_idx, u_val, u_milli, u_cnt, ku, user_base, n_users, tile, nt,

@@ -12,6 +12,7 @@ All arithmetic is in `stages` (CUDA kernels behind the C ABI); torch is plumbing
 """
 from __future__ import annotations
 
+import os
 import time
 from dataclasses import dataclass, field
 from typing import Dict, Optional
@@ -43,6 +44,7 @@ class PipelineOutput:
     covered_cells: int = 0                 # zero cells of R decided (predicted or proven "missed")
     stage_ms: Dict[str, float] = field(default_factory=dict)
     exchange_bytes: Dict[str, int] = field(default_factory=dict)   # several GPUs: bytes this rank sent per exchange
+    peer_rows_staged: bool = False         # several GPUs: remote neighbour rows were copied here before predicting
 
 
 class _Timer:
@@ -106,6 +108,12 @@ class LshCfPipeline:
         self._pred_capacity = {}
         self._cap = {}                      # learnt buffer capacities: candidate pairs, exchange slots
         self.peer_margin = 1.25             # several GPUs: the peer buffer is sized for this x the first shard's entries
+        # QRS_STAGE_PEER_ROWS=1: copy the neighbour rows of other ranks here before predicting instead of reading them
+        # in place.  Measured and NOT the default: the copy (SM loads over NVLink: 0.32-0.42 of the link rate) costs
+        # more than the predictor saves — C2 shards, N = 2: 6.79 vs 6.55 ms/step, N = 8: 10.14 vs 9.23
+        self.stage_peer_rows = os.environ.get("QRS_STAGE_PEER_ROWS", "0")
+        self.peer_stage_budget = 8 << 30    # ... unless a step would need more than this many bytes of them
+        self._stage_buf = None
         self.predict_chunks = 1             # > 1: predictions are produced (and can be shipped) chunk by chunk
         self.chunk_schedule = "equal"       # "ramp": geometric chunk sizes (see _chunk_bounds)
         self.chunk_growth = 1.5
@@ -252,7 +260,7 @@ class LshCfPipeline:
             chunks = max(1, min(self.predict_chunks, n_local))
             bounds = self._chunk_bounds(n_local, chunks)
             known = [self._pred_capacity.get((chunks, ci, self.cols_mode), 0) * regions for ci in range(chunks)]
-            peers = None
+            peers, stage = None, None
             if G > 1:
                 # neighbour rows of other ranks are read in place from their prepared buffers: nobody may rewrite
                 # its buffer while a peer still predicts from it (barrier 1), nobody may predict before every
@@ -267,9 +275,17 @@ class LshCfPipeline:
                 tm.mark("exchange:barrier")
                 remote = (idx >= 0) & ((idx < row_base) | (idx >= row_base + n_local))
                 tail.append(remote.sum().reshape(1).to(torch.int64))
+                if self.stage_peer_rows == "1" and hasattr(st, "PeerStage"):
+                    # the rows the neighbour tables name on other ranks are copied here in one sweep (NVLink at
+                    # bandwidth) instead of being read line by line by the predicting warps (NVLink at latency);
+                    # the buffer size is learnt like the other capacities: a step that needs more reads in place
+                    stage = st.PeerStage(plan, idx, cnt, self._cap.get("peer_stage", 0), keep=self._stage_buf)
+                    self._stage_buf = stage.buf
+                    tail.append(stage.needed.reshape(1))
+                    tm.mark("exchange:ratings")
             for ci in range(chunks):
                 launched.append(self._launch_chunk(st, plan, rowptr, colidx, val, idx, v, cnt, milli, ci, bounds, chunks,
-                                                   regions, tile, chunk_sink))
+                                                   regions, tile, chunk_sink, stage))
             tail.append((val != 0).sum().reshape(1).to(torch.int64))
         elif G > 1:
             self._all_reduce_max(flags)
@@ -296,6 +312,15 @@ class LshCfPipeline:
         if predict:
             if G > 1:
                 xbytes["ratings(peer reads)"] = int(int(host[7]) * (nnz / max(n_local, 1)) * 4)
+                if stage is not None:
+                    needed = int(host[8])
+                    xbytes["ratings(peer reads)"] = needed * 128
+                    out.peer_rows_staged = needed <= stage.cap_steps
+                    if needed * 128 <= self.peer_stage_budget:
+                        self._cap["peer_stage"] = int(needed * 1.1) + 1024
+                    else:                       # (strong-scaled C3: most neighbours are remote — tens of GB)
+                        self._cap["peer_stage"] = 0
+                        self.stage_peer_rows = "0"
             total = 0
             out.pred_chunks = []
             regions = self.pred_regions
@@ -313,7 +338,7 @@ class LshCfPipeline:
                     key = (c["chunks"], c["ci"], self.cols_mode)
                     self._pred_capacity[key] = int(need * 1.03) + 256
                     c.update(self._launch_chunk(st, plan, rowptr, colidx, val, idx, v, cnt, milli, c["ci"], c["bounds"],
-                                                c["chunks"], regions, c["tile"], chunk_sink))
+                                                c["chunks"], regions, c["tile"], chunk_sink, stage))
                     c["fresh"] = False
                 pos += regions + 1
                 total += nonzero
@@ -347,14 +372,16 @@ class LshCfPipeline:
                 return bounds
         return [n_local * ci // chunks for ci in range(chunks + 1)]
 
-    def _launch_chunk(self, st, plan, rowptr, colidx, val, idx, v, cnt, milli, ci, bounds, chunks, regions, tile, chunk_sink):
+    def _launch_chunk(self, st, plan, rowptr, colidx, val, idx, v, cnt, milli, ci, bounds, chunks, regions, tile, chunk_sink,
+                      stage=None):
         lo, hi = bounds[ci], bounds[ci + 1]
         rcap = self._pred_capacity.get((chunks, ci, self.cols_mode), 0)
         tab = (idx[lo:hi], v[lo:hi], cnt[lo:hi])
         mil = milli[lo:hi] if self.integer_predict else None
         rs, rc, cols, preds, cursors, nzc = st.predict_sparse(rowptr, colidx, val, self.m, tab, lo, hi - lo, tile,
                                                              rcap * regions, u_milli=mil, n_regions=regions,
-                                                             cols_mode=self.cols_mode, plan=plan)
+                                                             cols_mode=self.cols_mode, plan=plan,
+                                                             **({"stage": stage} if stage is not None else {}))
         chunk = {"user_lo": lo, "n_users": hi - lo, "row_start": rs, "row_cnt": rc, "cols": cols, "preds": preds,
                  "cols_mode": self.cols_mode, "tile": tile}
         if chunk_sink is not None and rcap > 0:

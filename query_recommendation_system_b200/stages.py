@@ -341,10 +341,28 @@ class PredictPlan:
                                       self.ws_ptr, self.ws_bytes, _stream()), "qrs_predict_prepare")
 
 
+class PeerStage:
+    """Rows of other ranks that the local users' neighbour table names, copied into a local buffer before the
+    predictor runs (qrs_peer_rows_stage).  `cap_steps` 128-byte steps fit; the device word `needed` tells how many
+    the table asked for — when it exceeds cap_steps nothing is staged and the predictor reads the rows in place, so
+    the caller can size the next step from a readback it does anyway.  Call once every rank has prepared."""
+
+    def __init__(self, plan: "PredictPlan", idx: torch.Tensor, cnt: torch.Tensor, cap_steps: int, keep=None):
+        assert plan.peers is not None and idx.dtype == torch.int32 and cnt.dtype == torch.int32
+        lib = _lib.load()
+        self.n_users, self.ku, self.cap_steps = idx.shape[0], idx.shape[1], int(cap_steps)
+        need = int(lib.qrs_peer_rows_stage_bytes(self.n_users, self.ku, plan.Q, plan.tile, self.cap_steps))
+        self.buf = keep if keep is not None and keep.numel() >= need else _ws(need, idx.device)
+        check(lib.qrs_peer_rows_stage(plan.peers.table, plan.peers.world, plan.peers.rank, plan.U, plan.Q, plan.tile,
+                                      ptr(idx), ptr(cnt), self.ku, self.n_users, self.cap_steps,
+                                      self.buf.data_ptr(), self.buf.numel(), _stream()), "qrs_peer_rows_stage")
+        self.needed = self.buf[:8].view(torch.int64)          # device: steps this table needs
+
+
 def predict_sparse(rowptr, colidx, val, Q: int, u_tab: Table, user_base: int, n_users: int, tile: int,
                    capacity: int, out_cols: Optional[torch.Tensor] = None, out_preds: Optional[torch.Tensor] = None,
                    u_milli: Optional[torch.Tensor] = None, n_regions: int = 1, cols_mode: int = 0,
-                   plan: Optional[PredictPlan] = None):
+                   plan: Optional[PredictPlan] = None, stage: Optional[PeerStage] = None):
     """User-branch predictions in sparse form.  Returns (row_start int64[n_users, nt],
     row_cnt int32[n_users, nt], cols, preds uint8[capacity], cursors int64[n_regions] on device = entries
     requested per region of capacity // n_regions entries, nonzero int64[1] = non-zero predictions).
@@ -386,6 +404,8 @@ def predict_sparse(rowptr, colidx, val, Q: int, u_tab: Table, user_base: int, n_
     check(lib.qrs_predict_sparse(ptr(rowptr), ptr(colidx), ptr(val), U, nnz, Q, ptr(ui), ptr(uv), ptr(u_milli), ptr(uc),
                                  ui.shape[1], user_base, n_users, tile, ws_ptr, ws_bytes, prepared,
                                  peer_tab, n_peers, my_peer,
+                                 stage.buf.data_ptr() if stage is not None else None,
+                                 stage.n_users if stage is not None else 0,
                                  ptr(row_start), ptr(row_cnt), ptr(cols), cols_mode, ptr(preds), capacity, n_regions,
                                  ptr(cursor), _stream()),
           "qrs_predict_sparse")

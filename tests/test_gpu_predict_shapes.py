@@ -192,3 +192,62 @@ def test_prepared_row_layouts(pack, integer, monkeypatch):
     cnt = np.maximum(cnt, 1)
     sims[:, 0] = np.maximum(sims[:, 0], 0.5)
     run_and_check(rowptr, colidx, val, m, idx, sims, cnt, 1024, integer, cols_mode=1 if integer else 0)
+
+
+class _TwoShardsOneDevice:
+    """Stands in for stages.PeerWorkspace: the prepared-row buffers of two 'ranks' live on ONE device, so the
+    sharded addressing of the predictor (global neighbour ids, rows read from another rank's buffer, staged or in
+    place) is exercised without a second GPU."""
+
+    def __init__(self, bufs, rank):
+        import ctypes
+        self.world, self.rank = len(bufs), rank
+        self.local, self.nbytes = bufs[rank].data_ptr(), bufs[rank].numel()
+        self.table = (ctypes.c_uint64 * self.world)(*[b.data_ptr() for b in bufs])
+
+
+@pytest.mark.parametrize("integer,tie_heavy", [(True, False), (True, True), (False, False)])
+@pytest.mark.parametrize("staging", ["in place", "staged", "staged: buffer too small"])
+def test_rows_of_another_rank(integer, tie_heavy, staging):
+    """Users of shard 0 whose neighbours live on both shards: rows of shard 1 read in place, copied into the
+    staging buffer first (qrs_peer_rows_stage), or — buffer too small — announced and read in place after all."""
+    from query_recommendation_system_b200 import stages
+    n, m, k, tile = 512, 3000, 20, 1024
+    h = n // 2
+    rowptr, colidx, val = random_csr(n, m, 0, 300, seed=61)
+    if tie_heavy:
+        val = np.random.default_rng(62).choice(np.array([5, 15, 25, 35], np.uint8), size=val.size)
+    idx, sims, cnt = random_tables(n, k, seed=63, tie_heavy=tie_heavy)
+    shards = []
+    for r in range(2):
+        lo, hi = rowptr[r * h], rowptr[(r + 1) * h]
+        shards.append((rowptr[r * h:(r + 1) * h + 1] - lo, colidx[lo:hi], val[lo:hi]))
+    need = max(stages.predict_workspace_bytes(h, s[1].size, m, tile, 1 << 20) for s in shards)
+    bufs = [torch.empty(need, dtype=torch.uint8, device="cuda") for _ in range(2)]
+    plans = []
+    for r, (rp, ci, va) in enumerate(shards):
+        plans.append(stages.PredictPlan(cu(rp), cu(ci), cu(va), m, tile, capacity_hint=1 << 20,
+                                        peers=_TwoShardsOneDevice(bufs, r)))
+    ref = spec.predict_user_branch_csr(rowptr, colidx, val, m, idx, sims, cnt, rows=range(h))
+    total = sum(v[0].size for v in ref.values())
+    tab = (cu(idx[:h]), cu(sims[:h]), cu(cnt[:h]))
+    milli = cu(np.rint(sims[:h] * 1000).astype(np.int32)) if integer else None
+    stage = None
+    if staging != "in place":
+        probe = stages.PeerStage(plans[0], tab[0], tab[2], 0)                    # cap 0: only counts
+        needed = int(probe.needed.item())
+        remote_rows = idx[:h][(np.arange(k)[None, :] < cnt[:h, None]) & (idx[:h] >= h)] - h
+        nt = (m + tile - 1) // tile
+        steps_of = lambda r: sum(-(-np.count_nonzero((shards[1][1][shards[1][0][r]:shards[1][0][r + 1]] // tile) == t) // 32)
+                                 for t in range(nt))
+        assert needed == sum(steps_of(r) for r in remote_rows)
+        stage = stages.PeerStage(plans[0], tab[0], tab[2], needed if staging == "staged" else needed // 2)
+        assert bool(stage.buf[8:16].view(torch.int64).item()) == (staging == "staged")
+    rp, ci, va = (cu(x) for x in shards[0])
+    rs, rc, cols, preds, cursor, nz = stages.predict_sparse(rp, ci, va, m, tab, 0, h, tile, capacity=total + 64,
+                                                            u_milli=milli, plan=plans[0], stage=stage)
+    assert int(nz.item()) == total
+    rs, rc, cols, preds = rs.cpu().numpy(), rc.cpu().numpy(), cols.cpu().numpy(), preds.cpu().numpy()
+    for t in range(h):
+        gc, gp = decode(rs, rc, cols, preds, 0, tile, t)
+        assert np.array_equal(gc, ref[t][0]) and np.array_equal(gp, ref[t][1]), "user %d" % t
