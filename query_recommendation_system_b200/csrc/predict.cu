@@ -451,14 +451,21 @@ __device__ __forceinline__ int prepared_rating(const PeerView &pv, int v, int co
     }
     if (!full) return 0;
     // every cell holds another entry of the class: the column may be one of the class's extras, anywhere
-    for (unsigned i = 0; i < steps * 32u; i += 4) {
-      const uint4 q = *reinterpret_cast<const uint4 *>(w + i);
-      if ((q.x >> 8) == (key >> 8)) return int(q.x & 0xFFu);
-      if ((q.y >> 8) == (key >> 8)) return int(q.y & 0xFFu);
-      if ((q.z >> 8) == (key >> 8)) return int(q.z & 0xFFu);
-      if ((q.w >> 8) == (key >> 8)) return int(q.w & 0xFFu);
+    int found = 0;
+    for (unsigned i = 0; i < steps * 32u; i += 32) {             // one step per round, its eight loads in flight together
+      uint4 q[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) q[j] = *reinterpret_cast<const uint4 *>(w + i + 4 * j);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if ((q[j].x >> 8) == (key >> 8)) found = int(q[j].x & 0xFFu) | 0x100;
+        if ((q[j].y >> 8) == (key >> 8)) found = int(q[j].y & 0xFFu) | 0x100;
+        if ((q[j].z >> 8) == (key >> 8)) found = int(q[j].z & 0xFFu) | 0x100;
+        if ((q[j].w >> 8) == (key >> 8)) found = int(q[j].w & 0xFFu) | 0x100;
+      }
+      if (found) break;
     }
-    return 0;
+    return found & 0xFF;
   }
   int lo = 0, hi = n;
   while (lo < hi) {
