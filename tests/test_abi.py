@@ -50,6 +50,10 @@ def test_version_status_strings_and_workspace_queries(lib):
     assert lib.qrs_predict_sparse_workspace_bytes(1000, 50_000, 10_000, 480, 0) >= 1000 * 22 * 8 + 4 * 50_000
     assert lib.qrs_predict_warps_per_sm(1024, 1) >= 16 and lib.qrs_predict_warps_per_sm(1000, 1) == 0
     assert lib.qrs_minhash_max_elements() >= 1_000_000
+    # staged peer rows: offset tables for every (user, slot, window) + cap_steps 128-byte steps
+    small, big = lib.qrs_peer_rows_stage_bytes(1000, 28, 10_000, 1024, 0), lib.qrs_peer_rows_stage_bytes(1000, 28, 10_000, 1024, 4096)
+    assert small >= 1000 * 28 * 10 * 8 and big - small == 4096 * 128
+    assert lib.qrs_peer_rows_stage_bytes(1000, 0, 10_000, 1024, 0) == 0
 
 
 def test_argument_validation_without_a_gpu(lib):
@@ -60,6 +64,9 @@ def test_argument_validation_without_a_gpu(lib):
     assert lib.qrs_band_keys(one, 10, 130, 32, one, None, None, None) == -1
     assert lib.qrs_band_records(one, 10, 128, 300, 0, one, 10, None, None) == -1      # b > QRS_MAX_BANDS
     assert lib.qrs_topk_tables(one, one, 5, 0, 10, 65, one, one, 1 << 20, one, one, None, one, None) == -2   # k > 64
+    # staging needs at least two ranks and a 256-byte aligned buffer of the announced size
+    assert lib.qrs_peer_rows_stage(one, 1, 0, 100, 1000, 1024, one, one, 8, 100, 0, one, 1 << 20, None) == -1
+    assert lib.qrs_peer_rows_stage(one, 2, 0, 100, 1000, 1024, one, one, 8, 100, 0, one, 1 << 20, None) == -3
 
 
 def test_package_refuses_to_run_without_cuda():
